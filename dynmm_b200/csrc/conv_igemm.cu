@@ -1,0 +1,484 @@
+// Implicit-GEMM convolution for sm_100a: TMA-fed tcgen05.mma with TMEM accumulators.
+//
+// GEMM view (NHWC bf16):  M = output pixels of a (w, h, sample) box, N = output
+// channels, K = taps x input channels.  The A operand of tap (dy,dx) is the SAME
+// activation tensor shifted by (dy,dx): it is fetched by one TMA box load whose
+// out-of-bounds rows/columns are zero-filled by the hardware, so the convolution's
+// zero padding costs nothing and no im2col buffer exists.  Strided convolutions
+// read a parity sub-lattice of the input through a strided tensor map.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer  (A box + weight tile per (tap, 64-channel chunk))
+//   warp 1      MMA issuer    (one elected lane; 4 x UMMA 128 x tile_n x 16 per stage)
+//   warps 2..5  epilogue      (TMEM -> registers -> scale/shift, residual, ReLU,
+//                              gated depth add -> bf16 NHWC)
+// Two TMEM accumulator buffers let the epilogue of tile i overlap the MMAs of
+// tile i+1.  The tile list is derived on the device from `count` (number of
+// active sample slots), so samples the gate switched off generate no TMA
+// traffic and no MMA work, and the launch is CUDA-graph capturable.
+#include <mutex>
+
+#include "common.cuh"
+
+namespace dynmm {
+
+namespace {
+
+constexpr int kBlockM = 128;       // UMMA M (TMEM lanes)
+constexpr int kBlockK = 64;        // bf16 elements per 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kMaxTaps = 9;
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 192;
+constexpr int kSmemBudget = 227 * 1024;
+constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB
+
+struct Tap {
+  int8_t map;   // which A tensor map (parity sub-lattice)
+  int8_t dw;    // coordinate offset along W (in the sub-lattice)
+  int8_t dh;    // coordinate offset along H
+  int8_t pad;
+};
+
+struct KernelArgs {
+  // tiling
+  int box_w, box_h, box_n;          // pixels per tile = box_w*box_h*box_n <= 128
+  int w_tiles, h_tiles;             // tiles per sample group
+  int c_tiles, tile_n;              // output channel tiles
+  int num_taps, k_chunks;
+  int stages, stage_bytes;
+  int acc_stride, tmem_cols;
+  Tap taps[kMaxTaps];
+  // problem
+  int n, h_out, w_out, c_out;
+  int out_ld, res_ld, gated_ld;
+  int relu;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* out;
+  const __nv_bfloat16* gated;
+  const float* gate;
+  const int32_t* gated_slot;
+  const int32_t* in_map;
+  const int32_t* res_map;
+  const int32_t* count;
+};
+
+struct __align__(8) SmemCtl {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+};
+
+struct TileCoord {
+  int c0, w0, h0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const KernelArgs& a, int tile) {
+  TileCoord t;
+  int ct = tile % a.c_tiles;
+  int r = tile / a.c_tiles;
+  int wt = r % a.w_tiles;
+  r /= a.w_tiles;
+  int ht = r % a.h_tiles;
+  int nt = r / a.h_tiles;
+  t.c0 = ct * a.tile_n;
+  t.w0 = wt * a.box_w;
+  t.h0 = ht * a.box_h;
+  t.n0 = nt * a.box_n;
+  return t;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                  const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
+                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ KernelArgs args) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + args.stages * args.stage_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int active = args.count ? min(*args.count, args.n) : args.n;
+  const int n_groups = (active + args.box_n - 1) / args.box_n;
+  const int total_tiles = n_groups * args.h_tiles * args.w_tiles * args.c_tiles;
+  const int k_iters = args.num_taps * args.k_chunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a0);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < args.stages; ++s) {
+      mbar_init(&ctl->full[s], 1);
+      mbar_init(&ctl->empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctl->acc_full[i], 1);
+      mbar_init(&ctl->acc_empty[i], 4);   // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&ctl->tmem_base, args.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const CUtensorMap* maps[4] = {&map_a0, &map_a1, &map_a2, &map_a3};
+      // TMA always delivers the full box (out-of-bounds elements arrive as zeros)
+      const uint32_t tx_bytes = (args.box_w * args.box_h * args.box_n + args.tile_n) * kBlockK * 2;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(args, tile);
+        const int n_in = args.in_map ? args.in_map[t.n0] : t.n0;
+        for (int it = 0; it < k_iters; ++it) {
+          const int tap = it / args.k_chunks;
+          const int kc = it - tap * args.k_chunks;
+          const Tap tp = args.taps[tap];
+          mbar_wait(&ctl->empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * args.stage_bytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_expect_tx(&ctl->full[stage], tx_bytes);
+          tma_load_4d(sa, maps[tp.map], &ctl->full[stage], kc * kBlockK, t.w0 + tp.dw, t.h0 + tp.dh, n_in);
+          tma_load_3d(sb, &map_b, &ctl->full[stage], kc * kBlockK, t.c0, tap);
+          if (++stage == args.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(kBlockM, args.tile_n);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(&ctl->acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * args.acc_stride;
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&ctl->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * args.stage_bytes);
+          const uint32_t sb = sa + kABytes;
+          const uint64_t da = umma_desc_sw128(sa);
+          const uint64_t db = umma_desc_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advancing K inside the swizzle atom = +32 bytes on the (16-byte unit) start address
+            umma_bf16(d_tmem, da + (k * 2), db + (k * 2), idesc, (it | k) != 0);
+          }
+          umma_commit(&ctl->empty[stage]);          // frees the smem stage when these MMAs retire
+          if (it == k_iters - 1) umma_commit(&ctl->acc_full[acc]);
+          if (++stage == args.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue
+    const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31 belong to this warp
+    const int row = quarter * 32 + lane;          // GEMM row == pixel inside the box
+    const int wl = row % args.box_w;
+    const int hl = (row / args.box_w) % args.box_h;
+    const int nl = row / (args.box_w * args.box_h);
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      const TileCoord t = decode_tile(args, tile);
+      const int n = t.n0 + nl, h = t.h0 + hl, w = t.w0 + wl;
+      const bool valid = nl < args.box_n && n < active && h < args.h_out && w < args.w_out;
+      const size_t pix = valid ? (static_cast<size_t>(n) * args.h_out + h) * args.w_out + w : 0;
+      size_t rpix = pix;
+      if (valid && args.residual && args.res_map) {
+        rpix = (static_cast<size_t>(args.res_map[n]) * args.h_out + h) * args.w_out + w;
+      }
+      float g = 0.f;
+      size_t gpix = 0;
+      if (valid && args.gated) {
+        g = args.gate[n];
+        const int slot = args.gated_slot ? args.gated_slot[n] : n;
+        gpix = (static_cast<size_t>(slot) * args.h_out + h) * args.w_out + w;
+      }
+      mbar_wait(&ctl->acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * args.acc_stride;
+      for (int cb = 0; cb < args.tile_n; cb += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_row + cb, v);
+        tmem_ld_wait();
+        if (!valid) continue;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const int c = t.c0 + cb + j;
+          if (cb + j >= args.tile_n || c >= args.c_out) break;
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
+          if (args.scale) {
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(args.scale + c));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(args.scale + c + 4));
+            f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
+            f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
+          }
+          if (args.shift) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(args.shift + c));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(args.shift + c + 4));
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+          }
+          if (args.residual) {
+            const uint4 r = __ldg(reinterpret_cast<const uint4*>(args.residual + rpix * args.res_ld + c));
+            f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x); f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
+            f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z); f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
+          }
+          if (args.relu) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+          }
+          if (g != 0.f) {
+            const uint4 r = __ldg(reinterpret_cast<const uint4*>(args.gated + gpix * args.gated_ld + c));
+            f[0] += g * bf16_lo(r.x); f[1] += g * bf16_hi(r.x); f[2] += g * bf16_lo(r.y); f[3] += g * bf16_hi(r.y);
+            f[4] += g * bf16_lo(r.z); f[5] += g * bf16_hi(r.z); f[6] += g * bf16_lo(r.w); f[7] += g * bf16_hi(r.w);
+          }
+          uint4 o;
+          o.x = pack_bf16(f[0], f[1]);
+          o.y = pack_bf16(f[2], f[3]);
+          o.z = pack_bf16(f[4], f[5]);
+          o.w = pack_bf16(f[6], f[7]);
+          *reinterpret_cast<uint4*>(args.out + pix * args.out_ld + c) = o;
+        }
+      }
+      // this warp is done reading the accumulator buffer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->acc_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, args.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  });
+  return fn;
+}
+
+int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return DYNMM_ECUDA;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with %d (rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+              (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1], box[2], rank > 3 ? box[3] : 0);
+    return DYNMM_ECUDA;
+  }
+  return DYNMM_OK;
+}
+
+// floor division / modulo for possibly negative tap offsets
+inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// choose the (w,h,n) pixel box of a tile: maximise useful rows per 128-row MMA
+void choose_box(int w, int h, int n, bool single_sample, int* bw, int* bh, int* bn) {
+  double best = -1;
+  for (int cw = 1; cw <= w && cw <= kBlockM; ++cw) {
+    for (int ch = 1; ch <= h && cw * ch <= kBlockM; ++ch) {
+      int cn = single_sample ? 1 : kBlockM / (cw * ch);
+      if (cn > n) cn = n;
+      if (cn < 1) cn = 1;
+      long long tiles = 1LL * ceil_div(w, cw) * ceil_div(h, ch) * ceil_div(n, cn);
+      double eff = (double)w * h * n / (double)(tiles * kBlockM);
+      // prefer wide boxes (contiguous NHWC rows) on ties
+      double score = eff + 1e-6 * cw;
+      if (score > best) {
+        best = score;
+        *bw = cw;
+        *bh = ch;
+        *bn = cn;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+}  // namespace dynmm
+
+using namespace dynmm;
+
+extern "C" int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DYNMM_CHECK_ARG(p && p->in && p->weight && p->out, "conv_igemm: null pointer");
+  DYNMM_CHECK_ARG(p->kh >= 1 && p->kw >= 1 && p->kh * p->kw <= kMaxTaps, "conv_igemm: at most %d taps", kMaxTaps);
+  DYNMM_CHECK_ARG(p->stride_h >= 1 && p->stride_h <= 2 && p->stride_w >= 1 && p->stride_w <= 2,
+                  "conv_igemm: stride must be 1 or 2");
+  DYNMM_CHECK_ARG(p->c_in % 8 == 0 && p->in_ld % 8 == 0 && p->in_ld >= p->c_in, "conv_igemm: c_in/in_ld %% 8");
+  DYNMM_CHECK_ARG(p->c_out % 8 == 0 && p->out_ld % 8 == 0 && p->out_ld >= p->c_out, "conv_igemm: c_out/out_ld %% 8");
+  DYNMM_CHECK_ARG(!p->residual || p->res_ld % 8 == 0, "conv_igemm: res_ld %% 8");
+  DYNMM_CHECK_ARG(!p->gated || (p->gated_ld % 8 == 0 && p->gate), "conv_igemm: gated needs gate[] and gated_ld %% 8");
+  DYNMM_CHECK_ARG(p->n >= 1 && p->n_in >= 1, "conv_igemm: empty batch");
+  const int h_exp = (p->h_in + 2 * p->pad_h - p->kh) / p->stride_h + 1;
+  const int w_exp = (p->w_in + 2 * p->pad_w - p->kw) / p->stride_w + 1;
+  DYNMM_CHECK_ARG(h_exp == p->h_out && w_exp == p->w_out, "conv_igemm: output size %dx%d does not match %dx%d",
+                  p->h_out, p->w_out, h_exp, w_exp);
+  DYNMM_CHECK_ARG((reinterpret_cast<uintptr_t>(p->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->out) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(p->weight) & 15) == 0,
+                  "conv_igemm: pointers must be 16-byte aligned");
+
+  KernelArgs a{};
+  const int c_out_pad = (p->c_out + 15) / 16 * 16;
+  int tile_n = p->tile_n;
+  const int sms = num_sms();
+  choose_box(p->w_out, p->h_out, p->n, p->in_map != nullptr, &a.box_w, &a.box_h, &a.box_n);
+  a.w_tiles = ceil_div(p->w_out, a.box_w);
+  a.h_tiles = ceil_div(p->h_out, a.box_h);
+  const int m_tiles = a.w_tiles * a.h_tiles * ceil_div(p->n, a.box_n);
+  if (tile_n == 0) {
+    // widest channel tile that still gives every SM a tile
+    tile_n = c_out_pad < 256 ? c_out_pad : 256;
+    while (tile_n > 64 && tile_n % 32 == 0 && m_tiles * ceil_div(c_out_pad, tile_n) < sms) tile_n /= 2;
+  }
+  DYNMM_CHECK_ARG(tile_n >= 16 && tile_n <= 256 && tile_n % 16 == 0, "conv_igemm: tile_n %d", tile_n);
+  a.tile_n = tile_n;
+  a.c_tiles = ceil_div(c_out_pad, tile_n);
+  a.num_taps = p->kh * p->kw;
+  a.k_chunks = ceil_div(p->c_in, kBlockK);
+  a.stage_bytes = kABytes + tile_n * kBlockK * 2;
+  a.stages = (kSmemBudget - 2048) / a.stage_bytes;
+  if (a.stages > kMaxStages) a.stages = kMaxStages;
+  DYNMM_CHECK_ARG(a.stages >= 2, "conv_igemm: not enough shared memory for 2 stages");
+  a.acc_stride = (tile_n + 31) / 32 * 32;
+  a.tmem_cols = 32;
+  while (a.tmem_cols < 2 * a.acc_stride) a.tmem_cols *= 2;
+  a.n = p->n;
+  a.h_out = p->h_out;
+  a.w_out = p->w_out;
+  a.c_out = p->c_out;
+  a.out_ld = p->out_ld;
+  a.res_ld = p->res_ld;
+  a.gated_ld = p->gated_ld;
+  a.relu = p->relu;
+  a.scale = p->scale;
+  a.shift = p->shift;
+  a.residual = static_cast<const __nv_bfloat16*>(p->residual);
+  a.out = static_cast<__nv_bfloat16*>(p->out);
+  a.gated = static_cast<const __nv_bfloat16*>(p->gated);
+  a.gate = p->gate;
+  a.gated_slot = p->gated_slot;
+  a.in_map = p->in_map;
+  a.res_map = p->res_map;
+  a.count = p->count;
+
+  // A maps: one per (parity_h, parity_w) sub-lattice of the input
+  CUtensorMap maps[4];
+  bool used[4] = {false, false, false, false};
+  for (int ky = 0; ky < p->kh; ++ky) {
+    for (int kx = 0; kx < p->kw; ++kx) {
+      const int dy = ky - p->pad_h, dx = kx - p->pad_w;
+      const int qy = floordiv(dy, p->stride_h), py = dy - qy * p->stride_h;
+      const int qx = floordiv(dx, p->stride_w), px = dx - qx * p->stride_w;
+      Tap& t = a.taps[ky * p->kw + kx];
+      t.map = static_cast<int8_t>(py * p->stride_w + px);
+      t.dw = static_cast<int8_t>(qx);
+      t.dh = static_cast<int8_t>(qy);
+      used[t.map] = true;
+    }
+  }
+  const uint64_t es = 2;
+  int first_used = -1;
+  for (int m = 0; m < 4; ++m) {
+    if (!used[m]) continue;
+    if (first_used < 0) first_used = m;
+    const int py = m / p->stride_w, px = m % p->stride_w;
+    const uint64_t dims[4] = {(uint64_t)p->c_in, (uint64_t)((p->w_in - px + p->stride_w - 1) / p->stride_w),
+                              (uint64_t)((p->h_in - py + p->stride_h - 1) / p->stride_h), (uint64_t)p->n_in};
+    const uint64_t strides[3] = {(uint64_t)p->in_ld * p->stride_w * es, (uint64_t)p->in_ld * p->w_in * p->stride_h * es,
+                                 (uint64_t)p->in_ld * p->w_in * p->h_in * es};
+    const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)a.box_w, (uint32_t)a.box_h, (uint32_t)a.box_n};
+    const __nv_bfloat16* base =
+        static_cast<const __nv_bfloat16*>(p->in) + (static_cast<size_t>(py) * p->w_in + px) * p->in_ld;
+    DYNMM_CHECK_ARG(dims[1] >= 1 && dims[2] >= 1, "conv_igemm: input too small for stride");
+    int rc = encode_map(&maps[m], base, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  for (int m = 0; m < 4; ++m)
+    if (!used[m]) maps[m] = maps[first_used];
+  CUtensorMap map_b;
+  {
+    const uint64_t dims[3] = {(uint64_t)p->c_in, (uint64_t)c_out_pad, (uint64_t)a.num_taps};
+    const uint64_t strides[2] = {(uint64_t)p->c_in * es, (uint64_t)p->c_in * c_out_pad * es};
+    const uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)tile_n, 1u};
+    int rc = encode_map(&map_b, p->weight, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+
+  const int smem_bytes = a.stages * a.stage_bytes + 1024 /*align slack*/ + (int)sizeof(SmemCtl);
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+  });
+  DYNMM_CUDA(attr_err);
+  const int max_tiles = m_tiles * a.c_tiles;
+  int grid = p->max_ctas > 0 ? p->max_ctas : sms;
+  if (grid > max_tiles) grid = max_tiles;
+  conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(maps[0], maps[1], maps[2], maps[3], map_b, a);
+  DYNMM_LAUNCH_CHECK();
+  return DYNMM_OK;
+}

@@ -1,0 +1,482 @@
+// Memory-bound glue of the gated path: gated adds, the modality-level expert mix,
+// row compaction, layout conversion, learned 2x upsampling and pyramid pooling.
+// All kernels are coalesced, 16-byte vectorised where the layout allows, and sized
+// as a multiple of the SM count with grid-stride loops.
+#include "common.cuh"
+
+namespace dynmm {
+namespace {
+
+inline int grid_for(long long work_items, int threads, int max_waves = 8) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = 1LL * num_sms() * max_waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ---------------------------------------------------------------- gated add (bf16, inference)
+__global__ void gated_add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
+                                      const float* __restrict__ gate, const int32_t* __restrict__ slot, int n,
+                                      long long vec_per_sample, uint4* __restrict__ out) {
+  const long long total = 1LL * n * vec_per_sample;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const int s = (int)(i / vec_per_sample);
+    const long long r = i - 1LL * s * vec_per_sample;
+    uint4 va = a[i];
+    const float g = gate[s];
+    if (g != 0.f) {   // gated-off samples never touch b
+      const int bs = slot ? slot[s] : s;
+      const uint4 vb = __ldg(&b[1LL * bs * vec_per_sample + r]);
+      va.x = pack_bf16(bf16_lo(va.x) + g * bf16_lo(vb.x), bf16_hi(va.x) + g * bf16_hi(vb.x));
+      va.y = pack_bf16(bf16_lo(va.y) + g * bf16_lo(vb.y), bf16_hi(va.y) + g * bf16_hi(vb.y));
+      va.z = pack_bf16(bf16_lo(va.z) + g * bf16_lo(vb.z), bf16_hi(va.z) + g * bf16_hi(vb.z));
+      va.w = pack_bf16(bf16_lo(va.w) + g * bf16_lo(vb.w), bf16_hi(va.w) + g * bf16_hi(vb.w));
+    }
+    out[i] = va;
+  }
+}
+
+// ---------------------------------------------------------------- gated add (fp32, training path)
+__global__ void gated_add_f32_fwd_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
+                                         const float* __restrict__ gate, int n, long long vec_per_sample,
+                                         float4* __restrict__ out) {
+  const long long total = 1LL * n * vec_per_sample;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const float g = gate[i / vec_per_sample];
+    float4 va = a[i];
+    const float4 vb = b[i];
+    va.x = fmaf(g, vb.x, va.x);
+    va.y = fmaf(g, vb.y, va.y);
+    va.z = fmaf(g, vb.z, va.z);
+    va.w = fmaf(g, vb.w, va.w);
+    out[i] = va;
+  }
+}
+
+// grad_b = g * grad ; grad_gate[n] = sum(grad * b) (fixed-order two-level reduction)
+__global__ void gated_add_f32_bwd_kernel(const float4* __restrict__ grad, const float4* __restrict__ b,
+                                         const float* __restrict__ gate, long long vec_per_sample,
+                                         float4* __restrict__ grad_b, float* __restrict__ partial) {
+  __shared__ float s_red[8];
+  const int s = blockIdx.y;
+  const float g = gate[s];
+  float acc = 0.f;
+  const long long base = 1LL * s * vec_per_sample;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < vec_per_sample;
+       i += 1LL * gridDim.x * blockDim.x) {
+    const float4 gr = grad[base + i];
+    const float4 vb = b[base + i];
+    acc += gr.x * vb.x + gr.y * vb.y + gr.z * vb.z + gr.w * vb.w;
+    if (grad_b) grad_b[base + i] = make_float4(g * gr.x, g * gr.y, g * gr.z, g * gr.w);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
+    partial[1LL * s * gridDim.x + blockIdx.x] = t;
+  }
+}
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int per_row, float* __restrict__ out) {
+  // one warp per row, lanes stride the partials, fixed butterfly order
+  const int row = blockIdx.x;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < per_row; i += 32) acc += partial[1LL * row * per_row + i];
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (threadIdx.x == 0) out[row] = acc;
+}
+
+// ---------------------------------------------------------------- modality-level expert mix
+struct MixArgs {
+  const float* pred[4];
+  const int32_t* rows[4];
+  float* grad_pred[4];
+};
+__global__ void softgate_mix_fwd_kernel(MixArgs a, const float* __restrict__ w, int b, int c, int ne,
+                                        float* __restrict__ out) {
+  const long long total = 1LL * b * c;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const int r = (int)(i / c), col = (int)(i - 1LL * r * c);
+    float acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (e >= ne) break;
+      const float we = w[r * ne + e];
+      if (we != 0.f) {   // an expert with zero weight may not have been evaluated for this row at all
+        const int src = a.rows[e] ? a.rows[e][r] : r;
+        acc = fmaf(we, a.pred[e][1LL * src * c + col], acc);
+      }
+    }
+    out[i] = acc;
+  }
+}
+// one warp per row: grad_pred[e] = w[e]*grad ; grad_w[e] = <grad, pred[e]>
+__global__ void softgate_mix_bwd_kernel(MixArgs a, const float* __restrict__ grad_out, const float* __restrict__ w,
+                                        int b, int c, int ne, float* __restrict__ grad_w) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= b) return;
+  float dots[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int col = lane; col < c; col += 32) {
+    const float g = grad_out[1LL * r * c + col];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (e >= ne) break;
+      dots[e] = fmaf(g, a.pred[e][1LL * r * c + col], dots[e]);
+      if (a.grad_pred[e]) a.grad_pred[e][1LL * r * c + col] = w[r * ne + e] * g;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) dots[e] += __shfl_xor_sync(0xffffffffu, dots[e], o);
+    if (lane == 0 && e < ne && grad_w) grad_w[r * ne + e] = dots[e];
+  }
+}
+
+// stable compaction of the rows that route to `expert` (single block; b is a batch)
+__global__ void compact_rows_kernel(const float* __restrict__ w, int b, int ne, int expert, int32_t* __restrict__ idx,
+                                    int32_t* __restrict__ inv, int32_t* __restrict__ count) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int start = 0; start < b; start += blockDim.x) {
+    const int i = start + threadIdx.x;
+    const bool keep = i < b && w[i * ne + expert] != 0.f;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int off = s_base;
+    for (int k = 0; k < warp; ++k) off += s_warp[k];
+    if (keep) {
+      const int pos = off + __popc(m & ((1u << lane) - 1));
+      idx[pos] = i;
+      inv[i] = pos;
+    } else if (i < b) {
+      inv[i] = -1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int k = 0; k < nwarps; ++k) t += s_warp[k];
+      s_base += t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = s_base;
+}
+
+// ---------------------------------------------------------------- layout conversion (32x32 smem transpose)
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ in, int c, long long hw,
+                                             __nv_bfloat16* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long p0 = blockIdx.x * 32LL;
+  const int c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int ch = c0 + j;
+    const long long p = p0 + threadIdx.x;
+    tile[j][threadIdx.x] = (ch < c && p < hw) ? in[(1LL * n * c + ch) * hw + p] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long p = p0 + j;
+    const int ch = c0 + threadIdx.x;
+    if (ch < c && p < hw) out[(1LL * n * hw + p) * c + ch] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+  }
+}
+__global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ in, int c, long long hw, int ld,
+                                             float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long p0 = blockIdx.x * 32LL;
+  const int c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long p = p0 + j;
+    const int ch = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (ch < c && p < hw) ? __bfloat162float(in[(1LL * n * hw + p) * ld + ch]) : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int ch = c0 + j;
+    const long long p = p0 + threadIdx.x;
+    if (ch < c && p < hw) out[(1LL * n * c + ch) * hw + p] = tile[threadIdx.x][j];
+  }
+}
+
+// ---------------------------------------------------------------- nearest x2 + depthwise 3x3 (zero pad) + bias (+ skip)
+// Each output pixel (Y,X) reads the 3x3 neighbourhood of the nearest-upsampled map, i.e. input
+// pixels ((Y+dy)>>1, (X+dx)>>1); the 4x larger intermediate of the reference never exists.
+// NHWC variant: a thread owns 8 channels of one output pixel (16-byte loads/stores).
+__global__ void upsample2x_dw_nhwc_kernel(const __nv_bfloat16* __restrict__ in, int n, int h, int w, int c,
+                                          const float* __restrict__ wgt, const float* __restrict__ bias,
+                                          const __nv_bfloat16* __restrict__ skip, __nv_bfloat16* __restrict__ out) {
+  const int cv = c >> 3;
+  const long long total = 1LL * n * 4 * h * w * cv;
+  const int H = 2 * h, W = 2 * w;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv) * 8;
+    long long r = i / cv;
+    const int X = (int)(r % W);
+    r /= W;
+    const int Y = (int)(r % H);
+    const int s = (int)(r / H);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = bias ? bias[c8 + e] : 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yy = Y + dy;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int xx = X + dx;
+        if (xx < 0 || xx >= W) continue;
+        const uint4 v =
+            __ldg(reinterpret_cast<const uint4*>(in + ((1LL * s * h + (yy >> 1)) * w + (xx >> 1)) * c + c8));
+        const float f[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
+                            bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
+        const int k = (dy + 1) * 3 + dx + 1;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(f[e], __ldg(&wgt[(c8 + e) * 9 + k]), acc[e]);
+      }
+    }
+    const long long o = ((1LL * s * H + Y) * W + X) * c + c8;
+    if (skip) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(skip + o));
+      acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+      acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+    }
+    uint4 ov;
+    ov.x = pack_bf16(acc[0], acc[1]);
+    ov.y = pack_bf16(acc[2], acc[3]);
+    ov.z = pack_bf16(acc[4], acc[5]);
+    ov.w = pack_bf16(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(out + o) = ov;
+  }
+}
+// Final upsample: NHWC bf16 in -> NCHW fp32 out (the module's return layout).  A CTA owns a
+// 32-pixel run of one output row for all channels: input reads are channel-contiguous,
+// output writes are pixel-contiguous per channel (transposed through shared memory).
+__global__ void upsample2x_dw_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int h, int w, int c,
+                                             const float* __restrict__ wgt, const float* __restrict__ bias,
+                                             float* __restrict__ out) {
+  extern __shared__ float s_out[];   // [c][33]
+  const int H = 2 * h, W = 2 * w;
+  const int X0 = blockIdx.x * 32, Y = blockIdx.y, s = blockIdx.z;
+  for (int i = threadIdx.x; i < 32 * c; i += blockDim.x) {
+    const int ch = i % c, px = i / c;
+    const int X = X0 + px;
+    float acc = 0.f;
+    if (X < W) {
+      acc = bias ? bias[ch] : 0.f;
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int yy = Y + dy;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int xx = X + dx;
+          if (xx < 0 || xx >= W) continue;
+          acc = fmaf(__bfloat162float(in[((1LL * s * h + (yy >> 1)) * w + (xx >> 1)) * c + ch]),
+                     __ldg(&wgt[ch * 9 + (dy + 1) * 3 + dx + 1]), acc);
+        }
+      }
+    }
+    s_out[ch * 33 + px] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * c; i += blockDim.x) {
+    const int px = i & 31, ch = i >> 5;
+    if (X0 + px < W) out[((1LL * s * c + ch) * H + Y) * W + X0 + px] = s_out[ch * 33 + px];
+  }
+}
+
+// ---------------------------------------------------------------- pyramid pooling helpers
+__global__ void adaptive_avgpool_kernel(const __nv_bfloat16* __restrict__ in, int h, int w, int c, int ld, int bins,
+                                        __nv_bfloat16* __restrict__ out) {
+  // grid (bins*bins, n); threads stride channels; window = [floor(i*h/bins), ceil((i+1)*h/bins))
+  const int by = blockIdx.x / bins, bx = blockIdx.x % bins, s = blockIdx.y;
+  const int y0 = (by * h) / bins, y1 = ((by + 1) * h + bins - 1) / bins;
+  const int x0 = (bx * w) / bins, x1 = ((bx + 1) * w + bins - 1) / bins;
+  const float inv = 1.f / (float)((y1 - y0) * (x1 - x0));
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float acc = 0.f;
+    for (int y = y0; y < y1; ++y)
+      for (int x = x0; x < x1; ++x) acc += __bfloat162float(in[((1LL * s * h + y) * w + x) * ld + ch]);
+    out[((1LL * s * bins + by) * bins + bx) * c + ch] = __float2bfloat16_rn(acc * inv);
+  }
+}
+__global__ void nearest_resize_into_kernel(const __nv_bfloat16* __restrict__ src, int n, int hs, int ws, int c,
+                                           __nv_bfloat16* __restrict__ dst, int h, int w, int ld, int c_off) {
+  const int cv = c >> 3;
+  const long long total = 1LL * n * h * w * cv;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv) * 8;
+    long long r = i / cv;
+    const int x = (int)(r % w);
+    r /= w;
+    const int y = (int)(r % h);
+    const int s = (int)(r / h);
+    // F.interpolate(mode='nearest'): src = floor(dst * in/out)
+    const int sy = min((int)((long long)y * hs / h), hs - 1), sx = min((int)((long long)x * ws / w), ws - 1);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + ((1LL * s * hs + sy) * ws + sx) * c + c8));
+    *reinterpret_cast<uint4*>(dst + ((1LL * s * h + y) * w + x) * ld + c_off + c8) = v;
+  }
+}
+
+}  // namespace
+}  // namespace dynmm
+
+using namespace dynmm;
+
+extern "C" int dynmm_gated_add_fwd(const void* a, const void* b, const float* gate, const int32_t* slot, int n,
+                                   long long per_sample, void* out, void* stream) {
+  DYNMM_CHECK_ARG(a && b && gate && out && n >= 1 && per_sample >= 8 && per_sample % 8 == 0,
+                  "gated_add: per_sample must be a positive multiple of 8");
+  const long long vec = per_sample / 8;
+  gated_add_bf16_kernel<<<grid_for(n * vec, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(a), static_cast<const uint4*>(b), gate, slot, n, vec, static_cast<uint4*>(out));
+  DYNMM_LAUNCH_CHECK();
+  return DYNMM_OK;
+}
+
+extern "C" int dynmm_gated_add_f32_fwd(const float* a, const float* b, const float* gate, int n, long long per_sample,
+                                       float* out, void* stream) {
+  DYNMM_CHECK_ARG(a && b && gate && out && n >= 1 && per_sample >= 4 && per_sample % 4 == 0,
+                  "gated_add_f32: per_sample must be a positive multiple of 4");
+  const long long vec = per_sample / 4;
+  gated_add_f32_fwd_kernel<<<grid_for(n * vec, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), gate, n, vec,
+      reinterpret_cast<float4*>(out));
+  DYNMM_LAUNCH_CHECK();
+  return DYNMM_OK;
+}
+
+// grad_gate needs n * kBwdBlocks floats of scratch: it is carved from grad_gate's tail, so
+// callers allocate grad_gate with n * (1 + 64) floats.
+static const int kBwdBlocks = 64;
+extern "C" int dynmm_gated_add_f32_bwd(const float* grad, const float* b, const float* gate, int n,
+                                       long long per_sample, float* grad_b, float* grad_gate, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DYNMM_CHECK_ARG(grad && b && gate && grad_gate && n >= 1 && per_sample >= 4 && per_sample % 4 == 0,
+                  "gated_add_f32_bwd: per_sample must be a positive multiple of 4");
+  const long long vec = per_sample / 4;
+  float* partial = grad_gate + n;
+  gated_add_f32_bwd_kernel<<<dim3(kBwdBlocks, n), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(grad), reinterpret_cast<const float4*>(b), gate, vec,
+      reinterpret_cast<float4*>(grad_b), partial);
+  DYNMM_LAUNCH_CHECK();
+  reduce_partials_kernel<<<n, 32, 0, stream>>>(partial, kBwdBlocks, grad_gate);
+  DYNMM_LAUNCH_CHECK();
+  return DYNMM_OK;
+}
+
+extern "C" int dynmm_softgate_mix_fwd(const float* const* preds, const int32_t* const* rows, const float* w, int b,
+                                      int c, int n_experts, float* out, void* stream) {
+  DYNMM_CHECK_ARG(preds && w && out && b >= 1 && c >= 1 && n_experts >= 1 && n_experts <= 4, "softgate_mix: bad args");
+  MixArgs a{};
+  for (int e = 0; e < n_experts; ++e) {
+    DYNMM_CHECK_ARG(preds[e], "softgate_mix: null expert output");
+    a.pred[e] = preds[e];
+    a.rows[e] = rows ? rows[e] : nullptr;
+  }
+  softgate_mix_fwd_kernel<<<grid_for(1LL * b * c, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, w, b, c,
+                                                                                                     n_experts, out);
+  DYNMM_LAUNCH_CHECK();
+  return DYNMM_OK;
+}
+
+extern "C" int dynmm_softgate_mix_bwd(const float* grad_out, const float* const* preds, const float* w, int b, int c,
+                                      int n_experts, float* const* grad_preds, float* grad_w, void* stream) {
+  DYNMM_CHECK_ARG(grad_out && preds && w && b >= 1 && c >= 1 && n_experts >= 1 && n_experts <= 4,
+                  "softgate_mix_bwd: bad args");
+  MixArgs a{};
+  for (int e = 0; e < n_experts; ++e) {
+    DYNMM_CHECK_ARG(preds[e], "softgate_mix_bwd: null expert output");
+    a.pred[e] = preds[e];
+    a.grad_pred[e] = grad_preds ? grad_preds[e] : nullptr;
+  }
+  softgate_mix_bwd_kernel<<<ceil_div(b, 4), 128, 0, static_cast<cudaStream_t>(stream)>>>(a, grad_out, w, b, c,
+                                                                                         n_experts, grad_w);
+  DYNMM_LAUNCH_CHECK();
+  return DYNMM_OK;
+}
+
+extern "C" int dynmm_compact_rows(const float* w, int b, int n_experts, int expert, int32_t* idx, int32_t* inv,
+                                  int32_t* count, void* stream) {
+  DYNMM_CHECK_ARG(w && idx && inv && count && b >= 1 && expert >= 0 && expert < n_experts, "compact_rows: bad args");
+  compact_rows_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, b, n_experts, expert, idx, inv, count);
+  DYNMM_LAUNCH_CHECK();
+  return DYNMM_OK;
+}
+
+extern "C" int dynmm_nchw_f32_to_nhwc_bf16(const float* in, int n, int c, int h, int w, void* out, void* stream) {
+  DYNMM_CHECK_ARG(in && out && n >= 1 && c >= 1 && h >= 1 && w >= 1, "nchw_to_nhwc: bad args");
+  const long long hw = 1LL * h * w;
+  dim3 grid((unsigned)ceil_div_ll(hw, 32), ceil_div(c, 32), n);
+  nchw_f32_to_nhwc_bf16_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+      in, c, hw, static_cast<__nv_bfloat16*>(out));
+  DYNMM_LAUNCH_CHECK();
+  return DYNMM_OK;
+}
+
+extern "C" int dynmm_nhwc_bf16_to_nchw_f32(const void* in, int n, int c, int h, int w, int ld, float* out,
+                                           void* stream) {
+  DYNMM_CHECK_ARG(in && out && n >= 1 && c >= 1 && h >= 1 && w >= 1 && ld >= c, "nhwc_to_nchw: bad args");
+  const long long hw = 1LL * h * w;
+  dim3 grid((unsigned)ceil_div_ll(hw, 32), ceil_div(c, 32), n);
+  nhwc_bf16_to_nchw_f32_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(in), c, hw, ld, out);
+  DYNMM_LAUNCH_CHECK();
+  return DYNMM_OK;
+}
+
+extern "C" int dynmm_upsample2x_dw3x3(const void* in, int n, int h, int w, int c, const float* weight,
+                                      const float* bias, const void* skip, void* out_nhwc_bf16, float* out_nchw_f32,
+                                      void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DYNMM_CHECK_ARG(in && weight && n >= 1 && h >= 1 && w >= 1 && c >= 8 && c % 8 == 0, "upsample2x: c %% 8");
+  DYNMM_CHECK_ARG((out_nhwc_bf16 != nullptr) != (out_nchw_f32 != nullptr), "upsample2x: exactly one output");
+  if (out_nhwc_bf16) {
+    const long long total = 1LL * n * 4 * h * w * (c / 8);
+    upsample2x_dw_nhwc_kernel<<<grid_for(total, 256, 16), 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(in), n, h, w, c, weight, bias, static_cast<const __nv_bfloat16*>(skip),
+        static_cast<__nv_bfloat16*>(out_nhwc_bf16));
+  } else {
+    DYNMM_CHECK_ARG(!skip, "upsample2x: skip is only supported for the NHWC output");
+    DYNMM_CHECK_ARG(c <= 256, "upsample2x: at most 256 channels for the NCHW output");
+    dim3 grid(ceil_div(2 * w, 32), 2 * h, n);
+    upsample2x_dw_to_nchw_kernel<<<grid, 256, c * 33 * sizeof(float), stream>>>(
+        static_cast<const __nv_bfloat16*>(in), h, w, c, weight, bias, out_nchw_f32);
+  }
+  DYNMM_LAUNCH_CHECK();
+  return DYNMM_OK;
+}
+
+extern "C" int dynmm_adaptive_avgpool(const void* in, int n, int h, int w, int c, int ld, int bins, void* out,
+                                      void* stream) {
+  DYNMM_CHECK_ARG(in && out && n >= 1 && h >= 1 && w >= 1 && c >= 1 && ld >= c && bins >= 1 && bins <= 64,
+                  "avgpool: bad args");
+  adaptive_avgpool_kernel<<<dim3(bins * bins, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(in), h, w, c, ld, bins, static_cast<__nv_bfloat16*>(out));
+  DYNMM_LAUNCH_CHECK();
+  return DYNMM_OK;
+}
+
+extern "C" int dynmm_nearest_resize_into(const void* src, int n, int hs, int ws, int c, void* dst, int h, int w, int ld,
+                                         int c_off, void* stream) {
+  DYNMM_CHECK_ARG(src && dst && c % 8 == 0 && ld % 8 == 0 && c_off % 8 == 0 && c_off + c <= ld,
+                  "resize: c/ld/c_off %% 8");
+  const long long total = 1LL * n * h * w * (c / 8);
+  nearest_resize_into_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), n, hs, ws, c, static_cast<__nv_bfloat16*>(dst), h, w, ld, c_off);
+  DYNMM_LAUNCH_CHECK();
+  return DYNMM_OK;
+}

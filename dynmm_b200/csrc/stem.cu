@@ -1,0 +1,215 @@
+// Fused stem: conv7x7/s2 + BN + ReLU on RGB and on depth, rgb+depth add, and both
+// 3x3/s2 max-pools in ONE kernel (resnet.py:352-358 + model_skip_mod_globalgate.py:256-261).
+//
+// Everything is fp32 on CUDA cores: K is only 147 / 49 (HBM/issue bound, not a
+// tensor-core shape) and the pooled maps feed the gate, whose hard decisions
+// must match the fp32 reference.  The two 64x240x320 stem maps never reach HBM:
+// a CTA produces an 8x8 tile of POOLED outputs from a 17x17 tile of stem outputs
+// held in shared memory (13 % halo recompute instead of a 2 x 157 MB round trip
+// per 8 images).
+#include "common.cuh"
+
+namespace dynmm {
+namespace {
+
+constexpr int kPT = 8;                    // pooled tile edge
+constexpr int kST = 2 * kPT + 1;          // stem tile edge (17)
+constexpr int kPatch = 2 * (kST - 1) + 7; // input patch edge (39)
+constexpr int kPos = kST * kST;           // 289 stem positions
+constexpr int kThreads = 256;
+constexpr int kPosThreads = 64;           // threads along positions; 4 channel groups of 16
+constexpr int kPosPerThread = (kPos + kPosThreads - 1) / kPosThreads;  // 5
+constexpr int kKRgb = 7 * 7 * 3, kKDepth = 7 * 7;
+
+constexpr size_t kSmemFloats = 2 * kPos * 64 + (kKRgb + kKDepth) * 64 + 4 * kPatch * kPatch + 4 * 64;
+
+// swizzled index into a [pos][64] fp32 tile: float4 column XOR (pos & 7)
+__device__ __forceinline__ int tile_idx(int pos, int c) {
+  return pos * 64 + ((((c >> 2) ^ (pos & 7)) << 2) | (c & 3));
+}
+
+template <int CIN>
+__device__ __forceinline__ void conv_accumulate(const float* __restrict__ patch, const float* __restrict__ wsm,
+                                                const int (&poff)[kPosPerThread], int cg,
+                                                float (&acc)[kPosPerThread][16]) {
+#pragma unroll 1
+  for (int ky = 0; ky < 7; ++ky) {
+#pragma unroll 1
+    for (int kx = 0; kx < 7; ++kx) {
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) {
+        const float4* w4 = reinterpret_cast<const float4*>(wsm + ((ky * 7 + kx) * CIN + ci) * 64 + cg * 16);
+        const float4 w0 = w4[0], w1 = w4[1], w2 = w4[2], w3 = w4[3];
+        const float* pp = patch + ci * kPatch * kPatch + ky * kPatch + kx;
+#pragma unroll
+        for (int i = 0; i < kPosPerThread; ++i) {
+          const float x = pp[poff[i]];
+          acc[i][0] = fmaf(x, w0.x, acc[i][0]);   acc[i][1] = fmaf(x, w0.y, acc[i][1]);
+          acc[i][2] = fmaf(x, w0.z, acc[i][2]);   acc[i][3] = fmaf(x, w0.w, acc[i][3]);
+          acc[i][4] = fmaf(x, w1.x, acc[i][4]);   acc[i][5] = fmaf(x, w1.y, acc[i][5]);
+          acc[i][6] = fmaf(x, w1.z, acc[i][6]);   acc[i][7] = fmaf(x, w1.w, acc[i][7]);
+          acc[i][8] = fmaf(x, w2.x, acc[i][8]);   acc[i][9] = fmaf(x, w2.y, acc[i][9]);
+          acc[i][10] = fmaf(x, w2.z, acc[i][10]); acc[i][11] = fmaf(x, w2.w, acc[i][11]);
+          acc[i][12] = fmaf(x, w3.x, acc[i][12]); acc[i][13] = fmaf(x, w3.y, acc[i][13]);
+          acc[i][14] = fmaf(x, w3.z, acc[i][14]); acc[i][15] = fmaf(x, w3.w, acc[i][15]);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+stem_kernel(const float* __restrict__ rgb, const float* __restrict__ depth, int H, int W,
+            const float* __restrict__ w_rgb, const float* __restrict__ scale_rgb, const float* __restrict__ shift_rgb,
+            const float* __restrict__ w_d, const float* __restrict__ scale_d, const float* __restrict__ shift_d,
+            float* __restrict__ rgb_f32, float* __restrict__ depth_f32, __nv_bfloat16* __restrict__ rgb_bf16,
+            __nv_bfloat16* __restrict__ depth_bf16) {
+  extern __shared__ __align__(16) float sm[];
+  float* s_fuse = sm;                          // [289][64] swizzled: rgb stem, then rgb+depth
+  float* s_dep = s_fuse + kPos * 64;           // [289][64] swizzled: depth stem
+  float* s_wr = s_dep + kPos * 64;             // [147][64]
+  float* s_wd = s_wr + kKRgb * 64;             // [49][64]
+  float* s_patch = s_wd + kKDepth * 64;        // [4][39][39]  (r,g,b,depth)
+  float* s_bn = s_patch + 4 * kPatch * kPatch; // scale_rgb, shift_rgb, scale_d, shift_d
+
+  const int Hs = (H + 2 * 3 - 7) / 2 + 1, Ws = (W + 2 * 3 - 7) / 2 + 1;   // stem map
+  const int Hp = (Hs + 2 - 3) / 2 + 1, Wp = (Ws + 2 - 3) / 2 + 1;         // pooled map
+  const int n = blockIdx.z;
+  const int py0 = blockIdx.y * kPT, px0 = blockIdx.x * kPT;
+  const int sy0 = 2 * py0 - 1, sx0 = 2 * px0 - 1;     // stem-tile origin
+  const int iy0 = 2 * sy0 - 3, ix0 = 2 * sx0 - 3;     // input-patch origin
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < kKRgb * 64; i += kThreads) s_wr[i] = w_rgb[i];
+  for (int i = tid; i < kKDepth * 64; i += kThreads) s_wd[i] = w_d[i];
+  if (tid < 64) {
+    s_bn[tid] = scale_rgb[tid];
+    s_bn[64 + tid] = shift_rgb[tid];
+    s_bn[128 + tid] = scale_d[tid];
+    s_bn[192 + tid] = shift_d[tid];
+  }
+  for (int i = tid; i < 4 * kPatch * kPatch; i += kThreads) {
+    const int ch = i / (kPatch * kPatch);
+    const int r = i % (kPatch * kPatch);
+    const int y = iy0 + r / kPatch, x = ix0 + r % kPatch;
+    float v = 0.f;
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      v = ch < 3 ? rgb[((static_cast<size_t>(n) * 3 + ch) * H + y) * W + x]
+                 : depth[(static_cast<size_t>(n) * H + y) * W + x];
+    }
+    s_patch[i] = v;
+  }
+  __syncthreads();
+
+  const int cg = tid / kPosThreads;       // warp-uniform channel group: weight loads broadcast
+  const int tpos = tid % kPosThreads;
+  int poff[kPosPerThread];
+  int pos[kPosPerThread];
+#pragma unroll
+  for (int i = 0; i < kPosPerThread; ++i) {
+    int p = tpos + i * kPosThreads;
+    pos[i] = p;
+    if (p >= kPos) p = kPos - 1;          // clamp: computed but never stored
+    poff[i] = (2 * (p / kST)) * kPatch + 2 * (p % kST);
+  }
+
+  float acc[kPosPerThread][16];
+  // ---- RGB stem conv
+#pragma unroll
+  for (int i = 0; i < kPosPerThread; ++i)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[i][c] = 0.f;
+  conv_accumulate<3>(s_patch, s_wr, poff, cg, acc);
+#pragma unroll
+  for (int i = 0; i < kPosPerThread; ++i) {
+    if (pos[i] < kPos) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = cg * 16 + q * 4;
+        float4 v;
+        v.x = fmaxf(fmaf(acc[i][q * 4 + 0], s_bn[c + 0], s_bn[64 + c + 0]), 0.f);
+        v.y = fmaxf(fmaf(acc[i][q * 4 + 1], s_bn[c + 1], s_bn[64 + c + 1]), 0.f);
+        v.z = fmaxf(fmaf(acc[i][q * 4 + 2], s_bn[c + 2], s_bn[64 + c + 2]), 0.f);
+        v.w = fmaxf(fmaf(acc[i][q * 4 + 3], s_bn[c + 3], s_bn[64 + c + 3]), 0.f);
+        *reinterpret_cast<float4*>(&s_fuse[tile_idx(pos[i], c)]) = v;
+      }
+    }
+  }
+  // ---- depth stem conv, then fuse = rgb + depth (same thread owns the same elements)
+#pragma unroll
+  for (int i = 0; i < kPosPerThread; ++i)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[i][c] = 0.f;
+  conv_accumulate<1>(s_patch + 3 * kPatch * kPatch, s_wd, poff, cg, acc);
+#pragma unroll
+  for (int i = 0; i < kPosPerThread; ++i) {
+    if (pos[i] < kPos) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = cg * 16 + q * 4;
+        float4 d;
+        d.x = fmaxf(fmaf(acc[i][q * 4 + 0], s_bn[128 + c + 0], s_bn[192 + c + 0]), 0.f);
+        d.y = fmaxf(fmaf(acc[i][q * 4 + 1], s_bn[128 + c + 1], s_bn[192 + c + 1]), 0.f);
+        d.z = fmaxf(fmaf(acc[i][q * 4 + 2], s_bn[128 + c + 2], s_bn[192 + c + 2]), 0.f);
+        d.w = fmaxf(fmaf(acc[i][q * 4 + 3], s_bn[128 + c + 3], s_bn[192 + c + 3]), 0.f);
+        const int idx = tile_idx(pos[i], c);
+        float4 r = *reinterpret_cast<float4*>(&s_fuse[idx]);
+        r.x += d.x; r.y += d.y; r.z += d.z; r.w += d.w;
+        *reinterpret_cast<float4*>(&s_fuse[idx]) = r;
+        *reinterpret_cast<float4*>(&s_dep[idx]) = d;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- 3x3 / stride 2 / pad 1 max-pool of both tiles, NHWC stores (64 consecutive channels per pixel)
+  const int c = tid & 63;
+  for (int pp = tid >> 6; pp < kPT * kPT; pp += kThreads >> 6) {
+    const int ly = pp / kPT, lx = pp % kPT;
+    const int py = py0 + ly, px = px0 + lx;
+    if (py >= Hp || px >= Wp) continue;
+    float mf = -INFINITY, md = -INFINITY;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int gy = sy0 + 2 * ly + dy;
+      if (gy < 0 || gy >= Hs) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int gx = sx0 + 2 * lx + dx;
+        if (gx < 0 || gx >= Ws) continue;
+        const int idx = tile_idx((2 * ly + dy) * kST + 2 * lx + dx, c);
+        mf = fmaxf(mf, s_fuse[idx]);
+        md = fmaxf(md, s_dep[idx]);
+      }
+    }
+    const size_t o = ((static_cast<size_t>(n) * Hp + py) * Wp + px) * 64 + c;
+    if (rgb_f32) rgb_f32[o] = mf;
+    if (depth_f32) depth_f32[o] = md;
+    if (rgb_bf16) rgb_bf16[o] = __float2bfloat16_rn(mf);
+    if (depth_bf16) depth_bf16[o] = __float2bfloat16_rn(md);
+  }
+}
+
+}  // namespace
+}  // namespace dynmm
+
+extern "C" int dynmm_stem_fwd(const float* rgb, const float* depth, int b, int h, int w, const float* w_rgb,
+                              const float* scale_rgb, const float* shift_rgb, const float* w_d, const float* scale_d,
+                              const float* shift_d, float* rgb_f32, float* depth_f32, void* rgb_bf16,
+                              void* depth_bf16, void* stream) {
+  using namespace dynmm;
+  DYNMM_CHECK_ARG(rgb && depth && w_rgb && w_d && scale_rgb && shift_rgb && scale_d && shift_d, "stem: null pointer");
+  DYNMM_CHECK_ARG(b >= 1 && h >= 7 && w >= 7, "stem: bad shape");
+  const int Hs = (h + 6 - 7) / 2 + 1, Ws = (w + 6 - 7) / 2 + 1;
+  const int Hp = (Hs + 2 - 3) / 2 + 1, Wp = (Ws + 2 - 3) / 2 + 1;
+  const size_t smem = kSmemFloats * sizeof(float);
+  static cudaError_t attr_err =
+      cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemFloats * sizeof(float)));
+  DYNMM_CUDA(attr_err);
+  dim3 grid(ceil_div(Wp, kPT), ceil_div(Hp, kPT), b);
+  stem_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      rgb, depth, h, w, w_rgb, scale_rgb, shift_rgb, w_d, scale_d, shift_d, rgb_f32, depth_f32,
+      static_cast<__nv_bfloat16*>(rgb_bf16), static_cast<__nv_bfloat16*>(depth_bf16));
+  DYNMM_LAUNCH_CHECK();
+  return DYNMM_OK;
+}

@@ -1,0 +1,302 @@
+"""Thin tensor-level wrappers over the C ABI (one function per exported symbol).
+
+Tensors carry device memory only; every function launches on the current
+CUDA stream through ``libdynmm_b200.so`` and raises on failure.  Layout
+conventions are those of ``include/dynmm_b200.h``: activations NHWC bf16,
+gate path fp32.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ConvParams, check, ptr, stream_ptr
+
+Tensor = torch.Tensor
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not (t.is_cuda and t.is_contiguous()):
+            raise _lib.DynmmError("dynmm ops need contiguous CUDA tensors")
+
+
+# ------------------------------------------------------------------ weights
+
+def pack_conv_weight(w: Tensor) -> Tensor:
+    """[c_out, c_in, kh, kw] fp32 -> bf16 [kh*kw, c_out_pad16, c_in] (K-major B operand)."""
+    c_out, c_in, kh, kw = w.shape
+    pad = (c_out + 15) // 16 * 16
+    out = torch.zeros(kh * kw, pad, c_in, dtype=torch.bfloat16, device=w.device)
+    out[:, :c_out] = w.permute(2, 3, 0, 1).reshape(kh * kw, c_out, c_in).to(torch.bfloat16)
+    return out.contiguous()
+
+
+def fold_bn(bn_w, bn_b, bn_m, bn_v, eps, conv_bias=None):
+    """Eval-mode BatchNorm (and an optional preceding conv bias) as y = x*scale + shift."""
+    scale = bn_w / torch.sqrt(bn_v + eps)
+    shift = bn_b - bn_m * scale
+    if conv_bias is not None:
+        shift = shift + conv_bias * scale
+    return scale.float().contiguous(), shift.float().contiguous()
+
+
+# ------------------------------------------------------------------ conv
+
+def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 1), pad=(0, 0),
+         scale: Optional[Tensor] = None, shift: Optional[Tensor] = None, residual: Optional[Tensor] = None,
+         relu: bool = False, gated: Optional[Tensor] = None, gate: Optional[Tensor] = None,
+         gated_slot: Optional[Tensor] = None, in_map: Optional[Tensor] = None, res_map: Optional[Tensor] = None,
+         count: Optional[Tensor] = None,
+         out: Optional[Tensor] = None, n_out: Optional[int] = None, c_in: Optional[int] = None,
+         out_c_off: int = 0, tile_n: int = 0, max_ctas: int = 0, direct: bool = False) -> Tensor:
+    """Fused conv + scale/shift + residual + ReLU + gated add (see dynmm_conv_igemm_fwd).
+
+    x: NHWC bf16 [n_in, h, w, in_ld] (``c_in`` <= in_ld selects a channel prefix);
+    weight: packed by :func:`pack_conv_weight`.  ``out`` may be a wider NHWC buffer, written
+    at channel offset ``out_c_off``.  ``direct=True`` runs the CUDA-core comparator."""
+    lib = _lib.load()
+    _cuda(x, weight, scale, shift, residual, gated, gate, gated_slot, in_map, count, out)
+    n_in, h_in, w_in, in_ld = x.shape
+    c_in = in_ld if c_in is None else c_in
+    n = n_in if n_out is None else n_out
+    h_out = (h_in + 2 * pad[0] - kh) // stride[0] + 1
+    w_out = (w_in + 2 * pad[1] - kw) // stride[1] + 1
+    if out is None:
+        out = torch.empty(n, h_out, w_out, c_out, dtype=torch.bfloat16, device=x.device)
+    p = ConvParams()
+    p.in_, p.weight, p.scale, p.shift = ptr(x), ptr(weight), ptr(scale), ptr(shift)
+    p.residual, p.res_map = ptr(residual), ptr(res_map)
+    p.out = out.data_ptr() + 2 * out_c_off
+    p.gated, p.gate, p.gated_slot = ptr(gated), ptr(gate), ptr(gated_slot)
+    p.in_map, p.count = ptr(in_map), ptr(count)
+    p.n, p.n_in = n, n_in
+    p.h_in, p.w_in, p.c_in, p.in_ld = h_in, w_in, c_in, in_ld
+    p.h_out, p.w_out, p.c_out, p.out_ld = h_out, w_out, c_out, out.shape[3]
+    p.res_ld = residual.shape[3] if residual is not None else 0
+    p.gated_ld = gated.shape[3] if gated is not None else 0
+    p.kh, p.kw, p.stride_h, p.stride_w, p.pad_h, p.pad_w = kh, kw, stride[0], stride[1], pad[0], pad[1]
+    p.relu, p.tile_n, p.max_ctas = int(relu), tile_n, max_ctas
+    fn = lib.dynmm_conv_direct_fwd if direct else lib.dynmm_conv_igemm_fwd
+    check(fn(ctypes.byref(p), stream_ptr()), "conv_direct" if direct else "conv_igemm")
+    return out
+
+
+# ------------------------------------------------------------------ stem / gate
+
+def stem(rgb: Tensor, depth: Tensor, w_rgb: Tensor, scale_rgb: Tensor, shift_rgb: Tensor, w_d: Tensor,
+         scale_d: Tensor, shift_d: Tensor, want_f32: bool = True):
+    """rgb [b,3,h,w], depth [b,1,h,w] NCHW fp32 -> pooled NHWC maps
+    (rgb_f32, depth_f32, rgb_bf16, depth_bf16); the fp32 pair is None when not wanted."""
+    lib = _lib.load()
+    _cuda(rgb, depth, w_rgb, w_d)
+    b, _, h, w = rgb.shape
+    hs, ws = (h + 6 - 7) // 2 + 1, (w + 6 - 7) // 2 + 1
+    hp, wp = (hs + 2 - 3) // 2 + 1, (ws + 2 - 3) // 2 + 1
+    dev = rgb.device
+    r32 = torch.empty(b, hp, wp, 64, dtype=torch.float32, device=dev) if want_f32 else None
+    d32 = torch.empty(b, hp, wp, 64, dtype=torch.float32, device=dev) if want_f32 else None
+    r16 = torch.empty(b, hp, wp, 64, dtype=torch.bfloat16, device=dev)
+    d16 = torch.empty(b, hp, wp, 64, dtype=torch.bfloat16, device=dev)
+    check(lib.dynmm_stem_fwd(ptr(rgb), ptr(depth), b, h, w, ptr(w_rgb), ptr(scale_rgb), ptr(shift_rgb), ptr(w_d),
+                             ptr(scale_d), ptr(shift_d), ptr(r32), ptr(d32), ptr(r16), ptr(d16), stream_ptr()), "stem")
+    return r32, d32, r16, d16
+
+
+def global_gate_logits(rgb32: Tensor, depth32: Tensor, w1, scale1, shift1, w2, scale2, shift2, wfc,
+                       work: Optional[Tensor] = None) -> Tensor:
+    lib = _lib.load()
+    _cuda(rgb32, depth32)
+    b, h, w, _ = rgb32.shape
+    need = lib.dynmm_global_gate_workspace(b, h, w)
+    if need < 0:
+        raise _lib.DynmmError(f"global gate: feature map {h}x{w} too small for two 5x5/s2 convolutions")
+    if work is None or work.numel() < need:
+        work = torch.empty(need, dtype=torch.uint8, device=rgb32.device)
+    logits = torch.empty(b, 5, dtype=torch.float32, device=rgb32.device)
+    check(lib.dynmm_global_gate_logits(ptr(rgb32), ptr(depth32), b, h, w, ptr(w1), ptr(scale1), ptr(shift1), ptr(w2),
+                                       ptr(scale2), ptr(shift2), ptr(wfc), ptr(work), ptr(logits), stream_ptr()),
+          "global_gate_logits")
+    return logits
+
+
+def diffsoftmax_fwd(logits: Tensor, tau: float, hard: bool):
+    """-> (y, y_soft, index) ; logits [rows, n] fp32."""
+    lib = _lib.load()
+    _cuda(logits)
+    rows, n = logits.shape
+    y = torch.empty_like(logits)
+    ys = torch.empty_like(logits)
+    idx = torch.empty(rows, dtype=torch.int32, device=logits.device)
+    check(lib.dynmm_diffsoftmax_fwd(ptr(logits), rows, n, float(tau), int(hard), ptr(y), ptr(ys), ptr(idx),
+                                    stream_ptr()), "diffsoftmax_fwd")
+    return y, ys, idx
+
+
+def diffsoftmax_bwd(grad_y: Tensor, y_soft: Tensor, tau: float) -> Tensor:
+    lib = _lib.load()
+    grad_y = grad_y.contiguous()
+    _cuda(grad_y, y_soft)
+    rows, n = y_soft.shape
+    g = torch.empty_like(y_soft)
+    check(lib.dynmm_diffsoftmax_bwd(ptr(grad_y), ptr(y_soft), rows, n, float(tau), ptr(g), stream_ptr()),
+          "diffsoftmax_bwd")
+    return g
+
+
+class GatePlan:
+    """Device-side skip lists derived from gate weights (see dynmm_gate_plan)."""
+
+    def __init__(self, b: int, device):
+        self.b = b
+        self.g = torch.empty(4, b, dtype=torch.float32, device=device)
+        self.perm = torch.empty(b, dtype=torch.int32, device=device)
+        self.slot = torch.empty(b, dtype=torch.int32, device=device)
+        self.count = torch.empty(4, dtype=torch.int32, device=device)
+
+
+def gate_plan(weight: Tensor, plan: Optional[GatePlan] = None, hist: Optional[Tensor] = None) -> GatePlan:
+    lib = _lib.load()
+    _cuda(weight, hist)
+    b = weight.shape[0]
+    if plan is None:
+        plan = GatePlan(b, weight.device)
+    check(lib.dynmm_gate_plan(ptr(weight), b, ptr(plan.g), ptr(plan.perm), ptr(plan.slot), ptr(plan.count), ptr(hist),
+                              stream_ptr()), "gate_plan")
+    return plan
+
+
+# ------------------------------------------------------------------ elementwise
+
+def gated_add(a: Tensor, b: Tensor, gate: Tensor, slot: Optional[Tensor] = None, out: Optional[Tensor] = None):
+    lib = _lib.load()
+    _cuda(a, b, gate, slot, out)
+    n = a.shape[0]
+    per = a.numel() // n
+    out = torch.empty_like(a) if out is None else out
+    check(lib.dynmm_gated_add_fwd(ptr(a), ptr(b), ptr(gate), ptr(slot), n, per, ptr(out), stream_ptr()), "gated_add")
+    return out
+
+
+def gated_add_f32_fwd(a: Tensor, b: Tensor, gate: Tensor) -> Tensor:
+    lib = _lib.load()
+    _cuda(a, b, gate)
+    n = a.shape[0]
+    out = torch.empty_like(a)
+    check(lib.dynmm_gated_add_f32_fwd(ptr(a), ptr(b), ptr(gate), n, a.numel() // n, ptr(out), stream_ptr()),
+          "gated_add_f32_fwd")
+    return out
+
+
+def gated_add_f32_bwd(grad: Tensor, b: Tensor, gate: Tensor, need_grad_b: bool = True):
+    lib = _lib.load()
+    grad = grad.contiguous()
+    _cuda(grad, b, gate)
+    n = b.shape[0]
+    grad_b = torch.empty_like(b) if need_grad_b else None
+    gg = torch.empty(n * 65, dtype=torch.float32, device=b.device)
+    check(lib.dynmm_gated_add_f32_bwd(ptr(grad), ptr(b), ptr(gate), n, b.numel() // n, ptr(grad_b), ptr(gg),
+                                      stream_ptr()), "gated_add_f32_bwd")
+    return grad_b, gg[:n]
+
+
+def _ptr_array(ts: Sequence[Optional[Tensor]]):
+    arr = (ctypes.c_void_p * len(ts))()
+    for i, t in enumerate(ts):
+        arr[i] = ptr(t)
+    return arr
+
+
+def softgate_mix_fwd(preds: Sequence[Tensor], w: Tensor, rows: Optional[Sequence[Optional[Tensor]]] = None) -> Tensor:
+    lib = _lib.load()
+    _cuda(w, *preds)
+    b, ne = w.shape
+    c = preds[0].shape[1]
+    out = torch.empty(b, c, dtype=torch.float32, device=w.device)
+    rows_arr = _ptr_array(rows) if rows is not None else None
+    check(lib.dynmm_softgate_mix_fwd(_ptr_array(preds), rows_arr, ptr(w), b, c, ne, ptr(out), stream_ptr()),
+          "softgate_mix_fwd")
+    return out
+
+
+def softgate_mix_bwd(grad_out: Tensor, preds: Sequence[Tensor], w: Tensor, need_pred_grads: Sequence[bool]):
+    lib = _lib.load()
+    grad_out = grad_out.contiguous()
+    _cuda(grad_out, w, *preds)
+    b, ne = w.shape
+    c = preds[0].shape[1]
+    grads = [torch.empty_like(p) if need else None for p, need in zip(preds, need_pred_grads)]
+    gw = torch.empty_like(w)
+    check(lib.dynmm_softgate_mix_bwd(ptr(grad_out), _ptr_array(preds), ptr(w), b, c, ne, _ptr_array(grads), ptr(gw),
+                                     stream_ptr()), "softgate_mix_bwd")
+    return grads, gw
+
+
+def compact_rows(w: Tensor, expert: int):
+    """-> (idx [b] int32, inv [b] int32, count [1] int32) for rows with w[:, expert] != 0."""
+    lib = _lib.load()
+    _cuda(w)
+    b, ne = w.shape
+    idx = torch.empty(b, dtype=torch.int32, device=w.device)
+    inv = torch.empty(b, dtype=torch.int32, device=w.device)
+    cnt = torch.empty(1, dtype=torch.int32, device=w.device)
+    check(lib.dynmm_compact_rows(ptr(w), b, ne, expert, ptr(idx), ptr(inv), ptr(cnt), stream_ptr()), "compact_rows")
+    return idx, inv, cnt
+
+
+def nchw_f32_to_nhwc_bf16(x: Tensor) -> Tensor:
+    lib = _lib.load()
+    _cuda(x)
+    n, c, h, w = x.shape
+    out = torch.empty(n, h, w, c, dtype=torch.bfloat16, device=x.device)
+    check(lib.dynmm_nchw_f32_to_nhwc_bf16(ptr(x), n, c, h, w, ptr(out), stream_ptr()), "nchw_f32_to_nhwc_bf16")
+    return out
+
+
+def nhwc_bf16_to_nchw_f32(x: Tensor, c: Optional[int] = None) -> Tensor:
+    lib = _lib.load()
+    _cuda(x)
+    n, h, w, ld = x.shape
+    c = ld if c is None else c
+    out = torch.empty(n, c, h, w, dtype=torch.float32, device=x.device)
+    check(lib.dynmm_nhwc_bf16_to_nchw_f32(ptr(x), n, c, h, w, ld, ptr(out), stream_ptr()), "nhwc_bf16_to_nchw_f32")
+    return out
+
+
+def upsample2x_dw3x3(x: Tensor, weight: Tensor, bias: Optional[Tensor], skip: Optional[Tensor] = None,
+                     to_nchw_f32: bool = False, out: Optional[Tensor] = None) -> Tensor:
+    """x NHWC bf16; weight fp32 [c,3,3] (or [c,1,3,3])."""
+    lib = _lib.load()
+    _cuda(x, weight, bias, skip, out)
+    n, h, w, c = x.shape
+    if to_nchw_f32:
+        out = torch.empty(n, c, 2 * h, 2 * w, dtype=torch.float32, device=x.device) if out is None else out
+        check(lib.dynmm_upsample2x_dw3x3(ptr(x), n, h, w, c, ptr(weight), ptr(bias), None, None, ptr(out),
+                                         stream_ptr()), "upsample2x_dw3x3")
+    else:
+        out = torch.empty(n, 2 * h, 2 * w, c, dtype=torch.bfloat16, device=x.device) if out is None else out
+        check(lib.dynmm_upsample2x_dw3x3(ptr(x), n, h, w, c, ptr(weight), ptr(bias), ptr(skip), ptr(out), None,
+                                         stream_ptr()), "upsample2x_dw3x3")
+    return out
+
+
+def adaptive_avgpool(x: Tensor, bins: int, c: Optional[int] = None) -> Tensor:
+    lib = _lib.load()
+    _cuda(x)
+    n, h, w, ld = x.shape
+    c = ld if c is None else c
+    out = torch.empty(n, bins, bins, c, dtype=torch.bfloat16, device=x.device)
+    check(lib.dynmm_adaptive_avgpool(ptr(x), n, h, w, c, ld, bins, ptr(out), stream_ptr()), "adaptive_avgpool")
+    return out
+
+
+def nearest_resize_into(src: Tensor, dst: Tensor, c_off: int) -> None:
+    lib = _lib.load()
+    _cuda(src, dst)
+    n, hs, ws, c = src.shape
+    _, h, w, ld = dst.shape
+    check(lib.dynmm_nearest_resize_into(ptr(src), n, hs, ws, c, ptr(dst), h, w, ld, c_off, stream_ptr()),
+          "nearest_resize_into")

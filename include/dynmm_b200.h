@@ -1,0 +1,200 @@
+/*
+ * dynmm_b200 -- C ABI of the B200 (sm_100a) kernels behind the DynMM gated hot path.
+ *
+ * The reference (zihuixue/DynMM) has no native/FFI layer: every op on its hot
+ * path is an ATen call made from Python.  The entry
+ * points below are therefore the operator boundary a maintainer would bind
+ * with ctypes from the reference's own modules; each one cites the reference
+ * code it replaces (paths relative to /root/reference).  INTEGRATION.md shows
+ * the binding stubs.
+ *
+ * Conventions
+ *   - plain C: raw device pointers, ints, floats; no torch types.
+ *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*),
+ *     never synchronises the host, never allocates, and is CUDA-graph
+ *     capturable.  Data-dependent work (gate decisions) stays on the device:
+ *     kernels read sample counts / slot maps from device memory.
+ *   - returns 0 on success, a negative DYNMM_E* code otherwise;
+ *     dynmm_last_error() gives a thread-local message.
+ *   - activations are NHWC ("channels last"); `ld` arguments are the pixel
+ *     pitch in elements (>= channels) so tensors can be channel slices of a
+ *     wider buffer.  bf16 unless stated.
+ */
+#ifndef DYNMM_B200_H_
+#define DYNMM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DYNMM_ABI_VERSION 1
+
+enum {
+  DYNMM_OK = 0,
+  DYNMM_EINVAL = -1,     /* bad argument / unsupported shape */
+  DYNMM_ECUDA = -2,      /* CUDA runtime / driver error */
+  DYNMM_ENODEV = -3      /* no sm_100 device */
+};
+
+int dynmm_abi_version(void);
+const char* dynmm_last_error(void);
+/* 1 if the current device is compute capability 10.x */
+int dynmm_device_ok(void);
+
+/* ------------------------------------------------------------------ gate */
+
+/* DiffSoftmax forward (model_skip_mod_globalgate.py:20-30, imdb_dyn.py:16-26,
+ * affect_dyn.py:18-28).  logits [rows, n] fp32 (n <= 32).  y = softmax(logits/tau);
+ * hard: one-hot of the FIRST maximum of y (the value the straight-through
+ * expression y_hard - y.detach() + y evaluates to).  y_soft (may be NULL) receives
+ * the soft probabilities needed by the backward; index (may be NULL) the argmax. */
+int dynmm_diffsoftmax_fwd(const float* logits, int rows, int n, float tau, int hard,
+                          float* y, float* y_soft, int32_t* index, void* stream);
+/* Backward of the above: hard or soft, the Jacobian is that of the tempered
+ * softmax (straight-through).  grad_logits = (y_soft * (g - sum(g*y_soft))) / tau. */
+int dynmm_diffsoftmax_bwd(const float* grad_y, const float* y_soft, int rows, int n, float tau,
+                          float* grad_logits, void* stream);
+
+/* Turn gate weights [b,5] (fp32, one-hot or soft) into what the encoder kernels
+ * consume (model_skip_mod_globalgate.py:282,291,300,309):
+ *   g[s*b + i]      = depth mixing coefficient of sample i at stage s+1 (s=0..3):
+ *                     1-w0, 1-w0-w1, 1-w0-w1-w2, w4
+ *   perm[i]         = sample index held by depth slot i (samples sorted by
+ *                     decreasing number of depth stages they need; stable)
+ *   slot[i]         = inverse of perm
+ *   count[s]        = number of samples with g[s] != 0 (a prefix of perm)
+ *   hist[k]        += number of samples whose arg-max branch is k (int64[5]);
+ *                     replaces the per-forward weight.cpu() of :273-274. */
+int dynmm_gate_plan(const float* weight, int b, float* g, int32_t* perm, int32_t* slot,
+                    int32_t* count, long long* hist, void* stream);
+
+/* GlobalGate.forward (model_skip_mod_globalgate.py:388-394) in fp32:
+ *   rgb, depth : NHWC fp32 [b,h,w,64] pooled stem features
+ *   w1 [8][5][5][128] (kh,kw,cin order, cin = 64 rgb then 64 depth), scale1/shift1 [8] = conv bias + BN folded
+ *   w2 [8][5][5][8], scale2/shift2 [8]; wfc [5][8]
+ *   work: >= dynmm_global_gate_workspace(b,h,w) bytes
+ *   logits [b,5] out.  DiffSoftmax is a separate call. */
+long long dynmm_global_gate_workspace(int b, int h, int w);
+int dynmm_global_gate_logits(const float* rgb, const float* depth, int b, int h, int w,
+                             const float* w1, const float* scale1, const float* shift1,
+                             const float* w2, const float* scale2, const float* shift2,
+                             const float* wfc, void* work, float* logits, void* stream);
+
+/* ------------------------------------------------------------------ stem */
+
+/* ResNet.forward_first_conv x2 + add + max_pool2d x2
+ * (resnet.py:352-358, model_skip_mod_globalgate.py:256-261), fp32 arithmetic:
+ *   rgb [b,3,h,w], depth [b,1,h,w] NCHW fp32 (the module's input layout)
+ *   w_rgb [7][7][3][64], w_d [7][7][1][64] fp32; scale/shift [64] = folded BN
+ *   outputs, pooled to (h/4, w/4), NHWC, 64 channels:
+ *     rgb_f32/depth_f32 : fp32 copies for the gate (NULL to skip)
+ *     rgb_bf16/depth_bf16 : bf16 copies for the encoders
+ *   rgb_* holds maxpool(relu(bn(conv(rgb))) + relu(bn(conv(depth)))), depth_* holds
+ *   maxpool(relu(bn(conv(depth)))). */
+int dynmm_stem_fwd(const float* rgb, const float* depth, int b, int h, int w,
+                   const float* w_rgb, const float* scale_rgb, const float* shift_rgb,
+                   const float* w_d, const float* scale_d, const float* shift_d,
+                   float* rgb_f32, float* depth_f32, void* rgb_bf16, void* depth_bf16, void* stream);
+
+/* --------------------------------------------------------- encoder convs */
+
+/* Implicit-GEMM convolution on tcgen05 tensor cores (TMA-fed, TMEM
+ * accumulators) with the whole post-conv chain of the reference fused into the
+ * epilogue.  Replaces F.conv2d + BatchNorm2d(eval) + ReLU + residual add of
+ * NonBottleneck1D.forward / BasicBlock.forward / Bottleneck.forward /
+ * ConvBNAct (resnet.py:66-84,124-147,173-192, model_utils.py:11-23) and the
+ * gated fusion `w*rgb + (1-w)*(rgb+depth)` (model_skip_mod_globalgate.py:279-310):
+ *
+ *   v   = conv(in)[n,h,w,c] * scale[c] + shift[c]
+ *   v  += residual[res_map(n),h,w,c]              (if residual)
+ *   v   = max(v, 0)                               (if relu)
+ *   v  += gate[n] * gated[slot(n),h,w,c]          (if gated and gate[n] != 0;
+ *                                                  gated-off samples never touch `gated`)
+ *   out[n,h,w,c] = bf16(v)
+ *
+ * Sample indirection (real skipping of gated-off depth stages): `count` (device
+ * int32, may be NULL = n) is the number of leading sample slots that are
+ * computed at all; `in_map` (device int32[n], may be NULL) gives the input
+ * sample read for output slot i. */
+typedef struct dynmm_conv_params {
+  const void* in;         /* bf16 NHWC [n_in, h_in, w_in, in_ld] */
+  const void* weight;     /* bf16 [kh*kw][c_out_pad][c_in], c_out_pad = c_out rounded up to 16 */
+  const float* scale;     /* [c_out] or NULL (1) */
+  const float* shift;     /* [c_out] or NULL (0) */
+  const void* residual;   /* bf16 NHWC [*, h_out, w_out, res_ld] or NULL */
+  const int32_t* res_map; /* device int32 [n]: sample of `residual` added to output slot i, or NULL (identity) */
+  void* out;              /* bf16 NHWC [n, h_out, w_out, out_ld] */
+  const void* gated;      /* bf16 NHWC [*, h_out, w_out, gated_ld] or NULL */
+  const float* gate;      /* device fp32 [n] */
+  const int32_t* gated_slot; /* device int32 [n] or NULL (identity) */
+  const int32_t* in_map;  /* device int32 [n] or NULL */
+  const int32_t* count;   /* device int32 or NULL */
+  int32_t n, n_in;        /* output sample slots; samples in `in` */
+  int32_t h_in, w_in, c_in, in_ld;
+  int32_t h_out, w_out, c_out, out_ld;
+  int32_t res_ld, gated_ld;
+  int32_t kh, kw, stride_h, stride_w, pad_h, pad_w;
+  int32_t relu;
+  int32_t tile_n;         /* 0 = choose; else 16..256 output channels per CTA tile */
+  int32_t max_ctas;       /* 0 = one per SM */
+} dynmm_conv_params;
+
+int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream);
+/* Same contract, one thread per output element, CUDA cores.  Test comparator
+ * for the tensor-core kernel at sizes the CPU oracle cannot reach; never used
+ * by the product path. */
+int dynmm_conv_direct_fwd(const dynmm_conv_params* p, void* stream);
+
+/* --------------------------------------------------------- elementwise */
+
+/* out = a + gate[n]*b[slot(n)]  (NHWC bf16; model_skip_mod_globalgate.py:283 etc. as a
+ * stand-alone op; b is only read where gate[n] != 0). */
+int dynmm_gated_add_fwd(const void* a, const void* b, const float* gate, const int32_t* slot,
+                        int n, long long per_sample, void* out, void* stream);
+/* fp32 training-path variant with both gradients:
+ * fuse = a + g[n]*b; grad_g[n] = sum(grad*b). */
+int dynmm_gated_add_f32_fwd(const float* a, const float* b, const float* gate, int n,
+                            long long per_sample, float* out, void* stream);
+int dynmm_gated_add_f32_bwd(const float* grad, const float* b, const float* gate, int n,
+                            long long per_sample, float* grad_b, float* grad_gate, void* stream);
+
+/* Modality-level mix (imdb_dyn.py:100, affect_dyn.py:95,164):
+ * out[i,:] = sum_e w[i,e]*pred_e[row_e(i),:], e < n_experts <= 4.  row maps
+ * (int32 [b] per expert, may be NULL = identity) let an expert be evaluated on a
+ * compacted subset only; experts with w[i,e]==0 are never read. */
+int dynmm_softgate_mix_fwd(const float* const* preds, const int32_t* const* rows, const float* w,
+                           int b, int c, int n_experts, float* out, void* stream);
+int dynmm_softgate_mix_bwd(const float* grad_out, const float* const* preds, const float* w,
+                           int b, int c, int n_experts, float* const* grad_preds, float* grad_w,
+                           void* stream);
+/* Stable compaction for expert skipping: rows with w[i,expert] != 0 first.
+ * idx [b] receives the selected row ids (prefix of length *count), inv [b] their
+ * position or -1. */
+int dynmm_compact_rows(const float* w, int b, int n_experts, int expert, int32_t* idx,
+                       int32_t* inv, int32_t* count, void* stream);
+
+/* layout / dtype plumbing */
+int dynmm_nchw_f32_to_nhwc_bf16(const float* in, int n, int c, int h, int w, void* out, void* stream);
+int dynmm_nhwc_bf16_to_nchw_f32(const void* in, int n, int c, int h, int w, int ld, float* out, void* stream);
+
+/* Upsample.forward for mode 'learned-3x3-zeropad' (model.py:403-410): nearest x2 then
+ * depthwise 3x3 (zero pad) + bias, optionally + skip (DecoderModule.forward :353-355).
+ * in NHWC bf16 [n,h,w,c]; weight fp32 [c][3][3]; out NHWC bf16 [n,2h,2w,c], or when
+ * out_nchw_f32 != NULL fp32 NCHW (the module's return layout). */
+int dynmm_upsample2x_dw3x3(const void* in, int n, int h, int w, int c, const float* weight,
+                           const float* bias, const void* skip, void* out_nhwc_bf16,
+                           float* out_nchw_f32, void* stream);
+
+/* PyramidPoolingModule pooling + broadcast (context_modules.py:69-84) for NHWC bf16 input
+ * [n,h,w,ld] (first c channels): adaptive average pool to bins x bins (fp32 accumulate) -> out [n,bins,bins,c] bf16. */
+int dynmm_adaptive_avgpool(const void* in, int n, int h, int w, int c, int ld, int bins, void* out, void* stream);
+/* nearest-neighbour resize of NHWC bf16 [n,hs,ws,c] into a channel slice of dst [n,h,w,ld]. */
+int dynmm_nearest_resize_into(const void* src, int n, int hs, int ws, int c, void* dst, int h, int w,
+                              int ld, int c_off, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* DYNMM_B200_H_ */
