@@ -1,0 +1,4 @@
+"""Fusion-level DynMM (RGB-D ESANet with a global gate) -- drop-in modules."""
+from .modules import (BasicBlock, Bottleneck, ConvBNAct, Decoder, DecoderModule, DiffSoftmax, GlobalGate,  # noqa: F401
+                      NonBottleneck1D, PyramidPoolingModule, ResNet, ResNet18, ResNet34, ResNet50, SkipGateESANet,
+                      SqueezeAndExcitation, SqueezeAndExciteFusionAdd, Upsample, get_context_module)

@@ -1,19 +1,32 @@
 """Inference engine of the gated RGB-D encoder/decoder on the CUDA kernels.
 
-Weight preparation (BN folding, bf16 K-major repacking) happens once per
-``state_dict``; the forward is a fixed sequence of C-ABI launches whose
-data-dependent parts (which samples run which depth stage) are resolved on the
-device, so the whole forward can be captured in a CUDA graph.
+Replaces the body of ``SkipGateESANet.forward`` in eval mode
+(model_skip_mod_globalgate.py:255-322 of the reference).  Weight preparation
+(BN folding, bf16 K-major repacking) happens once per ``state_dict``; the
+forward is a fixed sequence of C-ABI launches whose data-dependent parts (which
+samples run which depth stage) are resolved on the device from the gate's
+output, so the whole forward is CUDA-graph capturable and never syncs the host.
+
+Real skipping: depth samples are kept in *slot order* (sorted by how many depth
+stages their branch needs), so the set of samples a depth stage must process is
+always a prefix ``[0, count[s])`` -- the conv kernels size their tile lists from
+``count[s]`` on the device, and the RGB stage's last conv only reads the depth
+features of samples whose gate is non-zero.  The RGB and depth encoders run on
+two streams and meet at the four fusion points.
 """
 from __future__ import annotations
 
-from typing import Dict
+import dataclasses
+from typing import Callable, Dict, List, Optional, Sequence
 
 import torch
 
-from .. import ops
+from .. import _lib, ops
 
 Tensor = torch.Tensor
+
+_STAGE_BLOCKS = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3), "resnet50": (3, 4, 6, 3)}
+_PLANES = (64, 128, 256, 512)
 
 
 def pack_gate(sd: Dict[str, Tensor], prefix: str = "gate_layer.") -> Dict[str, Tensor]:
@@ -31,3 +44,290 @@ def pack_gate(sd: Dict[str, Tensor], prefix: str = "gate_layer.") -> Dict[str, T
         "s2": s2, "b2": b2,
         "wfc": g("fc.weight").reshape(g("fc.weight").shape[0], -1).contiguous(),
     }
+
+
+@dataclasses.dataclass
+class ConvLayer:
+    """One convolution with everything that follows it folded in."""
+    weight: Tensor                 # packed bf16 [taps, c_out_pad, c_in]
+    scale: Optional[Tensor]
+    shift: Optional[Tensor]
+    c_in: int
+    c_out: int
+    kh: int
+    kw: int
+    stride: tuple
+    pad: tuple
+    relu: bool
+
+    def __call__(self, x: Tensor, **kw) -> Tensor:
+        return ops.conv(x, self.weight, c_out=self.c_out, kh=self.kh, kw=self.kw, stride=self.stride, pad=self.pad,
+                        scale=self.scale, shift=self.shift, relu=self.relu, c_in=self.c_in, **kw)
+
+
+@dataclasses.dataclass
+class Block:
+    convs: List[ConvLayer]          # main path; the last one takes the residual
+    downsample: Optional[ConvLayer]
+
+
+class _Packer:
+    def __init__(self, sd: Dict[str, Tensor], device):
+        self.sd, self.dev = sd, device
+
+    def t(self, key):
+        return self.sd[key].detach().float().to(self.dev)
+
+    def conv(self, key, *, stride=(1, 1), pad=(0, 0), bn: Optional[str] = None, bn_eps=1e-5, relu=False) -> ConvLayer:
+        w = self.t(key + ".weight")
+        bias = self.t(key + ".bias") if key + ".bias" in self.sd else None
+        if bn is not None:
+            scale, shift = ops.fold_bn(self.t(bn + ".weight"), self.t(bn + ".bias"), self.t(bn + ".running_mean"),
+                                       self.t(bn + ".running_var"), bn_eps, bias)
+        else:
+            scale, shift = None, (bias.contiguous() if bias is not None else None)
+        c_out, c_in, kh, kw = w.shape
+        return ConvLayer(ops.pack_conv_weight(w), scale, shift, c_in, c_out, kh, kw, tuple(stride), tuple(pad), relu)
+
+    def nbt1d(self, key, stride=1) -> Block:
+        """resnet.py:124-147: 3x1 -> ReLU -> 1x3 -> BN(1e-3) -> ReLU -> 3x1 -> ReLU -> 1x3 -> BN -> +id -> ReLU."""
+        convs = [
+            self.conv(key + ".conv3x1_1", stride=(stride, 1), pad=(1, 0), relu=True),
+            self.conv(key + ".conv1x3_1", stride=(1, stride), pad=(0, 1), bn=key + ".bn1", bn_eps=1e-3, relu=True),
+            self.conv(key + ".conv3x1_2", pad=(1, 0), relu=True),
+            self.conv(key + ".conv1x3_2", pad=(0, 1), bn=key + ".bn2", bn_eps=1e-3, relu=True),
+        ]
+        return Block(convs, self._downsample(key, stride))
+
+    def basic(self, key, stride=1) -> Block:
+        """resnet.py:66-84."""
+        convs = [
+            self.conv(key + ".conv1", stride=(stride, stride), pad=(1, 1), bn=key + ".bn1", relu=True),
+            self.conv(key + ".conv2", pad=(1, 1), bn=key + ".bn2", relu=True),
+        ]
+        return Block(convs, self._downsample(key, stride))
+
+    def bottleneck(self, key, stride=1) -> Block:
+        """resnet.py:173-192."""
+        convs = [
+            self.conv(key + ".conv1", bn=key + ".bn1", relu=True),
+            self.conv(key + ".conv2", stride=(stride, stride), pad=(1, 1), bn=key + ".bn2", relu=True),
+            self.conv(key + ".conv3", bn=key + ".bn3", relu=True),
+        ]
+        return Block(convs, self._downsample(key, stride))
+
+    def _downsample(self, key, stride):
+        if key + ".downsample.0.weight" not in self.sd:
+            return None
+        return self.conv(key + ".downsample.0", stride=(stride, stride), bn=key + ".downsample.1")
+
+    def conv_bn_act(self, key, k) -> ConvLayer:
+        return self.conv(key + ".conv", pad=(k // 2, k // 2), bn=key + ".bn", relu=True)
+
+
+@dataclasses.dataclass
+class EngineConfig:
+    encoder: str = "resnet34"
+    encoder_block: str = "NonBottleneck1D"
+    fuse: str = "add"
+    nr_decoder_blocks: Sequence[int] = (3, 3, 3)
+    num_classes: int = 40
+    upsampling: str = "learned-3x3-zeropad"
+    context_module: str = "ppm"
+    activation: str = "relu"
+
+
+class FusionEngine:
+    """Packed weights + launch sequence for one ``state_dict``."""
+
+    def __init__(self, sd: Dict[str, Tensor], cfg: EngineConfig, device):
+        _lib.require_device()
+        if cfg.activation.lower() != "relu":
+            raise NotImplementedError("the CUDA engine fuses ReLU epilogues only; got activation=" + cfg.activation)
+        if cfg.fuse != "add":
+            raise NotImplementedError("the CUDA engine implements fuse_depth_in_rgb_encoder='add' (SE-add: next)")
+        if cfg.upsampling != "learned-3x3-zeropad":
+            raise NotImplementedError("the CUDA engine implements upsampling='learned-3x3-zeropad'")
+        if "ppm" not in cfg.context_module or cfg.context_module == "ppm-1-2-4-8" or "appm" in cfg.context_module:
+            raise NotImplementedError("the CUDA engine implements context_module='ppm' (bins 1,5)")
+        self.cfg, self.dev = cfg, device
+        p = _Packer(sd, device)
+        self.gate = {k: v.to(device) for k, v in pack_gate(sd).items()}
+        # stem: [7][7][cin][64] fp32 + folded BN
+        self.stem = {}
+        for enc in ("encoder_rgb", "encoder_depth"):
+            w = p.t(enc + ".conv1.weight").permute(2, 3, 1, 0).contiguous()
+            s, b = ops.fold_bn(p.t(enc + ".bn1.weight"), p.t(enc + ".bn1.bias"), p.t(enc + ".bn1.running_mean"),
+                               p.t(enc + ".bn1.running_var"), 1e-5)
+            self.stem[enc] = (w, s, b)
+        block_kind = "bottleneck" if cfg.encoder == "resnet50" else \
+            {"NonBottleneck1D": "nbt1d", "BasicBlock": "basic"}[cfg.encoder_block]
+        make = getattr(p, block_kind)
+        self.stages = {}
+        for enc in ("encoder_rgb", "encoder_depth"):
+            stages = []
+            for s, nblk in enumerate(_STAGE_BLOCKS[cfg.encoder]):
+                stages.append([make(f"{enc}.layer{s + 1}.{b}", 2 if (b == 0 and s > 0) else 1) for b in range(nblk)])
+            self.stages[enc] = stages
+        self.stage_channels = [st[-1].convs[-1].c_out for st in self.stages["encoder_rgb"]]
+        self.skips = [p.conv_bn_act(f"skip_layer{i}.0", 1) if f"skip_layer{i}.0.conv.weight" in sd else None
+                      for i in (1, 2, 3)]
+        self.ppm = [p.conv_bn_act(f"context_module.features.{i}.1", 1) for i in range(2)]
+        self.ppm_final = p.conv_bn_act("context_module.final_conv", 1)
+        self.dec = []
+        for i in range(3):
+            dk = f"decoder.decoder_module_{i + 1}"
+            self.dec.append({
+                "conv3x3": p.conv_bn_act(dk + ".conv3x3", 3),
+                "blocks": [p.nbt1d(f"{dk}.decoder_blocks.{b}") for b in range(cfg.nr_decoder_blocks[i])],
+                "up_w": p.t(dk + ".upsample.conv.weight").reshape(-1, 9).contiguous(),
+                "up_b": p.t(dk + ".upsample.conv.bias").contiguous(),
+            })
+        self.conv_out = p.conv("decoder.conv_out", pad=(1, 1))
+        self.up = [(p.t(f"decoder.{u}.conv.weight").reshape(-1, 9).contiguous(),
+                    p.t(f"decoder.{u}.conv.bias").contiguous()) for u in ("upsample1", "upsample2")]
+        self.side = torch.cuda.Stream(device=device)
+        self.launches = 0          # kernels launched by the last forward (for bench accounting)
+
+    # ------------------------------------------------------------------ blocks
+    def _block(self, x: Tensor, blk: Block, keep: list, *, count=None, in_map=None, before_last: Callable = None,
+               last_kw: Optional[dict] = None) -> Tensor:
+        n_out = x.shape[0]
+        y = x
+        for i, cv in enumerate(blk.convs[:-1]):
+            y = cv(y, count=count, in_map=in_map if i == 0 else None, n_out=n_out)
+            keep.append(y)
+            self.launches += 1
+        if blk.downsample is not None:
+            idn = blk.downsample(x, count=count, in_map=in_map, n_out=n_out)
+            keep.append(idn)
+            self.launches += 1
+            res_map = None
+        else:
+            idn, res_map = x, in_map
+        if before_last is not None:
+            before_last()
+        first = len(blk.convs) == 1
+        out = blk.convs[-1](y, residual=idn, res_map=res_map, count=count, in_map=in_map if first else None,
+                            n_out=n_out, **(last_kw or {}))
+        keep.append(out)
+        self.launches += 1
+        return out
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, rgb: Tensor, depth: Tensor, *, temp: float = 1.0, hard_gate: bool = False,
+                baseline: bool = False, ini_stage: bool = False, weight: Optional[Tensor] = None,
+                out: Optional[Tensor] = None, hist: Optional[Tensor] = None):
+        """rgb [B,3,H,W], depth [B,1,H,W] fp32 NCHW on the GPU ->
+        (logits [B,classes,H,W] fp32 NCHW, gate weight [B,5] fp32)."""
+        if not (rgb.is_cuda and depth.is_cuda):
+            raise _lib.DynmmError("FusionEngine.forward needs CUDA tensors")
+        rgb = rgb.float().contiguous()
+        depth = depth.float().contiguous()
+        b, _, h, w = rgb.shape
+        if h % 32 or w % 32:
+            raise _lib.DynmmError(f"input size {h}x{w} must be a multiple of 32 (five stride-2 stages)")
+        self.launches = 0
+        keep: list = []
+        main = torch.cuda.current_stream()
+        side = self.side
+        wr, sr, br = self.stem["encoder_rgb"]
+        wd, sdp, bd = self.stem["encoder_depth"]
+        learned = weight is None and not baseline and not ini_stage
+        r32, d32, r16, d16 = ops.stem(rgb, depth, wr, sr, br, wd, sdp, bd, want_f32=learned)
+        self.launches += 1
+        if weight is not None:
+            weight = weight.to(self.dev, torch.float32).contiguous()
+        elif baseline:                                     # :264-266
+            weight = torch.zeros(b, 5, device=self.dev)
+            weight[:, 4] = 1
+        elif ini_stage:                                    # :267-270, global CPU generator like the reference
+            idx = torch.randint(0, 5, (b,))
+            weight = torch.zeros(b, 5)
+            weight[range(b), idx] = 1
+            weight = weight.to(self.dev)
+        else:
+            gw = self.gate
+            logits = ops.global_gate_logits(r32, d32, gw["w1"], gw["s1"], gw["b1"], gw["w2"], gw["s2"], gw["b2"],
+                                            gw["wfc"])
+            weight, _, _ = ops.diffsoftmax_fwd(logits, temp, hard_gate)
+            self.launches += 4
+        plan = ops.gate_plan(weight, hist=hist)
+        self.launches += 1
+        keep += [r32, d32, r16, d16, weight, plan]
+
+        # ---- depth encoder on the side stream, in slot order, prefix-counted
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        done = [torch.cuda.Event() for _ in range(4)]
+        depth_out = []
+        with torch.cuda.stream(side):
+            d = d16
+            for s in range(4):
+                cnt = plan.count[s:s + 1]
+                for bi, blk in enumerate(self.stages["encoder_depth"][s]):
+                    d = self._block(d, blk, keep, count=cnt, in_map=plan.perm if (s == 0 and bi == 0) else None)
+                depth_out.append(d)
+                done[s].record(side)
+
+        # ---- RGB encoder on the main stream; the last conv of each stage adds g_s * depth_s
+        r = r16
+        fused = []
+        cat = None
+        for s in range(4):
+            blocks = self.stages["encoder_rgb"][s]
+            for bi, blk in enumerate(blocks):
+                if bi < len(blocks) - 1:
+                    r = self._block(r, blk, keep)
+                    continue
+                last_kw = dict(gated=depth_out[s], gate=plan.g[s], gated_slot=plan.slot)
+                if s == 3:
+                    # stage-4 output lands directly in the pyramid-pooling concat buffer
+                    c4 = self.stage_channels[3]
+                    cat = torch.empty(b, h // 32, w // 32, c4 + 2 * self.ppm[0].c_out, dtype=torch.bfloat16,
+                                      device=self.dev)
+                    last_kw.update(out=cat, out_c_off=0)
+                r = self._block(r, blk, keep, before_last=lambda s=s: main.wait_event(done[s]), last_kw=last_kw)
+            fused.append(r)
+
+        # ---- skip connections, context module, decoder (model.py:295-308, context_modules.py:69-87)
+        skips = []
+        for s in range(3):
+            if self.skips[s] is not None:
+                skips.append(self.skips[s](fused[s]))
+                self.launches += 1
+            else:
+                skips.append(fused[s])
+        c4 = self.stage_channels[3]
+        off = c4
+        for i, bins in enumerate((1, 5)):
+            pooled = ops.adaptive_avgpool(cat, bins, c=c4)
+            y = self.ppm[i](pooled)
+            ops.nearest_resize_into(y, cat, off)
+            off += y.shape[3]
+            keep += [pooled, y]
+            self.launches += 3
+        x = self.ppm_final(cat)
+        self.launches += 1
+        keep += [cat, x] + skips
+        for i, skip in enumerate((skips[2], skips[1], skips[0])):
+            m = self.dec[i]
+            x = m["conv3x3"](x)
+            self.launches += 1
+            keep.append(x)
+            for blk in m["blocks"]:
+                x = self._block(x, blk, keep)
+            x = ops.upsample2x_dw3x3(x, m["up_w"], m["up_b"], skip)
+            self.launches += 1
+            keep.append(x)
+        x = self.conv_out(x)
+        keep.append(x)
+        x = ops.upsample2x_dw3x3(x, self.up[0][0], self.up[0][1])
+        keep.append(x)
+        out = ops.upsample2x_dw3x3(x, self.up[1][0], self.up[1][1], to_nchw_f32=True, out=out)
+        self.launches += 3
+        # all side-stream work was joined by the stage-4 wait; temporaries may now be released
+        del keep
+        return out, weight
