@@ -32,7 +32,7 @@ class ConvParams(Structure):
         ("res_ld", c_int32), ("gated_ld", c_int32),
         ("kh", c_int32), ("kw", c_int32), ("stride_h", c_int32), ("stride_w", c_int32),
         ("pad_h", c_int32), ("pad_w", c_int32),
-        ("relu", c_int32), ("tile_n", c_int32), ("max_ctas", c_int32),
+        ("relu", c_int32), ("tile_n", c_int32), ("max_ctas", c_int32), ("trace", c_void_p),
     ]
 
 

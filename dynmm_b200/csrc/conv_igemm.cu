@@ -7,11 +7,12 @@
 // zero padding costs nothing and no im2col buffer exists.  Strided convolutions
 // read a parity sub-lattice of the input through a strided tensor map.
 //
-// One persistent CTA per SM, warp-specialised:
-//   warp 0      TMA producer  (A box + weight tile per (tap, 64-channel chunk))
+// One persistent CTA per SM, warp-specialised (320 threads):
+//   warp 0      TMA producer  (A box + weight tile per (tap, 64-channel chunk); residual
+//                              sub-tiles into a small ring, one tile ahead of the epilogue)
 //   warp 1      MMA issuer    (one elected lane; 4 x UMMA 128 x tile_n x 16 per stage)
-//   warps 2..5  epilogue      (TMEM -> registers -> scale/shift, residual, ReLU,
-//                              gated depth add -> bf16 NHWC)
+//   warps 2..9  epilogue      (TMEM -> registers -> scale/shift, residual, ReLU, gated depth
+//                              add -> bf16 -> swizzled smem staging -> TMA store)
 // Two TMEM accumulator buffers let the epilogue of tile i overlap the MMAs of
 // tile i+1.  The tile list is derived on the device from `count` (number of
 // active sample slots), so samples the gate switched off generate no TMA
@@ -29,9 +30,12 @@ constexpr int kBlockK = 64;        // bf16 elements per 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kMaxTaps = 9;
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;   // 320
 constexpr int kSmemBudget = 227 * 1024;
-constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB
+constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB: one [128 rows][64 ch] bf16 tile
+constexpr int kSubBytes = kABytes;               // epilogue sub-tile: same shape
+constexpr int kAuxSlots = 3;                     // residual sub-tiles in flight
 
 struct Tap {
   int8_t map;   // which A tensor map (parity sub-lattice)
@@ -48,6 +52,9 @@ struct KernelArgs {
   int num_taps, k_chunks;
   int stages, stage_bytes;
   int acc_stride, tmem_cols;
+  uint32_t m_c, m_w, m_h;           // magic multipliers for dividing by c_tiles / w_tiles / h_tiles
+  int tma_epi;                      // 1: TMA residual loads + TMA stores (tile_n % 64 == 0)
+  int aux_slots;                    // residual ring slots (0 without residual)
   Tap taps[kMaxTaps];
   // problem
   int n, h_out, w_out, c_out;
@@ -63,6 +70,7 @@ struct KernelArgs {
   const int32_t* in_map;
   const int32_t* res_map;
   const int32_t* count;
+  unsigned long long* trace;        // debug: 16 cycle stamps per CTA, or NULL
 };
 
 struct __align__(8) SmemCtl {
@@ -70,6 +78,8 @@ struct __align__(8) SmemCtl {
   uint64_t empty[kMaxStages];
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
+  uint64_t aux_full[kAuxSlots];
+  uint64_t aux_empty[kAuxSlots];
   uint32_t tmem_base;
 };
 
@@ -77,47 +87,147 @@ struct TileCoord {
   int c0, w0, h0, n0;
 };
 
+// x / d for x*d < 2^32 with m = ceil(2^32 / d) (host-computed); d == 1 has m == 0
+__device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t m) { return m ? __umulhi(x, m) : x; }
+
 __device__ __forceinline__ TileCoord decode_tile(const KernelArgs& a, int tile) {
   TileCoord t;
-  int ct = tile % a.c_tiles;
-  int r = tile / a.c_tiles;
-  int wt = r % a.w_tiles;
-  r /= a.w_tiles;
-  int ht = r % a.h_tiles;
-  int nt = r / a.h_tiles;
+  uint32_t r = fast_div(tile, a.m_c);
+  const int ct = tile - r * a.c_tiles;
+  uint32_t q = fast_div(r, a.m_w);
+  const int wt = r - q * a.w_tiles;
+  r = fast_div(q, a.m_h);
+  const int ht = q - r * a.h_tiles;
   t.c0 = ct * a.tile_n;
   t.w0 = wt * a.box_w;
   t.h0 = ht * a.box_h;
-  t.n0 = nt * a.box_n;
+  t.n0 = r * a.box_n;
   return t;
 }
 
+enum : int { kFlagRes = 1, kFlagGated = 2, kFlagRelu = 4, kFlagScale = 8 };
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+// One thread's share of an epilogue sub-tile: 32 consecutive output channels of one pixel.
+//   kTma: residual comes from the swizzled smem tile `res_smem`, result goes to the swizzled
+//         staging tile `out_smem` (both 32-bit shared addresses of this thread's row);
+//   else: direct global loads / stores (narrow channel tiles, partially active sample boxes).
+template <int kFlags, bool kTma>
+__device__ __forceinline__ void epilogue_chunk(const KernelArgs& args, const uint32_t (&v)[32], int c_first,
+                                               int cols_left, bool valid, uint32_t res_smem, uint32_t out_smem,
+                                               uint32_t chunk0, uint32_t swz, size_t pix, size_t rpix, size_t gpix,
+                                               float g, const float* shift_smem) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int c = c_first + j;
+    if (j < cols_left && c < args.c_out) {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
+      if (kFlags & kFlagScale) {
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(args.scale + c));
+        const float4 s1 = __ldg(reinterpret_cast<const float4*>(args.scale + c + 4));
+        f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
+        f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
+      }
+      {
+        const float4 b0 = *reinterpret_cast<const float4*>(shift_smem + c);      // warp-wide broadcast
+        const float4 b1 = *reinterpret_cast<const float4*>(shift_smem + c + 4);
+        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+        f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+      }
+      const uint32_t chunk = ((chunk0 + (j >> 3)) ^ swz) << 4;
+      if (kFlags & kFlagRes) {
+        uint4 r;
+        if (kTma) {
+          r = lds128(res_smem + chunk);
+        } else {
+          r = valid ? __ldg(reinterpret_cast<const uint4*>(args.residual + rpix * args.res_ld + c))
+                    : make_uint4(0, 0, 0, 0);
+        }
+        f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x); f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
+        f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z); f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
+      }
+      if (kFlags & kFlagRelu) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+      }
+      if (kFlags & kFlagGated) {
+        if (g != 0.f) {      // gated-off samples never touch the depth features
+          const uint4 r = __ldg(reinterpret_cast<const uint4*>(args.gated + gpix * args.gated_ld + c));
+          f[0] += g * bf16_lo(r.x); f[1] += g * bf16_hi(r.x); f[2] += g * bf16_lo(r.y); f[3] += g * bf16_hi(r.y);
+          f[4] += g * bf16_lo(r.z); f[5] += g * bf16_hi(r.z); f[6] += g * bf16_lo(r.w); f[7] += g * bf16_hi(r.w);
+        }
+      }
+      uint4 o;
+      o.x = pack_bf16(f[0], f[1]);
+      o.y = pack_bf16(f[2], f[3]);
+      o.z = pack_bf16(f[4], f[5]);
+      o.w = pack_bf16(f[6], f[7]);
+      if (kTma) {
+        sts128(out_smem + chunk, o);
+      } else if (valid) {
+        *reinterpret_cast<uint4*>(args.out + pix * args.out_ld + c) = o;
+      }
+    }
+  }
+}
+
+#define DYNMM_TRACE(slot)                                                              \
+  do {                                                                                 \
+    if (args.trace) args.trace[blockIdx.x * 16 + (slot)] = (unsigned long long)clock64(); \
+  } while (0)
+
+template <int kFlags>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                   const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
-                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ KernelArgs args) {
+                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_res,
+                  const __grid_constant__ CUtensorMap map_out, const __grid_constant__ KernelArgs args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + args.stages * args.stage_bytes);
+  uint8_t* smem_aux = smem + args.stages * args.stage_bytes;            // [aux_slots][16 KiB]
+  uint8_t* smem_stage_out = smem_aux + args.aux_slots * kSubBytes;      // [2][16 KiB] (tma_epi only)
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_stage_out + (args.tma_epi ? 2 * kSubBytes : 0));
+  // [c_out]: per-channel shift (zeros if absent), 16-byte aligned for float4 broadcast loads
+  float* smem_shift = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ctl + 1) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) DYNMM_TRACE(0);
   const int active = args.count ? min(*args.count, args.n) : args.n;
   const int n_groups = (active + args.box_n - 1) / args.box_n;
   const int total_tiles = n_groups * args.h_tiles * args.w_tiles * args.c_tiles;
   const int k_iters = args.num_taps * args.k_chunks;
+  const int n_sub = (args.tile_n + 63) >> 6;
+  const bool aux_on = (kFlags & kFlagRes) && args.tma_epi && args.aux_slots > 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0);
     tma_prefetch_desc(&map_b);
+    if (args.tma_epi) tma_prefetch_desc(&map_out);
+    if (aux_on) tma_prefetch_desc(&map_res);
     for (int s = 0; s < args.stages; ++s) {
       mbar_init(&ctl->full[s], 1);
       mbar_init(&ctl->empty[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctl->acc_full[i], 1);
-      mbar_init(&ctl->acc_empty[i], 4);   // one arrive per epilogue warp
+      mbar_init(&ctl->acc_empty[i], kEpiWarps);   // one arrive per epilogue warp
+    }
+    for (int i = 0; i < kAuxSlots; ++i) {
+      mbar_init(&ctl->aux_full[i], 1);
+      mbar_init(&ctl->aux_empty[i], kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -125,25 +235,31 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     tmem_alloc(&ctl->tmem_base, args.tmem_cols);
     tmem_relinquish();
   }
+  if (warp >= 2) {   // epilogue warps stage the shift vector once: no global loads inside the tile loop
+    for (int c = threadIdx.x - 64; c < args.c_out; c += 32 * kEpiWarps) smem_shift[c] = args.shift ? args.shift[c] : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
+  if (threadIdx.x == 0) DYNMM_TRACE(1);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       const CUtensorMap* maps[4] = {&map_a0, &map_a1, &map_a2, &map_a3};
       // TMA always delivers the full box (out-of-bounds elements arrive as zeros)
-      const uint32_t tx_bytes = (args.box_w * args.box_h * args.box_n + args.tile_n) * kBlockK * 2;
+      const uint32_t rows_bytes = args.box_w * args.box_h * args.box_n * kBlockK * 2;
+      const uint32_t tx_bytes = rows_bytes + args.tile_n * kBlockK * 2;
       int stage = 0;
       uint32_t phase = 0;
+      int aux = 0;
+      uint32_t aux_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(args, tile);
         const int n_in = args.in_map ? args.in_map[t.n0] : t.n0;
+        int tap = 0, kc = 0;
         for (int it = 0; it < k_iters; ++it) {
-          const int tap = it / args.k_chunks;
-          const int kc = it - tap * args.k_chunks;
           const Tap tp = args.taps[tap];
           mbar_wait(&ctl->empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * args.stage_bytes;
@@ -151,9 +267,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           mbar_expect_tx(&ctl->full[stage], tx_bytes);
           tma_load_4d(sa, maps[tp.map], &ctl->full[stage], kc * kBlockK, t.w0 + tp.dw, t.h0 + tp.dh, n_in);
           tma_load_3d(sb, &map_b, &ctl->full[stage], kc * kBlockK, t.c0, tap);
+          if (tile == (int)blockIdx.x && it == 0) DYNMM_TRACE(2);
+          if (++kc == args.k_chunks) {
+            kc = 0;
+            ++tap;
+          }
           if (++stage == args.stages) {
             stage = 0;
             phase ^= 1;
+          }
+        }
+        if (tile == (int)blockIdx.x) DYNMM_TRACE(11);
+        // residual sub-tiles of this tile, consumed by the epilogue while the next tile's MMAs run
+        if (aux_on && t.n0 + args.box_n <= active) {
+          const int n_res = args.res_map ? args.res_map[t.n0] : t.n0;
+          for (int sub = 0; sub < n_sub; ++sub) {
+            mbar_wait(&ctl->aux_empty[aux], aux_phase ^ 1);
+            mbar_expect_tx(&ctl->aux_full[aux], rows_bytes);
+            tma_load_4d(smem_aux + aux * kSubBytes, &map_res, &ctl->aux_full[aux], t.c0 + sub * 64, t.w0, t.h0,
+                        n_res);
+            if (++aux == args.aux_slots) {
+              aux = 0;
+              aux_phase ^= 1;
+            }
           }
         }
       }
@@ -174,6 +310,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(&ctl->full[stage], phase);
           tc_fence_after();
+          if (local == 0 && it == 0) DYNMM_TRACE(3);
           const uint32_t sa = smem_u32(smem + stage * args.stage_bytes);
           const uint32_t sb = sa + kABytes;
           const uint64_t da = umma_desc_sw128(sa);
@@ -183,6 +320,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             // advancing K inside the swizzle atom = +32 bytes on the (16-byte unit) start address
             umma_bf16(d_tmem, da + (k * 2), db + (k * 2), idesc, (it | k) != 0);
           }
+          if (local == 0 && it == 0) DYNMM_TRACE(12);
           umma_commit(&ctl->empty[stage]);          // frees the smem stage when these MMAs retire
           if (it == k_iters - 1) umma_commit(&ctl->acc_full[acc]);
           if (++stage == args.stages) {
@@ -190,87 +328,104 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             phase ^= 1;
           }
         }
+        if (local == 0) DYNMM_TRACE(4);
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------ epilogue (8 warps)
+    const int ewarp = warp - 2;
     const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31 belong to this warp
+    const int half = ewarp >> 2;                  // which 32 of the 64 columns of a sub-tile
     const int row = quarter * 32 + lane;          // GEMM row == pixel inside the box
     const int wl = row % args.box_w;
     const int hl = (row / args.box_w) % args.box_h;
     const int nl = row / (args.box_w * args.box_h);
+    const bool leader = (threadIdx.x == 64);
+    const uint32_t row_off = row * 128;           // byte offset of this row inside a [128][128 B] tile
+    const uint32_t swz = row & 7;                 // 128B swizzle: 16-byte chunk index ^= row % 8
+    const uint32_t aux_base = smem_u32(smem_aux) + row_off;
+    const uint32_t out_base = smem_u32(smem_stage_out) + row_off;
     int local = 0;
+    int aux = 0;
+    uint32_t aux_phase = 0;
+    int sbuf = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const TileCoord t = decode_tile(args, tile);
       const int n = t.n0 + nl, h = t.h0 + hl, w = t.w0 + wl;
       const bool valid = nl < args.box_n && n < active && h < args.h_out && w < args.w_out;
+      const bool tile_tma = args.tma_epi && (t.n0 + args.box_n <= active);   // uniform over the CTA
       const size_t pix = valid ? (static_cast<size_t>(n) * args.h_out + h) * args.w_out + w : 0;
       size_t rpix = pix;
-      if (valid && args.residual && args.res_map) {
+      if ((kFlags & kFlagRes) && valid && args.res_map) {
         rpix = (static_cast<size_t>(args.res_map[n]) * args.h_out + h) * args.w_out + w;
       }
       float g = 0.f;
       size_t gpix = 0;
-      if (valid && args.gated) {
+      if ((kFlags & kFlagGated) && valid) {
         g = args.gate[n];
         const int slot = args.gated_slot ? args.gated_slot[n] : n;
         gpix = (static_cast<size_t>(slot) * args.h_out + h) * args.w_out + w;
       }
       mbar_wait(&ctl->acc_full[acc], acc_phase);
       tc_fence_after();
+      if (leader && local == 0) DYNMM_TRACE(5);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * args.acc_stride;
-      for (int cb = 0; cb < args.tile_n; cb += 32) {
+      for (int sub = 0; sub < n_sub; ++sub) {
+        const int cb = sub * 64 + half * 32;       // first of this thread's 32 columns inside the tile
+        const bool cols_live = cb < args.acc_stride;
         uint32_t v[32];
-        tmem_ld32(t_row + cb, v);
-        tmem_ld_wait();
-        if (!valid) continue;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          const int c = t.c0 + cb + j;
-          if (cb + j >= args.tile_n || c >= args.c_out) break;
-          float f[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
-          if (args.scale) {
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(args.scale + c));
-            const float4 s1 = __ldg(reinterpret_cast<const float4*>(args.scale + c + 4));
-            f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
-            f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
+        if (cols_live) {                            // warp-uniform
+          tmem_ld32(t_row + cb, v);
+          tmem_ld_wait();
+        }
+        if (leader && local == 0 && sub == 0) DYNMM_TRACE(13);
+        if (tile_tma) {
+          uint32_t res_smem = 0;
+          if (aux_on) {
+            mbar_wait(&ctl->aux_full[aux], aux_phase);
+            res_smem = aux_base + aux * kSubBytes;
           }
-          if (args.shift) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(args.shift + c));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(args.shift + c + 4));
-            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+          const uint32_t out_smem = out_base + sbuf * kSubBytes;
+          if (cols_live) {
+            epilogue_chunk<kFlags, true>(args, v, t.c0 + cb, args.tile_n - cb, valid, res_smem, out_smem, half * 4,
+                                         swz, pix, rpix, gpix, g, smem_shift);
           }
-          if (args.residual) {
-            const uint4 r = __ldg(reinterpret_cast<const uint4*>(args.residual + rpix * args.res_ld + c));
-            f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x); f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
-            f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z); f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
+          if (aux_on) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->aux_empty[aux]);
+            if (++aux == args.aux_slots) {
+              aux = 0;
+              aux_phase ^= 1;
+            }
           }
-          if (args.relu) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+          if (leader && local == 0 && sub == 0) DYNMM_TRACE(14);
+          fence_async_smem();                   // staging writes -> visible to the TMA engine
+          if (leader) bulk_wait_read<0>();      // the previous store (other buffer) has drained its smem
+          named_barrier(1, 32 * kEpiWarps);
+          if (leader && local == 0 && sub == 0) DYNMM_TRACE(15);
+          if (leader) {
+            tma_store_4d(&map_out, smem_stage_out + sbuf * kSubBytes, t.c0 + sub * 64, t.w0, t.h0, t.n0);
+            bulk_commit();
           }
-          if (g != 0.f) {
-            const uint4 r = __ldg(reinterpret_cast<const uint4*>(args.gated + gpix * args.gated_ld + c));
-            f[0] += g * bf16_lo(r.x); f[1] += g * bf16_hi(r.x); f[2] += g * bf16_lo(r.y); f[3] += g * bf16_hi(r.y);
-            f[4] += g * bf16_lo(r.z); f[5] += g * bf16_hi(r.z); f[6] += g * bf16_lo(r.w); f[7] += g * bf16_hi(r.w);
-          }
-          uint4 o;
-          o.x = pack_bf16(f[0], f[1]);
-          o.y = pack_bf16(f[2], f[3]);
-          o.z = pack_bf16(f[4], f[5]);
-          o.w = pack_bf16(f[6], f[7]);
-          *reinterpret_cast<uint4*>(args.out + pix * args.out_ld + c) = o;
+          sbuf ^= 1;
+        } else if (cols_live) {
+          epilogue_chunk<kFlags, false>(args, v, t.c0 + cb, args.tile_n - cb, valid, 0, 0, 0, 0, pix, rpix, gpix, g,
+                                        smem_shift);
         }
       }
       // this warp is done reading the accumulator buffer
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->acc_empty[acc]);
+      if (leader && local == 0) DYNMM_TRACE(6);
+    }
+    if (leader) {
+      DYNMM_TRACE(7);
+      bulk_wait<0>();
+      DYNMM_TRACE(8);
+      if (args.trace) args.trace[blockIdx.x * 16 + 10] = local;
     }
   }
 
@@ -280,6 +435,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     tc_fence_after();
     tmem_dealloc(tmem_base, args.tmem_cols);
   }
+  if (threadIdx.x == 0) DYNMM_TRACE(9);
 }
 
 // ------------------------------------------------------------------ host side
@@ -385,14 +541,16 @@ extern "C" int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream_) {
   const int c_out_pad = (p->c_out + 15) / 16 * 16;
   int tile_n = p->tile_n;
   const int sms = num_sms();
-  choose_box(p->w_out, p->h_out, p->n, p->in_map != nullptr, &a.box_w, &a.box_h, &a.box_n);
+  choose_box(p->w_out, p->h_out, p->n, p->in_map != nullptr || p->res_map != nullptr, &a.box_w, &a.box_h, &a.box_n);
   a.w_tiles = ceil_div(p->w_out, a.box_w);
   a.h_tiles = ceil_div(p->h_out, a.box_h);
   const int m_tiles = a.w_tiles * a.h_tiles * ceil_div(p->n, a.box_n);
   if (tile_n == 0) {
-    // widest channel tile that still gives every SM a tile
-    tile_n = c_out_pad < 256 ? c_out_pad : 256;
-    while (tile_n > 64 && tile_n % 32 == 0 && m_tiles * ceil_div(c_out_pad, tile_n) < sms) tile_n /= 2;
+    // multiples of 64 channels (TMA epilogue); widest tile that still gives every SM a tile
+    const int c64 = (c_out_pad + 63) / 64 * 64;
+    tile_n = c64 < 256 ? c64 : 256;
+    if (tile_n == 192) tile_n = 64;
+    while (tile_n > 64 && m_tiles * ceil_div(c_out_pad, tile_n) < sms) tile_n /= 2;
   }
   DYNMM_CHECK_ARG(tile_n >= 16 && tile_n <= 256 && tile_n % 16 == 0, "conv_igemm: tile_n %d", tile_n);
   a.tile_n = tile_n;
@@ -400,7 +558,11 @@ extern "C" int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream_) {
   a.num_taps = p->kh * p->kw;
   a.k_chunks = ceil_div(p->c_in, kBlockK);
   a.stage_bytes = kABytes + tile_n * kBlockK * 2;
-  a.stages = (kSmemBudget - 2048) / a.stage_bytes;
+  a.tma_epi = (tile_n % 64 == 0) ? 1 : 0;
+  a.aux_slots = (a.tma_epi && p->residual) ? kAuxSlots : 0;
+  const int epi_bytes = (a.tma_epi ? 2 * kSubBytes : 0) + a.aux_slots * kSubBytes;
+  DYNMM_CHECK_ARG(p->c_out <= 4096, "conv_igemm: c_out too large");
+  a.stages = (kSmemBudget - 2048 - epi_bytes - (p->c_out + 8) * 4 - 16) / a.stage_bytes;
   if (a.stages > kMaxStages) a.stages = kMaxStages;
   DYNMM_CHECK_ARG(a.stages >= 2, "conv_igemm: not enough shared memory for 2 stages");
   a.acc_stride = (tile_n + 31) / 32 * 32;
@@ -424,6 +586,11 @@ extern "C" int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream_) {
   a.in_map = p->in_map;
   a.res_map = p->res_map;
   a.count = p->count;
+  a.trace = static_cast<unsigned long long*>(p->trace);
+  auto magic = [](int d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)(((1ULL << 32) + d - 1) / d); };
+  a.m_c = magic(a.c_tiles);
+  a.m_w = magic(a.w_tiles);
+  a.m_h = magic(a.h_tiles);
 
   // A maps: one per (parity_h, parity_w) sub-lattice of the input
   CUtensorMap maps[4];
@@ -468,17 +635,52 @@ extern "C" int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream_) {
     if (rc) return rc;
   }
 
-  const int smem_bytes = a.stages * a.stage_bytes + 1024 /*align slack*/ + (int)sizeof(SmemCtl);
+  // epilogue maps: residual (load) and output (store), one [box pixels][64 channels] sub-tile per transfer
+  CUtensorMap map_res = map_b, map_out = map_b;
+  if (a.tma_epi) {
+    const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)a.box_w, (uint32_t)a.box_h, (uint32_t)a.box_n};
+    {
+      const uint64_t dims[4] = {(uint64_t)p->c_out, (uint64_t)p->w_out, (uint64_t)p->h_out, (uint64_t)p->n};
+      const uint64_t strides[3] = {(uint64_t)p->out_ld * es, (uint64_t)p->out_ld * p->w_out * es,
+                                   (uint64_t)p->out_ld * p->w_out * p->h_out * es};
+      int rc = encode_map(&map_out, p->out, 4, dims, strides, box);
+      if (rc) return rc;
+    }
+    if (a.aux_slots) {
+      DYNMM_CHECK_ARG((reinterpret_cast<uintptr_t>(p->residual) & 15) == 0, "conv_igemm: residual must be 16-byte aligned");
+      // the residual may hold more samples than n (res_map gathers); the sample extent only bounds the box
+      const uint64_t dims[4] = {(uint64_t)p->c_out, (uint64_t)p->w_out, (uint64_t)p->h_out,
+                                (uint64_t)(p->res_map ? 65536 : p->n)};
+      const uint64_t strides[3] = {(uint64_t)p->res_ld * es, (uint64_t)p->res_ld * p->w_out * es,
+                                   (uint64_t)p->res_ld * p->w_out * p->h_out * es};
+      int rc = encode_map(&map_res, p->residual, 4, dims, strides, box);
+      if (rc) return rc;
+    }
+  }
+
+  const int shift_bytes = (p->c_out + 8) * 4 + 16;
+  const int smem_bytes = a.stages * a.stage_bytes + epi_bytes + 1024 /*align slack*/ + (int)sizeof(SmemCtl) + shift_bytes;
+  const int max_tiles = m_tiles * a.c_tiles;
+  DYNMM_CHECK_ARG((long long)max_tiles * a.c_tiles < (1LL << 31) && max_tiles < (1 << 20), "conv_igemm: too many tiles");
+  int grid = p->max_ctas > 0 ? p->max_ctas : sms;
+  if (grid > max_tiles) grid = max_tiles;
+  const int flags = (p->residual ? kFlagRes : 0) | (p->gated ? kFlagGated : 0) | (p->relu ? kFlagRelu : 0) |
+                    (p->scale ? kFlagScale : 0);
+  typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap,
+                           KernelArgs);
+  static const KernelFn table[16] = {
+      conv_igemm_kernel<0>,  conv_igemm_kernel<1>,  conv_igemm_kernel<2>,  conv_igemm_kernel<3>,
+      conv_igemm_kernel<4>,  conv_igemm_kernel<5>,  conv_igemm_kernel<6>,  conv_igemm_kernel<7>,
+      conv_igemm_kernel<8>,  conv_igemm_kernel<9>,  conv_igemm_kernel<10>, conv_igemm_kernel<11>,
+      conv_igemm_kernel<12>, conv_igemm_kernel<13>, conv_igemm_kernel<14>, conv_igemm_kernel<15>};
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    for (int i = 0; i < 16 && attr_err == cudaSuccess; ++i)
+      attr_err = cudaFuncSetAttribute(table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
   });
   DYNMM_CUDA(attr_err);
-  const int max_tiles = m_tiles * a.c_tiles;
-  int grid = p->max_ctas > 0 ? p->max_ctas : sms;
-  if (grid > max_tiles) grid = max_tiles;
-  conv_igemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(maps[0], maps[1], maps[2], maps[3], map_b, a);
+  table[flags]<<<grid, kThreads, smem_bytes, stream>>>(maps[0], maps[1], maps[2], maps[3], map_b, map_res, map_out, a);
   DYNMM_LAUNCH_CHECK();
   return DYNMM_OK;
 }

@@ -84,6 +84,9 @@ class _Packer:
         if bn is not None:
             scale, shift = ops.fold_bn(self.t(bn + ".weight"), self.t(bn + ".bias"), self.t(bn + ".running_mean"),
                                        self.t(bn + ".running_var"), bn_eps, bias)
+            # the BN scale goes into the (fp32) weights before bf16 packing: the epilogue only adds `shift`
+            w = w * scale.view(-1, 1, 1, 1)
+            scale = None
         else:
             scale, shift = None, (bias.contiguous() if bias is not None else None)
         c_out, c_in, kh, kw = w.shape

@@ -52,7 +52,8 @@ def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 
          gated_slot: Optional[Tensor] = None, in_map: Optional[Tensor] = None, res_map: Optional[Tensor] = None,
          count: Optional[Tensor] = None,
          out: Optional[Tensor] = None, n_out: Optional[int] = None, c_in: Optional[int] = None,
-         out_c_off: int = 0, tile_n: int = 0, max_ctas: int = 0, direct: bool = False) -> Tensor:
+         out_c_off: int = 0, tile_n: int = 0, max_ctas: int = 0, direct: bool = False,
+         trace: Optional[Tensor] = None) -> Tensor:
     """Fused conv + scale/shift + residual + ReLU + gated add (see dynmm_conv_igemm_fwd).
 
     x: NHWC bf16 [n_in, h, w, in_ld] (``c_in`` <= in_ld selects a channel prefix);
@@ -80,6 +81,7 @@ def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 
     p.gated_ld = gated.shape[3] if gated is not None else 0
     p.kh, p.kw, p.stride_h, p.stride_w, p.pad_h, p.pad_w = kh, kw, stride[0], stride[1], pad[0], pad[1]
     p.relu, p.tile_n, p.max_ctas = int(relu), tile_n, max_ctas
+    p.trace = ptr(trace)
     fn = lib.dynmm_conv_direct_fwd if direct else lib.dynmm_conv_igemm_fwd
     if CONV_PROFILER is not None and not direct:
         CONV_PROFILER(p, lambda: check(fn(ctypes.byref(p), stream_ptr()), "conv_igemm"))

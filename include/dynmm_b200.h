@@ -139,6 +139,7 @@ typedef struct dynmm_conv_params {
   int32_t relu;
   int32_t tile_n;         /* 0 = choose; else 16..256 output channels per CTA tile */
   int32_t max_ctas;       /* 0 = one per SM */
+  void* trace;            /* debug: device uint64[16 * ctas] in-kernel cycle stamps, or NULL */
 } dynmm_conv_params;
 
 int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream);

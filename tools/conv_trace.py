@@ -1,0 +1,44 @@
+"""In-kernel cycle trace of the conv kernel (DYNMM trace slots, see conv_igemm.cu)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from dynmm_b200 import ops
+from tools.conv_shapes import SHAPES
+
+NAMES = ["entry", "prologue done", "first TMA issued", "first full", "tile0 MMAs issued", "tile0 acc_full",
+         "tile0 epilogue done", "all tiles done", "stores drained", "exit", "(tiles)", "producer: tile0 issued",
+         "mma: k-iter0 issued", "epi: tmem loaded", "epi: computed", "epi: barrier passed"]
+
+def main():
+    dev = "cuda"
+    only = os.environ.get("ONLY")
+    for name, n, h, w, cin, cout, kh, kw, stride, res in SHAPES:
+        if only and only not in name:
+            continue
+        x = torch.randn(n, h, w, cin, device=dev).to(torch.bfloat16)
+        wt = ops.pack_conv_weight(torch.randn(cout, cin, kh, kw, device=dev) * 0.05)
+        ho = (h + 2 * (kh // 2) - kh) // stride[0] + 1
+        wo = (w + 2 * (kw // 2) - kw) // stride[1] + 1
+        r = torch.randn(n, ho, wo, cout, device=dev).to(torch.bfloat16) if res else None
+        sh = torch.randn(cout, device=dev)
+        out = torch.empty(n, ho, wo, cout, dtype=torch.bfloat16, device=dev)
+        trace = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+        kw_ = dict(c_out=cout, kh=kh, kw=kw, stride=stride, pad=(kh // 2, kw // 2), shift=sh, residual=r, relu=True,
+                   out=out)
+        for _ in range(3):
+            ops.conv(x, wt, **kw_)
+        ops.conv(x, wt, trace=trace, **kw_)
+        torch.cuda.synchronize()
+        t = trace.view(148, 16).cpu()
+        used = t[:, 0] > 0
+        t = t[used]
+        rel = (t[:, :16] - t[:, :1]).float()
+        tiles = t[:, 10].float()
+        print(f"== {name}: {int(used.sum())} CTAs, tiles/CTA avg {tiles.mean():.1f} max {tiles.max():.0f}")
+        order = [0, 1, 2, 3, 12, 11, 4, 5, 13, 14, 15, 6, 7, 8, 9]
+        for i in order:
+            nm = NAMES[i]
+            print(f"   {nm:22s} mean {rel[:, i].mean():9.0f}  max {rel[:, i].max():9.0f} cycles")
+
+if __name__ == "__main__":
+    main()
