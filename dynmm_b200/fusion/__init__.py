@@ -2,3 +2,4 @@
 from .modules import (BasicBlock, Bottleneck, ConvBNAct, Decoder, DecoderModule, DiffSoftmax, GlobalGate,  # noqa: F401
                       NonBottleneck1D, PyramidPoolingModule, ResNet, ResNet18, ResNet34, ResNet50, SkipGateESANet,
                       SqueezeAndExcitation, SqueezeAndExciteFusionAdd, Upsample, get_context_module)
+from .build import build_model  # noqa: F401,E402

@@ -1,0 +1,88 @@
+"""Host-side logic of the fusion drop-in: state_dict compatibility with the reference
+(key list stored in the golden files by a strict load into the REFERENCE model), the
+differentiable PyTorch graph against reference-generated vectors, build_model()."""
+import argparse
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fusion_oracle as fo
+from oracle.make_golden import sample_inputs
+from tests.test_oracle_golden import CASES
+
+warnings.filterwarnings("ignore")
+
+
+def _model(cfg):
+    from dynmm_b200.fusion import SkipGateESANet
+    return SkipGateESANet(height=cfg.height, width=cfg.width, encoder_rgb=cfg.encoder, encoder_depth=cfg.encoder,
+                          encoder_block=cfg.encoder_block, channels_decoder=list(cfg.channels_decoder),
+                          nr_decoder_blocks=list(cfg.nr_decoder_blocks),
+                          fuse_depth_in_rgb_encoder=cfg.fuse_depth_in_rgb_encoder)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_state_dict_and_torch_path_match_reference(name, golden_dir):
+    cfg, seed, b = CASES[name]
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    model = _model(cfg)
+    assert sorted(model.state_dict().keys()) == list(gold["keys"])
+    sd = fo.make_state_dict(cfg, seed, float(gold["gate_scale"]))
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    rgb, depth = sample_inputs(seed + 1, b, cfg.height, cfg.width)
+    with torch.no_grad():
+        model.hard_gate = True
+        out, w = model(rgb, depth, True, True)
+    np.testing.assert_array_equal(w.numpy(), gold["hard_t1_weight"])
+    ref = gold["hard_t1_out_sample"]
+    np.testing.assert_allclose(out[:, :, ::4, ::4].numpy(), ref, rtol=2e-4, atol=2e-4 * np.abs(ref).max())
+    model.train()
+    model.hard_gate = False
+    outs, loss = model(rgb, depth)
+    assert len(outs) == 4 and abs(loss.item() - float(gold["train_loss"])) < 1e-5 * abs(float(gold["train_loss"])) + 1e-7
+    for i, o in enumerate(outs):
+        assert list(o.shape) == list(gold[f"train_out{i}_shape"])
+        assert abs(o.double().abs().sum().item() - gold[f"train_out{i}_abssum"]) <= 5e-4 * gold[f"train_out{i}_abssum"]
+
+
+def test_mode_attributes_and_freeze():
+    cfg = fo.FusionConfig(height=64, width=64)
+    model = _model(cfg)
+    for attr in ("temp", "hard_gate", "baseline", "ini_stage", "save_weight_info", "weight_list", "flop",
+                 "depth_enc_flop", "total_flop"):
+        assert hasattr(model, attr)
+    assert torch.allclose(model.total_flop, torch.tensor(fo.TOTAL_FLOP_R34))
+    model.freeze()
+    trainable = [n for n, p in model.named_parameters() if p.requires_grad]
+    assert trainable and all("gate" in n for n in trainable)
+    model.eval()
+    model.start_weight()
+    rgb, depth = sample_inputs(1, 2, 64, 64)
+    with torch.no_grad():
+        model.baseline = True
+        model(rgb, depth, True)
+    stats = model.end_weight(print_flop=True)
+    assert stats[0].tolist() == [0, 0, 0, 0, 2]
+    assert abs(stats[2] - fo.TOTAL_FLOP_R34[4]) < 1e-4
+
+
+def test_build_model_signature():
+    from dynmm_b200.fusion import build_model
+    args = argparse.Namespace(dynamic=True, global_gate=True, block_rule="1111", height=64, width=64,
+                              encoder="resnet34", encoder_depth=None, encoder_block="NonBottleneck1D", activation="relu",
+                              encoder_decoder_fusion="add", context_module="ppm", nr_decoder_blocks=[3],
+                              channels_decoder=128, decoder_channels_mode="constant", fuse_depth_in_rgb_encoder="add",
+                              upsampling="learned-3x3-zeropad", temp=1.0, pretrained_on_imagenet=False, last_ckpt="",
+                              pretrained_scenenet="", pretrained_dir="", he_init=True, finetune=None)
+    model, device = build_model(args, n_classes=40)
+    assert isinstance(device, torch.device) and model.decoder.conv_out.out_channels == 40
+    args.global_gate = False
+    with pytest.raises(NotImplementedError):
+        build_model(args, 40)
+    with pytest.raises(NotImplementedError):
+        from dynmm_b200.fusion import SkipGateESANet
+        SkipGateESANet(encoder_rgb="vgg16")
