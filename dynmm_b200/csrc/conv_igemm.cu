@@ -17,6 +17,8 @@
 // tile i+1.  The tile list is derived on the device from `count` (number of
 // active sample slots), so samples the gate switched off generate no TMA
 // traffic and no MMA work, and the launch is CUDA-graph capturable.
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -205,9 +207,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) DYNMM_TRACE(0);
-  const int active = args.count ? min(*args.count, args.n) : args.n;
-  const int n_groups = (active + args.box_n - 1) / args.box_n;
-  const int total_tiles = n_groups * args.h_tiles * args.w_tiles * args.c_tiles;
   const int k_iters = args.num_taps * args.k_chunks;
   const int n_sub = (args.tile_n + 63) >> 6;
   const bool aux_on = (kFlags & kFlagRes) && args.tma_epi && args.aux_slots > 0;
@@ -242,6 +241,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
+  // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch, shift
+  // staging -- constants only) overlapped the tail of the previous kernel in the stream.  From here
+  // on we touch tensors it produced, so wait for it; then let OUR dependent start its prologue.
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+  const int active = args.count ? min(*args.count, args.n) : args.n;
+  const int n_groups = (active + args.box_n - 1) / args.box_n;
+  const int total_tiles = n_groups * args.h_tiles * args.w_tiles * args.c_tiles;
   if (threadIdx.x == 0) DYNMM_TRACE(1);
 
   if (warp == 0) {
@@ -680,7 +687,21 @@ extern "C" int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream_) {
       attr_err = cudaFuncSetAttribute(table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
   });
   DYNMM_CUDA(attr_err);
-  table[flags]<<<grid, kThreads, smem_bytes, stream>>>(maps[0], maps[1], maps[2], maps[3], map_b, map_res, map_out, a);
+  static const bool use_pdl = [] {
+    const char* e = getenv("DYNMM_PDL");
+    return !(e && e[0] == '0');
+  }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  DYNMM_CUDA(cudaLaunchKernelEx(&cfg, table[flags], maps[0], maps[1], maps[2], maps[3], map_b, map_res, map_out, a));
   DYNMM_LAUNCH_CHECK();
   return DYNMM_OK;
 }

@@ -243,8 +243,12 @@ __global__ void upsample2x_dw_nhwc_kernel(const __nv_bfloat16* __restrict__ in, 
         const float f[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
                             bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
         const int k = (dy + 1) * 3 + dx + 1;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = fmaf(f[e], __ldg(&wgt[(c8 + e) * 9 + k]), acc[e]);
+        const float4 wa = __ldg(reinterpret_cast<const float4*>(wgt + k * c + c8));       // weights are [9][c]
+        const float4 wb = __ldg(reinterpret_cast<const float4*>(wgt + k * c + c8 + 4));
+        acc[0] = fmaf(f[0], wa.x, acc[0]); acc[1] = fmaf(f[1], wa.y, acc[1]);
+        acc[2] = fmaf(f[2], wa.z, acc[2]); acc[3] = fmaf(f[3], wa.w, acc[3]);
+        acc[4] = fmaf(f[4], wb.x, acc[4]); acc[5] = fmaf(f[5], wb.y, acc[5]);
+        acc[6] = fmaf(f[6], wb.z, acc[6]); acc[7] = fmaf(f[7], wb.w, acc[7]);
       }
     }
     const long long o = ((1LL * s * H + Y) * W + X) * c + c8;
@@ -261,40 +265,83 @@ __global__ void upsample2x_dw_nhwc_kernel(const __nv_bfloat16* __restrict__ in, 
     *reinterpret_cast<uint4*>(out + o) = ov;
   }
 }
-// Final upsample: NHWC bf16 in -> NCHW fp32 out (the module's return layout).  A CTA owns a
-// 32-pixel run of one output row for all channels: input reads are channel-contiguous,
-// output writes are pixel-contiguous per channel (transposed through shared memory).
-__global__ void upsample2x_dw_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int h, int w, int c,
-                                             const float* __restrict__ wgt, const float* __restrict__ bias,
-                                             float* __restrict__ out) {
-  extern __shared__ float s_out[];   // [c][33]
+// Final upsample: NHWC bf16 in -> NCHW fp32 out (the module's return layout; 393 MB of stores at
+// 8x40x480x640, the HBM-bound tail of the forward).  A CTA stages an 8x32 input tile (+1 halo) for
+// all channels in shared memory as fp32 [c][row][col]; then one warp per (channel, output row)
+// produces 64 consecutive output columns: lane l owns columns 2l, 2l+1 (one 8-byte store, 256 B per
+// warp, fully coalesced), reading 2x3 staged inputs without bank conflicts.
+constexpr int kUpTy = 8, kUpTx = 32;
+__global__ void __launch_bounds__(256)
+upsample2x_dw_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int h, int w, int c,
+                             const float* __restrict__ wgt, const float* __restrict__ bias,
+                             float* __restrict__ out) {
+  extern __shared__ float s_in[];                 // [c][kUpTy + 2][kUpTx + 2 (+1 pad)]
+  constexpr int RS = kUpTx + 3;                   // row stride (35): odd -> conflict-free transposed fill
+  constexpr int CS = (kUpTy + 2) * RS;            // channel stride
   const int H = 2 * h, W = 2 * w;
-  const int X0 = blockIdx.x * 32, Y = blockIdx.y, s = blockIdx.z;
-  for (int i = threadIdx.x; i < 32 * c; i += blockDim.x) {
-    const int ch = i % c, px = i / c;
-    const int X = X0 + px;
-    float acc = 0.f;
-    if (X < W) {
-      acc = bias ? bias[ch] : 0.f;
-#pragma unroll
-      for (int dy = -1; dy <= 1; ++dy) {
-        const int yy = Y + dy;
-        if (yy < 0 || yy >= H) continue;
-#pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-          const int xx = X + dx;
-          if (xx < 0 || xx >= W) continue;
-          acc = fmaf(__bfloat162float(in[((1LL * s * h + (yy >> 1)) * w + (xx >> 1)) * c + ch]),
-                     __ldg(&wgt[ch * 9 + (dy + 1) * 3 + dx + 1]), acc);
-        }
-      }
+  const int x0 = blockIdx.x * kUpTx, y0 = blockIdx.y * kUpTy, s = blockIdx.z;
+  const int cv = c >> 3;
+  // fill: one thread per (pixel, 8-channel chunk); zero outside the image (the conv's zero padding
+  // applies to the UPSAMPLED map, handled below by tap masks; here out-of-image inputs are never used)
+  for (int i = threadIdx.x; i < (kUpTy + 2) * (kUpTx + 2) * cv; i += blockDim.x) {
+    const int ch8 = (i % cv) * 8;
+    const int p = i / cv;
+    const int lx = p % (kUpTx + 2), ly = p / (kUpTx + 2);
+    const int y = y0 + ly - 1, x = x0 + lx - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (y >= 0 && y < h && x >= 0 && x < w) {
+      v = __ldg(reinterpret_cast<const uint4*>(in + ((1LL * s * h + y) * w + x) * c + ch8));
     }
-    s_out[ch * 33 + px] = acc;
+    float* d = s_in + ch8 * CS + ly * RS + lx;
+    d[0 * CS] = bf16_lo(v.x); d[1 * CS] = bf16_hi(v.x); d[2 * CS] = bf16_lo(v.y); d[3 * CS] = bf16_hi(v.y);
+    d[4 * CS] = bf16_lo(v.z); d[5 * CS] = bf16_hi(v.z); d[6 * CS] = bf16_lo(v.w); d[7 * CS] = bf16_hi(v.w);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 32 * c; i += blockDim.x) {
-    const int px = i & 31, ch = i >> 5;
-    if (X0 + px < W) out[((1LL * s * c + ch) * H + Y) * W + X0 + px] = s_out[ch * 33 + px];
+  // A lane owns input column x = x0 + lane and produces the 2x2 output block (2y..2y+1, 2x..2x+1).
+  // Nearest-x2 followed by a 3x3 conv collapses to a 2x2 stencil on the INPUT per output parity:
+  //   rows: parity 0 uses inputs (y-1: w[-1]) and (y: w[0]+w[+1]); parity 1 uses (y: w[-1]+w[0]) and (y+1: w[+1])
+  // (same for columns).  Inputs outside the image were staged as zeros, which is exactly the conv's
+  // zero padding of the upsampled map, so no border masks are needed.
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const bool x_ok = x0 + lane < w;
+  for (int ch = warp; ch < c; ch += nwarps) {
+    float k[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) k[t] = __ldg(wgt + t * c + ch);
+    const float b0 = bias ? __ldg(bias + ch) : 0.f;
+    // column-combined weights per kernel row r: parity 0 -> (left: k[r][0], mid: k[r][1]+k[r][2]);
+    //                                           parity 1 -> (mid: k[r][0]+k[r][1], right: k[r][2])
+    float cl0[3], cm0[3], cm1[3], cr1[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      cl0[r] = k[r * 3 + 0];
+      cm0[r] = k[r * 3 + 1] + k[r * 3 + 2];
+      cm1[r] = k[r * 3 + 0] + k[r * 3 + 1];
+      cr1[r] = k[r * 3 + 2];
+    }
+    const float* base = s_in + ch * CS + lane;
+    float* obase = out + ((1LL * s * c + ch) * H) * W + 2 * (x0 + lane);
+    // sliding window over input rows: a = row y-1, b = row y, d = row y+1 (each: left, mid, right)
+    float al = base[0], am = base[1], ar = base[2];
+    float bl = base[RS], bm = base[RS + 1], br = base[RS + 2];
+#pragma unroll
+    for (int ly = 0; ly < kUpTy; ++ly) {
+      const float* nr = base + (ly + 2) * RS;
+      const float dl = nr[0], dm = nr[1], dr = nr[2];
+      const int y = y0 + ly;
+      if (y < h && x_ok) {
+        // output row 2y   : kernel row 0 on input row y-1, kernel rows 1+2 on input row y
+        // output row 2y+1 : kernel rows 0+1 on input row y, kernel row 2 on input row y+1
+        const float o00 = b0 + cl0[0] * al + cm0[0] * am + (cl0[1] + cl0[2]) * bl + (cm0[1] + cm0[2]) * bm;
+        const float o01 = b0 + cm1[0] * am + cr1[0] * ar + (cm1[1] + cm1[2]) * bm + (cr1[1] + cr1[2]) * br;
+        const float o10 = b0 + (cl0[0] + cl0[1]) * bl + (cm0[0] + cm0[1]) * bm + cl0[2] * dl + cm0[2] * dm;
+        const float o11 = b0 + (cm1[0] + cm1[1]) * bm + (cr1[0] + cr1[1]) * br + cm1[2] * dm + cr1[2] * dr;
+        *reinterpret_cast<float2*>(obase + (2LL * y) * W) = make_float2(o00, o01);
+        *reinterpret_cast<float2*>(obase + (2LL * y + 1) * W) = make_float2(o10, o11);
+      }
+      al = bl; am = bm; ar = br;
+      bl = dl; bm = dm; br = dr;
+    }
   }
 }
 
@@ -451,10 +498,16 @@ extern "C" int dynmm_upsample2x_dw3x3(const void* in, int n, int h, int w, int c
         static_cast<__nv_bfloat16*>(out_nhwc_bf16));
   } else {
     DYNMM_CHECK_ARG(!skip, "upsample2x: skip is only supported for the NHWC output");
-    DYNMM_CHECK_ARG(c <= 256, "upsample2x: at most 256 channels for the NCHW output");
-    dim3 grid(ceil_div(2 * w, 32), 2 * h, n);
-    upsample2x_dw_to_nchw_kernel<<<grid, 256, c * 33 * sizeof(float), stream>>>(
-        static_cast<const __nv_bfloat16*>(in), h, w, c, weight, bias, out_nchw_f32);
+    const int smem = c * (kUpTy + 2) * (kUpTx + 3) * (int)sizeof(float);
+    DYNMM_CHECK_ARG(smem <= 200 * 1024, "upsample2x: too many channels for the NCHW output");
+    static int configured = 0;
+    if (smem > configured) {
+      DYNMM_CUDA(cudaFuncSetAttribute(upsample2x_dw_to_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      configured = smem;
+    }
+    dim3 grid(ceil_div(w, kUpTx), ceil_div(h, kUpTy), n);
+    upsample2x_dw_to_nchw_kernel<<<grid, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(in), h, w, c, weight,
+                                                              bias, out_nchw_f32);
   }
   DYNMM_LAUNCH_CHECK();
   return DYNMM_OK;

@@ -21,37 +21,60 @@ constexpr int kPosThreads = 64;           // threads along positions; 4 channel 
 constexpr int kPosPerThread = (kPos + kPosThreads - 1) / kPosThreads;  // 5
 constexpr int kKRgb = 7 * 7 * 3, kKDepth = 7 * 7;
 
-constexpr size_t kSmemFloats = 2 * kPos * 64 + (kKRgb + kKDepth) * 64 + 4 * kPatch * kPatch + 4 * 64;
+constexpr size_t kSmemFloats = 2 * kPos * 64 + (kKRgb + kKDepth) * 64 + 4 * kPatch * (kPatch + 1) + 4 * 64;
 
 // swizzled index into a [pos][64] fp32 tile: float4 column XOR (pos & 7)
 __device__ __forceinline__ int tile_idx(int pos, int c) {
   return pos * 64 + ((((c >> 2) ^ (pos & 7)) << 2) | (c & 3));
 }
 
+// packed fp32x2 FMA (FFMA2): plain 3-register FFMA issues at half rate on sm_100, the packed
+// form restores the full fp32 rate.  acc.xy += x * w.xy
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long long xx, float wa, float wb) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(xx), "l"(pack2(wa, wb)));
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+
+// The input patch is stored de-interleaved by column parity: [ch][row][parity][kHalf], so that
+// the stride-2 reads of a 7x7/s2 convolution (col = 2*sx + kx) are unit-stride across lanes.
+constexpr int kHalf = (kPatch + 1) / 2;          // 20
+constexpr int kRowStride = 2 * kHalf;            // 40 floats per patch row
+constexpr int kChStride = kPatch * kRowStride;   // per input channel
+
 template <int CIN>
 __device__ __forceinline__ void conv_accumulate(const float* __restrict__ patch, const float* __restrict__ wsm,
                                                 const int (&poff)[kPosPerThread], int cg,
-                                                float (&acc)[kPosPerThread][16]) {
+                                                unsigned long long (&acc)[kPosPerThread][8]) {
 #pragma unroll 1
   for (int ky = 0; ky < 7; ++ky) {
-#pragma unroll 1
+#pragma unroll
     for (int kx = 0; kx < 7; ++kx) {
 #pragma unroll
       for (int ci = 0; ci < CIN; ++ci) {
         const float4* w4 = reinterpret_cast<const float4*>(wsm + ((ky * 7 + kx) * CIN + ci) * 64 + cg * 16);
         const float4 w0 = w4[0], w1 = w4[1], w2 = w4[2], w3 = w4[3];
-        const float* pp = patch + ci * kPatch * kPatch + ky * kPatch + kx;
+        const float* pp = patch + ci * kChStride + ky * kRowStride + (kx & 1) * kHalf + (kx >> 1);
 #pragma unroll
         for (int i = 0; i < kPosPerThread; ++i) {
           const float x = pp[poff[i]];
-          acc[i][0] = fmaf(x, w0.x, acc[i][0]);   acc[i][1] = fmaf(x, w0.y, acc[i][1]);
-          acc[i][2] = fmaf(x, w0.z, acc[i][2]);   acc[i][3] = fmaf(x, w0.w, acc[i][3]);
-          acc[i][4] = fmaf(x, w1.x, acc[i][4]);   acc[i][5] = fmaf(x, w1.y, acc[i][5]);
-          acc[i][6] = fmaf(x, w1.z, acc[i][6]);   acc[i][7] = fmaf(x, w1.w, acc[i][7]);
-          acc[i][8] = fmaf(x, w2.x, acc[i][8]);   acc[i][9] = fmaf(x, w2.y, acc[i][9]);
-          acc[i][10] = fmaf(x, w2.z, acc[i][10]); acc[i][11] = fmaf(x, w2.w, acc[i][11]);
-          acc[i][12] = fmaf(x, w3.x, acc[i][12]); acc[i][13] = fmaf(x, w3.y, acc[i][13]);
-          acc[i][14] = fmaf(x, w3.z, acc[i][14]); acc[i][15] = fmaf(x, w3.w, acc[i][15]);
+          const unsigned long long xx = pack2(x, x);
+          ffma2(acc[i][0], xx, w0.x, w0.y);
+          ffma2(acc[i][1], xx, w0.z, w0.w);
+          ffma2(acc[i][2], xx, w1.x, w1.y);
+          ffma2(acc[i][3], xx, w1.z, w1.w);
+          ffma2(acc[i][4], xx, w2.x, w2.y);
+          ffma2(acc[i][5], xx, w2.z, w2.w);
+          ffma2(acc[i][6], xx, w3.x, w3.y);
+          ffma2(acc[i][7], xx, w3.z, w3.w);
         }
       }
     }
@@ -69,8 +92,8 @@ stem_kernel(const float* __restrict__ rgb, const float* __restrict__ depth, int 
   float* s_dep = s_fuse + kPos * 64;           // [289][64] swizzled: depth stem
   float* s_wr = s_dep + kPos * 64;             // [147][64]
   float* s_wd = s_wr + kKRgb * 64;             // [49][64]
-  float* s_patch = s_wd + kKDepth * 64;        // [4][39][39]  (r,g,b,depth)
-  float* s_bn = s_patch + 4 * kPatch * kPatch; // scale_rgb, shift_rgb, scale_d, shift_d
+  float* s_patch = s_wd + kKDepth * 64;        // [4][39][2][20]  (r,g,b,depth), columns split by parity
+  float* s_bn = s_patch + 4 * kPatch * (kPatch + 1);   // scale_rgb, shift_rgb, scale_d, shift_d
 
   const int Hs = (H + 2 * 3 - 7) / 2 + 1, Ws = (W + 2 * 3 - 7) / 2 + 1;   // stem map
   const int Hp = (Hs + 2 - 3) / 2 + 1, Wp = (Ws + 2 - 3) / 2 + 1;         // pooled map
@@ -91,13 +114,14 @@ stem_kernel(const float* __restrict__ rgb, const float* __restrict__ depth, int 
   for (int i = tid; i < 4 * kPatch * kPatch; i += kThreads) {
     const int ch = i / (kPatch * kPatch);
     const int r = i % (kPatch * kPatch);
-    const int y = iy0 + r / kPatch, x = ix0 + r % kPatch;
+    const int py = r / kPatch, px = r % kPatch;
+    const int y = iy0 + py, x = ix0 + px;
     float v = 0.f;
     if (y >= 0 && y < H && x >= 0 && x < W) {
       v = ch < 3 ? rgb[((static_cast<size_t>(n) * 3 + ch) * H + y) * W + x]
                  : depth[(static_cast<size_t>(n) * H + y) * W + x];
     }
-    s_patch[i] = v;
+    s_patch[ch * kChStride + py * kRowStride + (px & 1) * kHalf + (px >> 1)] = v;
   }
   __syncthreads();
 
@@ -110,16 +134,25 @@ stem_kernel(const float* __restrict__ rgb, const float* __restrict__ depth, int 
     int p = tpos + i * kPosThreads;
     pos[i] = p;
     if (p >= kPos) p = kPos - 1;          // clamp: computed but never stored
-    poff[i] = (2 * (p / kST)) * kPatch + 2 * (p % kST);
+    poff[i] = (2 * (p / kST)) * kRowStride + (p % kST);
   }
 
+  unsigned long long acc2[kPosPerThread][8];
   float acc[kPosPerThread][16];
   // ---- RGB stem conv
 #pragma unroll
   for (int i = 0; i < kPosPerThread; ++i)
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[i][c] = 0.f;
-  conv_accumulate<3>(s_patch, s_wr, poff, cg, acc);
+    for (int c = 0; c < 8; ++c) acc2[i][c] = 0ull;
+  conv_accumulate<3>(s_patch, s_wr, poff, cg, acc2);
+#pragma unroll
+  for (int i = 0; i < kPosPerThread; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float2 t = unpack2(acc2[i][c]);
+      acc[i][2 * c] = t.x;
+      acc[i][2 * c + 1] = t.y;
+    }
 #pragma unroll
   for (int i = 0; i < kPosPerThread; ++i) {
     if (pos[i] < kPos) {
@@ -139,8 +172,16 @@ stem_kernel(const float* __restrict__ rgb, const float* __restrict__ depth, int 
 #pragma unroll
   for (int i = 0; i < kPosPerThread; ++i)
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[i][c] = 0.f;
-  conv_accumulate<1>(s_patch + 3 * kPatch * kPatch, s_wd, poff, cg, acc);
+    for (int c = 0; c < 8; ++c) acc2[i][c] = 0ull;
+  conv_accumulate<1>(s_patch + 3 * kChStride, s_wd, poff, cg, acc2);
+#pragma unroll
+  for (int i = 0; i < kPosPerThread; ++i)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float2 t = unpack2(acc2[i][c]);
+      acc[i][2 * c] = t.x;
+      acc[i][2 * c + 1] = t.y;
+    }
 #pragma unroll
   for (int i = 0; i < kPosPerThread; ++i) {
     if (pos[i] < kPos) {

@@ -183,11 +183,11 @@ class FusionEngine:
             self.dec.append({
                 "conv3x3": p.conv_bn_act(dk + ".conv3x3", 3),
                 "blocks": [p.nbt1d(f"{dk}.decoder_blocks.{b}") for b in range(cfg.nr_decoder_blocks[i])],
-                "up_w": p.t(dk + ".upsample.conv.weight").reshape(-1, 9).contiguous(),
+                "up_w": p.t(dk + ".upsample.conv.weight").reshape(-1, 9).t().contiguous(),   # [9][C]
                 "up_b": p.t(dk + ".upsample.conv.bias").contiguous(),
             })
         self.conv_out = p.conv("decoder.conv_out", pad=(1, 1))
-        self.up = [(p.t(f"decoder.{u}.conv.weight").reshape(-1, 9).contiguous(),
+        self.up = [(p.t(f"decoder.{u}.conv.weight").reshape(-1, 9).t().contiguous(),
                     p.t(f"decoder.{u}.conv.bias").contiguous()) for u in ("upsample1", "upsample2")]
         self.side = torch.cuda.Stream(device=device)
         self.launches = 0          # kernels launched by the last forward (for bench accounting)

@@ -82,7 +82,8 @@ class DynMMNetV2(nn.Module):
             weight = torch.ones_like(weight) / self.branch_num
         if self.infer_mode == 0 and can_route(weight, self.hard_gate, self.training):
             def sub(rows):
-                return [[f[rows] for f in feats], [ln[rows] if torch.is_tensor(ln) else ln for ln in lens]]
+                pick = lambda ln: ln[rows.to(ln.device)] if torch.is_tensor(ln) else ln   # lengths may live on the host
+                return [[f[rows] for f in feats], [pick(ln) for ln in lens]]
             experts = [lambda rows: self._expert1(*sub(rows)), lambda rows: self.branch2(sub(rows))]
             output, self.last_route_counts = routed_mix(weight, experts, 1)
         else:

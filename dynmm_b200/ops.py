@@ -277,7 +277,7 @@ def nhwc_bf16_to_nchw_f32(x: Tensor, c: Optional[int] = None) -> Tensor:
 
 def upsample2x_dw3x3(x: Tensor, weight: Tensor, bias: Optional[Tensor], skip: Optional[Tensor] = None,
                      to_nchw_f32: bool = False, out: Optional[Tensor] = None) -> Tensor:
-    """x NHWC bf16; weight fp32 [c,3,3] (or [c,1,3,3])."""
+    """x NHWC bf16; weight fp32 tap-major [9, c] (``conv.weight.reshape(c, 9).t().contiguous()``)."""
     lib = _lib.load()
     _cuda(x, weight, bias, skip, out)
     n, h, w, c = x.shape

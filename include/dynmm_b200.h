@@ -182,7 +182,8 @@ int dynmm_nhwc_bf16_to_nchw_f32(const void* in, int n, int c, int h, int w, int 
 
 /* Upsample.forward for mode 'learned-3x3-zeropad' (model.py:403-410): nearest x2 then
  * depthwise 3x3 (zero pad) + bias, optionally + skip (DecoderModule.forward :353-355).
- * in NHWC bf16 [n,h,w,c]; weight fp32 [c][3][3]; out NHWC bf16 [n,2h,2w,c], or when
+ * in NHWC bf16 [n,h,w,c]; weight fp32 TAP-MAJOR [3*3][c] (= conv.weight[c,1,3,3] transposed); out NHWC bf16
+ * [n,2h,2w,c], or when
  * out_nchw_f32 != NULL fp32 NCHW (the module's return layout). */
 int dynmm_upsample2x_dw3x3(const void* in, int n, int h, int w, int c, const float* weight,
                            const float* bias, const void* skip, void* out_nhwc_bf16,

@@ -305,9 +305,9 @@ def test_elementwise_ops():
     skip = torch.randn(2, 14, 18, 40, device=dev, generator=g).to(torch.bfloat16)
     up_ref = F.conv2d(F.interpolate(xin.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest"), wdw, bias, 1, 1,
                       1, 40)
-    got = ops.upsample2x_dw3x3(xin, wdw.view(40, 9).contiguous(), bias, skip)
+    got = ops.upsample2x_dw3x3(xin, wdw.view(40, 9).t().contiguous(), bias, skip)
     _bf16_close(got, up_ref.permute(0, 2, 3, 1) + skip.float(), "upsample+skip")
-    got32 = ops.upsample2x_dw3x3(xin, wdw.view(40, 9).contiguous(), bias, to_nchw_f32=True)
+    got32 = ops.upsample2x_dw3x3(xin, wdw.view(40, 9).t().contiguous(), bias, to_nchw_f32=True)
     np.testing.assert_allclose(got32.cpu().numpy(), up_ref.cpu().numpy(), rtol=1e-5, atol=1e-5)
     # pyramid pooling helpers
     feat = torch.randn(2, 15, 20, 64, device=dev, generator=g).to(torch.bfloat16)
