@@ -292,7 +292,10 @@ def main():
                     "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s", "frac": achieved / tf_sust,
                     "peak_source": f"{src} (bf16 sustained; burst {tf_burst})", "traffic": None,
                     "launches_per_step": n_conv, "gflop_per_step": gflop, "kernel_s_per_step": t_conv,
-                    "share_of_step": t_conv / step_s if step_s > 0 else None}
+                    "note": "kernel_s_per_step sums the conv launches of BOTH encoder streams timed back to back "
+                            "(CUDA events on the launching stream); in the timed step the two streams overlap, so "
+                            "the sum may exceed ms_per_step. Kernel share of the step: profiles/ (ncu launch list).",
+                    "step_s": step_s}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             v, per = cpu_reference_images_per_s(model.state_dict(), 2, 1, 3, threads)
