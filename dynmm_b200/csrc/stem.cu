@@ -86,7 +86,7 @@ stem_kernel(const float* __restrict__ rgb, const float* __restrict__ depth, int 
             const float* __restrict__ w_rgb, const float* __restrict__ scale_rgb, const float* __restrict__ shift_rgb,
             const float* __restrict__ w_d, const float* __restrict__ scale_d, const float* __restrict__ shift_d,
             float* __restrict__ rgb_f32, float* __restrict__ depth_f32, __nv_bfloat16* __restrict__ rgb_bf16,
-            __nv_bfloat16* __restrict__ depth_bf16) {
+            __nv_bfloat16* __restrict__ depth_bf16, int tiles_x, int tiles_y, int batch) {
   extern __shared__ __align__(16) float sm[];
   float* s_fuse = sm;                          // [289][64] swizzled: rgb stem, then rgb+depth
   float* s_dep = s_fuse + kPos * 64;           // [289][64] swizzled: depth stem
@@ -97,31 +97,61 @@ stem_kernel(const float* __restrict__ rgb, const float* __restrict__ depth, int 
 
   const int Hs = (H + 2 * 3 - 7) / 2 + 1, Ws = (W + 2 * 3 - 7) / 2 + 1;   // stem map
   const int Hp = (Hs + 2 - 3) / 2 + 1, Wp = (Ws + 2 - 3) / 2 + 1;         // pooled map
-  const int n = blockIdx.z;
-  const int py0 = blockIdx.y * kPT, px0 = blockIdx.x * kPT;
-  const int sy0 = 2 * py0 - 1, sx0 = 2 * px0 - 1;     // stem-tile origin
-  const int iy0 = 2 * sy0 - 3, ix0 = 2 * sx0 - 3;     // input-patch origin
   const int tid = threadIdx.x;
+  const int total_tiles = tiles_x * tiles_y * batch;
 
-  for (int i = tid; i < kKRgb * 64; i += kThreads) s_wr[i] = w_rgb[i];
-  for (int i = tid; i < kKDepth * 64; i += kThreads) s_wd[i] = w_d[i];
+  // persistent CTA: the 50 KB of weights and the BN constants are staged ONCE
+  for (int i = tid; i < kKRgb * 16; i += kThreads)
+    reinterpret_cast<float4*>(s_wr)[i] = __ldg(reinterpret_cast<const float4*>(w_rgb) + i);
+  for (int i = tid; i < kKDepth * 16; i += kThreads)
+    reinterpret_cast<float4*>(s_wd)[i] = __ldg(reinterpret_cast<const float4*>(w_d) + i);
   if (tid < 64) {
     s_bn[tid] = scale_rgb[tid];
     s_bn[64 + tid] = shift_rgb[tid];
     s_bn[128 + tid] = scale_d[tid];
     s_bn[192 + tid] = shift_d[tid];
   }
-  for (int i = tid; i < 4 * kPatch * kPatch; i += kThreads) {
-    const int ch = i / (kPatch * kPatch);
-    const int r = i % (kPatch * kPatch);
-    const int py = r / kPatch, px = r % kPatch;
-    const int y = iy0 + py, x = ix0 + px;
-    float v = 0.f;
-    if (y >= 0 && y < H && x >= 0 && x < W) {
-      v = ch < 3 ? rgb[((static_cast<size_t>(n) * 3 + ch) * H + y) * W + x]
-                 : depth[(static_cast<size_t>(n) * H + y) * W + x];
+
+  // input patch: element e = tid + 256*j of the [4][39][39] patch; fetched into registers (so the next
+  // tile's global loads overlap this tile's pooling) and scattered into the parity-split layout
+  constexpr int kPatchElems = 4 * kPatch * kPatch;
+  constexpr int kPerThread = (kPatchElems + kThreads - 1) / kThreads;     // 24
+  float pre[kPerThread];
+  auto fetch_patch = [&](int tile) {
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, nn = tile / (tiles_x * tiles_y);
+    const int iy0 = 2 * (2 * ty * kPT - 1) - 3, ix0 = 2 * (2 * tx * kPT - 1) - 3;
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) {
+      const int e = tid + j * kThreads;
+      float v = 0.f;
+      if (e < kPatchElems) {
+        const int ch = e / (kPatch * kPatch);
+        const int r = e - ch * (kPatch * kPatch);
+        const int py = r / kPatch, px = r - py * kPatch;
+        const int y = iy0 + py, x = ix0 + px;
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+          v = ch < 3 ? __ldg(rgb + ((static_cast<size_t>(nn) * 3 + ch) * H + y) * W + x)
+                     : __ldg(depth + (static_cast<size_t>(nn) * H + y) * W + x);
+        }
+      }
+      pre[j] = v;
     }
-    s_patch[ch * kChStride + py * kRowStride + (px & 1) * kHalf + (px >> 1)] = v;
+  };
+  auto store_patch = [&]() {
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) {
+      const int e = tid + j * kThreads;
+      if (e < kPatchElems) {
+        const int ch = e / (kPatch * kPatch);
+        const int r = e - ch * (kPatch * kPatch);
+        const int py = r / kPatch, px = r - py * kPatch;
+        s_patch[ch * kChStride + py * kRowStride + (px & 1) * kHalf + (px >> 1)] = pre[j];
+      }
+    }
+  };
+  if ((int)blockIdx.x < total_tiles) {
+    fetch_patch(blockIdx.x);
+    store_patch();
   }
   __syncthreads();
 
@@ -137,97 +167,108 @@ stem_kernel(const float* __restrict__ rgb, const float* __restrict__ depth, int 
     poff[i] = (2 * (p / kST)) * kRowStride + (p % kST);
   }
 
-  unsigned long long acc2[kPosPerThread][8];
-  float acc[kPosPerThread][16];
-  // ---- RGB stem conv
-#pragma unroll
-  for (int i = 0; i < kPosPerThread; ++i)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) acc2[i][c] = 0ull;
-  conv_accumulate<3>(s_patch, s_wr, poff, cg, acc2);
-#pragma unroll
-  for (int i = 0; i < kPosPerThread; ++i)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float2 t = unpack2(acc2[i][c]);
-      acc[i][2 * c] = t.x;
-      acc[i][2 * c + 1] = t.y;
-    }
-#pragma unroll
-  for (int i = 0; i < kPosPerThread; ++i) {
-    if (pos[i] < kPos) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int c = cg * 16 + q * 4;
-        float4 v;
-        v.x = fmaxf(fmaf(acc[i][q * 4 + 0], s_bn[c + 0], s_bn[64 + c + 0]), 0.f);
-        v.y = fmaxf(fmaf(acc[i][q * 4 + 1], s_bn[c + 1], s_bn[64 + c + 1]), 0.f);
-        v.z = fmaxf(fmaf(acc[i][q * 4 + 2], s_bn[c + 2], s_bn[64 + c + 2]), 0.f);
-        v.w = fmaxf(fmaf(acc[i][q * 4 + 3], s_bn[c + 3], s_bn[64 + c + 3]), 0.f);
-        *reinterpret_cast<float4*>(&s_fuse[tile_idx(pos[i], c)]) = v;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int n = tile / (tiles_x * tiles_y);
+    const int py0 = ((tile / tiles_x) % tiles_y) * kPT, px0 = (tile % tiles_x) * kPT;
+    const int sy0 = 2 * py0 - 1, sx0 = 2 * px0 - 1;     // stem-tile origin
+    unsigned long long acc2[kPosPerThread][8];
+    float acc[kPosPerThread][16];
+    // ---- RGB stem conv
+  #pragma unroll
+    for (int i = 0; i < kPosPerThread; ++i)
+  #pragma unroll
+      for (int c = 0; c < 8; ++c) acc2[i][c] = 0ull;
+    conv_accumulate<3>(s_patch, s_wr, poff, cg, acc2);
+  #pragma unroll
+    for (int i = 0; i < kPosPerThread; ++i)
+  #pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float2 t = unpack2(acc2[i][c]);
+        acc[i][2 * c] = t.x;
+        acc[i][2 * c + 1] = t.y;
+      }
+  #pragma unroll
+    for (int i = 0; i < kPosPerThread; ++i) {
+      if (pos[i] < kPos) {
+  #pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = cg * 16 + q * 4;
+          float4 v;
+          v.x = fmaxf(fmaf(acc[i][q * 4 + 0], s_bn[c + 0], s_bn[64 + c + 0]), 0.f);
+          v.y = fmaxf(fmaf(acc[i][q * 4 + 1], s_bn[c + 1], s_bn[64 + c + 1]), 0.f);
+          v.z = fmaxf(fmaf(acc[i][q * 4 + 2], s_bn[c + 2], s_bn[64 + c + 2]), 0.f);
+          v.w = fmaxf(fmaf(acc[i][q * 4 + 3], s_bn[c + 3], s_bn[64 + c + 3]), 0.f);
+          *reinterpret_cast<float4*>(&s_fuse[tile_idx(pos[i], c)]) = v;
+        }
       }
     }
-  }
-  // ---- depth stem conv, then fuse = rgb + depth (same thread owns the same elements)
-#pragma unroll
-  for (int i = 0; i < kPosPerThread; ++i)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) acc2[i][c] = 0ull;
-  conv_accumulate<1>(s_patch + 3 * kChStride, s_wd, poff, cg, acc2);
-#pragma unroll
-  for (int i = 0; i < kPosPerThread; ++i)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float2 t = unpack2(acc2[i][c]);
-      acc[i][2 * c] = t.x;
-      acc[i][2 * c + 1] = t.y;
-    }
-#pragma unroll
-  for (int i = 0; i < kPosPerThread; ++i) {
-    if (pos[i] < kPos) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int c = cg * 16 + q * 4;
-        float4 d;
-        d.x = fmaxf(fmaf(acc[i][q * 4 + 0], s_bn[128 + c + 0], s_bn[192 + c + 0]), 0.f);
-        d.y = fmaxf(fmaf(acc[i][q * 4 + 1], s_bn[128 + c + 1], s_bn[192 + c + 1]), 0.f);
-        d.z = fmaxf(fmaf(acc[i][q * 4 + 2], s_bn[128 + c + 2], s_bn[192 + c + 2]), 0.f);
-        d.w = fmaxf(fmaf(acc[i][q * 4 + 3], s_bn[128 + c + 3], s_bn[192 + c + 3]), 0.f);
-        const int idx = tile_idx(pos[i], c);
-        float4 r = *reinterpret_cast<float4*>(&s_fuse[idx]);
-        r.x += d.x; r.y += d.y; r.z += d.z; r.w += d.w;
-        *reinterpret_cast<float4*>(&s_fuse[idx]) = r;
-        *reinterpret_cast<float4*>(&s_dep[idx]) = d;
+    // ---- depth stem conv, then fuse = rgb + depth (same thread owns the same elements)
+  #pragma unroll
+    for (int i = 0; i < kPosPerThread; ++i)
+  #pragma unroll
+      for (int c = 0; c < 8; ++c) acc2[i][c] = 0ull;
+    conv_accumulate<1>(s_patch + 3 * kChStride, s_wd, poff, cg, acc2);
+  #pragma unroll
+    for (int i = 0; i < kPosPerThread; ++i)
+  #pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float2 t = unpack2(acc2[i][c]);
+        acc[i][2 * c] = t.x;
+        acc[i][2 * c + 1] = t.y;
+      }
+  #pragma unroll
+    for (int i = 0; i < kPosPerThread; ++i) {
+      if (pos[i] < kPos) {
+  #pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = cg * 16 + q * 4;
+          float4 d;
+          d.x = fmaxf(fmaf(acc[i][q * 4 + 0], s_bn[128 + c + 0], s_bn[192 + c + 0]), 0.f);
+          d.y = fmaxf(fmaf(acc[i][q * 4 + 1], s_bn[128 + c + 1], s_bn[192 + c + 1]), 0.f);
+          d.z = fmaxf(fmaf(acc[i][q * 4 + 2], s_bn[128 + c + 2], s_bn[192 + c + 2]), 0.f);
+          d.w = fmaxf(fmaf(acc[i][q * 4 + 3], s_bn[128 + c + 3], s_bn[192 + c + 3]), 0.f);
+          const int idx = tile_idx(pos[i], c);
+          float4 r = *reinterpret_cast<float4*>(&s_fuse[idx]);
+          r.x += d.x; r.y += d.y; r.z += d.z; r.w += d.w;
+          *reinterpret_cast<float4*>(&s_fuse[idx]) = r;
+          *reinterpret_cast<float4*>(&s_dep[idx]) = d;
+        }
       }
     }
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // ---- 3x3 / stride 2 / pad 1 max-pool of both tiles, NHWC stores (64 consecutive channels per pixel)
-  const int c = tid & 63;
-  for (int pp = tid >> 6; pp < kPT * kPT; pp += kThreads >> 6) {
-    const int ly = pp / kPT, lx = pp % kPT;
-    const int py = py0 + ly, px = px0 + lx;
-    if (py >= Hp || px >= Wp) continue;
-    float mf = -INFINITY, md = -INFINITY;
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      const int gy = sy0 + 2 * ly + dy;
-      if (gy < 0 || gy >= Hs) continue;
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const int gx = sx0 + 2 * lx + dx;
-        if (gx < 0 || gx >= Ws) continue;
-        const int idx = tile_idx((2 * ly + dy) * kST + 2 * lx + dx, c);
-        mf = fmaxf(mf, s_fuse[idx]);
-        md = fmaxf(md, s_dep[idx]);
+    // the patch is free again: start fetching the next tile's pixels while we pool this one
+    const int next_tile = tile + gridDim.x;
+    if (next_tile < total_tiles) fetch_patch(next_tile);
+
+    // ---- 3x3 / stride 2 / pad 1 max-pool of both tiles, NHWC stores (64 consecutive channels per pixel)
+    const int c = tid & 63;
+    for (int pp = tid >> 6; pp < kPT * kPT; pp += kThreads >> 6) {
+      const int ly = pp / kPT, lx = pp % kPT;
+      const int py = py0 + ly, px = px0 + lx;
+      if (py >= Hp || px >= Wp) continue;
+      float mf = -INFINITY, md = -INFINITY;
+  #pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        const int gy = sy0 + 2 * ly + dy;
+        if (gy < 0 || gy >= Hs) continue;
+  #pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const int gx = sx0 + 2 * lx + dx;
+          if (gx < 0 || gx >= Ws) continue;
+          const int idx = tile_idx((2 * ly + dy) * kST + 2 * lx + dx, c);
+          mf = fmaxf(mf, s_fuse[idx]);
+          md = fmaxf(md, s_dep[idx]);
+        }
       }
+      const size_t o = ((static_cast<size_t>(n) * Hp + py) * Wp + px) * 64 + c;
+      if (rgb_f32) rgb_f32[o] = mf;
+      if (depth_f32) depth_f32[o] = md;
+      if (rgb_bf16) rgb_bf16[o] = __float2bfloat16_rn(mf);
+      if (depth_bf16) depth_bf16[o] = __float2bfloat16_rn(md);
     }
-    const size_t o = ((static_cast<size_t>(n) * Hp + py) * Wp + px) * 64 + c;
-    if (rgb_f32) rgb_f32[o] = mf;
-    if (depth_f32) depth_f32[o] = md;
-    if (rgb_bf16) rgb_bf16[o] = __float2bfloat16_rn(mf);
-    if (depth_bf16) depth_bf16[o] = __float2bfloat16_rn(md);
+    if (next_tile < total_tiles) store_patch();
+    __syncthreads();     // tiles of the next iteration may be overwritten; its patch is in place
   }
 }
 
@@ -247,10 +288,13 @@ extern "C" int dynmm_stem_fwd(const float* rgb, const float* depth, int b, int h
   static cudaError_t attr_err =
       cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemFloats * sizeof(float)));
   DYNMM_CUDA(attr_err);
-  dim3 grid(ceil_div(Wp, kPT), ceil_div(Hp, kPT), b);
+  const int tiles_x = ceil_div(Wp, kPT), tiles_y = ceil_div(Hp, kPT);
+  const long long total = 1LL * tiles_x * tiles_y * b;
+  DYNMM_CHECK_ARG(total < (1LL << 30), "stem: too many tiles");
+  const int grid = (int)(total < num_sms() ? total : num_sms());
   stem_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       rgb, depth, h, w, w_rgb, scale_rgb, shift_rgb, w_d, scale_d, shift_d, rgb_f32, depth_f32,
-      static_cast<__nv_bfloat16*>(rgb_bf16), static_cast<__nv_bfloat16*>(depth_bf16));
+      static_cast<__nv_bfloat16*>(rgb_bf16), static_cast<__nv_bfloat16*>(depth_bf16), tiles_x, tiles_y, b);
   DYNMM_LAUNCH_CHECK();
   return DYNMM_OK;
 }
