@@ -69,39 +69,49 @@ def build_model(seed: int = 0):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons while the timed region runs (NVML, 10 ms period)."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.sm, self.reasons, self._stop_evt = index, [], set(), threading.Event()
+        self.max_sm = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # honour CUDA_VISIBLE_DEVICES: NVML indexes physical devices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].strip().isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
 
     def run(self):
+        nv = self.nv
+        if nv is None:
+            return
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(",")])
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.01)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=5)
-        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 7:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                                   r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 def measured_peaks():
@@ -185,7 +195,7 @@ def profile_conv_kernel(model, rgb, depth):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -239,25 +249,22 @@ def main():
             _, wgt = model(*batches[i], True, True)
             hist += torch.bincount(wgt.argmax(1), minlength=5)
 
-        # ---------------- end to end through the public module API, host buffers
+        # ---------------- end to end through the public API with HOST buffers: every step uploads its
+        # pinned inputs, runs SkipGateESANet.forward, arg-maxes (eval.py:109-120) and reads the labels back.
+        # EvalPipeline overlaps batch i+1's upload / batch i-1's read-back with batch i's forward.
+        from dynmm_b200.fusion import EvalPipeline
         host = [tuple(t.pin_memory() for t in synthetic_batch(1000 * rank + i, BATCH)) for i in range(3)]
-        labels_host = torch.empty(BATCH, H, W, dtype=torch.uint8).pin_memory()
-
-        def e2e_step(i):
-            rgb = host[i % 3][0].to(dev, non_blocking=True)
-            depth = host[i % 3][1].to(dev, non_blocking=True)
-            pred = model(rgb, depth, True)                       # eval.py:109-115
-            labels = torch.argmax(pred, dim=1).to(torch.uint8)   # eval.py:120
-            labels_host.copy_(labels, non_blocking=True)
-            torch.cuda.current_stream().synchronize()            # the caller consumes the labels
-        for i in range(args.warmup):
-            e2e_step(i)
+        pipe = EvalPipeline(model, BATCH, H, W, dev)
+        for _ in pipe.run(host[i % 3] for i in range(args.warmup)):
+            pass
         barrier()
         t0 = time.perf_counter()
-        for i in range(args.steps):
-            e2e_step(i)
+        n_out = 0
+        for labels in pipe.run(host[i % 3] for i in range(args.steps)):
+            n_out += labels.shape[0]
         barrier()
         t_e2e = time.perf_counter() - t0
+        assert n_out == BATCH * args.steps
 
     t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -317,7 +324,8 @@ def main():
                        "gate_branch_histogram": h, "gate_skip_flop_savings_pct": 100.0 * saved},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": BATCH * 4 * H * W * 4,
                     "d2h_bytes_per_step": BATCH * H * W, "ms_per_step": t_e2e / args.steps * 1e3,
-                    "api": "SkipGateESANet.forward(rgb, depth, True) + argmax, pinned host buffers both ways"},
+                    "api": "dynmm_b200.fusion.EvalPipeline: pinned host inputs -> SkipGateESANet.forward -> argmax -> "
+                           "uint8 labels in pinned host memory, copies overlapped with compute (2 slots)"},
             "gpu_launches": launches * args.steps,
             "gpu_launches_per_step": launches,
             "clocks": clocks,

@@ -3,3 +3,4 @@ from .modules import (BasicBlock, Bottleneck, ConvBNAct, Decoder, DecoderModule,
                       NonBottleneck1D, PyramidPoolingModule, ResNet, ResNet18, ResNet34, ResNet50, SkipGateESANet,
                       SqueezeAndExcitation, SqueezeAndExciteFusionAdd, Upsample, get_context_module)
 from .build import build_model  # noqa: F401,E402
+from .pipeline import EvalPipeline  # noqa: F401,E402
