@@ -47,7 +47,15 @@ SIGNATURES = {
     "dynmm_global_gate_workspace": (c_longlong, [c_int, c_int, c_int]),
     "dynmm_global_gate_logits": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [c_void_p] * 7
                                  + [c_void_p, c_void_p, c_void_p]),
-    "dynmm_stem_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [c_void_p] * 6 + [c_void_p] * 4 + [c_void_p]),
+    "dynmm_stem_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [c_void_p] * 6 + [c_void_p] * 4
+                       + [c_void_p] * 3 + [c_void_p]),
+    "dynmm_stem_gap_tiles": (c_longlong, [c_int, c_int, c_int]),
+    "dynmm_gap_workspace": (c_longlong, [c_int, c_int]),
+    "dynmm_gap_partial": (c_int, [c_void_p, c_int, c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "dynmm_se_mlp": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dynmm_se_gated_fuse": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong,
+                                    c_int, c_int, c_void_p, c_void_p]),
     "dynmm_conv_igemm_fwd": (c_int, [POINTER(ConvParams), c_void_p]),
     "dynmm_conv_direct_fwd": (c_int, [POINTER(ConvParams), c_void_p]),
     "dynmm_gated_add_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p]),

@@ -86,7 +86,8 @@ stem_kernel(const float* __restrict__ rgb, const float* __restrict__ depth, int 
             const float* __restrict__ w_rgb, const float* __restrict__ scale_rgb, const float* __restrict__ shift_rgb,
             const float* __restrict__ w_d, const float* __restrict__ scale_d, const float* __restrict__ shift_d,
             float* __restrict__ rgb_f32, float* __restrict__ depth_f32, __nv_bfloat16* __restrict__ rgb_bf16,
-            __nv_bfloat16* __restrict__ depth_bf16, int tiles_x, int tiles_y, int batch) {
+            __nv_bfloat16* __restrict__ depth_bf16, int tiles_x, int tiles_y, int batch,
+            const float* __restrict__ se_rgb, const float* __restrict__ se_depth, float* __restrict__ gap_partial) {
   extern __shared__ __align__(16) float sm[];
   float* s_fuse = sm;                          // [289][64] swizzled: rgb stem, then rgb+depth
   float* s_dep = s_fuse + kPos * 64;           // [289][64] swizzled: depth stem
@@ -229,7 +230,15 @@ stem_kernel(const float* __restrict__ rgb, const float* __restrict__ depth, int 
           d.w = fmaxf(fmaf(acc[i][q * 4 + 3], s_bn[128 + c + 3], s_bn[192 + c + 3]), 0.f);
           const int idx = tile_idx(pos[i], c);
           float4 r = *reinterpret_cast<float4*>(&s_fuse[idx]);
-          r.x += d.x; r.y += d.y; r.z += d.z; r.w += d.w;
+          if (se_rgb) {
+            // SqueezeAndExciteFusionAdd (rgb_depth_fusion.py:22-26): rgb*sigma_r + depth*sigma_d
+            const float4 sr = __ldg(reinterpret_cast<const float4*>(se_rgb + n * 64 + c));
+            const float4 sd = __ldg(reinterpret_cast<const float4*>(se_depth + n * 64 + c));
+            r.x = r.x * sr.x + d.x * sd.x; r.y = r.y * sr.y + d.y * sd.y;
+            r.z = r.z * sr.z + d.z * sd.z; r.w = r.w * sr.w + d.w * sd.w;
+          } else if (!gap_partial) {
+            r.x += d.x; r.y += d.y; r.z += d.z; r.w += d.w;
+          }
           *reinterpret_cast<float4*>(&s_fuse[idx]) = r;
           *reinterpret_cast<float4*>(&s_dep[idx]) = d;
         }
@@ -241,8 +250,32 @@ stem_kernel(const float* __restrict__ rgb, const float* __restrict__ depth, int 
     const int next_tile = tile + gridDim.x;
     if (next_tile < total_tiles) fetch_patch(next_tile);
 
-    // ---- 3x3 / stride 2 / pad 1 max-pool of both tiles, NHWC stores (64 consecutive channels per pixel)
     const int c = tid & 63;
+    if (gap_partial) {
+      // squeeze pass: per-tile channel sums of the UNFUSED stem maps over the positions this tile owns
+      // (row/column 0 of the 17x17 tile belong to the neighbouring tile); fixed order -> deterministic
+      float sr = 0.f, sd = 0.f;
+      for (int p = tid >> 6; p < kPos; p += kThreads >> 6) {
+        const int ly = p / kST, lx = p % kST;
+        const int gy = sy0 + ly, gx = sx0 + lx;
+        if (ly >= 1 && lx >= 1 && gy < Hs && gx < Ws) {
+          sr += s_fuse[tile_idx(p, c)];
+          sd += s_dep[tile_idx(p, c)];
+        }
+      }
+      __syncthreads();                      // tiles fully read; reuse the head of s_fuse as scratch
+      s_fuse[(tid >> 6) * 128 + c] = sr;
+      s_fuse[(tid >> 6) * 128 + 64 + c] = sd;
+      __syncthreads();
+      if (tid < 128) {
+        const float t = (s_fuse[tid] + s_fuse[128 + tid]) + (s_fuse[256 + tid] + s_fuse[384 + tid]);
+        gap_partial[static_cast<size_t>(tile) * 128 + tid] = t;      // [tile][rgb 64 | depth 64]
+      }
+      if (next_tile < total_tiles) store_patch();
+      __syncthreads();
+      continue;
+    }
+    // ---- 3x3 / stride 2 / pad 1 max-pool of both tiles, NHWC stores (64 consecutive channels per pixel)
     for (int pp = tid >> 6; pp < kPT * kPT; pp += kThreads >> 6) {
       const int ly = pp / kPT, lx = pp % kPT;
       const int py = py0 + ly, px = px0 + lx;
@@ -275,13 +308,21 @@ stem_kernel(const float* __restrict__ rgb, const float* __restrict__ depth, int 
 }  // namespace
 }  // namespace dynmm
 
+extern "C" long long dynmm_stem_gap_tiles(int b, int h, int w) {
+  const int Hs = (h + 6 - 7) / 2 + 1, Ws = (w + 6 - 7) / 2 + 1;
+  const int Hp = (Hs + 2 - 3) / 2 + 1, Wp = (Ws + 2 - 3) / 2 + 1;
+  return 1LL * dynmm::ceil_div(Wp, dynmm::kPT) * dynmm::ceil_div(Hp, dynmm::kPT) * b;
+}
+
 extern "C" int dynmm_stem_fwd(const float* rgb, const float* depth, int b, int h, int w, const float* w_rgb,
                               const float* scale_rgb, const float* shift_rgb, const float* w_d, const float* scale_d,
                               const float* shift_d, float* rgb_f32, float* depth_f32, void* rgb_bf16,
-                              void* depth_bf16, void* stream) {
+                              void* depth_bf16, const float* se_rgb, const float* se_depth, float* gap_partial,
+                              void* stream) {
   using namespace dynmm;
   DYNMM_CHECK_ARG(rgb && depth && w_rgb && w_d && scale_rgb && shift_rgb && scale_d && shift_d, "stem: null pointer");
   DYNMM_CHECK_ARG(b >= 1 && h >= 7 && w >= 7, "stem: bad shape");
+  DYNMM_CHECK_ARG((se_rgb == nullptr) == (se_depth == nullptr), "stem: SE scales come in pairs");
   const int Hs = (h + 6 - 7) / 2 + 1, Ws = (w + 6 - 7) / 2 + 1;
   const int Hp = (Hs + 2 - 3) / 2 + 1, Wp = (Ws + 2 - 3) / 2 + 1;
   const size_t smem = kSmemFloats * sizeof(float);
@@ -294,7 +335,8 @@ extern "C" int dynmm_stem_fwd(const float* rgb, const float* depth, int b, int h
   const int grid = (int)(total < num_sms() ? total : num_sms());
   stem_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       rgb, depth, h, w, w_rgb, scale_rgb, shift_rgb, w_d, scale_d, shift_d, rgb_f32, depth_f32,
-      static_cast<__nv_bfloat16*>(rgb_bf16), static_cast<__nv_bfloat16*>(depth_bf16), tiles_x, tiles_y, b);
+      static_cast<__nv_bfloat16*>(rgb_bf16), static_cast<__nv_bfloat16*>(depth_bf16), tiles_x, tiles_y, b, se_rgb,
+      se_depth, gap_partial);
   DYNMM_LAUNCH_CHECK();
   return DYNMM_OK;
 }

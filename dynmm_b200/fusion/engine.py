@@ -147,8 +147,8 @@ class FusionEngine:
         _lib.require_device()
         if cfg.activation.lower() != "relu":
             raise NotImplementedError("the CUDA engine fuses ReLU epilogues only; got activation=" + cfg.activation)
-        if cfg.fuse != "add":
-            raise NotImplementedError("the CUDA engine implements fuse_depth_in_rgb_encoder='add' (SE-add: next)")
+        if cfg.fuse not in ("add", "SE-add"):
+            raise NotImplementedError("fuse_depth_in_rgb_encoder must be 'add' or 'SE-add', got " + str(cfg.fuse))
         if cfg.upsampling != "learned-3x3-zeropad":
             raise NotImplementedError("the CUDA engine implements upsampling='learned-3x3-zeropad'")
         if "ppm" not in cfg.context_module or cfg.context_module == "ppm-1-2-4-8" or "appm" in cfg.context_module:
@@ -189,6 +189,19 @@ class FusionEngine:
         self.conv_out = p.conv("decoder.conv_out", pad=(1, 1))
         self.up = [(p.t(f"decoder.{u}.conv.weight").reshape(-1, 9).t().contiguous(),
                     p.t(f"decoder.{u}.conv.bias").contiguous()) for u in ("upsample1", "upsample2")]
+        # SE-add fusion: the 1x1 convs of SqueezeAndExcitation as fp32 matrices (model_utils.py:40-45)
+        self.se = None
+        if cfg.fuse == "SE-add":
+            self.se = []
+            for i in range(5):
+                layer = {}
+                for stream in ("se_rgb", "se_depth"):
+                    k = f"se_layer{i}.{stream}.fc"
+                    w1 = p.t(k + ".0.weight")
+                    w2 = p.t(k + ".2.weight")
+                    layer[stream] = (w1.reshape(w1.shape[0], -1).contiguous(), p.t(k + ".0.bias").contiguous(),
+                                     w2.reshape(w2.shape[0], -1).contiguous(), p.t(k + ".2.bias").contiguous())
+                self.se.append(layer)
         self.side = torch.cuda.Stream(device=device)
         self.launches = 0          # kernels launched by the last forward (for bench accounting)
 
@@ -217,6 +230,20 @@ class FusionEngine:
         self.launches += 1
         return out
 
+    def _se_fuse(self, s: int, rgb: Tensor, depth: Tensor, plan, keep: list, out: Optional[Tensor]) -> Tensor:
+        """fuse = w*rgb + (1-w)*se_layer{s+1}(rgb, depth)  (model_skip_mod_globalgate.py:280-283)."""
+        layer = self.se[s + 1]
+        n, hh, ww, c = rgb.shape
+        inv_area = 1.0 / (hh * ww)
+        pr = ops.gap_partial(rgb)
+        pd = ops.gap_partial(depth, count=plan.count[s:s + 1])
+        sig_r = ops.se_mlp(pr, inv_area, *layer["se_rgb"])
+        sig_d = ops.se_mlp(pd, inv_area, *layer["se_depth"], count=plan.count[s:s + 1])
+        fused = ops.se_gated_fuse(rgb, depth, sig_r, sig_d, plan.g[s], plan.slot, out=out)
+        keep += [pr, pd, sig_r, sig_d, fused]
+        self.launches += 5
+        return fused
+
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, rgb: Tensor, depth: Tensor, *, temp: float = 1.0, hard_gate: bool = False,
@@ -238,8 +265,19 @@ class FusionEngine:
         wr, sr, br = self.stem["encoder_rgb"]
         wd, sdp, bd = self.stem["encoder_depth"]
         learned = weight is None and not baseline and not ini_stage
-        r32, d32, r16, d16 = ops.stem(rgb, depth, wr, sr, br, wd, sdp, bd, want_f32=learned)
-        self.launches += 1
+        if self.se is None:
+            r32, d32, r16, d16 = ops.stem(rgb, depth, wr, sr, br, wd, sdp, bd, want_f32=learned)
+            self.launches += 1
+        else:
+            # se_layer0 needs the global average of both FULL stem maps before they can be fused:
+            # squeeze pass (channel sums only), excite (tiny MLP), then the fused stem with the scales
+            part, inv_area = ops.stem_squeeze(rgb, depth, wr, sr, br, wd, sdp, bd)
+            sig_r = ops.se_mlp(part, inv_area, *self.se[0]["se_rgb"], c_off=0, c=64)
+            sig_d = ops.se_mlp(part, inv_area, *self.se[0]["se_depth"], c_off=64, c=64)
+            r32, d32, r16, d16 = ops.stem(rgb, depth, wr, sr, br, wd, sdp, bd, want_f32=learned, se_rgb=sig_r,
+                                          se_depth=sig_d)
+            keep += [part, sig_r, sig_d]
+            self.launches += 4
         if weight is not None:
             weight = weight.to(self.dev, torch.float32).contiguous()
         elif baseline:                                     # :264-266
@@ -285,14 +323,21 @@ class FusionEngine:
                 if bi < len(blocks) - 1:
                     r = self._block(r, blk, keep)
                     continue
-                last_kw = dict(gated=depth_out[s], gate=plan.g[s], gated_slot=plan.slot)
                 if s == 3:
                     # stage-4 output lands directly in the pyramid-pooling concat buffer
                     c4 = self.stage_channels[3]
                     cat = torch.empty(b, h // 32, w // 32, c4 + 2 * self.ppm[0].c_out, dtype=torch.bfloat16,
                                       device=self.dev)
-                    last_kw.update(out=cat, out_c_off=0)
-                r = self._block(r, blk, keep, before_last=lambda s=s: main.wait_event(done[s]), last_kw=last_kw)
+                if self.se is None:
+                    last_kw = dict(gated=depth_out[s], gate=plan.g[s], gated_slot=plan.slot)
+                    if s == 3:
+                        last_kw.update(out=cat, out_c_off=0)
+                    r = self._block(r, blk, keep, before_last=lambda s=s: main.wait_event(done[s]), last_kw=last_kw)
+                else:
+                    # SE-add: both stage outputs must be complete before they can be squeezed
+                    r = self._block(r, blk, keep)
+                    main.wait_event(done[s])
+                    r = self._se_fuse(s, r, depth_out[s], plan, keep, cat if s == 3 else None)
             fused.append(r)
 
         # ---- skip connections, context module, decoder (model.py:295-308, context_modules.py:69-87)

@@ -97,9 +97,11 @@ CONV_PROFILER = None
 # ------------------------------------------------------------------ stem / gate
 
 def stem(rgb: Tensor, depth: Tensor, w_rgb: Tensor, scale_rgb: Tensor, shift_rgb: Tensor, w_d: Tensor,
-         scale_d: Tensor, shift_d: Tensor, want_f32: bool = True):
+         scale_d: Tensor, shift_d: Tensor, want_f32: bool = True, se_rgb: Optional[Tensor] = None,
+         se_depth: Optional[Tensor] = None):
     """rgb [b,3,h,w], depth [b,1,h,w] NCHW fp32 -> pooled NHWC maps
-    (rgb_f32, depth_f32, rgb_bf16, depth_bf16); the fp32 pair is None when not wanted."""
+    (rgb_f32, depth_f32, rgb_bf16, depth_bf16); the fp32 pair is None when not wanted.
+    se_rgb / se_depth [b,64]: SE scales of the two stem streams (SE-add fusion)."""
     lib = _lib.load()
     _cuda(rgb, depth, w_rgb, w_d)
     b, _, h, w = rgb.shape
@@ -111,8 +113,61 @@ def stem(rgb: Tensor, depth: Tensor, w_rgb: Tensor, scale_rgb: Tensor, shift_rgb
     r16 = torch.empty(b, hp, wp, 64, dtype=torch.bfloat16, device=dev)
     d16 = torch.empty(b, hp, wp, 64, dtype=torch.bfloat16, device=dev)
     check(lib.dynmm_stem_fwd(ptr(rgb), ptr(depth), b, h, w, ptr(w_rgb), ptr(scale_rgb), ptr(shift_rgb), ptr(w_d),
-                             ptr(scale_d), ptr(shift_d), ptr(r32), ptr(d32), ptr(r16), ptr(d16), stream_ptr()), "stem")
+                             ptr(scale_d), ptr(shift_d), ptr(r32), ptr(d32), ptr(r16), ptr(d16), ptr(se_rgb),
+                             ptr(se_depth), None, stream_ptr()), "stem")
     return r32, d32, r16, d16
+
+
+def stem_squeeze(rgb: Tensor, depth: Tensor, w_rgb, scale_rgb, shift_rgb, w_d, scale_d, shift_d):
+    """Pass 1 of the SE-add stem: per-tile channel sums of the two unfused stem maps.
+    -> (partial [b, tiles_per_sample, 128] fp32 with rows [rgb 64 | depth 64], 1 / stem map area)."""
+    lib = _lib.load()
+    _cuda(rgb, depth)
+    b, _, h, w = rgb.shape
+    tiles = lib.dynmm_stem_gap_tiles(b, h, w)
+    partial = torch.empty(b, tiles // b, 128, dtype=torch.float32, device=rgb.device)
+    check(lib.dynmm_stem_fwd(ptr(rgb), ptr(depth), b, h, w, ptr(w_rgb), ptr(scale_rgb), ptr(shift_rgb), ptr(w_d),
+                             ptr(scale_d), ptr(shift_d), None, None, None, None, None, None, ptr(partial),
+                             stream_ptr()), "stem_squeeze")
+    hs, ws = (h + 6 - 7) // 2 + 1, (w + 6 - 7) // 2 + 1
+    return partial, 1.0 / (hs * ws)
+
+
+def gap_partial(x: Tensor, c: Optional[int] = None, count: Optional[Tensor] = None) -> Tensor:
+    """x NHWC bf16 [n,h,w,ld] -> partial channel sums [n, 64, c] fp32 (deterministic)."""
+    lib = _lib.load()
+    _cuda(x, count)
+    n, h, w, ld = x.shape
+    c = ld if c is None else c
+    out = torch.empty(n, 64, c, dtype=torch.float32, device=x.device)
+    check(lib.dynmm_gap_partial(ptr(x), n, h * w, c, ld, ptr(count), ptr(out), stream_ptr()), "gap_partial")
+    return out
+
+
+def se_mlp(partial: Tensor, inv_area: float, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor,
+           count: Optional[Tensor] = None, c_off: int = 0, c: Optional[int] = None) -> Tensor:
+    """partial [rows, chunks, ld] fp32 channel sums; the SE block acts on columns [c_off, c_off+c).
+    -> sigma [rows, c]."""
+    lib = _lib.load()
+    _cuda(partial, w1, b1, w2, b2, count)
+    rows, chunks, ld = partial.shape
+    c = ld - c_off if c is None else c
+    hidden = w1.shape[0]
+    sigma = torch.empty(rows, c, dtype=torch.float32, device=partial.device)
+    check(lib.dynmm_se_mlp(ptr(partial), rows, chunks, ld, c_off, float(inv_area), c, hidden, ptr(w1), ptr(b1),
+                           ptr(w2), ptr(b2), ptr(count), ptr(sigma), stream_ptr()), "se_mlp")
+    return sigma
+
+
+def se_gated_fuse(rgb: Tensor, depth: Tensor, sig_r: Tensor, sig_d: Tensor, gate: Tensor,
+                  slot: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+    lib = _lib.load()
+    _cuda(rgb, depth, sig_r, sig_d, gate, slot, out)
+    n, h, w, c = rgb.shape
+    out = torch.empty_like(rgb) if out is None else out
+    check(lib.dynmm_se_gated_fuse(ptr(rgb), ptr(depth), ptr(sig_r), ptr(sig_d), ptr(gate), ptr(slot), n, h * w, c,
+                                  out.shape[3], ptr(out), stream_ptr()), "se_gated_fuse")
+    return out
 
 
 def global_gate_logits(rgb32: Tensor, depth32: Tensor, w1, scale1, shift1, w2, scale2, shift2, wfc,

@@ -96,7 +96,34 @@ int dynmm_global_gate_logits(const float* rgb, const float* depth, int b, int h,
 int dynmm_stem_fwd(const float* rgb, const float* depth, int b, int h, int w,
                    const float* w_rgb, const float* scale_rgb, const float* shift_rgb,
                    const float* w_d, const float* scale_d, const float* shift_d,
-                   float* rgb_f32, float* depth_f32, void* rgb_bf16, void* depth_bf16, void* stream);
+                   float* rgb_f32, float* depth_f32, void* rgb_bf16, void* depth_bf16,
+                   const float* se_rgb, const float* se_depth, float* gap_partial, void* stream);
+/* SE-add fusion at stage 0 (se_layer0; rgb_depth_fusion.py:22-26) is a two-pass use of the call above:
+ *   pass 1: gap_partial != NULL (float[dynmm_stem_gap_tiles() * 128]): only per-tile channel sums of the two
+ *           UNFUSED stem maps are produced (no pooled outputs); finish them with dynmm_se_mlp
+ *           (chunks = tiles per sample, inv_area = 1 / (h/2 * w/2), rows of 128 = [rgb 64 | depth 64]);
+ *   pass 2: se_rgb / se_depth (float [b][64]) scale the two streams before the add. */
+long long dynmm_stem_gap_tiles(int b, int h, int w);
+
+/* ------------------------------------------------------ SE-add fusion */
+
+/* Squeeze: partial[n][64 chunks][c] channel sums of NHWC bf16 x [n,hw,ld] (model_utils.py:48).  `count`
+ * (device int32 or NULL): only the first *count samples are reduced. */
+long long dynmm_gap_workspace(int n, int c);
+int dynmm_gap_partial(const void* x, int n, long long hw, int c, int ld, const int32_t* count, float* partial,
+                      void* stream);
+/* Excite: sigma[row] = sigmoid(W2 relu(W1 mean + b1) + b2) with mean = inv_area * sum of `chunks` partial rows
+ * (model_utils.py:40-45,49); partial rows have pitch ld and the c channels start at column c_off.
+ * w1 [hidden][c], w2 [c][hidden] (the 1x1 conv weights). */
+int dynmm_se_mlp(const float* partial, int rows, int chunks, int ld, int c_off, float inv_area, int c, int hidden,
+                 const float* w1, const float* b1, const float* w2, const float* b2, const int32_t* count,
+                 float* sigma, void* stream);
+/* Gated SE fusion (model_skip_mod_globalgate.py:280-283 with se_layer{s}):
+ *   out[n] = rgb[n]*(1 - g + g*sig_r[n]) + g*sig_d[slot(n)]*depth[slot(n)],  g = gate[n];
+ * samples with g == 0 never read depth.  rgb/depth NHWC bf16 [*,hw,c], out pitch out_ld. */
+int dynmm_se_gated_fuse(const void* rgb, const void* depth, const float* sig_r, const float* sig_d,
+                        const float* gate, const int32_t* slot, int n, long long hw, int c, int out_ld, void* out,
+                        void* stream);
 
 /* --------------------------------------------------------- encoder convs */
 

@@ -94,6 +94,36 @@ def test_engine_matches_reference_golden_vectors(golden_dir):
         assert abs(loss.item() - ref_loss.item()) < 1e-6
 
 
+@pytest.mark.parametrize("name", ["fusion_r34_nbt1d_seadd_64x64", "fusion_r50_seadd_decr_64x64",
+                                  "fusion_r18_basic_add_64x64"])
+def test_engine_matches_reference_golden_other_configs(name, golden_dir):
+    """SE-add fusion (the CLI default, args.py:159), ResNet-50 Bottleneck encoders with 'decreasing' decoder
+    channels (args.py:105-113,151) and ResNet-18 BasicBlock -- against the reference's own outputs."""
+    from tests.test_oracle_golden import CASES
+    from oracle.make_golden import sample_inputs
+    cfg, seed, b = CASES[name]
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    model, sd = _build(cfg, seed, float(gold["gate_scale"]))
+    rgb, depth = sample_inputs(seed + 1, b, cfg.height, cfg.width)
+    rgb, depth = rgb.cuda(), depth.cuda()
+    with torch.no_grad():
+        for tag, temp, hard in (("hard_t1", 1.0, True), ("soft_t1", 1.0, False)):
+            model.temp, model.hard_gate = temp, hard
+            out, w = model(rgb, depth, True, True)
+            if hard:
+                np.testing.assert_array_equal(w.cpu().numpy(), gold[tag + "_weight"])
+            ref = torch.from_numpy(gold[tag + "_out_sample"])
+            err = _rel_l2(out[:, :, ::4, ::4].cpu(), ref)
+            assert err <= REL_L2_TOL, f"{name}/{tag}: relative L2 error {err:.4f}"
+        eng = model.engine()
+        for k in (0, 2, 4):
+            wk = torch.eye(5)[torch.full((b,), k)].cuda()
+            out, _ = eng.forward(rgb, depth, weight=wk)
+            ref = torch.from_numpy(gold[f"branch{k}_out_sample"])
+            err = _rel_l2(out[:, :, ::4, ::4].cpu(), ref)
+            assert err <= REL_L2_TOL, f"{name}/branch{k}: relative L2 error {err:.4f}"
+
+
 @pytest.mark.parametrize("variant", ["r18_basic", "r34_nbt1d_odd"])
 def test_engine_matches_oracle_other_configs(variant):
     from oracle import fusion_oracle as fo

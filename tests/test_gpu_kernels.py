@@ -347,3 +347,41 @@ def test_softgate_mix_and_compaction():
     out = ops.softgate_mix_fwd([p0, p1_small], hard, rows=[None, inv])
     ref = hard[:, 0:1] * p0 + hard[:, 1:2] * p1
     assert torch.equal(out, ref)
+
+
+def test_se_fusion_kernels():
+    """Squeeze (deterministic GAP), excite (MLP + sigmoid) and the gated SE blend vs PyTorch."""
+    from dynmm_b200 import ops
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(4)
+    n, h, w, c = 5, 15, 20, 128
+    rgb = torch.randn(n, h, w, c, device=dev, generator=g).to(torch.bfloat16)
+    depth = torch.randn(n, h, w, c, device=dev, generator=g).to(torch.bfloat16)
+    w1 = torch.randn(c // 16, c, device=dev, generator=g) * 0.2
+    b1 = torch.randn(c // 16, device=dev, generator=g) * 0.1
+    w2 = torch.randn(c, c // 16, device=dev, generator=g) * 0.2
+    b2 = torch.randn(c, device=dev, generator=g) * 0.1
+    part = ops.gap_partial(rgb)
+    np.testing.assert_allclose(part.sum(1).cpu().numpy() / (h * w), rgb.float().mean((1, 2)).cpu().numpy(),
+                               rtol=1e-4, atol=1e-5)
+    assert torch.equal(part, ops.gap_partial(rgb))                       # deterministic
+    sig = ops.se_mlp(part, 1.0 / (h * w), w1, b1, w2, b2)
+    mean = rgb.float().mean((1, 2))
+    ref_sig = torch.sigmoid(F.relu(mean @ w1.t() + b1) @ w2.t() + b2)
+    np.testing.assert_allclose(sig.cpu().numpy(), ref_sig.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    sig_d = torch.rand(n, c, device=dev, generator=g)
+    gate = torch.tensor([1.0, 0.0, 0.3, 1.0, 0.0], device=dev)
+    slot = torch.tensor([1, 4, 0, 2, 3], dtype=torch.int32, device=dev)
+    depth_nan = depth.clone()
+    depth_nan[4] = float("nan")                                          # slot of a gated-off sample: never read
+    depth_nan[3] = float("nan")
+    sig_d_nan = sig_d.clone()
+    sig_d_nan[4] = float("nan")
+    sig_d_nan[3] = float("nan")
+    out = ops.se_gated_fuse(rgb, depth_nan, sig, sig_d_nan, gate, slot)
+    gg = gate.view(-1, 1, 1, 1)
+    d_sel = torch.nan_to_num(depth_nan.float()[slot.long()])
+    sd_sel = torch.nan_to_num(sig_d_nan[slot.long()])
+    ref = rgb.float() * (1 - gg + gg * sig.view(n, 1, 1, c)) + gg * sd_sel.view(n, 1, 1, c) * d_sel
+    _bf16_close(out, ref, "se_gated_fuse")
+    assert torch.isfinite(out.float()).all()
