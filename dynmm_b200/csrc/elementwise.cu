@@ -348,16 +348,26 @@ upsample2x_dw_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int h, int w,
 // ---------------------------------------------------------------- pyramid pooling helpers
 __global__ void adaptive_avgpool_kernel(const __nv_bfloat16* __restrict__ in, int h, int w, int c, int ld, int bins,
                                         __nv_bfloat16* __restrict__ out) {
-  // grid (bins*bins, n); threads stride channels; window = [floor(i*h/bins), ceil((i+1)*h/bins))
+  // grid (bins*bins, n, c/64); a block owns 64 channels of one window: 4 pixel lanes x 64 channels,
+  // fixed-order reduction.  window = [floor(i*h/bins), ceil((i+1)*h/bins))  (adaptive_avg_pool2d)
+  __shared__ float s_part[4][64];
   const int by = blockIdx.x / bins, bx = blockIdx.x % bins, s = blockIdx.y;
   const int y0 = (by * h) / bins, y1 = ((by + 1) * h + bins - 1) / bins;
   const int x0 = (bx * w) / bins, x1 = ((bx + 1) * w + bins - 1) / bins;
-  const float inv = 1.f / (float)((y1 - y0) * (x1 - x0));
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-    float acc = 0.f;
-    for (int y = y0; y < y1; ++y)
-      for (int x = x0; x < x1; ++x) acc += __bfloat162float(in[((1LL * s * h + y) * w + x) * ld + ch]);
-    out[((1LL * s * bins + by) * bins + bx) * c + ch] = __float2bfloat16_rn(acc * inv);
+  const int ww = x1 - x0, npix = (y1 - y0) * ww;
+  const int ch = blockIdx.z * 64 + (threadIdx.x & 63), lane_p = threadIdx.x >> 6;
+  float acc = 0.f;
+  if (ch < c) {
+    for (int p = lane_p; p < npix; p += 4) {
+      const int y = y0 + p / ww, x = x0 + p % ww;
+      acc += __bfloat162float(in[((1LL * s * h + y) * w + x) * ld + ch]);
+    }
+  }
+  s_part[lane_p][threadIdx.x & 63] = acc;
+  __syncthreads();
+  if (lane_p == 0 && ch < c) {
+    const float t = (s_part[0][threadIdx.x] + s_part[1][threadIdx.x]) + (s_part[2][threadIdx.x] + s_part[3][threadIdx.x]);
+    out[((1LL * s * bins + by) * bins + bx) * c + ch] = __float2bfloat16_rn(t / (float)npix);
   }
 }
 __global__ void nearest_resize_into_kernel(const __nv_bfloat16* __restrict__ src, int n, int hs, int ws, int c,
@@ -517,7 +527,7 @@ extern "C" int dynmm_adaptive_avgpool(const void* in, int n, int h, int w, int c
                                       void* stream) {
   DYNMM_CHECK_ARG(in && out && n >= 1 && h >= 1 && w >= 1 && c >= 1 && ld >= c && bins >= 1 && bins <= 64,
                   "avgpool: bad args");
-  adaptive_avgpool_kernel<<<dim3(bins * bins, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  adaptive_avgpool_kernel<<<dim3(bins * bins, n, ceil_div(c, 64)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(in), h, w, c, ld, bins, static_cast<__nv_bfloat16*>(out));
   DYNMM_LAUNCH_CHECK();
   return DYNMM_OK;

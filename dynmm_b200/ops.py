@@ -364,3 +364,29 @@ def nearest_resize_into(src: Tensor, dst: Tensor, c_off: int) -> None:
     _, h, w, ld = dst.shape
     check(lib.dynmm_nearest_resize_into(ptr(src), n, hs, ws, c, ptr(dst), h, w, ld, c_off, stream_ptr()),
           "nearest_resize_into")
+
+
+# ------------------------------------------------------------------ eval post-processing
+
+def argmax_confusion(logits: Tensor, label_orig: Optional[Tensor] = None, cm: Optional[Tensor] = None,
+                     want_pred: bool = False):
+    """logits NCHW fp32; label_orig uint8 [n,h,w] (0 = void); cm int64 [c,c] accumulated in place.
+    -> pred uint8 [n,h,w] or None."""
+    lib = _lib.load()
+    _cuda(logits, label_orig, cm)
+    n, c, h, w = logits.shape
+    pred = torch.empty(n, h, w, dtype=torch.uint8, device=logits.device) if want_pred else None
+    check(lib.dynmm_argmax_confusion(ptr(logits), ptr(label_orig), n, c, h, w, ptr(cm), ptr(pred), stream_ptr()),
+          "argmax_confusion")
+    return pred
+
+
+def miou(cm: Tensor):
+    """-> (miou [1] float64, iou [c] float64) device tensors."""
+    lib = _lib.load()
+    _cuda(cm)
+    c = cm.shape[0]
+    iou = torch.empty(c, dtype=torch.float64, device=cm.device)
+    m = torch.empty(1, dtype=torch.float64, device=cm.device)
+    check(lib.dynmm_miou(ptr(cm), c, ptr(iou), ptr(m), stream_ptr()), "miou")
+    return m, iou

@@ -203,6 +203,18 @@ int dynmm_softgate_mix_bwd(const float* grad_out, const float* const* preds, con
 int dynmm_compact_rows(const float* w, int b, int n_experts, int expert, int32_t* idx,
                        int32_t* inv, int32_t* count, void* stream);
 
+/* -------------------------------------------------- eval post-processing */
+
+/* eval.py:120-141 + confusion_matrix.py:122-133 fused: pred = argmax_c logits (first maximum), void pixels
+ * (label_orig == 0) ignored, label -= 1, cm[label*c + pred] += 1.  logits NCHW fp32 [n,c,h,w] at label
+ * resolution; label_orig uint8 [n,h,w]; cm int64 [c*c] is ACCUMULATED; pred_out uint8 [n,h,w] optional.
+ * Pass label_orig = cm = NULL for a pure arg-max. */
+int dynmm_argmax_confusion(const float* logits, const uint8_t* label_orig, int n, int c, int h, int w,
+                           long long* cm, uint8_t* pred_out, void* stream);
+/* iou_pytorch / miou_pytorch (confusion_matrix.py:139-178): iou[k] = diag/(row+col-diag+1e-15) in fp64,
+ * miou = mean(iou).  iou (double[c]) optional. */
+int dynmm_miou(const long long* cm, int c, double* iou, double* miou, void* stream);
+
 /* layout / dtype plumbing */
 int dynmm_nchw_f32_to_nhwc_bf16(const float* in, int n, int c, int h, int w, void* out, void* stream);
 int dynmm_nhwc_bf16_to_nchw_f32(const void* in, int n, int c, int h, int w, int ld, float* out, void* stream);

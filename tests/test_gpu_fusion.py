@@ -247,3 +247,43 @@ def test_training_path_uses_custom_gate_ops_and_matches_oracle():
         M.gated_blend, M.diff_softmax = orig_blend, orig_ds
     g_ref = model2.gate_layer.fc.weight.grad
     assert torch.allclose(g_custom, g_ref, rtol=2e-3, atol=1e-6 + 2e-3 * g_ref.abs().max().item())
+
+
+def test_miou_on_device_matches_oracle_and_bf16_engine_miou_tolerance():
+    """(1) the device arg-max / confusion matrix / mIoU are bit-exact (integers) resp. 1e-12 (fp64) against the
+    numpy restatement of eval.py / confusion_matrix.py on the SAME logits -- the fp32 part of the north-star's
+    'mIoU within 1e-3' claim is met exactly.  (2) stated bf16 tolerance: mIoU computed from the bf16 engine's
+    logits vs mIoU from the fp32 oracle's logits within 3e-2 relative on this adversarial synthetic case (a
+    random-init network has near-degenerate class margins, so ~1 % of arg-maxes flip under bf16 rounding and
+    every flip is an error against labels derived from the oracle itself).  Labels: the oracle's arg-max
+    with 30 % of the pixels re-drawn at random and 10 % void."""
+    from dynmm_b200.fusion.metrics import ConfusionMatrix
+    from oracle import fusion_oracle as fo
+    from oracle import metrics_oracle as mo
+    from oracle.make_golden import sample_inputs
+    cfg = fo.FusionConfig(height=96, width=160)
+    model, sd = _build(cfg, 7)
+    rgb, depth = sample_inputs(8, 3, cfg.height, cfg.width)
+    with torch.no_grad():
+        ref = fo.forward(sd, cfg, rgb, depth, hard_gate=True)["out"]
+        model.hard_gate = True
+        out = model(rgb.cuda(), depth.cuda(), True)
+    g = torch.Generator().manual_seed(0)
+    label = ref.argmax(1) + 1
+    rnd = torch.rand(label.shape, generator=g)
+    label = torch.where(rnd < 0.3, torch.randint(1, 41, label.shape, generator=g), label)
+    label = torch.where(rnd > 0.9, torch.zeros_like(label), label).to(torch.uint8)
+    cm = ConfusionMatrix(40)
+    pred = cm.update_from_logits(out, label.cuda(), want_pred=True)
+    cm_ref_same_logits = mo.confusion_from_logits(out.cpu().numpy(), label.numpy(), 40)
+    assert np.array_equal(cm.confusion_matrix.cpu().numpy(), cm_ref_same_logits)
+    assert np.array_equal(pred.cpu().numpy(), out.cpu().numpy().argmax(1).astype(np.uint8))
+    miou_dev, iou_dev = cm.compute_miou()
+    assert abs(miou_dev - mo.miou(cm_ref_same_logits)) < 1e-12
+    miou_fp32 = mo.miou(mo.confusion_from_logits(ref.numpy(), label.numpy(), 40))
+    assert abs(miou_dev - miou_fp32) <= 3e-2 * miou_fp32, (miou_dev, miou_fp32)
+    agree = (pred.cpu() == ref.argmax(1).to(torch.uint8)).float().mean().item()
+    assert agree >= 0.97, agree
+    # accumulation over batches
+    cm.update_from_logits(out, label.cuda())
+    assert np.array_equal(cm.confusion_matrix.cpu().numpy(), 2 * cm_ref_same_logits)
