@@ -274,7 +274,7 @@ constexpr int kUpTy = 8, kUpTx = 32;
 __global__ void __launch_bounds__(256)
 upsample2x_dw_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int h, int w, int c,
                              const float* __restrict__ wgt, const float* __restrict__ bias,
-                             float* __restrict__ out) {
+                             float* __restrict__ out, uint8_t* __restrict__ labels) {
   extern __shared__ float s_in[];                 // [c][kUpTy + 2][kUpTx + 2 (+1 pad)]
   constexpr int RS = kUpTx + 3;                   // row stride (35): odd -> conflict-free transposed fill
   constexpr int CS = (kUpTy + 2) * RS;            // channel stride
@@ -302,45 +302,48 @@ upsample2x_dw_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int h, int w,
   //   rows: parity 0 uses inputs (y-1: w[-1]) and (y: w[0]+w[+1]); parity 1 uses (y: w[-1]+w[0]) and (y+1: w[+1])
   // (same for columns).  Inputs outside the image were staged as zeros, which is exactly the conv's
   // zero padding of the upsampled map, so no border masks are needed.
+  // A warp owns one input row of the tile and walks the channels, so the per-pixel arg-max over
+  // classes (eval.py:120) can be kept in registers and emitted without re-reading the logits.
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const bool x_ok = x0 + lane < w;
-  for (int ch = warp; ch < c; ch += nwarps) {
-    float k[9];
+  for (int ly = warp; ly < kUpTy; ly += nwarps) {
+    const int y = y0 + ly;
+    if (y >= h) continue;
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int arg[4] = {0, 0, 0, 0};
+    for (int ch = 0; ch < c; ++ch) {
+      float k[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) k[t] = __ldg(wgt + t * c + ch);
-    const float b0 = bias ? __ldg(bias + ch) : 0.f;
-    // column-combined weights per kernel row r: parity 0 -> (left: k[r][0], mid: k[r][1]+k[r][2]);
-    //                                           parity 1 -> (mid: k[r][0]+k[r][1], right: k[r][2])
-    float cl0[3], cm0[3], cm1[3], cr1[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      cl0[r] = k[r * 3 + 0];
-      cm0[r] = k[r * 3 + 1] + k[r * 3 + 2];
-      cm1[r] = k[r * 3 + 0] + k[r * 3 + 1];
-      cr1[r] = k[r * 3 + 2];
-    }
-    const float* base = s_in + ch * CS + lane;
-    float* obase = out + ((1LL * s * c + ch) * H) * W + 2 * (x0 + lane);
-    // sliding window over input rows: a = row y-1, b = row y, d = row y+1 (each: left, mid, right)
-    float al = base[0], am = base[1], ar = base[2];
-    float bl = base[RS], bm = base[RS + 1], br = base[RS + 2];
-#pragma unroll
-    for (int ly = 0; ly < kUpTy; ++ly) {
-      const float* nr = base + (ly + 2) * RS;
-      const float dl = nr[0], dm = nr[1], dr = nr[2];
-      const int y = y0 + ly;
-      if (y < h && x_ok) {
-        // output row 2y   : kernel row 0 on input row y-1, kernel rows 1+2 on input row y
-        // output row 2y+1 : kernel rows 0+1 on input row y, kernel row 2 on input row y+1
-        const float o00 = b0 + cl0[0] * al + cm0[0] * am + (cl0[1] + cl0[2]) * bl + (cm0[1] + cm0[2]) * bm;
-        const float o01 = b0 + cm1[0] * am + cr1[0] * ar + (cm1[1] + cm1[2]) * bm + (cr1[1] + cr1[2]) * br;
-        const float o10 = b0 + (cl0[0] + cl0[1]) * bl + (cm0[0] + cm0[1]) * bm + cl0[2] * dl + cm0[2] * dm;
-        const float o11 = b0 + (cm1[0] + cm1[1]) * bm + (cr1[0] + cr1[1]) * br + cm1[2] * dm + cr1[2] * dr;
-        *reinterpret_cast<float2*>(obase + (2LL * y) * W) = make_float2(o00, o01);
-        *reinterpret_cast<float2*>(obase + (2LL * y + 1) * W) = make_float2(o10, o11);
+      for (int t = 0; t < 9; ++t) k[t] = __ldg(wgt + t * c + ch);
+      const float b0 = bias ? __ldg(bias + ch) : 0.f;
+      const float* base = s_in + ch * CS + ly * RS + lane;          // staged rows ly, ly+1, ly+2 = y-1, y, y+1
+      const float al = base[0], am = base[1], ar = base[2];
+      const float bl = base[RS], bm = base[RS + 1], br = base[RS + 2];
+      const float dl = base[2 * RS], dm = base[2 * RS + 1], dr = base[2 * RS + 2];
+      // column-combined weights of kernel row r: parity 0 -> (left k[r][0], mid k[r][1]+k[r][2]);
+      //                                          parity 1 -> (mid k[r][0]+k[r][1], right k[r][2])
+      const float m0_0 = k[1] + k[2], m0_1 = k[4] + k[5], m0_2 = k[7] + k[8];
+      const float m1_0 = k[0] + k[1], m1_1 = k[3] + k[4], m1_2 = k[6] + k[7];
+      // output row 2y   : kernel row 0 on input row y-1, kernel rows 1+2 on input row y
+      // output row 2y+1 : kernel rows 0+1 on input row y, kernel row 2 on input row y+1
+      const float o00 = b0 + k[0] * al + m0_0 * am + (k[3] + k[6]) * bl + (m0_1 + m0_2) * bm;
+      const float o01 = b0 + m1_0 * am + k[2] * ar + (m1_1 + m1_2) * bm + (k[5] + k[8]) * br;
+      const float o10 = b0 + (k[0] + k[3]) * bl + (m0_0 + m0_1) * bm + k[6] * dl + m0_2 * dm;
+      const float o11 = b0 + (m1_0 + m1_1) * bm + (k[2] + k[5]) * br + m1_2 * dm + k[8] * dr;
+      if (out && x_ok) {
+        float* o = out + ((1LL * s * c + ch) * H + 2LL * y) * W + 2 * (x0 + lane);
+        *reinterpret_cast<float2*>(o) = make_float2(o00, o01);
+        *reinterpret_cast<float2*>(o + W) = make_float2(o10, o11);
       }
-      al = bl; am = bm; ar = br;
-      bl = dl; bm = dm; br = dr;
+      if (o00 > best[0]) { best[0] = o00; arg[0] = ch; }      // strict '>': first maximum, like torch.argmax
+      if (o01 > best[1]) { best[1] = o01; arg[1] = ch; }
+      if (o10 > best[2]) { best[2] = o10; arg[2] = ch; }
+      if (o11 > best[3]) { best[3] = o11; arg[3] = ch; }
+    }
+    if (labels && x_ok) {
+      uint8_t* l = labels + (1LL * s * H + 2LL * y) * W + 2 * (x0 + lane);
+      *reinterpret_cast<uchar2*>(l) = make_uchar2((unsigned char)arg[0], (unsigned char)arg[1]);
+      *reinterpret_cast<uchar2*>(l + W) = make_uchar2((unsigned char)arg[2], (unsigned char)arg[3]);
     }
   }
 }
@@ -497,10 +500,12 @@ extern "C" int dynmm_nhwc_bf16_to_nchw_f32(const void* in, int n, int c, int h, 
 
 extern "C" int dynmm_upsample2x_dw3x3(const void* in, int n, int h, int w, int c, const float* weight,
                                       const float* bias, const void* skip, void* out_nhwc_bf16, float* out_nchw_f32,
-                                      void* stream_) {
+                                      uint8_t* labels, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DYNMM_CHECK_ARG(in && weight && n >= 1 && h >= 1 && w >= 1 && c >= 8 && c % 8 == 0, "upsample2x: c %% 8");
-  DYNMM_CHECK_ARG((out_nhwc_bf16 != nullptr) != (out_nchw_f32 != nullptr), "upsample2x: exactly one output");
+  DYNMM_CHECK_ARG(!(out_nhwc_bf16 && (out_nchw_f32 || labels)) && (out_nhwc_bf16 || out_nchw_f32 || labels),
+                  "upsample2x: either the NHWC output, or the NCHW logits and/or the arg-max labels");
+  DYNMM_CHECK_ARG(!labels || c <= 256, "upsample2x: labels are uint8");
   if (out_nhwc_bf16) {
     const long long total = 1LL * n * 4 * h * w * (c / 8);
     upsample2x_dw_nhwc_kernel<<<grid_for(total, 256, 16), 256, 0, stream>>>(
@@ -517,7 +522,7 @@ extern "C" int dynmm_upsample2x_dw3x3(const void* in, int n, int h, int w, int c
     }
     dim3 grid(ceil_div(w, kUpTx), ceil_div(h, kUpTy), n);
     upsample2x_dw_to_nchw_kernel<<<grid, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(in), h, w, c, weight,
-                                                              bias, out_nchw_f32);
+                                                              bias, out_nchw_f32, labels);
   }
   DYNMM_LAUNCH_CHECK();
   return DYNMM_OK;

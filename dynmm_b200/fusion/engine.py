@@ -248,9 +248,12 @@ class FusionEngine:
     @torch.no_grad()
     def forward(self, rgb: Tensor, depth: Tensor, *, temp: float = 1.0, hard_gate: bool = False,
                 baseline: bool = False, ini_stage: bool = False, weight: Optional[Tensor] = None,
-                out: Optional[Tensor] = None, hist: Optional[Tensor] = None):
+                out: Optional[Tensor] = None, hist: Optional[Tensor] = None, labels: Optional[Tensor] = None,
+                want_logits: bool = True):
         """rgb [B,3,H,W], depth [B,1,H,W] fp32 NCHW on the GPU ->
-        (logits [B,classes,H,W] fp32 NCHW, gate weight [B,5] fp32)."""
+        (logits [B,classes,H,W] fp32 NCHW, gate weight [B,5] fp32).
+        ``labels`` (uint8 [B,H,W]): also emit argmax_c(logits) from the final kernel (eval.py:120);
+        with ``want_logits=False`` the logits are never written and None is returned for them."""
         if not (rgb.is_cuda and depth.is_cuda):
             raise _lib.DynmmError("FusionEngine.forward needs CUDA tensors")
         rgb = rgb.float().contiguous()
@@ -374,7 +377,8 @@ class FusionEngine:
         keep.append(x)
         x = ops.upsample2x_dw3x3(x, self.up[0][0], self.up[0][1])
         keep.append(x)
-        out = ops.upsample2x_dw3x3(x, self.up[1][0], self.up[1][1], to_nchw_f32=True, out=out)
+        out = ops.upsample2x_dw3x3(x, self.up[1][0], self.up[1][1], to_nchw_f32=True, out=out, labels=labels,
+                                   want_logits=want_logits)
         self.launches += 3
         # all side-stream work was joined by the stage-4 wait; temporaries may now be released
         del keep

@@ -561,18 +561,38 @@ class SkipGateESANet(nn.Module):
             self._graphs = {}
         return self._engine
 
-    def _forward_engine(self, rgb, depth):
+    def _forward_engine(self, rgb, depth, labels_only=False):
         eng = self.engine(rgb.device)
         modes = dict(temp=float(self.temp), hard_gate=bool(self.hard_gate), baseline=bool(self.baseline),
                      ini_stage=bool(self.ini_stage))
         if self.use_cuda_graph and not self.ini_stage:
             from .graph import GraphedForward
-            key = (tuple(rgb.shape), tuple(sorted(modes.items())))
+            key = (tuple(rgb.shape), tuple(sorted(modes.items())), labels_only)
             g = self._graphs.get(key)
             if g is None:
-                g = self._graphs[key] = GraphedForward(eng, rgb, depth, modes)
+                g = self._graphs[key] = GraphedForward(eng, rgb, depth, modes, labels_only)
             return g(rgb, depth)
+        if labels_only:
+            b, _, h, w = rgb.shape
+            labels = torch.empty(b, h, w, dtype=torch.uint8, device=rgb.device)
+            _, weight = eng.forward(rgb, depth, labels=labels, want_logits=False, **modes)
+            return labels, weight
         return eng.forward(rgb, depth, **modes)
+
+    @torch.no_grad()
+    def predict_labels(self, rgb, depth, out=None):
+        """argmax_c(self(rgb, depth, True)) as uint8 [B,H,W] -- what eval.py:109-120 computes per batch --
+        produced by the final upsampling kernel itself, so the 40-channel full-resolution logits are
+        never written to memory.  Eval mode, CUDA tensors."""
+        if self.training or not rgb.is_cuda:
+            raise RuntimeError("predict_labels runs the CUDA engine: call model.eval() and pass CUDA tensors")
+        labels, weight = self._forward_engine(rgb, depth, labels_only=True)
+        if self.save_weight_info:
+            self._pending_weights.append(weight.detach().clone())
+        if out is not None:
+            out.copy_(labels)
+            return out
+        return labels
 
     # ------------------------------------------------------------------ forward
     def forward(self, rgb, depth, test=False, return_weight=False):      # :255-322

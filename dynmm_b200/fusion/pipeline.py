@@ -1,7 +1,8 @@
 """Host-buffer inference pipeline: what ``eval.py``'s loop does per batch
 (``image.to(device)`` / ``depth.to(device)`` -> ``model(image, depth, True)`` -> ``argmax`` ->
 ``.cpu()``; eval.py:89-90,109-120,129), with the copies of batch i+1 and the label read-back of
-batch i-1 overlapped with the forward of batch i on separate CUDA streams."""
+batch i-1 overlapped with the forward of batch i on separate CUDA streams.  The arg-max is fused
+into the model's last kernel (``SkipGateESANet.predict_labels``)."""
 from __future__ import annotations
 
 from typing import Iterable, Iterator, Tuple
@@ -54,8 +55,7 @@ class EvalPipeline:
             if nxt is not None:                               # overlap: upload batch i+1 now
                 self._upload(self.slots[(i + 1) % len(self.slots)], *nxt)
             main.wait_event(slot["in_ready"])
-            pred = self.model(slot["rgb"], slot["depth"], True)
-            slot["labels_dev"].copy_(torch.argmax(pred, dim=1))
+            self.model.predict_labels(slot["rgb"], slot["depth"], out=slot["labels_dev"])
             slot["computed"].record(main)
             slot["free"].record(main)
             with torch.cuda.stream(self.copy_out):

@@ -331,18 +331,24 @@ def nhwc_bf16_to_nchw_f32(x: Tensor, c: Optional[int] = None) -> Tensor:
 
 
 def upsample2x_dw3x3(x: Tensor, weight: Tensor, bias: Optional[Tensor], skip: Optional[Tensor] = None,
-                     to_nchw_f32: bool = False, out: Optional[Tensor] = None) -> Tensor:
-    """x NHWC bf16; weight fp32 tap-major [9, c] (``conv.weight.reshape(c, 9).t().contiguous()``)."""
+                     to_nchw_f32: bool = False, out: Optional[Tensor] = None, labels: Optional[Tensor] = None,
+                     want_logits: bool = True):
+    """x NHWC bf16; weight fp32 tap-major [9, c] (``conv.weight.reshape(c, 9).t().contiguous()``).
+    Final upsampling (``to_nchw_f32``): returns the NCHW fp32 logits; with ``labels`` (uint8 [n,2h,2w]) the
+    arg-max over channels is produced in the same pass, and ``want_logits=False`` skips the logits."""
     lib = _lib.load()
-    _cuda(x, weight, bias, skip, out)
+    _cuda(x, weight, bias, skip, out, labels)
     n, h, w, c = x.shape
-    if to_nchw_f32:
-        out = torch.empty(n, c, 2 * h, 2 * w, dtype=torch.float32, device=x.device) if out is None else out
+    if to_nchw_f32 or labels is not None:
+        if want_logits:
+            out = torch.empty(n, c, 2 * h, 2 * w, dtype=torch.float32, device=x.device) if out is None else out
+        else:
+            out = None
         check(lib.dynmm_upsample2x_dw3x3(ptr(x), n, h, w, c, ptr(weight), ptr(bias), None, None, ptr(out),
-                                         stream_ptr()), "upsample2x_dw3x3")
+                                         ptr(labels), stream_ptr()), "upsample2x_dw3x3")
     else:
         out = torch.empty(n, 2 * h, 2 * w, c, dtype=torch.bfloat16, device=x.device) if out is None else out
-        check(lib.dynmm_upsample2x_dw3x3(ptr(x), n, h, w, c, ptr(weight), ptr(bias), ptr(skip), ptr(out), None,
+        check(lib.dynmm_upsample2x_dw3x3(ptr(x), n, h, w, c, ptr(weight), ptr(bias), ptr(skip), ptr(out), None, None,
                                          stream_ptr()), "upsample2x_dw3x3")
     return out
 

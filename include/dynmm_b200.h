@@ -222,11 +222,12 @@ int dynmm_nhwc_bf16_to_nchw_f32(const void* in, int n, int c, int h, int w, int 
 /* Upsample.forward for mode 'learned-3x3-zeropad' (model.py:403-410): nearest x2 then
  * depthwise 3x3 (zero pad) + bias, optionally + skip (DecoderModule.forward :353-355).
  * in NHWC bf16 [n,h,w,c]; weight fp32 TAP-MAJOR [3*3][c] (= conv.weight[c,1,3,3] transposed); out NHWC bf16
- * [n,2h,2w,c], or when
- * out_nchw_f32 != NULL fp32 NCHW (the module's return layout). */
+ * [n,2h,2w,c]; or (final upsampling) out_nchw_f32 fp32 NCHW -- the module's return layout -- and/or
+ * labels uint8 [n,2h,2w] = argmax over channels of those logits (first maximum; eval.py:120), produced in the
+ * same pass so an evaluation loop never has to write or re-read the logits. */
 int dynmm_upsample2x_dw3x3(const void* in, int n, int h, int w, int c, const float* weight,
                            const float* bias, const void* skip, void* out_nhwc_bf16,
-                           float* out_nchw_f32, void* stream);
+                           float* out_nchw_f32, uint8_t* labels, void* stream);
 
 /* PyramidPoolingModule pooling + broadcast (context_modules.py:69-84) for NHWC bf16 input
  * [n,h,w,ld] (first c channels): adaptive average pool to bins x bins (fp32 accumulate) -> out [n,bins,bins,c] bf16. */

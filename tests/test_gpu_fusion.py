@@ -201,6 +201,14 @@ def test_weight_statistics_api():
     stats = model.end_weight(print_flop=True)
     assert stats is not None and stats[0].sum() == 12
     assert model.weight_list.numel() == 0
+    # predict_labels == argmax of forward (fused into the last kernel), and the host pipeline agrees
+    from dynmm_b200.fusion import EvalPipeline
+    with torch.no_grad():
+        ref_labels = model(rgb.cuda(), depth.cuda(), True).argmax(1).to(torch.uint8)
+        assert torch.equal(model.predict_labels(rgb.cuda(), depth.cuda()), ref_labels)
+        pipe = EvalPipeline(model, 4, 64, 96)
+        outs = [l.clone() for l in pipe.run([(rgb.pin_memory(), depth.pin_memory())] * 3)]
+    assert len(outs) == 3 and all(torch.equal(o, ref_labels.cpu()) for o in outs)
 
 
 def test_training_path_uses_custom_gate_ops_and_matches_oracle():

@@ -309,6 +309,12 @@ def test_elementwise_ops():
     _bf16_close(got, up_ref.permute(0, 2, 3, 1) + skip.float(), "upsample+skip")
     got32 = ops.upsample2x_dw3x3(xin, wdw.view(40, 9).t().contiguous(), bias, to_nchw_f32=True)
     np.testing.assert_allclose(got32.cpu().numpy(), up_ref.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    lab = torch.empty(2, 14, 18, dtype=torch.uint8, device=dev)
+    got_l = ops.upsample2x_dw3x3(xin, wdw.view(40, 9).t().contiguous(), bias, labels=lab)
+    assert torch.equal(got_l, got32) and torch.equal(lab.long(), got32.argmax(1))        # fused arg-max
+    lab2 = torch.zeros_like(lab)
+    assert ops.upsample2x_dw3x3(xin, wdw.view(40, 9).t().contiguous(), bias, labels=lab2, want_logits=False) is None
+    assert torch.equal(lab2, lab)
     # pyramid pooling helpers
     feat = torch.randn(2, 15, 20, 64, device=dev, generator=g).to(torch.bfloat16)
     for bins in (1, 5):
