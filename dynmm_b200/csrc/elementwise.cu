@@ -275,9 +275,25 @@ __global__ void __launch_bounds__(256)
 upsample2x_dw_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int h, int w, int c,
                              const float* __restrict__ wgt, const float* __restrict__ bias,
                              float* __restrict__ out, uint8_t* __restrict__ labels) {
-  extern __shared__ float s_in[];                 // [c][kUpTy + 2][kUpTx + 2 (+1 pad)]
+  extern __shared__ float s_in[];                 // [c][kUpTy + 2][kUpTx + 2 (+1 pad)], then [c][16] stencil weights
   constexpr int RS = kUpTx + 3;                   // row stride (35): odd -> conflict-free transposed fill
   constexpr int CS = (kUpTy + 2) * RS;            // channel stride
+  float* s_w = s_in + c * CS;
+  // per-channel 2x2-parity stencils on the input, combined once per CTA from the 3x3 weights:
+  //   [0..3]  output (2y  ,2x  ): inputs (y-1,x-1) (y-1,x) (y,x-1) (y,x)
+  //   [4..7]  output (2y  ,2x+1): inputs (y-1,x) (y-1,x+1) (y,x) (y,x+1)
+  //   [8..11] output (2y+1,2x  ): inputs (y,x-1) (y,x) (y+1,x-1) (y+1,x)
+  //   [12..15]output (2y+1,2x+1): inputs (y,x) (y,x+1) (y+1,x) (y+1,x+1)
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float k[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) k[t] = __ldg(wgt + t * c + ch);
+    float* o = s_w + ch * 16;
+    o[0] = k[0];                 o[1] = k[1] + k[2];               o[2] = k[3] + k[6];           o[3] = (k[4] + k[5]) + (k[7] + k[8]);
+    o[4] = k[0] + k[1];          o[5] = k[2];                      o[6] = (k[3] + k[4]) + (k[6] + k[7]); o[7] = k[5] + k[8];
+    o[8] = k[0] + k[3];          o[9] = (k[1] + k[2]) + (k[4] + k[5]); o[10] = k[6];             o[11] = k[7] + k[8];
+    o[12] = (k[0] + k[1]) + (k[3] + k[4]); o[13] = (k[2] + k[5]);  o[14] = k[6] + k[7];          o[15] = k[8];
+  }
   const int H = 2 * h, W = 2 * w;
   const int x0 = blockIdx.x * kUpTx, y0 = blockIdx.y * kUpTy, s = blockIdx.z;
   const int cv = c >> 3;
@@ -311,25 +327,21 @@ upsample2x_dw_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int h, int w,
     if (y >= h) continue;
     float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     int arg[4] = {0, 0, 0, 0};
+#pragma unroll 2
     for (int ch = 0; ch < c; ++ch) {
-      float k[9];
-#pragma unroll
-      for (int t = 0; t < 9; ++t) k[t] = __ldg(wgt + t * c + ch);
       const float b0 = bias ? __ldg(bias + ch) : 0.f;
       const float* base = s_in + ch * CS + ly * RS + lane;          // staged rows ly, ly+1, ly+2 = y-1, y, y+1
       const float al = base[0], am = base[1], ar = base[2];
       const float bl = base[RS], bm = base[RS + 1], br = base[RS + 2];
       const float dl = base[2 * RS], dm = base[2 * RS + 1], dr = base[2 * RS + 2];
-      // column-combined weights of kernel row r: parity 0 -> (left k[r][0], mid k[r][1]+k[r][2]);
-      //                                          parity 1 -> (mid k[r][0]+k[r][1], right k[r][2])
-      const float m0_0 = k[1] + k[2], m0_1 = k[4] + k[5], m0_2 = k[7] + k[8];
-      const float m1_0 = k[0] + k[1], m1_1 = k[3] + k[4], m1_2 = k[6] + k[7];
-      // output row 2y   : kernel row 0 on input row y-1, kernel rows 1+2 on input row y
-      // output row 2y+1 : kernel rows 0+1 on input row y, kernel row 2 on input row y+1
-      const float o00 = b0 + k[0] * al + m0_0 * am + (k[3] + k[6]) * bl + (m0_1 + m0_2) * bm;
-      const float o01 = b0 + m1_0 * am + k[2] * ar + (m1_1 + m1_2) * bm + (k[5] + k[8]) * br;
-      const float o10 = b0 + (k[0] + k[3]) * bl + (m0_0 + m0_1) * bm + k[6] * dl + m0_2 * dm;
-      const float o11 = b0 + (m1_0 + m1_1) * bm + (k[2] + k[5]) * br + m1_2 * dm + k[8] * dr;
+      const float4 w0 = *reinterpret_cast<const float4*>(s_w + ch * 16);        // warp-wide broadcasts
+      const float4 w1 = *reinterpret_cast<const float4*>(s_w + ch * 16 + 4);
+      const float4 w2 = *reinterpret_cast<const float4*>(s_w + ch * 16 + 8);
+      const float4 w3 = *reinterpret_cast<const float4*>(s_w + ch * 16 + 12);
+      const float o00 = b0 + w0.x * al + w0.y * am + w0.z * bl + w0.w * bm;
+      const float o01 = b0 + w1.x * am + w1.y * ar + w1.z * bm + w1.w * br;
+      const float o10 = b0 + w2.x * bl + w2.y * bm + w2.z * dl + w2.w * dm;
+      const float o11 = b0 + w3.x * bm + w3.y * br + w3.z * dm + w3.w * dr;
       if (out && x_ok) {
         float* o = out + ((1LL * s * c + ch) * H + 2LL * y) * W + 2 * (x0 + lane);
         *reinterpret_cast<float2*>(o) = make_float2(o00, o01);
@@ -513,7 +525,7 @@ extern "C" int dynmm_upsample2x_dw3x3(const void* in, int n, int h, int w, int c
         static_cast<__nv_bfloat16*>(out_nhwc_bf16));
   } else {
     DYNMM_CHECK_ARG(!skip, "upsample2x: skip is only supported for the NHWC output");
-    const int smem = c * (kUpTy + 2) * (kUpTx + 3) * (int)sizeof(float);
+    const int smem = (c * (kUpTy + 2) * (kUpTx + 3) + c * 16) * (int)sizeof(float);
     DYNMM_CHECK_ARG(smem <= 200 * 1024, "upsample2x: too many channels for the NCHW output");
     static int configured = 0;
     if (smem > configured) {
