@@ -122,6 +122,15 @@ def measured_peaks():
     return 6650.0, 1400.0, 1590.0, "fallback"
 
 
+def conv_traffic():
+    """DRAM bytes per conv launch from the committed ncu capture (profiles/r1_conv_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r1_conv_traffic.json")
+    try:
+        return json.load(open(p))["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def cpu_reference_images_per_s(state_dict, batch: int, warmup: int, steps: int, threads: int):
     """The reference algorithm (oracle restatement, pinned to reference-generated vectors) on the
     host cores: eval forward, hard gate, fp32 -- the reference always computes every branch."""
@@ -297,7 +306,7 @@ def main():
         step_s = t_dev / args.steps
         roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, all launches of a step)",
                     "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s", "frac": achieved / tf_sust,
-                    "peak_source": f"{src} (bf16 sustained; burst {tf_burst})", "traffic": None,
+                    "peak_source": f"{src} (bf16 sustained; burst {tf_burst})", "traffic": conv_traffic(),
                     "launches_per_step": n_conv, "gflop_per_step": gflop, "kernel_s_per_step": t_conv,
                     "note": "kernel_s_per_step sums the conv launches of BOTH encoder streams timed back to back "
                             "(CUDA events on the launching stream); in the timed step the two streams overlap, so "

@@ -295,3 +295,27 @@ def test_miou_on_device_matches_oracle_and_bf16_engine_miou_tolerance():
     # accumulation over batches
     cm.update_from_logits(out, label.cuda())
     assert np.array_equal(cm.confusion_matrix.cpu().numpy(), 2 * cm_ref_same_logits)
+
+
+def test_edge_cases_batch_one_all_skipped_and_bad_sizes():
+    """Ragged / degenerate inputs: batch 1; a batch in which NO sample keeps any depth stage (every depth-stage
+    kernel gets count = 0 and must produce nothing); input sizes that are not a multiple of 32 are refused."""
+    from dynmm_b200 import _lib
+    from oracle import fusion_oracle as fo
+    from oracle.make_golden import sample_inputs
+    cfg = fo.FusionConfig(height=64, width=96)
+    model, sd = _build(cfg, 0)
+    eng = model.engine()
+    rgb, depth = sample_inputs(1, 3, 64, 96)
+    with torch.no_grad():
+        w0 = torch.eye(5)[torch.zeros(3, dtype=torch.long)].cuda()            # branch 0 everywhere
+        out, _ = eng.forward(rgb.cuda(), depth.cuda(), weight=w0)
+        ref = fo.forward(sd, cfg, rgb, depth, weight=torch.eye(5)[torch.zeros(3, dtype=torch.long)])["out"]
+        assert _rel_l2(out.cpu(), ref) <= REL_L2_TOL
+        # the depth image must not matter at all when every depth stage is gated off (only the stem reads it)
+        one, _ = eng.forward(rgb[:1].cuda(), depth[:1].cuda(), weight=w0[:1])
+        assert torch.equal(one[0], out[0])
+        with pytest.raises(_lib.DynmmError):
+            eng.forward(torch.zeros(1, 3, 70, 96).cuda(), torch.zeros(1, 1, 70, 96).cuda())
+        with pytest.raises(_lib.DynmmError):
+            eng.forward(rgb, depth)                                           # CPU tensors
