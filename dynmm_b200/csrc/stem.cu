@@ -7,6 +7,8 @@
 // a CTA produces an 8x8 tile of POOLED outputs from a 17x17 tile of stem outputs
 // held in shared memory (13 % halo recompute instead of a 2 x 157 MB round trip
 // per 8 images).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dynmm {
@@ -308,7 +310,26 @@ stem_kernel(const float* __restrict__ rgb, const float* __restrict__ depth, int 
 }  // namespace
 }  // namespace dynmm
 
+namespace dynmm {
+// tensor-core implementation (stem_tc.cu)
+long long stem_tc_tiles(int b, int h, int w);
+int stem_tc_launch(const float* rgb, const float* depth, int b, int h, int w, const float* w_rgb, const float* scale_rgb,
+                   const float* shift_rgb, const float* w_d, const float* scale_d, const float* shift_d,
+                   float* rgb_f32, float* depth_f32, void* rgb_bf16, void* depth_bf16, const float* se_rgb,
+                   const float* se_depth, float* gap_partial, cudaStream_t stream);
+// DYNMM_STEM=fp32 selects the CUDA-core FFMA2 kernel of this file (kept as the exact-fp32 variant and as
+// an independent cross-check of the tensor-core kernel); default is the tensor-core split-bf16 kernel.
+static bool stem_use_tc() {
+  static const bool v = [] {
+    const char* e = getenv("DYNMM_STEM");
+    return !(e && (e[0] == 'f' || e[0] == 'F'));
+  }();
+  return v;
+}
+}  // namespace dynmm
+
 extern "C" long long dynmm_stem_gap_tiles(int b, int h, int w) {
+  if (dynmm::stem_use_tc()) return dynmm::stem_tc_tiles(b, h, w);
   const int Hs = (h + 6 - 7) / 2 + 1, Ws = (w + 6 - 7) / 2 + 1;
   const int Hp = (Hs + 2 - 3) / 2 + 1, Wp = (Ws + 2 - 3) / 2 + 1;
   return 1LL * dynmm::ceil_div(Wp, dynmm::kPT) * dynmm::ceil_div(Hp, dynmm::kPT) * b;
@@ -323,6 +344,10 @@ extern "C" int dynmm_stem_fwd(const float* rgb, const float* depth, int b, int h
   DYNMM_CHECK_ARG(rgb && depth && w_rgb && w_d && scale_rgb && shift_rgb && scale_d && shift_d, "stem: null pointer");
   DYNMM_CHECK_ARG(b >= 1 && h >= 7 && w >= 7, "stem: bad shape");
   DYNMM_CHECK_ARG((se_rgb == nullptr) == (se_depth == nullptr), "stem: SE scales come in pairs");
+  if (stem_use_tc()) {
+    return stem_tc_launch(rgb, depth, b, h, w, w_rgb, scale_rgb, shift_rgb, w_d, scale_d, shift_d, rgb_f32, depth_f32,
+                          rgb_bf16, depth_bf16, se_rgb, se_depth, gap_partial, static_cast<cudaStream_t>(stream));
+  }
   const int Hs = (h + 6 - 7) / 2 + 1, Ws = (w + 6 - 7) / 2 + 1;
   const int Hp = (Hs + 2 - 3) / 2 + 1, Wp = (Ws + 2 - 3) / 2 + 1;
   const size_t smem = kSmemFloats * sizeof(float);
