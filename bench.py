@@ -171,22 +171,28 @@ def run_reference_arm(args, rank):
 
 
 def profile_conv_kernel(model, rgb, depth):
-    """Instrumented eager pass: CUDA events around every tensor-core conv launch (repeated 3x inside
-    the bracket to amortise event overhead), on the stream it is launched on.
+    """Instrumented pass over one step: every tensor-core conv launch is additionally captured REP times into a
+    small CUDA graph and that graph is replayed between two CUDA events on the stream the launch belongs to
+    (a bare eager launch costs more host time than the kernel runs, so eager brackets would time the host).
     -> (seconds in conv kernels per step, launches, gate weights, per-launch records)"""
     from dynmm_b200 import ops
     recs = []
-    REP = 3
+    REP = 4
 
     def prof(p, launch):
+        launch()                                        # the real launch of the forward
         s = torch.cuda.current_stream()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(REP):
+                launch()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g.replay()                                      # warm
         e0.record(s)
-        for _ in range(REP):
-            launch()
+        g.replay()
         e1.record(s)
         macs_per_sample = p.h_out * p.w_out * p.c_out * p.c_in * p.kh * p.kw
-        recs.append((e0, e1, macs_per_sample, p.n, p.count))
+        recs.append((e0, e1, macs_per_sample, p.n, p.count, g))
     eng = model.engine(rgb.device)
     with torch.no_grad():
         eng.forward(rgb, depth, temp=1.0, hard_gate=True)
@@ -197,8 +203,8 @@ def profile_conv_kernel(model, rgb, depth):
         finally:
             ops.CONV_PROFILER = None
         torch.cuda.synchronize()
-    total_s = sum(e0.elapsed_time(e1) / REP * 1e-3 for e0, e1, _, _, _ in recs)
-    return total_s, len(recs), weight, recs
+    total_s = sum(r[0].elapsed_time(r[1]) / REP * 1e-3 for r in recs)
+    return total_s, len(recs), weight, [r[:5] for r in recs]
 
 
 def main():
@@ -308,9 +314,10 @@ def main():
                     "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s", "frac": achieved / tf_sust,
                     "peak_source": f"{src} (bf16 sustained; burst {tf_burst})", "traffic": conv_traffic(),
                     "launches_per_step": n_conv, "gflop_per_step": gflop, "kernel_s_per_step": t_conv,
-                    "note": "kernel_s_per_step sums the conv launches of BOTH encoder streams timed back to back "
-                            "(CUDA events on the launching stream); in the timed step the two streams overlap, so "
-                            "the sum may exceed ms_per_step. Kernel share of the step: profiles/ (ncu launch list).",
+                    "note": "kernel_s_per_step = sum over the step's conv launches of their device time (each launch "
+                            "replayed 4x from a CUDA graph between events on its own stream); the RGB and depth "
+                            "encoder streams overlap in the timed step, so this sum is not a share of ms_per_step. "
+                            "Kernel shares of the step: profiles/r1_step_metrics_summary.txt (ncu).",
                     "step_s": step_s}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
