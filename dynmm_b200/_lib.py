@@ -36,6 +36,17 @@ class ConvParams(Structure):
     ]
 
 
+class WgradParams(Structure):
+    """Mirror of ``dynmm_wgrad_params`` (include/dynmm_b200.h)."""
+    _fields_ = [
+        ("x", c_void_p), ("dy", c_void_p), ("dw", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_longlong),
+        ("n", c_int32), ("h_in", c_int32), ("w_in", c_int32), ("c_in", c_int32), ("x_ld", c_int32),
+        ("h_out", c_int32), ("w_out", c_int32), ("c_out", c_int32), ("dy_ld", c_int32),
+        ("kh", c_int32), ("kw", c_int32), ("stride_h", c_int32), ("stride_w", c_int32),
+        ("pad_h", c_int32), ("pad_w", c_int32), ("accumulate", c_int32), ("max_ctas", c_int32),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/dynmm_b200.h declares
 SIGNATURES = {
     "dynmm_abi_version": (c_int, []),
@@ -58,6 +69,13 @@ SIGNATURES = {
                                     c_int, c_int, c_void_p, c_void_p]),
     "dynmm_conv_igemm_fwd": (c_int, [POINTER(ConvParams), c_void_p]),
     "dynmm_conv_direct_fwd": (c_int, [POINTER(ConvParams), c_void_p]),
+    "dynmm_conv_wgrad_workspace": (c_longlong, [POINTER(WgradParams)]),
+    "dynmm_conv_wgrad": (c_int, [POINTER(WgradParams), c_void_p]),
+    "dynmm_conv_wgrad_direct": (c_int, [POINTER(WgradParams), c_void_p]),
+    "dynmm_pack_conv_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "dynmm_channel_sum_workspace": (c_longlong, [c_longlong, c_int]),
+    "dynmm_channel_sum": (c_int, [c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p, c_longlong, c_int,
+                                  c_void_p]),
     "dynmm_gated_add_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p]),
     "dynmm_gated_add_f32_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p]),
     "dynmm_gated_add_f32_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p]),

@@ -67,12 +67,24 @@ def _make_activation(name: str) -> nn.Module:
         'Only relu, swish and hswish as activation function are supported so far. Got {}'.format(name))
 
 
+class Conv2d(nn.Conv2d):
+    """``nn.Conv2d`` (same parameters / state_dict keys) whose bf16 CUDA inputs run on the tcgen05
+    forward, data-gradient and weight-gradient kernels (train_ops.py); fp32 inputs take the
+    stock library path, i.e. the reference's arithmetic."""
+
+    def forward(self, x):
+        if x.is_cuda and x.dtype == torch.bfloat16 and not torch.is_autocast_enabled():
+            from .train_ops import conv2d
+            return conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+        return super().forward(x)
+
+
 class ConvBNAct(nn.Sequential):
     """model_utils.py:11-23 (keys: conv, bn, act)."""
 
     def __init__(self, channels_in, channels_out, kernel_size, activation=nn.ReLU(inplace=True), dilation=1, stride=1):
         super().__init__()
-        self.add_module("conv", nn.Conv2d(channels_in, channels_out, kernel_size, stride=stride,
+        self.add_module("conv", Conv2d(channels_in, channels_out, kernel_size, stride=stride,
                                           padding=kernel_size // 2 + dilation - 1, dilation=dilation, bias=False))
         self.add_module("bn", nn.BatchNorm2d(channels_out))
         self.add_module("act", activation)
@@ -83,8 +95,8 @@ class SqueezeAndExcitation(nn.Module):
 
     def __init__(self, channel, reduction=16, activation=nn.ReLU(inplace=True)):
         super().__init__()
-        self.fc = nn.Sequential(nn.Conv2d(channel, channel // reduction, 1), activation,
-                                nn.Conv2d(channel // reduction, channel, 1), nn.Sigmoid())
+        self.fc = nn.Sequential(Conv2d(channel, channel // reduction, 1), activation,
+                                Conv2d(channel // reduction, channel, 1), nn.Sigmoid())
 
     def forward(self, x):
         return x * self.fc(F.adaptive_avg_pool2d(x, 1))
@@ -110,12 +122,12 @@ class NonBottleneck1D(nn.Module):
 
     def __init__(self, inplanes, planes, stride=1, downsample=None, dilation=1, activation=nn.ReLU(inplace=True)):
         super().__init__()
-        self.conv3x1_1 = nn.Conv2d(inplanes, planes, (3, 1), stride=(stride, 1), padding=(1, 0), bias=True)
-        self.conv1x3_1 = nn.Conv2d(planes, planes, (1, 3), stride=(1, stride), padding=(0, 1), bias=True)
+        self.conv3x1_1 = Conv2d(inplanes, planes, (3, 1), stride=(stride, 1), padding=(1, 0), bias=True)
+        self.conv1x3_1 = Conv2d(planes, planes, (1, 3), stride=(1, stride), padding=(0, 1), bias=True)
         self.bn1 = nn.BatchNorm2d(planes, eps=1e-3)
         self.act = activation
-        self.conv3x1_2 = nn.Conv2d(planes, planes, (3, 1), padding=(dilation, 0), dilation=(dilation, 1), bias=True)
-        self.conv1x3_2 = nn.Conv2d(planes, planes, (1, 3), padding=(0, dilation), dilation=(1, dilation), bias=True)
+        self.conv3x1_2 = Conv2d(planes, planes, (3, 1), padding=(dilation, 0), dilation=(dilation, 1), bias=True)
+        self.conv1x3_2 = Conv2d(planes, planes, (1, 3), padding=(0, dilation), dilation=(1, dilation), bias=True)
         self.bn2 = nn.BatchNorm2d(planes, eps=1e-3)
         self.downsample = downsample
         self.stride = stride
@@ -135,10 +147,10 @@ class BasicBlock(nn.Module):
 
     def __init__(self, inplanes, planes, stride=1, downsample=None, dilation=1, activation=nn.ReLU(inplace=True)):
         super().__init__()
-        self.conv1 = nn.Conv2d(inplanes, planes, 3, stride, dilation, dilation, bias=False)
+        self.conv1 = Conv2d(inplanes, planes, 3, stride, dilation, dilation, bias=False)
         self.bn1 = nn.BatchNorm2d(planes)
         self.act = activation
-        self.conv2 = nn.Conv2d(planes, planes, 3, 1, dilation, dilation, bias=False)
+        self.conv2 = Conv2d(planes, planes, 3, 1, dilation, dilation, bias=False)
         self.bn2 = nn.BatchNorm2d(planes)
         self.downsample = downsample
         self.stride = stride
@@ -156,11 +168,11 @@ class Bottleneck(nn.Module):
 
     def __init__(self, inplanes, planes, stride=1, downsample=None, dilation=1, activation=nn.ReLU(inplace=True)):
         super().__init__()
-        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.conv1 = Conv2d(inplanes, planes, 1, bias=False)
         self.bn1 = nn.BatchNorm2d(planes)
-        self.conv2 = nn.Conv2d(planes, planes, 3, stride, dilation, dilation, bias=False)
+        self.conv2 = Conv2d(planes, planes, 3, stride, dilation, dilation, bias=False)
         self.bn2 = nn.BatchNorm2d(planes)
-        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.conv3 = Conv2d(planes, planes * 4, 1, bias=False)
         self.bn3 = nn.BatchNorm2d(planes * 4)
         self.act = activation
         self.downsample = downsample
@@ -184,7 +196,7 @@ class ResNet(nn.Module):
 
     def __init__(self, layers: Sequence[int], block, input_channels=3, activation=nn.ReLU(inplace=True)):
         super().__init__()
-        self.conv1 = nn.Conv2d(input_channels, 64, 7, 2, 3, bias=False)
+        self.conv1 = Conv2d(input_channels, 64, 7, 2, 3, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
         self.act = activation
         self.maxpool = nn.MaxPool2d(3, 2, 1)
@@ -199,7 +211,7 @@ class ResNet(nn.Module):
             for b in range(n):
                 ds = None
                 if b == 0 and (stride != 1 or inplanes != planes * e):
-                    ds = nn.Sequential(nn.Conv2d(inplanes, planes * e, 1, stride, bias=False),
+                    ds = nn.Sequential(Conv2d(inplanes, planes * e, 1, stride, bias=False),
                                        nn.BatchNorm2d(planes * e))
                 blocks.append(block(inplanes, planes, stride if b == 0 else 1, ds, activation=activation))
                 inplanes = planes * e
@@ -312,10 +324,10 @@ class Upsample(nn.Module):
         if "learned-3x3" in mode:
             if mode == "learned-3x3":
                 self.pad = nn.ReplicationPad2d((1, 1, 1, 1))
-                self.conv = nn.Conv2d(channels, channels, 3, groups=channels, padding=0)
+                self.conv = Conv2d(channels, channels, 3, groups=channels, padding=0)
             else:
                 self.pad = nn.Identity()
-                self.conv = nn.Conv2d(channels, channels, 3, groups=channels, padding=1)
+                self.conv = Conv2d(channels, channels, 3, groups=channels, padding=1)
             stencil = torch.tensor([[0.0625, 0.125, 0.0625], [0.125, 0.25, 0.125], [0.0625, 0.125, 0.0625]])
             with torch.no_grad():
                 self.conv.weight.copy_(stencil.expand(channels, 1, 3, 3))
@@ -342,7 +354,7 @@ class DecoderModule(nn.Module):
         self.decoder_blocks = nn.Sequential(
             *[NonBottleneck1D(channels_dec, channels_dec, activation=activation) for _ in range(nr_decoder_blocks)])
         self.upsample = Upsample(upsampling_mode, channels_dec)
-        self.side_output = nn.Conv2d(channels_dec, num_classes, 1)
+        self.side_output = Conv2d(channels_dec, num_classes, 1)
 
     def forward(self, decoder_features, encoder_features):
         out = self.decoder_blocks(self.conv3x3(decoder_features))
@@ -365,7 +377,7 @@ class Decoder(nn.Module):
                     DecoderModule(cin, channels_decoder[i], activation, nr_decoder_blocks[i], encoder_decoder_fusion,
                                   upsampling_mode, num_classes))
             cin = channels_decoder[i]
-        self.conv_out = nn.Conv2d(cin, num_classes, 3, padding=1)
+        self.conv_out = Conv2d(cin, num_classes, 3, padding=1)
         self.upsample1 = Upsample(upsampling_mode, num_classes)
         self.upsample2 = Upsample(upsampling_mode, num_classes)
 
@@ -389,9 +401,9 @@ class GlobalGate(nn.Module):
         super().__init__()
         self.bnum = branch_num
         self.conv = nn.Sequential(
-            nn.Conv2d(128, hidden_dim, 5, 2), nn.BatchNorm2d(hidden_dim), nn.Tanh(),
-            nn.Conv2d(hidden_dim, hidden_dim, 5, 2), nn.BatchNorm2d(hidden_dim), nn.Tanh())
-        self.fc = nn.Conv2d(hidden_dim, branch_num, 1, bias=False)
+            Conv2d(128, hidden_dim, 5, 2), nn.BatchNorm2d(hidden_dim), nn.Tanh(),
+            Conv2d(hidden_dim, hidden_dim, 5, 2), nn.BatchNorm2d(hidden_dim), nn.Tanh())
+        self.fc = Conv2d(hidden_dim, branch_num, 1, bias=False)
 
     def logits(self, rgb, depth):
         y = self.conv(torch.cat([rgb, depth], 1))
@@ -472,6 +484,9 @@ class SkipGateESANet(nn.Module):
         self._engine_key = None
         self._pending_weights: List[Tensor] = []
         self.use_cuda_graph = False          # opt-in: replay one captured graph per input shape
+        # training arithmetic on CUDA: "fp32" = the reference's (library convs, our gate ops);
+        # "bf16" = encoder/decoder convolutions forward + backward on the tcgen05 kernels (train_ops.py)
+        self.train_precision = "fp32"
         self._graphs = {}
 
     # ------------------------------------------------------------------ reference API
@@ -635,6 +650,13 @@ class SkipGateESANet(nn.Module):
             weight = self.gate_layer(r, d, self.temp, self.hard_gate)
         g = torch.stack([1 - weight[:, 0], 1 - (weight[:, 0] + weight[:, 1]),
                          1 - (weight[:, 0] + weight[:, 1] + weight[:, 2]), weight[:, 4]])
+        low = rgb.is_cuda and self.train_precision == "bf16"
+        if self.train_precision not in ("fp32", "bf16"):
+            raise ValueError("train_precision must be 'fp32' or 'bf16'")
+        if low:
+            # stem + gate stay fp32 (decisions must match the reference); everything after runs bf16 NHWC
+            r = r.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+            d = d.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
         fused = []
         for s in range(4):
             r = getattr(self.encoder_rgb, f"layer{s + 1}")(r if s == 0 else fuse)
@@ -642,11 +664,15 @@ class SkipGateESANet(nn.Module):
             if se:
                 # w*rgb + (1-w)*se(rgb,depth)  with w = 1 - g_s
                 b1 = getattr(self, f"se_layer{s + 1}")(r, d)
-                gs = g[s].view(-1, 1, 1, 1)
+                gs = g[s].view(-1, 1, 1, 1).to(r.dtype)
                 fuse = (1 - gs) * r + gs * b1
+            elif low:
+                fuse = r + g[s].view(-1, 1, 1, 1).to(r.dtype) * d
             else:
                 fuse = gated_blend(r, d, g[s])              # rgb + g_s * depth
             fused.append(fuse)
         skips = [getattr(self, f"skip_layer{i + 1}")(fused[i]) for i in range(3)]
         out = self.decoder([self.context_module(fused[3]), skips[2], skips[1], skips[0]])
+        if low:
+            out = tuple(o.float() for o in out) if isinstance(out, tuple) else out.float()
         return out, weight

@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import ConvParams, check, ptr, stream_ptr
+from ._lib import ConvParams, WgradParams, check, ptr, stream_ptr
 
 Tensor = torch.Tensor
 
@@ -87,6 +87,85 @@ def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 
         CONV_PROFILER(p, lambda: check(fn(ctypes.byref(p), stream_ptr()), "conv_igemm"))
     else:
         check(fn(ctypes.byref(p), stream_ptr()), "conv_direct" if direct else "conv_igemm")
+    return out
+
+
+def pack_conv_weight_dgrad(w: Tensor) -> Tensor:
+    """[c_out, c_in, kh, kw] fp32 -> the packed weight of the DATA-GRADIENT convolution:
+    bf16 [kh*kw, c_in_pad16, c_out] with the taps mirrored (dx = conv(dy, w^T flipped))."""
+    return pack_conv_weight(w.flip(2, 3).transpose(0, 1))
+
+
+def pack_conv_weight_pair(w: Tensor):
+    """fp32 [c_out, c_in, kh, kw] (CUDA) -> (forward, data-gradient) packed bf16 weights in one launch."""
+    lib = _lib.load()
+    w = w.detach().float().contiguous()
+    _cuda(w)
+    c_out, c_in, kh, kw = w.shape
+    fwd = torch.empty(kh * kw, (c_out + 15) // 16 * 16, c_in, dtype=torch.bfloat16, device=w.device)
+    dgr = torch.empty(kh * kw, (c_in + 15) // 16 * 16, c_out, dtype=torch.bfloat16, device=w.device)
+    check(lib.dynmm_pack_conv_weight(ptr(w), c_out, c_in, kh, kw, ptr(fwd), ptr(dgr), stream_ptr()), "pack_conv_weight")
+    return fwd, dgr
+
+
+_WGRAD_WS = {}
+
+
+def _workspace(device, need: int) -> Tensor:
+    # one scratch buffer per (device, stream): calls on a stream are ordered, so it can be shared
+    key = (device.index, stream_ptr())
+    ws = _WGRAD_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = _WGRAD_WS[key] = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=device)
+    return ws
+
+
+def channel_sum(x: Tensor, c: Optional[int] = None, out: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
+    """x NHWC bf16 [..., ld] -> fp32 [c] sums over all leading dimensions (the bias gradient)."""
+    lib = _lib.load()
+    _cuda(x, out)
+    ld = x.shape[-1]
+    c = ld if c is None else c
+    rows = x.numel() // ld
+    if out is None:
+        out = torch.empty(c, dtype=torch.float32, device=x.device)
+    need = lib.dynmm_channel_sum_workspace(rows, c)
+    if need < 0:
+        raise _lib.DynmmError("channel_sum: c must be a multiple of 8 (<= 2048)")
+    ws = _workspace(x.device, need)
+    check(lib.dynmm_channel_sum(ptr(x), rows, c, ld, ptr(out), ws.data_ptr(), ws.numel(), int(accumulate),
+                                stream_ptr()), "channel_sum")
+    return out
+
+
+def conv_wgrad(x: Tensor, dy: Tensor, *, kh: int, kw: int, stride=(1, 1), pad=(0, 0), c_in: Optional[int] = None,
+               c_out: Optional[int] = None, out: Optional[Tensor] = None, accumulate: bool = False,
+               direct: bool = False, max_ctas: int = 0) -> Tensor:
+    """Weight gradient of ``conv`` (see dynmm_conv_wgrad): x NHWC bf16 [n,h,w,x_ld], dy NHWC bf16
+    [n,ho,wo,dy_ld] -> fp32 [c_out, c_in, kh, kw].  ``direct=True`` runs the CUDA-core comparator."""
+    lib = _lib.load()
+    _cuda(x, dy, out)
+    n, h_in, w_in, x_ld = x.shape
+    _, h_out, w_out, dy_ld = dy.shape
+    c_in = x_ld if c_in is None else c_in
+    c_out = dy_ld if c_out is None else c_out
+    if out is None:
+        out = torch.empty(c_out, c_in, kh, kw, dtype=torch.float32, device=x.device)
+    p = WgradParams()
+    p.x, p.dy, p.dw = ptr(x), ptr(dy), ptr(out)
+    p.n, p.h_in, p.w_in, p.c_in, p.x_ld = n, h_in, w_in, c_in, x_ld
+    p.h_out, p.w_out, p.c_out, p.dy_ld = h_out, w_out, c_out, dy_ld
+    p.kh, p.kw, p.stride_h, p.stride_w, p.pad_h, p.pad_w = kh, kw, stride[0], stride[1], pad[0], pad[1]
+    p.accumulate, p.max_ctas = int(accumulate), max_ctas
+    if direct:
+        check(lib.dynmm_conv_wgrad_direct(ctypes.byref(p), stream_ptr()), "conv_wgrad_direct")
+        return out
+    need = lib.dynmm_conv_wgrad_workspace(ctypes.byref(p))
+    if need < 0:
+        check(-1, "conv_wgrad_workspace")
+    ws = _workspace(x.device, need)
+    p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
+    check(lib.dynmm_conv_wgrad(ctypes.byref(p), stream_ptr()), "conv_wgrad")
     return out
 
 

@@ -175,6 +175,53 @@ int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream);
  * by the product path. */
 int dynmm_conv_direct_fwd(const dynmm_conv_params* p, void* stream);
 
+/* ------------------------------------------------- convolution backward
+ *
+ * the reference has no explicit backward code; autograd
+ * (train.py:323) differentiates every F.conv2d of the encoder/decoder blocks
+ * (resnet.py:124-147, 66-84, 173-192; model_utils.py:11-23).
+ *
+ * Data gradient: a convolution again -- dynmm_conv_igemm_fwd over dy with the
+ * taps mirrored and the channel roles swapped (weight packed as
+ * [kh*kw][c_in_pad][c_out]); stride-2 layers run it on the zero-interleaved dy.
+ *
+ * Weight gradient: dw[co][ci][ky][kx] = sum over (n, ho, wo) of
+ *   dy[n, ho, wo, co] * x[n, ho*stride_h + ky - pad_h, wo*stride_w + kx - pad_w, ci]
+ * as a tcgen05 GEMM whose K dimension is the pixel index: both operands are the
+ * NHWC tensors themselves (MN-major shared-memory tiles), shifted per tap by the
+ * TMA coordinates, out-of-image pixels zero-filled.  The pixel range is split over
+ * CTAs; the fp32 partial sums go to `workspace` and are reduced in a fixed order
+ * (deterministic), written in the framework's weight layout [c_out][c_in][kh][kw]. */
+typedef struct dynmm_wgrad_params {
+  const void* x;          /* bf16 NHWC [n, h_in, w_in, x_ld] */
+  const void* dy;         /* bf16 NHWC [n, h_out, w_out, dy_ld] */
+  float* dw;              /* fp32 [c_out][c_in][kh][kw] */
+  void* workspace;        /* device scratch of dynmm_conv_wgrad_workspace() bytes */
+  long long workspace_bytes;
+  int32_t n, h_in, w_in, c_in, x_ld;
+  int32_t h_out, w_out, c_out, dy_ld;
+  int32_t kh, kw, stride_h, stride_w, pad_h, pad_w;
+  int32_t accumulate;     /* 0: dw = result, 1: dw += result */
+  int32_t max_ctas;       /* 0 = one per SM */
+} dynmm_wgrad_params;
+
+/* bytes of scratch the call needs for these shapes (<0: invalid arguments) */
+long long dynmm_conv_wgrad_workspace(const dynmm_wgrad_params* p);
+int dynmm_conv_wgrad(const dynmm_wgrad_params* p, void* stream);
+/* CUDA-core comparator with the same contract (tests only; no workspace needed). */
+int dynmm_conv_wgrad_direct(const dynmm_wgrad_params* p, void* stream);
+
+/* fp32 master weight [c_out][c_in][kh][kw] -> the bf16 operand layouts, in one pass (either may be NULL):
+ *   fwd   [kh*kw][c_out_pad16][c_in]   (dynmm_conv_params.weight of the forward convolution)
+ *   dgrad [kh*kw][c_in_pad16][c_out]   taps mirrored: the weight of the data-gradient convolution */
+int dynmm_pack_conv_weight(const float* w, int c_out, int c_in, int kh, int kw, void* fwd, void* dgrad,
+                           void* stream);
+/* Bias gradient: out[ch] (=|+=) sum over rows of x[row][ch], x bf16 [rows][ld] (NHWC flattened), fp32
+ * accumulation in a fixed order (deterministic).  workspace: dynmm_channel_sum_workspace(rows, c) bytes. */
+long long dynmm_channel_sum_workspace(long long rows, int c);
+int dynmm_channel_sum(const void* x, long long rows, int c, int ld, float* out, void* workspace,
+                      long long workspace_bytes, int accumulate, void* stream);
+
 /* --------------------------------------------------------- elementwise */
 
 /* out = a + gate[n]*b[slot(n)]  (NHWC bf16; model_skip_mod_globalgate.py:283 etc. as a
