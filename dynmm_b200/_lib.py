@@ -61,6 +61,10 @@ SIGNATURES = {
     "dynmm_stem_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [c_void_p] * 6 + [c_void_p] * 4
                        + [c_void_p] * 3 + [c_void_p]),
     "dynmm_stem_gap_tiles": (c_longlong, [c_int, c_int, c_int]),
+    "dynmm_stem_s2d_workspace": (c_longlong, [c_int, c_int, c_int]),
+    "dynmm_stem_s2d_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dynmm_stem_s2d_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p] + [c_void_p] * 4
+                           + [c_void_p, c_longlong] + [c_void_p] * 4 + [c_void_p]),
     "dynmm_gap_workspace": (c_longlong, [c_int, c_int]),
     "dynmm_gap_partial": (c_int, [c_void_p, c_int, c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dynmm_se_mlp": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
@@ -69,6 +73,10 @@ SIGNATURES = {
                                     c_int, c_int, c_void_p, c_void_p]),
     "dynmm_conv_igemm_fwd": (c_int, [POINTER(ConvParams), c_void_p]),
     "dynmm_conv_direct_fwd": (c_int, [POINTER(ConvParams), c_void_p]),
+    "dynmm_conv_program_bytes": (c_longlong, [c_int]),
+    "dynmm_conv_program_build": (c_int, [POINTER(ConvParams), POINTER(c_int32), c_int, c_void_p, c_longlong,
+                                         POINTER(c_int32)]),
+    "dynmm_conv_program_launch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dynmm_conv_wgrad_workspace": (c_longlong, [POINTER(WgradParams)]),
     "dynmm_conv_wgrad": (c_int, [POINTER(WgradParams), c_void_p]),
     "dynmm_conv_wgrad_direct": (c_int, [POINTER(WgradParams), c_void_p]),

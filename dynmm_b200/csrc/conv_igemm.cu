@@ -28,177 +28,13 @@
 // The tile list is derived on the device from `count` (number of active sample slots), so
 // samples the gate switched off generate no TMA traffic and no MMA work, and the launch is
 // CUDA-graph capturable.
-#include <stdlib.h>
-
-#include <mutex>
-
-#include "common.cuh"
-#include "tma_host.cuh"
+#include "conv_plan.cuh"
 
 namespace dynmm {
 
 namespace {
 
-constexpr int kBlockM = 128;       // UMMA M (TMEM lanes)
-constexpr int kBlockK = 64;        // bf16 elements per 128-byte swizzle row
-constexpr int kUmmaK = 16;
-constexpr int kMaxGroups = 9;
-constexpr int kMaxStages = 8;
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpiWarps;   // 320
-constexpr int kSmemBudget = 227 * 1024;
-constexpr int kSubBytes = kBlockM * kBlockK * 2; // 16 KiB: one [128 rows][64 ch] bf16 epilogue sub-tile
-constexpr int kAuxSlots = 3;                     // residual sub-tiles in flight
-constexpr int kResidentBudget = 100 * 1024;      // weights kept in shared memory when they fit
-
-// one A-tile load: `tpg` taps (along d2) share it
-struct Group {
-  int8_t map;   // which A tensor map (parity sub-lattice)
-  int8_t o1;    // coordinate offset along d1
-  int8_t o2;    // coordinate offset along d2 (start of the halo in halo mode)
-  int8_t pad;
-};
-
-struct KernelArgs {
-  // tiling.  (d1, d2) = (W, H) or (H, W) when `swap` -- d1 is the fastest pixel index of a tile.
-  int b1, b2, bn;                   // pixels per tile = b1*b2*bn <= 128
-  int tiles1, tiles2;               // tiles per sample group along d1 / d2
-  int c_tiles, tile_n;              // output channel tiles
-  int num_groups, tpg, k_chunks;    // A loads per K chunk; taps per load (1 or 3)
-  int stages, stage_bytes, a_bytes; // pipeline; a_bytes = A part of a stage (1024-aligned)
-  int a_rows;                       // rows TMA writes per A load (b1 * (b2 + tpg - 1) * bn)
-  int acc_stride, tmem_cols;
-  uint32_t m_c, m_1, m_2;           // magic multipliers for dividing by c_tiles / tiles1 / tiles2
-  int tma_epi;                      // 1: TMA residual loads + TMA stores (tile_n % 64 == 0)
-  int aux_slots;                    // residual ring slots (0 without residual)
-  int b_resident;                   // 1: all weights live in smem for the kernel's lifetime
-  int swap;                         // 1: d1 = H, d2 = W
-  Group groups[kMaxGroups];
-  // problem
-  int n, h_out, w_out, c_out;
-  int out_ld, res_ld, gated_ld;
-  const float* shift;
-  const float* scale;
-  const __nv_bfloat16* residual;
-  __nv_bfloat16* out;
-  const __nv_bfloat16* gated;
-  const float* gate;
-  const int32_t* gated_slot;
-  const int32_t* in_map;
-  const int32_t* res_map;
-  const int32_t* count;
-  unsigned long long* trace;        // debug: 16 cycle stamps per CTA, or NULL
-};
-
-struct __align__(8) SmemCtl {
-  uint64_t full[kMaxStages];
-  uint64_t empty[kMaxStages];
-  uint64_t acc_full[2];
-  uint64_t acc_empty[2];
-  uint64_t aux_full[kAuxSlots];
-  uint64_t aux_empty[kAuxSlots];
-  uint64_t b_full;
-  uint32_t tmem_base;
-};
-
-struct TileCoord {
-  int c0, x1, x2, n0;               // channel, d1, d2, sample origin of a tile
-};
-
-// x / d for x*d < 2^32 with m = ceil(2^32 / d) (host-computed); d == 1 has m == 0
-__device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t m) { return m ? __umulhi(x, m) : x; }
-
-__device__ __forceinline__ TileCoord decode_tile(const KernelArgs& a, int tile) {
-  TileCoord t;
-  uint32_t r = fast_div(tile, a.m_c);
-  const int ct = tile - r * a.c_tiles;
-  uint32_t q = fast_div(r, a.m_1);
-  const int t1 = r - q * a.tiles1;
-  r = fast_div(q, a.m_2);
-  const int t2 = q - r * a.tiles2;
-  t.c0 = ct * a.tile_n;
-  t.x1 = t1 * a.b1;
-  t.x2 = t2 * a.b2;
-  t.n0 = r * a.bn;
-  return t;
-}
-
-enum : int { kFlagRes = 1, kFlagGated = 2, kFlagRelu = 4, kFlagScale = 8 };
-
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-               : "memory");
-}
-
-// One thread's share of an epilogue sub-tile: 32 consecutive output channels of one pixel.
-//   kTma: residual comes from the swizzled smem tile `res_smem`, result goes to the swizzled
-//         staging tile `out_smem` (both 32-bit shared addresses of this thread's row);
-//   else: direct global loads / stores (narrow channel tiles, partially active sample boxes).
-template <int kFlags, bool kTma>
-__device__ __forceinline__ void epilogue_chunk(const KernelArgs& args, const uint32_t (&v)[32], int c_first,
-                                               int cols_left, bool valid, uint32_t res_smem, uint32_t out_smem,
-                                               uint32_t chunk0, uint32_t swz, size_t pix, size_t rpix, size_t gpix,
-                                               float g, const float* shift_smem) {
-#pragma unroll
-  for (int j = 0; j < 32; j += 8) {
-    const int c = c_first + j;
-    if (j < cols_left && c < args.c_out) {
-      float f[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
-      if (kFlags & kFlagScale) {
-        const float4 s0 = __ldg(reinterpret_cast<const float4*>(args.scale + c));
-        const float4 s1 = __ldg(reinterpret_cast<const float4*>(args.scale + c + 4));
-        f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
-        f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
-      }
-      {
-        const float4 b0 = *reinterpret_cast<const float4*>(shift_smem + c);      // warp-wide broadcast
-        const float4 b1 = *reinterpret_cast<const float4*>(shift_smem + c + 4);
-        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-        f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-      }
-      const uint32_t chunk = ((chunk0 + (j >> 3)) ^ swz) << 4;
-      if (kFlags & kFlagRes) {
-        uint4 r;
-        if (kTma) {
-          r = lds128(res_smem + chunk);
-        } else {
-          r = valid ? __ldg(reinterpret_cast<const uint4*>(args.residual + rpix * args.res_ld + c))
-                    : make_uint4(0, 0, 0, 0);
-        }
-        f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x); f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
-        f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z); f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
-      }
-      if (kFlags & kFlagRelu) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
-      }
-      if (kFlags & kFlagGated) {
-        if (g != 0.f) {      // gated-off samples never touch the depth features
-          const uint4 r = __ldg(reinterpret_cast<const uint4*>(args.gated + gpix * args.gated_ld + c));
-          f[0] += g * bf16_lo(r.x); f[1] += g * bf16_hi(r.x); f[2] += g * bf16_lo(r.y); f[3] += g * bf16_hi(r.y);
-          f[4] += g * bf16_lo(r.z); f[5] += g * bf16_hi(r.z); f[6] += g * bf16_lo(r.w); f[7] += g * bf16_hi(r.w);
-        }
-      }
-      uint4 o;
-      o.x = pack_bf16(f[0], f[1]);
-      o.y = pack_bf16(f[2], f[3]);
-      o.z = pack_bf16(f[4], f[5]);
-      o.w = pack_bf16(f[6], f[7]);
-      if (kTma) {
-        sts128(out_smem + chunk, o);
-      } else if (valid) {
-        *reinterpret_cast<uint4*>(args.out + pix * args.out_ld + c) = o;
-      }
-    }
-  }
-}
+using namespace convk;
 
 #define DYNMM_TRACE(slot)                                                              \
   do {                                                                                 \
@@ -259,7 +95,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     }
   }
   if (warp == 1) {
-    tmem_alloc(&ctl->tmem_base, args.tmem_cols);
+    tmem_alloc(&ctl->tmem_base, 512);
     tmem_relinquish();
   }
   if (warp >= 2) {   // epilogue warps stage the shift vector once: no global loads inside the tile loop
@@ -268,7 +104,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = ctl->tmem_base;
+  // The CTA owns all 512 TMEM columns, so the allocation starts at column 0 / lane 0: using the CONSTANT keeps
+  // every tcgen05.mma operand in uniform registers (a base read back from shared memory forces an
+  // ELECT / R2UR / branch sequence around each MMA: ~70 issue cycles per 32-cycle UMMA at N = 64).
+  if (ctl->tmem_base != 0) __trap();
+  constexpr uint32_t tmem_base = 0;
   // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch, shift
   // staging, resident weights -- constants only) overlapped the tail of the previous kernel in the
   // stream.  From here on we touch tensors it produced, so wait for it; then let OUR dependent
@@ -433,7 +273,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
           const uint32_t out_smem = out_base + sbuf * kSubBytes;
           if (cols_live) {
-            epilogue_chunk<kFlags, true>(args, v, t.c0 + cb, args.tile_n - cb, valid, res_smem, out_smem, half * 4,
+            epilogue_chunk<true, false>(kFlags, args, v, t.c0 + cb, args.tile_n - cb, valid, res_smem, out_smem, half * 4,
                                          swz, pix, rpix, gpix, g, smem_shift);
           }
           if (aux_on) {
@@ -455,7 +295,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
           sbuf ^= 1;
         } else if (cols_live) {
-          epilogue_chunk<kFlags, false>(args, v, t.c0 + cb, args.tile_n - cb, valid, 0, 0, 0, 0, pix, rpix, gpix, g,
+          epilogue_chunk<false, false>(kFlags, args, v, t.c0 + cb, args.tile_n - cb, valid, 0, 0, 0, 0, pix, rpix, gpix, g,
                                         smem_shift);
         }
       }
@@ -477,56 +317,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, args.tmem_cols);
+    tmem_dealloc(tmem_base, 512);
   }
   if (threadIdx.x == 0) DYNMM_TRACE(9);
-}
-
-// ------------------------------------------------------------------ host side
-
-// floor division for possibly negative tap offsets
-inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
-
-// generic mode: the (w,h,n) pixel box of a tile, maximising useful rows per 128-row MMA
-void choose_box(int w, int h, int n, bool single_sample, int* bw, int* bh, int* bn) {
-  double best = -1;
-  for (int cw = 1; cw <= w && cw <= kBlockM; ++cw) {
-    for (int ch = 1; ch <= h && cw * ch <= kBlockM; ++ch) {
-      int cn = single_sample ? 1 : kBlockM / (cw * ch);
-      if (cn > n) cn = n;
-      if (cn < 1) cn = 1;
-      long long tiles = 1LL * ceil_div(w, cw) * ceil_div(h, ch) * ceil_div(n, cn);
-      double eff = (double)w * h * n / (double)(tiles * kBlockM);
-      double score = eff + 1e-6 * cw;      // prefer wide boxes (contiguous NHWC rows) on ties
-      if (score > best) {
-        best = score;
-        *bw = cw;
-        *bh = ch;
-        *bn = cn;
-      }
-    }
-  }
-}
-double box_eff(int w, int h, int n, int bw, int bh, int bn) {
-  long long tiles = 1LL * ceil_div(w, bw) * ceil_div(h, bh) * ceil_div(n, bn);
-  return (double)w * h * n / (double)(tiles * kBlockM);
-}
-
-// halo mode: b1 in {8,16,32} rows along d1 (multiple of 8 keeps tap views 1024-byte aligned), b2 = 128 / b1
-void choose_halo_box(int d1, int d2, bool tapped, int* b1, int* b2, double* eff_out) {
-  double best = -1;
-  for (int c1 = 8; c1 <= (tapped ? 32 : 128); c1 *= 2) {
-    const int c2 = kBlockM / c1;
-    const double eff = (double)d1 * d2 / ((double)ceil_div(d1, c1) * c1 * ceil_div(d2, c2) * c2);
-    const double halo = tapped ? (double)(c2 + 2) / c2 : 1.0;    // operand bytes per useful row
-    const double score = eff / halo;
-    if (score > best) {
-      best = score;
-      *b1 = c1;
-      *b2 = c2;
-      *eff_out = eff;
-    }
-  }
 }
 
 }  // namespace
@@ -537,232 +330,14 @@ using namespace dynmm;
 
 extern "C" int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  DYNMM_CHECK_ARG(p && p->in && p->weight && p->out, "conv_igemm: null pointer");
-  DYNMM_CHECK_ARG(p->kh >= 1 && p->kw >= 1 && p->kh * p->kw <= kMaxGroups, "conv_igemm: at most %d taps", kMaxGroups);
-  DYNMM_CHECK_ARG(p->stride_h >= 1 && p->stride_h <= 2 && p->stride_w >= 1 && p->stride_w <= 2,
-                  "conv_igemm: stride must be 1 or 2");
-  DYNMM_CHECK_ARG(p->c_in % 8 == 0 && p->in_ld % 8 == 0 && p->in_ld >= p->c_in, "conv_igemm: c_in/in_ld %% 8");
-  DYNMM_CHECK_ARG(p->c_out % 8 == 0 && p->out_ld % 8 == 0 && p->out_ld >= p->c_out, "conv_igemm: c_out/out_ld %% 8");
-  DYNMM_CHECK_ARG(p->c_out <= 4096, "conv_igemm: c_out too large");
-  DYNMM_CHECK_ARG(!p->residual || p->res_ld % 8 == 0, "conv_igemm: res_ld %% 8");
-  DYNMM_CHECK_ARG(!p->gated || (p->gated_ld % 8 == 0 && p->gate), "conv_igemm: gated needs gate[] and gated_ld %% 8");
-  DYNMM_CHECK_ARG(p->n >= 1 && p->n_in >= 1, "conv_igemm: empty batch");
-  const int h_exp = (p->h_in + 2 * p->pad_h - p->kh) / p->stride_h + 1;
-  const int w_exp = (p->w_in + 2 * p->pad_w - p->kw) / p->stride_w + 1;
-  DYNMM_CHECK_ARG(h_exp == p->h_out && w_exp == p->w_out, "conv_igemm: output size %dx%d does not match %dx%d",
-                  p->h_out, p->w_out, h_exp, w_exp);
-  DYNMM_CHECK_ARG((reinterpret_cast<uintptr_t>(p->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->out) & 15) == 0 &&
-                      (reinterpret_cast<uintptr_t>(p->weight) & 15) == 0,
-                  "conv_igemm: pointers must be 16-byte aligned");
-
-  KernelArgs a{};
-  const uint64_t es = 2;
-  const int c_out_pad = (p->c_out + 15) / 16 * 16;
   const int sms = num_sms();
-  const int num_taps = p->kh * p->kw;
-  const bool single_sample = p->in_map != nullptr || p->res_map != nullptr;
-
-  // ---- generic box and its efficiency
-  int gw = 1, gh = 1, gn = 1;
-  choose_box(p->w_out, p->h_out, p->n, single_sample, &gw, &gh, &gn);
-  const double generic_eff = box_eff(p->w_out, p->h_out, p->n, gw, gh, gn);
-
-  // ---- halo mode: unit stride, "same" padding, at most one tapped direction per load
-  static const bool allow_halo = [] {
-    const char* e = getenv("DYNMM_CONV_HALO");
-    return !(e && e[0] == '0');
-  }();
-  bool halo = allow_halo && p->stride_h == 1 && p->stride_w == 1 && (p->kh == 1 || p->kh == 3) &&
-              (p->kw == 1 || p->kw == 3) && p->pad_h == p->kh / 2 && p->pad_w == p->kw / 2;
-  int hb1 = 0, hb2 = 0;
-  if (halo) {
-    // d2 is the direction whose taps share one load: W for 1x3 and 3x3 (swap: d1 = H), H for 3x1
-    a.swap = (p->kw == 3) ? 1 : 0;
-    const int d1 = a.swap ? p->h_out : p->w_out, d2 = a.swap ? p->w_out : p->h_out;
-    double eff = 0;
-    choose_halo_box(d1, d2, num_taps > 1, &hb1, &hb2, &eff);
-    if (eff < 0.8 * generic_eff) halo = false;      // tiny maps: multi-sample generic boxes fill the MMA better
-  }
-  int tile_n = 0, m_tiles = 0, b_tile_bytes = 0, b_total = 0, shift_bytes = 0, epi_bytes = 0;
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    // second attempt: the halo layout did not leave room for two pipeline stages (wide channel tiles
-    // with streamed 3-tap weight tiles) -> per-tap loads
-    if (attempt == 1) halo = false;
-    if (halo) {
-      a.b1 = hb1;
-      a.b2 = hb2;
-      a.bn = 1;
-      a.tpg = (num_taps > 1) ? 3 : 1;
-      a.num_groups = num_taps / a.tpg;                 // 1 (1x3, 3x1, 1x1) or 3 (3x3: one load per kernel row)
-      for (int g = 0; g < a.num_groups; ++g) {
-        a.groups[g].map = 0;
-        a.groups[g].o1 = (a.num_groups == 3) ? static_cast<int8_t>(g - 1) : 0;   // 3x3: kernel row ky -> H offset
-        a.groups[g].o2 = (a.tpg == 3) ? -1 : 0;                                  // start of the halo
-      }
-    } else {
-      a.swap = 0;
-      a.b1 = gw;
-      a.b2 = gh;
-      a.bn = gn;
-      a.tpg = 1;
-      a.num_groups = num_taps;
-    }
-    const int D1 = a.swap ? p->h_out : p->w_out, D2 = a.swap ? p->w_out : p->h_out;
-    a.tiles1 = ceil_div(D1, a.b1);
-    a.tiles2 = ceil_div(D2, a.b2);
-    m_tiles = a.tiles1 * a.tiles2 * ceil_div(p->n, a.bn);
-
-    tile_n = p->tile_n;
-    if (tile_n == 0) {
-      // multiples of 64 channels (TMA epilogue); widest tile that still gives every SM a tile
-      const int c64 = (c_out_pad + 63) / 64 * 64;
-      tile_n = c64 < 256 ? c64 : 256;
-      if (tile_n == 192) tile_n = 64;
-      while (tile_n > 64 && m_tiles * ceil_div(c_out_pad, tile_n) < sms) tile_n /= 2;
-    }
-    DYNMM_CHECK_ARG(tile_n >= 16 && tile_n <= 256 && tile_n % 16 == 0, "conv_igemm: tile_n %d", tile_n);
-    a.tile_n = tile_n;
-    a.c_tiles = ceil_div(c_out_pad, tile_n);
-    a.k_chunks = ceil_div(p->c_in, kBlockK);
-    a.a_rows = a.b1 * (a.b2 + a.tpg - 1) * a.bn;
-    a.a_bytes = (a.a_rows * kBlockK * 2 + 1023) / 1024 * 1024;
-    if (a.a_bytes < kBlockM * kBlockK * 2) a.a_bytes = kBlockM * kBlockK * 2;   // UMMA reads 128 rows
-    if (a.tpg == 3) {
-      // the last tap's view spans rows [2*b1, 2*b1 + 128)
-      const int need = (2 * a.b1 + kBlockM) * kBlockK * 2;
-      if (a.a_bytes < need) a.a_bytes = (need + 1023) / 1024 * 1024;
-    }
-    b_tile_bytes = tile_n * kBlockK * 2;
-    b_total = num_taps * a.k_chunks * b_tile_bytes;
-    a.tma_epi = (tile_n % 64 == 0) ? 1 : 0;
-    a.aux_slots = (a.tma_epi && p->residual) ? kAuxSlots : 0;
-    a.b_resident = (a.c_tiles == 1 && b_total <= kResidentBudget) ? 1 : 0;
-    if (a.b_resident && a.aux_slots) a.aux_slots = 2;
-    shift_bytes = (p->c_out + 8) * 4 + 16;
-    epi_bytes = (a.tma_epi ? 2 * kSubBytes : 0) + a.aux_slots * kSubBytes;
-    a.stage_bytes = a.a_bytes + (a.b_resident ? 0 : a.tpg * b_tile_bytes);
-    a.stages = (kSmemBudget - 2048 - epi_bytes - shift_bytes - (a.b_resident ? b_total : 0)) / a.stage_bytes;
-    if (a.stages < 2 && a.b_resident) {     // not enough room next to the resident weights: stream them instead
-      a.b_resident = 0;
-      a.aux_slots = (a.tma_epi && p->residual) ? kAuxSlots : 0;
-      epi_bytes = (a.tma_epi ? 2 * kSubBytes : 0) + a.aux_slots * kSubBytes;
-      a.stage_bytes = a.a_bytes + a.tpg * b_tile_bytes;
-      a.stages = (kSmemBudget - 2048 - epi_bytes - shift_bytes) / a.stage_bytes;
-    }
-    if (a.stages > kMaxStages) a.stages = kMaxStages;
-    if (a.stages >= 2 || !halo) break;
-  }
-  DYNMM_CHECK_ARG(a.stages >= 2, "conv_igemm: not enough shared memory for 2 stages");
-  a.acc_stride = (tile_n + 31) / 32 * 32;
-  a.tmem_cols = 32;
-  while (a.tmem_cols < 2 * a.acc_stride) a.tmem_cols *= 2;
-  a.n = p->n;
-  a.h_out = p->h_out;
-  a.w_out = p->w_out;
-  a.c_out = p->c_out;
-  a.out_ld = p->out_ld;
-  a.res_ld = p->res_ld;
-  a.gated_ld = p->gated_ld;
-  a.scale = p->scale;
-  a.shift = p->shift;
-  a.residual = static_cast<const __nv_bfloat16*>(p->residual);
-  a.out = static_cast<__nv_bfloat16*>(p->out);
-  a.gated = static_cast<const __nv_bfloat16*>(p->gated);
-  a.gate = p->gate;
-  a.gated_slot = p->gated_slot;
-  a.in_map = p->in_map;
-  a.res_map = p->res_map;
-  a.count = p->count;
-  a.trace = static_cast<unsigned long long*>(p->trace);
-  auto magic = [](int d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)(((1ULL << 32) + d - 1) / d); };
-  a.m_c = magic(a.c_tiles);
-  a.m_1 = magic(a.tiles1);
-  a.m_2 = magic(a.tiles2);
-
-  // pixel tensor map over an NHWC buffer, dims ordered (c, d1, d2, n)
-  auto pixel_map = [&](CUtensorMap* m, const void* base, int c, int w, int h, int n, uint64_t st_w, uint64_t st_h,
-                       uint64_t st_n, int box2) -> int {
-    const uint64_t dims[4] = {(uint64_t)c, (uint64_t)(a.swap ? h : w), (uint64_t)(a.swap ? w : h), (uint64_t)n};
-    const uint64_t strides[3] = {a.swap ? st_h : st_w, a.swap ? st_w : st_h, st_n};
-    const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)a.b1, (uint32_t)box2, (uint32_t)a.bn};
-    return encode_map(m, base, 4, dims, strides, box);
-  };
-
-  // A maps
-  CUtensorMap maps[4];
-  bool used[4] = {false, false, false, false};
-  if (halo) {
-    used[0] = true;
-    int rc = pixel_map(&maps[0], p->in, p->c_in, p->w_in, p->h_in, p->n_in, (uint64_t)p->in_ld * es,
-                       (uint64_t)p->in_ld * p->w_in * es, (uint64_t)p->in_ld * p->w_in * p->h_in * es,
-                       a.b2 + a.tpg - 1);
-    if (rc) return rc;
-  } else {
-    // one map per (parity_h, parity_w) sub-lattice of the input
-    for (int ky = 0; ky < p->kh; ++ky) {
-      for (int kx = 0; kx < p->kw; ++kx) {
-        const int dy = ky - p->pad_h, dx = kx - p->pad_w;
-        const int qy = floordiv(dy, p->stride_h), py = dy - qy * p->stride_h;
-        const int qx = floordiv(dx, p->stride_w), px = dx - qx * p->stride_w;
-        Group& t = a.groups[ky * p->kw + kx];
-        t.map = static_cast<int8_t>(py * p->stride_w + px);
-        t.o1 = static_cast<int8_t>(qx);
-        t.o2 = static_cast<int8_t>(qy);
-        used[t.map] = true;
-      }
-    }
-    for (int m = 0; m < 4; ++m) {
-      if (!used[m]) continue;
-      const int py = m / p->stride_w, px = m % p->stride_w;
-      const int sub_w = (p->w_in - px + p->stride_w - 1) / p->stride_w;
-      const int sub_h = (p->h_in - py + p->stride_h - 1) / p->stride_h;
-      DYNMM_CHECK_ARG(sub_w >= 1 && sub_h >= 1, "conv_igemm: input too small for stride");
-      const __nv_bfloat16* base =
-          static_cast<const __nv_bfloat16*>(p->in) + (static_cast<size_t>(py) * p->w_in + px) * p->in_ld;
-      int rc = pixel_map(&maps[m], base, p->c_in, sub_w, sub_h, p->n_in, (uint64_t)p->in_ld * p->stride_w * es,
-                         (uint64_t)p->in_ld * p->w_in * p->stride_h * es,
-                         (uint64_t)p->in_ld * p->w_in * p->h_in * es, a.b2);
-      if (rc) return rc;
-    }
-  }
-  int first_used = 0;
-  while (!used[first_used]) ++first_used;
-  for (int m = 0; m < 4; ++m)
-    if (!used[m]) maps[m] = maps[first_used];
-  CUtensorMap map_b;
-  {
-    const uint64_t dims[3] = {(uint64_t)p->c_in, (uint64_t)c_out_pad, (uint64_t)num_taps};
-    const uint64_t strides[2] = {(uint64_t)p->c_in * es, (uint64_t)p->c_in * c_out_pad * es};
-    const uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)tile_n, (uint32_t)a.tpg};
-    int rc = encode_map(&map_b, p->weight, 3, dims, strides, box);
-    if (rc) return rc;
-  }
-  // epilogue maps: residual (load) and output (store), one [box pixels][64 channels] sub-tile per transfer
-  CUtensorMap map_res = map_b, map_out = map_b;
-  if (a.tma_epi) {
-    int rc = pixel_map(&map_out, p->out, p->c_out, p->w_out, p->h_out, p->n, (uint64_t)p->out_ld * es,
-                       (uint64_t)p->out_ld * p->w_out * es, (uint64_t)p->out_ld * p->w_out * p->h_out * es, a.b2);
-    if (rc) return rc;
-    if (a.aux_slots) {
-      DYNMM_CHECK_ARG((reinterpret_cast<uintptr_t>(p->residual) & 15) == 0,
-                      "conv_igemm: residual must be 16-byte aligned");
-      // the residual may hold more samples than n (res_map gathers); the sample extent only bounds the box
-      rc = pixel_map(&map_res, p->residual, p->c_out, p->w_out, p->h_out, p->res_map ? 65536 : p->n,
-                     (uint64_t)p->res_ld * es, (uint64_t)p->res_ld * p->w_out * es,
-                     (uint64_t)p->res_ld * p->w_out * p->h_out * es, a.b2);
-      if (rc) return rc;
-    }
-  }
-
-  const int smem_bytes = a.stages * a.stage_bytes + (a.b_resident ? b_total : 0) + epi_bytes + 1024 /*align*/ +
-                         (int)sizeof(SmemCtl) + shift_bytes;
-  DYNMM_CHECK_ARG(smem_bytes <= kSmemBudget, "conv_igemm: internal smem accounting error (%d bytes)", smem_bytes);
-  const int max_tiles = m_tiles * a.c_tiles;
-  DYNMM_CHECK_ARG((long long)max_tiles * a.c_tiles < (1LL << 31) && max_tiles < (1 << 20), "conv_igemm: too many tiles");
+  ConvPlan plan;
+  int rc = plan_conv(p, &plan, sms);
+  if (rc) return rc;
+  const KernelArgs& a = plan.a;
   int grid = p->max_ctas > 0 ? p->max_ctas : sms;
-  if (grid > max_tiles) grid = max_tiles;
-  const int flags = (p->residual ? kFlagRes : 0) | (p->gated ? kFlagGated : 0) | (p->relu ? kFlagRelu : 0) |
-                    (p->scale ? kFlagScale : 0);
+  if (grid > plan.max_tiles) grid = plan.max_tiles;
+  const int flags = a.flags;
   typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap,
                            KernelArgs);
   static const KernelFn table[16] = {
@@ -784,13 +359,14 @@ extern "C" int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream_) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.dynamicSmemBytes = plan.smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl ? 1 : 0;
-  DYNMM_CUDA(cudaLaunchKernelEx(&cfg, table[flags], maps[0], maps[1], maps[2], maps[3], map_b, map_res, map_out, a));
+  DYNMM_CUDA(cudaLaunchKernelEx(&cfg, table[flags], plan.maps[0], plan.maps[1], plan.maps[2], plan.maps[3], plan.map_b,
+                                plan.map_res, plan.map_out, a));
   return DYNMM_OK;
 }

@@ -17,6 +17,7 @@ two streams and meet at the four fusion points.
 from __future__ import annotations
 
 import dataclasses
+import os
 from typing import Callable, Dict, List, Optional, Sequence
 
 import torch
@@ -163,6 +164,10 @@ class FusionEngine:
             s, b = ops.fold_bn(p.t(enc + ".bn1.weight"), p.t(enc + ".bn1.bias"), p.t(enc + ".bn1.running_mean"),
                                p.t(enc + ".bn1.running_var"), 1e-5)
             self.stem[enc] = (w, s, b)
+        # plain `add` fusion: TMA-gathered stem (dynmm_stem_s2d_fwd); DYNMM_STEM=tc|fp32 selects the older kernels
+        self.stem_packed = None
+        if cfg.fuse == "add" and os.environ.get("DYNMM_STEM", "s2d") == "s2d":
+            self.stem_packed = ops.stem_s2d_pack_weights(self.stem["encoder_rgb"][0], self.stem["encoder_depth"][0])
         block_kind = "bottleneck" if cfg.encoder == "resnet50" else \
             {"NonBottleneck1D": "nbt1d", "BasicBlock": "basic"}[cfg.encoder_block]
         make = getattr(p, block_kind)
@@ -204,6 +209,12 @@ class FusionEngine:
                 self.se.append(layer)
         self.side = torch.cuda.Stream(device=device)
         self.launches = 0          # kernels launched by the last forward (for bench accounting)
+        # DYNMM_PROGRAM=1 ('add' fusion only): the encoders, the skip convs and each decoder module run as persistent
+        # convolution PROGRAMS (one cooperative launch per chain of dependent convs, dynmm_conv_program_*) instead of
+        # one launch per convolution on two streams.  Same arithmetic, bit-identical results; measured slower at
+        # batch 8 in round 1 (profiles/r1_program_*), so the per-launch path stays the default.
+        self.use_programs = cfg.fuse == "add" and os.environ.get("DYNMM_PROGRAM", "0") == "1"
+        self.programs: list = []   # ConvPrograms of the last forward (a captured graph must keep them alive)
 
     # ------------------------------------------------------------------ blocks
     def _block(self, x: Tensor, blk: Block, keep: list, *, count=None, in_map=None, before_last: Callable = None,
@@ -244,6 +255,92 @@ class FusionEngine:
         self.launches += 5
         return fused
 
+
+    # ------------------------------------------------------------------ convolution programs
+    def _block_steps(self, x: Tensor, blk: Block, keep: list, result: list, *, count=None, in_map=None,
+                     last_kw: Optional[dict] = None):
+        """Generator form of :meth:`_block`: records one phase worth of convolutions per step (the first
+        conv together with the block's down-sampling conv), the block output is appended to ``result``."""
+        n_out = x.shape[0]
+        assert len(blk.convs) >= 2 or blk.downsample is None
+        y, idn, res_map = x, x, in_map
+        for i, cv in enumerate(blk.convs):
+            kw = dict(count=count, in_map=in_map if i == 0 else None, n_out=n_out)
+            if i == 0 and blk.downsample is not None:
+                idn, res_map = blk.downsample(x, count=count, in_map=in_map, n_out=n_out), None
+                keep.append(idn)
+            if i == len(blk.convs) - 1:
+                # evaluated only now: the depth features a gated add reads were recorded one phase earlier
+                kw.update(residual=idn, res_map=res_map, **(last_kw() if callable(last_kw) else (last_kw or {})))
+            y = cv(y, **kw)
+            keep.append(y)
+            yield
+        result.append(y)
+
+    def _encoder_chain(self, x: Tensor, enc: str, keep: list, outs: list, plan, *, depth_outs=None, cat=None):
+        """All blocks of one encoder as a generator of phases.  Depth encoder (``depth_outs is None``): slot
+        order, prefix-counted.  RGB encoder: the last conv of stage s adds g_s * depth_s."""
+        is_depth = depth_outs is None
+        for s in range(4):
+            blocks = self.stages[enc][s]
+            for bi, blk in enumerate(blocks):
+                kw, last_kw = {}, None
+                if is_depth:
+                    kw = dict(count=plan.count[s:s + 1], in_map=plan.perm if (s == 0 and bi == 0) else None)
+                elif bi == len(blocks) - 1:
+                    def last_kw(s=s):
+                        kw_ = dict(gated=depth_outs[s], gate=plan.g[s], gated_slot=plan.slot)
+                        if s == 3:
+                            kw_.update(out=cat, out_c_off=0)
+                        return kw_
+                res: list = []
+                yield from self._block_steps(x, blk, keep, res, last_kw=last_kw, **kw)
+                x = res[0]
+            outs.append(x)
+
+    def _encoder_program(self, r16: Tensor, d16: Tensor, plan, cat: Tensor, keep: list):
+        """Both encoders and the skip 1x1 convs as ONE program.  Phase k holds depth conv k and RGB conv k-1:
+        the depth encoder runs one layer ahead, so depth_s is complete when the RGB stage's last conv reads it."""
+        depth_out, fused, skips = [], [], []
+        with ops.ConvProgram() as prog:
+            dgen = self._encoder_chain(d16, "encoder_depth", keep, depth_out, plan)
+            rgen = self._encoder_chain(r16, "encoder_rgb", keep, fused, plan, depth_outs=depth_out, cat=cat)
+            d_live, r_live, first = True, True, True
+            while d_live or r_live:
+                if d_live:
+                    d_live = next(dgen, StopIteration) is not StopIteration
+                if r_live and not first:
+                    r_live = next(rgen, StopIteration) is not StopIteration
+                first = False
+                while len(skips) < min(len(fused), 3) and prog.jobs_in_phase() < 4:
+                    sk = self.skips[len(skips)]
+                    skips.append(sk(fused[len(skips)]) if sk is not None else fused[len(skips)])
+                prog.next_phase()
+            while len(skips) < 3:
+                sk = self.skips[len(skips)]
+                skips.append(sk(fused[len(skips)]) if sk is not None else fused[len(skips)])
+        self.programs.append(prog)
+        self.launches += 2          # program image upload + the cooperative launch
+        keep += skips
+        return fused, skips
+
+    def _sequence_program(self, x: Tensor, items: Sequence, keep: list) -> Tensor:
+        """A chain of dependent ConvLayers / Blocks as one program (one phase per convolution)."""
+        with ops.ConvProgram() as prog:
+            for it in items:
+                if isinstance(it, Block):
+                    res: list = []
+                    for _ in self._block_steps(x, it, keep, res):
+                        prog.next_phase()
+                    x = res[0]
+                else:
+                    x = it(x)
+                    keep.append(x)
+                    prog.next_phase()
+        self.programs.append(prog)
+        self.launches += 2
+        return x
+
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, rgb: Tensor, depth: Tensor, *, temp: float = 1.0, hard_gate: bool = False,
@@ -268,7 +365,10 @@ class FusionEngine:
         wr, sr, br = self.stem["encoder_rgb"]
         wd, sdp, bd = self.stem["encoder_depth"]
         learned = weight is None and not baseline and not ini_stage
-        if self.se is None:
+        if self.stem_packed is not None:
+            r32, d32, r16, d16 = ops.stem_s2d(rgb, depth, self.stem_packed, sr, br, sdp, bd, want_f32=learned)
+            self.launches += 2
+        elif self.se is None:
             r32, d32, r16, d16 = ops.stem(rgb, depth, wr, sr, br, wd, sdp, bd, want_f32=learned)
             self.launches += 1
         else:
@@ -301,78 +401,108 @@ class FusionEngine:
         self.launches += 1
         keep += [r32, d32, r16, d16, weight, plan]
 
-        # ---- depth encoder on the side stream, in slot order, prefix-counted
-        fork = torch.cuda.Event()
-        fork.record(main)
-        side.wait_event(fork)
-        done = [torch.cuda.Event() for _ in range(4)]
-        depth_out = []
-        with torch.cuda.stream(side):
-            d = d16
-            for s in range(4):
-                cnt = plan.count[s:s + 1]
-                for bi, blk in enumerate(self.stages["encoder_depth"][s]):
-                    d = self._block(d, blk, keep, count=cnt, in_map=plan.perm if (s == 0 and bi == 0) else None)
-                depth_out.append(d)
-                done[s].record(side)
+        self.programs = []
+        skips = None
+        if self.use_programs:
+            c4 = self.stage_channels[3]
+            cat = torch.empty(b, h // 32, w // 32, c4 + 2 * self.ppm[0].c_out, dtype=torch.bfloat16, device=self.dev)
+            fused, skips = self._encoder_program(r16, d16, plan, cat, keep)
+        else:
+            # ---- depth encoder on the side stream, in slot order, prefix-counted
+            fork = torch.cuda.Event()
+            fork.record(main)
+            side.wait_event(fork)
+            done = [torch.cuda.Event() for _ in range(4)]
+            depth_out = []
+            with torch.cuda.stream(side):
+                d = d16
+                for s in range(4):
+                    cnt = plan.count[s:s + 1]
+                    for bi, blk in enumerate(self.stages["encoder_depth"][s]):
+                        d = self._block(d, blk, keep, count=cnt, in_map=plan.perm if (s == 0 and bi == 0) else None)
+                    depth_out.append(d)
+                    done[s].record(side)
 
-        # ---- RGB encoder on the main stream; the last conv of each stage adds g_s * depth_s
-        r = r16
-        fused = []
-        cat = None
-        for s in range(4):
-            blocks = self.stages["encoder_rgb"][s]
-            for bi, blk in enumerate(blocks):
-                if bi < len(blocks) - 1:
-                    r = self._block(r, blk, keep)
-                    continue
-                if s == 3:
-                    # stage-4 output lands directly in the pyramid-pooling concat buffer
-                    c4 = self.stage_channels[3]
-                    cat = torch.empty(b, h // 32, w // 32, c4 + 2 * self.ppm[0].c_out, dtype=torch.bfloat16,
-                                      device=self.dev)
-                if self.se is None:
-                    last_kw = dict(gated=depth_out[s], gate=plan.g[s], gated_slot=plan.slot)
+            # ---- RGB encoder on the main stream; the last conv of each stage adds g_s * depth_s
+            r = r16
+            fused = []
+            cat = None
+            for s in range(4):
+                blocks = self.stages["encoder_rgb"][s]
+                for bi, blk in enumerate(blocks):
+                    if bi < len(blocks) - 1:
+                        r = self._block(r, blk, keep)
+                        continue
                     if s == 3:
-                        last_kw.update(out=cat, out_c_off=0)
-                    r = self._block(r, blk, keep, before_last=lambda s=s: main.wait_event(done[s]), last_kw=last_kw)
-                else:
-                    # SE-add: both stage outputs must be complete before they can be squeezed
-                    r = self._block(r, blk, keep)
-                    main.wait_event(done[s])
-                    r = self._se_fuse(s, r, depth_out[s], plan, keep, cat if s == 3 else None)
-            fused.append(r)
+                        # stage-4 output lands directly in the pyramid-pooling concat buffer
+                        c4 = self.stage_channels[3]
+                        cat = torch.empty(b, h // 32, w // 32, c4 + 2 * self.ppm[0].c_out, dtype=torch.bfloat16,
+                                          device=self.dev)
+                    if self.se is None:
+                        last_kw = dict(gated=depth_out[s], gate=plan.g[s], gated_slot=plan.slot)
+                        if s == 3:
+                            last_kw.update(out=cat, out_c_off=0)
+                        r = self._block(r, blk, keep, before_last=lambda s=s: main.wait_event(done[s]), last_kw=last_kw)
+                    else:
+                        # SE-add: both stage outputs must be complete before they can be squeezed
+                        r = self._block(r, blk, keep)
+                        main.wait_event(done[s])
+                        r = self._se_fuse(s, r, depth_out[s], plan, keep, cat if s == 3 else None)
+                fused.append(r)
 
         # ---- skip connections, context module, decoder (model.py:295-308, context_modules.py:69-87)
-        skips = []
-        for s in range(3):
-            if self.skips[s] is not None:
-                skips.append(self.skips[s](fused[s]))
-                self.launches += 1
-            else:
-                skips.append(fused[s])
+        if skips is None:
+            skips = []
+            for s in range(3):
+                if self.skips[s] is not None:
+                    skips.append(self.skips[s](fused[s]))
+                    self.launches += 1
+                else:
+                    skips.append(fused[s])
         c4 = self.stage_channels[3]
         off = c4
-        for i, bins in enumerate((1, 5)):
-            pooled = ops.adaptive_avgpool(cat, bins, c=c4)
-            y = self.ppm[i](pooled)
-            ops.nearest_resize_into(y, cat, off)
-            off += y.shape[3]
-            keep += [pooled, y]
-            self.launches += 3
-        x = self.ppm_final(cat)
-        self.launches += 1
-        keep += [cat, x] + skips
-        for i, skip in enumerate((skips[2], skips[1], skips[0])):
-            m = self.dec[i]
-            x = m["conv3x3"](x)
+        if self.use_programs:
+            pooled = [ops.adaptive_avgpool(cat, bins, c=c4) for bins in (1, 5)]
+            with ops.ConvProgram() as prog:          # the two pyramid branches are independent: one phase
+                ys = [self.ppm[i](pooled[i]) for i in range(2)]
+            self.programs.append(prog)
+            for y in ys:
+                ops.nearest_resize_into(y, cat, off)
+                off += y.shape[3]
+            keep += pooled + ys
+            self.launches += 6
+        else:
+            for i, bins in enumerate((1, 5)):
+                pooled = ops.adaptive_avgpool(cat, bins, c=c4)
+                y = self.ppm[i](pooled)
+                ops.nearest_resize_into(y, cat, off)
+                off += y.shape[3]
+                keep += [pooled, y]
+                self.launches += 3
+        keep += [cat] + skips
+        if self.use_programs:
+            x = cat
+            for i, skip in enumerate((skips[2], skips[1], skips[0])):
+                m = self.dec[i]
+                items = ([self.ppm_final] if i == 0 else []) + [m["conv3x3"]] + list(m["blocks"])
+                x = self._sequence_program(x, items, keep)
+                x = ops.upsample2x_dw3x3(x, m["up_w"], m["up_b"], skip)
+                self.launches += 1
+                keep.append(x)
+        else:
+            x = self.ppm_final(cat)
             self.launches += 1
             keep.append(x)
-            for blk in m["blocks"]:
-                x = self._block(x, blk, keep)
-            x = ops.upsample2x_dw3x3(x, m["up_w"], m["up_b"], skip)
-            self.launches += 1
-            keep.append(x)
+            for i, skip in enumerate((skips[2], skips[1], skips[0])):
+                m = self.dec[i]
+                x = m["conv3x3"](x)
+                self.launches += 1
+                keep.append(x)
+                for blk in m["blocks"]:
+                    x = self._block(x, blk, keep)
+                x = ops.upsample2x_dw3x3(x, m["up_w"], m["up_b"], skip)
+                self.launches += 1
+                keep.append(x)
         x = self.conv_out(x)
         keep.append(x)
         x = ops.upsample2x_dw3x3(x, self.up[0][0], self.up[0][1])

@@ -34,6 +34,8 @@ class GraphedForward:
         with torch.cuda.graph(self.graph):
             self.out, self.weight = engine.forward(self.rgb, self.depth, **modes, **extra)
         self.launches = engine.launches
+        # program images are re-uploaded from pinned host memory on every replay: keep them (and their tensors) alive
+        self._programs = list(engine.programs)
 
     def __call__(self, rgb, depth):
         """Outputs are static buffers, valid until the next call."""

@@ -82,6 +82,10 @@ def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 
     p.kh, p.kw, p.stride_h, p.stride_w, p.pad_h, p.pad_w = kh, kw, stride[0], stride[1], pad[0], pad[1]
     p.relu, p.tile_n, p.max_ctas = int(relu), tile_n, max_ctas
     p.trace = ptr(trace)
+    if CONV_RECORDER is not None and not direct:
+        # inside `with ConvProgram()`: the convolution becomes a job of the program's current phase
+        CONV_RECORDER._record(p, (x, weight, scale, shift, residual, res_map, out, gated, gate, gated_slot, in_map, count))
+        return out
     fn = lib.dynmm_conv_direct_fwd if direct else lib.dynmm_conv_igemm_fwd
     if CONV_PROFILER is not None and not direct:
         CONV_PROFILER(p, lambda: check(fn(ctypes.byref(p), stream_ptr()), "conv_igemm"))
@@ -171,6 +175,97 @@ def conv_wgrad(x: Tensor, dy: Tensor, *, kh: int, kw: int, stride=(1, 1), pad=(0
 
 # bench.py installs a callable(params, launch) here to time every tensor-core conv launch
 CONV_PROFILER = None
+CONV_RECORDER = None
+
+
+class ConvProgram:
+    """Records :func:`conv` calls and runs them as ONE persistent cooperative launch (dynmm_conv_program_*).
+
+    ::
+
+        with ops.ConvProgram() as prog:
+            y = ops.conv(x, w1, ...)          # phase 0
+            prog.next_phase()
+            z = ops.conv(y, w2, ...)          # phase 1: may read what phase 0 wrote
+        # leaving the block builds the program image, uploads it and launches it on the current stream
+
+    Convolutions recorded in one phase must be independent (at most 4).  Tensors are allocated as usual while
+    recording, only the launches are deferred.  ``prog.hold`` keeps the pinned host image and the device
+    buffers alive: a CUDA graph that captured the launch replays the upload from that pinned memory."""
+
+    def __init__(self):
+        self.jobs, self.phases, self.keep = [], [], []
+        self.phase = 0
+        self.hold = None
+        self.cfg = None
+        self._prev = None
+
+    def next_phase(self):
+        if self.phases and self.phases[-1] == self.phase:     # empty phases are not numbered
+            self.phase += 1
+
+    def jobs_in_phase(self) -> int:
+        return sum(1 for ph in self.phases if ph == self.phase)
+
+    def _record(self, p, tensors):
+        if self.jobs_in_phase() >= 4:
+            raise _lib.DynmmError("ConvProgram: at most 4 convolutions per phase")
+        self.jobs.append(p)
+        self.phases.append(self.phase)
+        self.keep.append(tensors)
+
+    def __enter__(self):
+        global CONV_RECORDER
+        if CONV_RECORDER is not None:
+            raise _lib.DynmmError("ConvProgram blocks do not nest")
+        CONV_RECORDER = self
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        global CONV_RECORDER
+        CONV_RECORDER = None
+        if exc_type is None and self.jobs:
+            self.launch()
+        return False
+
+    def flops(self) -> float:
+        """2 x MACs the program executes (samples beyond a job's device-side ``count`` are not computed)."""
+        total = 0.0
+        for p, tensors in zip(self.jobs, self.keep):
+            count = tensors[-1]
+            active = min(int(count.item()), p.n) if count is not None else p.n
+            total += 2.0 * p.h_out * p.w_out * p.c_out * p.c_in * p.kh * p.kw * active
+        return total
+
+    def launch(self, upload: bool = True, trace: Optional[Tensor] = None):
+        lib = _lib.load()
+        n = len(self.jobs)
+        dev = self.keep[0][0].device
+        if self.hold is None:
+            nbytes = lib.dynmm_conv_program_bytes(n)
+            host = torch.empty(nbytes + 128, dtype=torch.uint8).pin_memory()
+            off = (-host.data_ptr()) % 128
+            host_img = host[off:off + nbytes]
+            jobs = (ConvParams * n)(*self.jobs)
+            phases = (ctypes.c_int32 * n)(*self.phases)
+            cfg = (ctypes.c_int32 * 3)()
+            check(lib.dynmm_conv_program_build(jobs, phases, n, host_img.data_ptr(), nbytes, cfg), "conv_program_build")
+            dev_buf = torch.empty(nbytes + 128, dtype=torch.uint8, device=dev)
+            doff = (-dev_buf.data_ptr()) % 128
+            dev_img = dev_buf[doff:doff + nbytes]
+            barrier = torch.empty(2, dtype=torch.int32, device=dev)
+            self.cfg = cfg
+            self.hold = (host, host_img, dev_buf, dev_img, barrier)
+        _, host_img, _, dev_img, barrier = self.hold
+        if upload:
+            dev_img.copy_(host_img, non_blocking=True)
+        check(lib.dynmm_conv_program_launch(dev_img.data_ptr(), host_img.data_ptr(), barrier.data_ptr(), ptr(trace),
+                                            stream_ptr()),
+              "conv_program_launch")
+
+    @property
+    def n_phases(self):
+        return int(self.cfg[2]) if self.cfg is not None else 0
 
 
 # ------------------------------------------------------------------ stem / gate
@@ -194,6 +289,36 @@ def stem(rgb: Tensor, depth: Tensor, w_rgb: Tensor, scale_rgb: Tensor, shift_rgb
     check(lib.dynmm_stem_fwd(ptr(rgb), ptr(depth), b, h, w, ptr(w_rgb), ptr(scale_rgb), ptr(shift_rgb), ptr(w_d),
                              ptr(scale_d), ptr(shift_d), ptr(r32), ptr(d32), ptr(r16), ptr(d16), ptr(se_rgb),
                              ptr(se_depth), None, stream_ptr()), "stem")
+    return r32, d32, r16, d16
+
+
+def stem_s2d_pack_weights(w_rgb: Tensor, w_d: Tensor) -> Tensor:
+    """[7][7][3][64] / [7][7][1][64] fp32 stem weights -> bf16 [2 (hi, lo)][128][256] for :func:`stem_s2d`."""
+    lib = _lib.load()
+    _cuda(w_rgb, w_d)
+    out = torch.empty(2, 128, 256, dtype=torch.bfloat16, device=w_rgb.device)
+    check(lib.dynmm_stem_s2d_pack_weights(ptr(w_rgb), ptr(w_d), ptr(out), stream_ptr()), "stem_s2d_pack_weights")
+    return out
+
+
+def stem_s2d(rgb: Tensor, depth: Tensor, w_packed: Tensor, scale_rgb: Tensor, shift_rgb: Tensor, scale_d: Tensor,
+             shift_d: Tensor, want_f32: bool = True):
+    """:func:`stem` for plain `add` fusion with the im2col done by TMA (dynmm_stem_s2d_fwd); 2 launches."""
+    lib = _lib.load()
+    _cuda(rgb, depth, w_packed)
+    b, _, h, w = rgb.shape
+    hs, ws = (h + 6 - 7) // 2 + 1, (w + 6 - 7) // 2 + 1
+    hp, wp = (hs + 2 - 3) // 2 + 1, (ws + 2 - 3) // 2 + 1
+    dev = rgb.device
+    r32 = torch.empty(b, hp, wp, 64, dtype=torch.float32, device=dev) if want_f32 else None
+    d32 = torch.empty(b, hp, wp, 64, dtype=torch.float32, device=dev) if want_f32 else None
+    r16 = torch.empty(b, hp, wp, 64, dtype=torch.bfloat16, device=dev)
+    d16 = torch.empty(b, hp, wp, 64, dtype=torch.bfloat16, device=dev)
+    need = lib.dynmm_stem_s2d_workspace(b, h, w)
+    ws_buf = torch.empty(need, dtype=torch.uint8, device=dev)
+    check(lib.dynmm_stem_s2d_fwd(ptr(rgb), ptr(depth), b, h, w, ptr(w_packed), ptr(scale_rgb), ptr(shift_rgb),
+                                 ptr(scale_d), ptr(shift_d), ptr(ws_buf), need, ptr(r32), ptr(d32), ptr(r16), ptr(d16),
+                                 stream_ptr()), "stem_s2d")
     return r32, d32, r16, d16
 
 

@@ -105,6 +105,21 @@ int dynmm_stem_fwd(const float* rgb, const float* depth, int b, int h, int w,
  *   pass 2: se_rgb / se_depth (float [b][64]) scale the two streams before the add. */
 long long dynmm_stem_gap_tiles(int b, int h, int w);
 
+/* The same fused stem (plain `add` fusion: no SE scales, no squeeze pass) with the im2col done by TMA:
+ * a pre-pass rewrites the 4-channel fp32 NCHW input as a zero-bordered space-to-depth image (bf16 hi + lo
+ * planes, 16 channels = 2x2 positions x (3 RGB + 1 depth)) in `workspace`; the 7x7/s2 convolutions of both
+ * encoders (resnet.py:352-358) then are one 4x4 unit-stride convolution = one tcgen05 GEMM with N = 128
+ * whose A rows TMA gathers as overlapping 128-byte windows.  Same arithmetic class as dynmm_stem_fwd's
+ * tensor-core path (three bf16 split products, fp32 accumulation).
+ *   w_packed: bf16 [2 (hi, lo)][128][256] from dynmm_stem_s2d_pack_weights (inputs: the [7][7][cin][64] fp32
+ *   weights dynmm_stem_fwd takes).  workspace: dynmm_stem_s2d_workspace(b, h, w) bytes of device scratch. */
+long long dynmm_stem_s2d_workspace(int b, int h, int w);
+int dynmm_stem_s2d_pack_weights(const float* w_rgb, const float* w_d, void* w_packed, void* stream);
+int dynmm_stem_s2d_fwd(const float* rgb, const float* depth, int b, int h, int w, const void* w_packed,
+                       const float* scale_rgb, const float* shift_rgb, const float* scale_d, const float* shift_d,
+                       void* workspace, long long workspace_bytes, float* rgb_f32, float* depth_f32,
+                       void* rgb_bf16, void* depth_bf16, void* stream);
+
 /* ------------------------------------------------------ SE-add fusion */
 
 /* Squeeze: partial[n][64 chunks][c] channel sums of NHWC bf16 x [n,hw,ld] (model_utils.py:48).  `count`
@@ -170,6 +185,32 @@ typedef struct dynmm_conv_params {
 } dynmm_conv_params;
 
 int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream);
+/* ------------------------------------------------- convolution programs
+ *
+ * Many dependent convolutions in ONE persistent cooperative launch.  At batch 8 a layer of the gated
+ * encoders (resnet.py:124-147 run twice in lock step, model_skip_mod_globalgate.py:276-310) is a few
+ * microseconds of work; the launch boundary between two layers costs as much again.  A program is a list
+ * of jobs (dynmm_conv_params, exactly as for dynmm_conv_igemm_fwd) grouped into phases: jobs of one phase
+ * are independent (at most 4), every job of phase k+1 may read what phase k wrote.  The CTAs of a phase
+ * are split between its jobs on the device, in proportion to the tiles that the jobs' `count` leaves.
+ *
+ *   bytes  = dynmm_conv_program_bytes(n_jobs)
+ *   dynmm_conv_program_build(jobs, phase_of_job, n_jobs, host_image, bytes, cfg)   host only, no CUDA work
+ *   copy host_image -> device (128-byte aligned), then per forward:
+ *   dynmm_conv_program_launch(device_image, host_image, barrier, trace, stream)
+ *
+ * phase_of_job is non-decreasing, starts at 0 and has no gaps.  The image embeds the tensor addresses of the
+ * jobs: it stays valid as long as those buffers do.  `barrier` is 8 bytes of device scratch owned by this
+ * launch (zeroed by it).  cfg = {grid, dynamic shared memory, phases} (informational); the launch reads its
+ * configuration and the per-job MMA parameters (passed as kernel parameters) from the HOST image.  `trace` (debug, may be NULL): device
+ * uint64 [grid][97], receives the %globaltimer value at which each CTA was released into each phase and, in the
+ * last used column, at which it finished.  Results are bit-identical to launching the jobs one by one. */
+long long dynmm_conv_program_bytes(int n_jobs);
+int dynmm_conv_program_build(const dynmm_conv_params* jobs, const int32_t* phase_of_job, int n_jobs,
+                             void* host_image, long long image_bytes, int32_t* cfg /* [3] */);
+int dynmm_conv_program_launch(const void* device_image, const void* host_image, void* barrier, void* trace,
+                              void* stream);
+
 /* Same contract, one thread per output element, CUDA cores.  Test comparator
  * for the tensor-core kernel at sizes the CPU oracle cannot reach; never used
  * by the product path. */

@@ -180,8 +180,9 @@ def _stem_weights(sd, enc):
     return w, s.cuda(), b.cuda()
 
 
+@pytest.mark.parametrize("kernel", ["tc", "s2d"])
 @pytest.mark.parametrize("hw", [(64, 96), (480, 640), (70, 90)])
-def test_stem_and_gate_match_oracle(hw):
+def test_stem_and_gate_match_oracle(hw, kernel):
     """fp32 stem + global gate vs the CPU oracle; gate logits to 1e-4 relative, hard decisions
     exact wherever the oracle's top-2 logit margin exceeds 1e-4 of the logit scale."""
     from dynmm_b200 import ops
@@ -201,7 +202,11 @@ def test_stem_and_gate_match_oracle(hw):
         logits_ref = fo.global_gate_logits(c, r, d) if min(r.shape[2:]) >= 13 else None
     wr, sr, br = _stem_weights(sd, "encoder_rgb")
     wd, sdp, bd = _stem_weights(sd, "encoder_depth")
-    r32, d32, r16, d16 = ops.stem(rgb.cuda(), depth.cuda(), wr, sr, br, wd, sdp, bd)
+    if kernel == "s2d":      # TMA-gathered im2col (dynmm_stem_s2d_fwd)
+        packed = ops.stem_s2d_pack_weights(wr, wd)
+        r32, d32, r16, d16 = ops.stem_s2d(rgb.cuda(), depth.cuda(), packed, sr, br, sdp, bd)
+    else:
+        r32, d32, r16, d16 = ops.stem(rgb.cuda(), depth.cuda(), wr, sr, br, wd, sdp, bd)
     torch.cuda.synchronize()
     np.testing.assert_allclose(r32.permute(0, 3, 1, 2).cpu().numpy(), r.numpy(), rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose(d32.permute(0, 3, 1, 2).cpu().numpy(), d.numpy(), rtol=1e-4, atol=1e-4)
