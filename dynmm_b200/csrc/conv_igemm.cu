@@ -170,7 +170,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The WHOLE warp runs the loops converged; only the tcgen05 instructions sit under elect.sync.  With one lane
+    // running the loop inside `if (lane == 0)` the compiler wraps every UTCHMMA in an ELECT / BRA.U.ANY loop and a
+    // thread cannot issue more than one MMA per ~90 cycles (tools/umma_issue_bench.cu: 90 vs 61.5 / 64 cycles per
+    // 128x64x16 / 128x128x16 UMMA) -- more than the MMAs themselves take.
+    {
       const uint32_t idesc = umma_idesc_bf16(kBlockM, args.tile_n);
       const uint32_t tap_step = args.b1 * kBlockK * 2;      // bytes between the A views of consecutive taps
       int stage = 0;
@@ -190,27 +194,30 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(&ctl->full[stage], phase);
           tc_fence_after();
-          if (local == 0 && it == 0) DYNMM_TRACE(3);
+          if (lane == 0 && local == 0 && it == 0) DYNMM_TRACE(3);
           const uint32_t sa = smem_u32(smem + stage * args.stage_bytes);
           const uint32_t sb = args.b_resident ? smem_u32(smem_bres + it * b_iter_bytes) : sa + args.a_bytes;
-          for (int tp = 0; tp < args.tpg; ++tp) {
-            const uint64_t da = umma_desc_sw128(sa + tp * tap_step);
-            const uint64_t db = umma_desc_sw128(sb + tp * b_tile_bytes);
+          if (elect_one()) {
+            for (int tp = 0; tp < args.tpg; ++tp) {
+              const uint64_t da = umma_desc_sw128(sa + tp * tap_step);
+              const uint64_t db = umma_desc_sw128(sb + tp * b_tile_bytes);
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              // advancing K inside the swizzle atom = +32 bytes on the (16-byte unit) start address
-              umma_bf16(d_tmem, da + (k * 2), db + (k * 2), idesc, (it | tp | k) != 0);
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                // advancing K inside the swizzle atom = +32 bytes on the (16-byte unit) start address
+                umma_bf16(d_tmem, da + (k * 2), db + (k * 2), idesc, (it | tp | k) != 0);
+              }
             }
+            umma_commit(&ctl->empty[stage]);          // frees the smem stage when these MMAs retire
+            if (it == k_iters - 1) umma_commit(&ctl->acc_full[acc]);
           }
-          if (local == 0 && it == 0) DYNMM_TRACE(12);
-          umma_commit(&ctl->empty[stage]);          // frees the smem stage when these MMAs retire
-          if (it == k_iters - 1) umma_commit(&ctl->acc_full[acc]);
+          __syncwarp();
+          if (lane == 0 && local == 0 && it == 0) DYNMM_TRACE(12);
           if (++stage == args.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        if (local == 0) DYNMM_TRACE(4);
+        if (lane == 0 && local == 0) DYNMM_TRACE(4);
       }
     }
   } else {

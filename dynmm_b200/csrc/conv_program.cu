@@ -177,8 +177,10 @@ __device__ void split_phase(const ProgramHeader* hdr, const JobBrief* briefs, in
 template <uint32_t kAcc>
 __device__ __forceinline__ void issue_kiter(uint32_t sa, uint32_t sb, const MmaJob& mj, int it) {
   for (int tp = 0; tp < mj.tpg; ++tp) {
-    umma_bf16_x4<kAcc>(umma_desc_lo_sw128(sa + tp * mj.tap_step), umma_desc_lo_sw128(sb + tp * mj.b_tile_bytes), mj.idesc,
-                       (it | tp) != 0);
+    const uint64_t da = umma_desc_sw128(sa + tp * mj.tap_step);
+    const uint64_t db = umma_desc_sw128(sb + tp * mj.b_tile_bytes);
+#pragma unroll
+    for (int k = 0; k < kBlockK / kUmmaK; ++k) umma_bf16(kAcc, da + (k * 2), db + (k * 2), mj.idesc, (it | tp | k) != 0);
   }
 }
 
@@ -334,13 +336,16 @@ conv_program_kernel(const __grid_constant__ ProgramParams params, const uint8_t*
           tc_fence_after();
           const uint32_t sa = smem_u + stage * mj.stage_bytes;
           const uint32_t sb = mj.b_resident ? smem_u + mj.bres_off + it * mj.b_iter_bytes : sa + mj.a_bytes;
-          if (me == 0) {
-            issue_kiter<0>(sa, sb, mj, it);
-          } else {
-            issue_kiter<kAccCols>(sa, sb, mj, it);
+          if (elect_one()) {       // the warp runs the loops converged; only the tcgen05 instructions are single-lane
+            if (me == 0) {
+              issue_kiter<0>(sa, sb, mj, it);
+            } else {
+              issue_kiter<kAccCols>(sa, sb, mj, it);
+            }
+            umma_commit(&ctl->empty[stage]);
+            if (it == mj.k_iters - 1) umma_commit(&ctl->acc_full[me]);
           }
-          umma_commit(&ctl->empty[stage]);
-          if (it == mj.k_iters - 1) umma_commit(&ctl->acc_full[me]);
+          __syncwarp();
           if (++slot == half) slot = 0;
         }
       }
@@ -415,9 +420,9 @@ conv_program_kernel(const __grid_constant__ ProgramParams params, const uint8_t*
         // warp 10 -> buffer 1 (alternate tiles).  One thread needs ~70-100 issue cycles per tcgen05.mma here (its
         // operands travel from ordinary to uniform registers behind an ELECT / R2UR / branch sequence), more than
         // the 32 / 64 cycles a 128 x 64 / 128 x 128 x 16 MMA executes: two issuers keep the tensor pipe fed.
-        if (lane == 0) mma_role(0);
+        mma_role(0);
       } else if (warp == kEpiWarps + 2) {
-        if (lane == 0) mma_role(1);
+        mma_role(1);
       } else {
         // ------------------------------------------------------------ epilogue (8 warps)
         const int flags = args.flags;

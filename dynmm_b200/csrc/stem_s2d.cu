@@ -14,15 +14,18 @@
 // its innermost extent (128 B) lets TMA deliver exactly that overlapping window per GEMM row, already in the
 // K-major SWIZZLE_128B layout tcgen05 wants: the im2col costs no instructions at all.
 //
-// GEMM per tile (11 x 11 stem pixels = 5 x 5 pooled outputs, M = 121 of 128 rows):  K = 4 kernel rows x 64,
+// One box load per plane brings the 10 s2d rows a tile touches; kernel row qy is the view 16 windows (2 KiB,
+// swizzle phase preserved) further into the same tile, so each s2d pixel is fetched once per plane, not 4 times.
+//
+// GEMM per tile (16 x 7 stem pixels, 15 used = 7 x 3 pooled outputs, M = 112 of 128 rows):  K = 4 kernel rows x 64,
 // N = 128 = [64 RGB | 64 depth] output channels (the RGB rows of the weight matrix are zero on the depth
 // channels and vice versa), fp32-grade through three bf16 products  hi*hi + hi*lo + lo*hi  into one TMEM
 // accumulator (the stem feeds the gate, whose hard decisions must equal the fp32 reference's).
 //
-// Persistent warp-specialised CTAs: warp 0 TMA producer (16 KiB slabs, ring of 5), warp 1 MMA issuer (48 UMMAs
-// 128x128x16 per tile, all operands in uniform registers: the CTA owns the whole TMEM, base 0), 8 epilogue warps
-// (TMEM -> BN + ReLU -> fuse -> shared memory -> max-pool -> NHWC stores, 16 channels at a time, double-buffered
-// accumulators so the epilogue of tile i overlaps the MMAs of tile i+1).  The split weights (128 KiB) stay in
+// Persistent warp-specialised CTAs: warp 0 TMA producer (2 x 20 KiB per tile, 2 tiles in flight), warp 1 MMA issuer (48 UMMAs
+// 128x128x16 per tile, the CTA owns the whole TMEM, base 0), two groups of 8 epilogue warps, one per accumulator buffer
+// (TMEM -> BN + ReLU -> fuse -> shared memory -> max-pool -> NHWC stores, 8 channels at a time), so the epilogues of
+// tiles i and i+1 and the MMAs of tile i+2 overlap.  The split weights (128 KiB) stay in
 // shared memory for the kernel's lifetime.
 #include "common.cuh"
 #include "tma_host.cuh"
@@ -30,29 +33,35 @@
 namespace dynmm {
 namespace stems2d {
 
-constexpr int kPT = 5;                      // pooled tile edge
-constexpr int kST = 2 * kPT + 1;            // stem tile edge (11)
-constexpr int kPos = kST * kST;             // 121 GEMM rows of 128
-constexpr int kSlab = 128 * 128;            // one [128 rows][64 bf16] operand slab (16 KiB)
-constexpr int kRing = 5;                    // A slabs in flight
-constexpr int kEpiWarps = 8;
+constexpr int kPW = 7, kPH = 3;             // pooled tile: 7 wide, 3 tall
+constexpr int kSW = 16;                     // stem columns fetched per tile (2*kPW + 1 = 15 used, +1 keeps views aligned)
+constexpr int kSH = 2 * kPH + 1;            // stem rows per tile (7)
+constexpr int kRows = kSW * kSH;            // 112 GEMM rows of 128, row = ly * 16 + lx
+constexpr int kFetchRows = kSH + 3;         // s2d rows a tile needs: kernel rows qy = 0..3 are views 16 rows apart
+constexpr int kPlane = kSW * kFetchRows * 128;   // 20 KiB: one plane (hi or lo) of a tile, [10][16] windows x 128 B
+constexpr int kStage = 2 * kPlane;          // hi + lo
+constexpr int kWSlab = 128 * 128;           // one [128 n][64 k] weight slab (16 KiB)
+constexpr int kRing = 2;                    // tiles in flight
+constexpr int kEpiWarps = 16;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
-constexpr int kPassCh = 16;                 // channels per epilogue pass
+constexpr int kPassCh = 8;                  // channels per epilogue pass
+constexpr int kGroupWarps = kEpiWarps / 2;  // two epilogue groups, one per accumulator buffer, work on alternate tiles
 // shared memory layout (after 1024-byte alignment)
 constexpr int kOffW = 0;                                   // [4 qy][hi, lo][128 n][128 B]
-constexpr int kOffA = kOffW + 8 * kSlab;                   // [kRing][128 rows][128 B]
-constexpr int kOffTile = kOffA + kRing * kSlab;            // s_fuse, s_dep: [121][16] fp32 each (swizzled)
-constexpr int kTileBytes = kPos * kPassCh * 4;             // 7744
-constexpr int kOffBn = kOffTile + 2 * kTileBytes;          // scale_rgb, shift_rgb, scale_d, shift_d (64 each)
+constexpr int kOffA = kOffW + 8 * kWSlab;                  // [kRing][hi, lo][160 rows][128 B]
+constexpr int kOffTile = kOffA + kRing * kStage;           // per group: s_fuse, s_dep: [112][8] fp32 each (swizzled)
+constexpr int kTileBytes = kRows * kPassCh * 4;            // 3584
+constexpr int kOffBn = kOffTile + 4 * kTileBytes;          // scale_rgb, shift_rgb, scale_d, shift_d (64 each)
 constexpr int kOffCtl = kOffBn + 256 * 4;
 constexpr int kSmemBytes = 1024 + kOffCtl + 256;
 static_assert(kSmemBytes <= 227 * 1024, "stem_s2d shared memory");
+static_assert(kPlane % 1024 == 0 && (kSW * 128) % 1024 == 0, "tap views must keep the 128B-swizzle phase");
 
 struct __align__(8) Ctl {
   uint64_t full[kRing];
   uint64_t empty[kRing];
-  uint64_t acc_full[2];
-  uint64_t acc_empty[2];
+  uint64_t acc_full[4];
+  uint64_t acc_empty[4];
   uint64_t w_full;
   uint32_t tmem_base;
 };
@@ -121,16 +130,16 @@ __global__ void s2d_pack_weights_kernel(const float* __restrict__ w_rgb, const f
   out[128 * 256 + i] = lo;
 }
 
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(taddr)
                : "memory");
 }
-// byte offset of (row, ch) in a [121][16] fp32 tile; 16-byte chunks XOR-swizzled so that 8 consecutive rows
-// writing the same chunk hit 8 different bank groups
+// byte offset of (row, ch) in a [112][8] fp32 tile (32 B per row); the two 16-byte halves swap every 4 rows so that
+// 8 consecutive rows writing the same half hit 8 different bank groups
 __device__ __forceinline__ uint32_t tile_off(int row, int ch) {
-  return row * 64 + ((((ch >> 2) ^ ((row >> 1) & 3)) << 4) | ((ch & 3) << 2));
+  return row * 32 + ((((ch >> 2) ^ ((row >> 2) & 1)) << 4) | ((ch & 3) << 2));
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -143,8 +152,6 @@ stem_s2d_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_w = smem + kOffW;
   uint8_t* s_a = smem + kOffA;
-  uint8_t* s_fuse = smem + kOffTile;
-  uint8_t* s_dep = s_fuse + kTileBytes;
   float* s_bn = reinterpret_cast<float*>(smem + kOffBn);
   Ctl* ctl = reinterpret_cast<Ctl*>(smem + kOffCtl);
 
@@ -160,16 +167,16 @@ stem_s2d_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
       mbar_init(&ctl->full[s], 1);
       mbar_init(&ctl->empty[s], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&ctl->acc_full[i], 1);
-      mbar_init(&ctl->acc_empty[i], kEpiWarps);
+      mbar_init(&ctl->acc_empty[i], kGroupWarps);
     }
     mbar_init(&ctl->w_full, 1);
     fence_mbar_init();
     // split weights: 8 slabs [128 n][64 k] = (qy, hi / lo), once per CTA
-    mbar_expect_tx(&ctl->w_full, 8 * kSlab);
+    mbar_expect_tx(&ctl->w_full, 8 * kWSlab);
     for (int qy = 0; qy < 4; ++qy)
-      for (int hl = 0; hl < 2; ++hl) tma_load_3d(s_w + (qy * 2 + hl) * kSlab, &map_w, &ctl->w_full, qy * 64, 0, hl);
+      for (int hl = 0; hl < 2; ++hl) tma_load_3d(s_w + (qy * 2 + hl) * kWSlab, &map_w, &ctl->w_full, qy * 64, 0, hl);
   }
   if (warp == 1) {
     tmem_alloc(&ctl->tmem_base, 512);      // the whole TMEM: base 0, MMA operands stay in uniform registers
@@ -188,30 +195,29 @@ stem_s2d_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
   if (ctl->tmem_base != 0) __trap();
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------ TMA producer: two box loads per tile
     if (lane == 0) {
       int slot = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n = tile / (tiles_x * tiles_y);
-        const int sy0 = 2 * (((tile / tiles_x) % tiles_y) * kPT) - 1, sx0 = 2 * ((tile % tiles_x) * kPT) - 1;
-        for (int qy = 0; qy < 4; ++qy) {
-          for (int hl = 0; hl < 2; ++hl) {
-            mbar_wait(&ctl->empty[slot], phase ^ 1);
-            mbar_expect_tx(&ctl->full[slot], kPos * 128);
-            // GEMM row (ly, lx) <- P[sy0 + ly + qy (+2 border, -2 kernel offset)][sx0 + lx .. + 3][16]
-            tma_load_4d(s_a + slot * kSlab, hl ? &map_lo : &map_hi, &ctl->full[slot], 0, sx0, sy0 + qy, n);
-            if (++slot == kRing) {
-              slot = 0;
-              phase ^= 1;
-            }
-          }
+        const int sy0 = 2 * (((tile / tiles_x) % tiles_y) * kPH) - 1, sx0 = 2 * ((tile % tiles_x) * kPW) - 1;
+        mbar_wait(&ctl->empty[slot], phase ^ 1);
+        mbar_expect_tx(&ctl->full[slot], kStage);
+        // window (wy, lx) of the box <- P[sy0 + wy][sx0 + lx .. + 3][16]  (border 2, kernel offset -2 cancel)
+        tma_load_4d(s_a + slot * kStage, &map_hi, &ctl->full[slot], 0, sx0, sy0, n);
+        tma_load_4d(s_a + slot * kStage + kPlane, &map_lo, &ctl->full[slot], 0, sx0, sy0, n);
+        if (++slot == kRing) {
+          slot = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer: the whole warp runs the loop
+    // converged, only the tcgen05 instructions sit under elect.sync (one lane looping inside `if (lane == 0)` cannot
+    // issue more than one UMMA per ~90 cycles, tools/umma_issue_bench.cu)
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
       const uint32_t a_base = smem_u32(s_a), w_base = smem_u32(s_w);
       mbar_wait(&ctl->w_full, 0);
@@ -220,66 +226,76 @@ stem_s2d_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
       uint32_t phase = 0;
       int local = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-        const uint32_t acc = local & 1;
-        mbar_wait(&ctl->acc_empty[acc], ((local >> 1) & 1) ^ 1);
+        const uint32_t acc = local & 3;       // four 128-column accumulators: the MMAs run up to 3 tiles ahead
+        mbar_wait(&ctl->acc_empty[acc], ((local >> 2) & 1) ^ 1);
+        mbar_wait(&ctl->full[slot], phase);
         tc_fence_after();
         const uint32_t d_tmem = acc * 128;
-        for (int qy = 0; qy < 4; ++qy) {
-          const uint32_t wh = w_base + (qy * 2) * kSlab, wl = wh + kSlab;
-          // hi slab: A_hi x W_hi and A_hi x W_lo
-          mbar_wait(&ctl->full[slot], phase);
-          tc_fence_after();
-          {
-            const uint32_t sa = a_base + slot * kSlab;
+        const uint32_t stage = a_base + slot * kStage;
+        if (elect_one()) {
+#pragma unroll
+          for (int qy = 0; qy < 4; ++qy) {
+            // kernel row qy: GEMM row (ly, lx) reads window (ly + qy, lx) = the same planes, 16 rows (2 KiB) further
+            const uint32_t ah = stage + qy * (kSW * 128), al = ah + kPlane;
+            const uint32_t wh = w_base + (qy * 2) * kWSlab, wl = wh + kWSlab;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              umma_bf16(d_tmem, umma_desc_sw128(sa) + 2 * k, umma_desc_sw128(wh) + 2 * k, idesc, (qy | k) != 0);
-              umma_bf16(d_tmem, umma_desc_sw128(sa) + 2 * k, umma_desc_sw128(wl) + 2 * k, idesc, 1u);
+              umma_bf16(d_tmem, umma_desc_sw128(ah) + 2 * k, umma_desc_sw128(wh) + 2 * k, idesc, (qy | k) != 0);
+              umma_bf16(d_tmem, umma_desc_sw128(ah) + 2 * k, umma_desc_sw128(wl) + 2 * k, idesc, 1u);
+              umma_bf16(d_tmem, umma_desc_sw128(al) + 2 * k, umma_desc_sw128(wh) + 2 * k, idesc, 1u);
             }
           }
           umma_commit(&ctl->empty[slot]);
-          if (++slot == kRing) {
-            slot = 0;
-            phase ^= 1;
-          }
-          // lo slab: A_lo x W_hi
-          mbar_wait(&ctl->full[slot], phase);
-          tc_fence_after();
-          {
-            const uint32_t sa = a_base + slot * kSlab;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(d_tmem, umma_desc_sw128(sa) + 2 * k, umma_desc_sw128(wh) + 2 * k, idesc, 1u);
-          }
-          umma_commit(&ctl->empty[slot]);
-          if (qy == 3) umma_commit(&ctl->acc_full[acc]);
-          if (++slot == kRing) {
-            slot = 0;
-            phase ^= 1;
-          }
+          umma_commit(&ctl->acc_full[acc]);
+        }
+        __syncwarp();
+        if (++slot == kRing) {
+          slot = 0;
+          phase ^= 1;
         }
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (8 warps)
-    const int et = tid - 64;                      // 0..255
+    // ------------------------------------------------------------ epilogue: 2 groups x 8 warps.  Group g owns
+    // accumulator buffer g, i.e. every other tile of this CTA, with its own staging tiles and named barrier: the
+    // barrier / TMEM-load / store latencies of one group hide behind the other group's work.
+    const int ewarp = warp - 2;
+    const int g = ewarp / kGroupWarps;            // group g: tiles with local index = g (mod 2)
+    const int gt = tid - 64 - g * 32 * kGroupWarps;   // 0..255 inside the group
     const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31
-    const int hh = (warp - 2) >> 2;               // which 8 of the 16 channels of a pass
-    const int row = quarter * 32 + lane;          // GEMM row = stem position (ly * 11 + lx)
-    int local = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-      const uint32_t acc = local & 1;
+    const int half = (ewarp % kGroupWarps) >> 2;  // which 4 of the 8 channels of a pass
+    const int row = quarter * 32 + lane;          // GEMM row = stem position ly * 16 + lx
+    uint8_t* s_fuse = smem + kOffTile + g * 2 * kTileBytes;
+    uint8_t* s_dep = s_fuse + kTileBytes;
+    // pooling: the first 42 threads of the group own (pooled pixel pp = gt >> 1 < 21) x (channel quad c4 of the pass);
+    // the nine window offsets inside the swizzled tiles never change
+    const int pp = gt >> 1, c4 = (gt & 1) * 4;
+    const int ply = pp / kPW, plx = pp - ply * kPW;
+    uint32_t woff[9];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) woff[dy * 3 + dx] = tile_off(min((2 * ply + dy) * kSW + 2 * plx + dx, kRows - 1), c4);
+    const uint32_t t_lane = static_cast<uint32_t>(quarter * 32) << 16;
+    for (int local = g; blockIdx.x + static_cast<long long>(local) * gridDim.x < total_tiles; local += 2) {
+      const int tile = blockIdx.x + local * gridDim.x;
       const int n = tile / (tiles_x * tiles_y);
-      const int py0 = ((tile / tiles_x) % tiles_y) * kPT, px0 = (tile % tiles_x) * kPT;
+      const int py0 = ((tile / tiles_x) % tiles_y) * kPH, px0 = (tile % tiles_x) * kPW;
       const int sy0 = 2 * py0 - 1, sx0 = 2 * px0 - 1;
-      mbar_wait(&ctl->acc_full[acc], (local >> 1) & 1);
+      const int py = py0 + ply, px = px0 + plx;
+      const bool item = pp < kPW * kPH && py < Hp && px < Wp;
+      // every pooling window of the tile lies inside the stem map: no bounds logic in the hot path
+      const bool interior = sy0 >= 0 && sy0 + kSH <= Hs && sx0 >= 0 && sx0 + 2 * kPW + 1 <= Ws;
+      const uint32_t acc = local & 3;             // group g reads buffers g and g + 2
+      mbar_wait(&ctl->acc_full[acc], (local >> 2) & 1);
       tc_fence_after();
-      const uint32_t t_row = (static_cast<uint32_t>(quarter * 32) << 16) + acc * 128;
+      const uint32_t t_row = t_lane + acc * 128;
+#pragma unroll 1
       for (int pass = 0; pass < 64 / kPassCh; ++pass) {
-        const int c = pass * kPassCh + hh * 8;    // first of this thread's 8 channels
-        uint32_t vr[8], vd[8];
-        tmem_ld8(t_row + c, vr);
-        tmem_ld8(t_row + 64 + c, vd);
+        const int c = pass * kPassCh + half * 4;  // first of this thread's 4 channels
+        uint32_t vr[4], vd[4];
+        tmem_ld4(t_row + c, vr);
+        tmem_ld4(t_row + 64 + c, vd);
         tmem_ld_wait();
         if (pass == 64 / kPassCh - 1) {
           // accumulator fully read: the MMAs of the tile after next may start
@@ -287,53 +303,68 @@ stem_s2d_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive(&ctl->acc_empty[acc]);
         }
-        if (row < kPos) {
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const int cc = c + q * 4;
-            float4 r, d;
-            r.x = fmaxf(fmaf(__uint_as_float(vr[q * 4 + 0]), s_bn[cc + 0], s_bn[64 + cc + 0]), 0.f);
-            r.y = fmaxf(fmaf(__uint_as_float(vr[q * 4 + 1]), s_bn[cc + 1], s_bn[64 + cc + 1]), 0.f);
-            r.z = fmaxf(fmaf(__uint_as_float(vr[q * 4 + 2]), s_bn[cc + 2], s_bn[64 + cc + 2]), 0.f);
-            r.w = fmaxf(fmaf(__uint_as_float(vr[q * 4 + 3]), s_bn[cc + 3], s_bn[64 + cc + 3]), 0.f);
-            d.x = fmaxf(fmaf(__uint_as_float(vd[q * 4 + 0]), s_bn[128 + cc + 0], s_bn[192 + cc + 0]), 0.f);
-            d.y = fmaxf(fmaf(__uint_as_float(vd[q * 4 + 1]), s_bn[128 + cc + 1], s_bn[192 + cc + 1]), 0.f);
-            d.z = fmaxf(fmaf(__uint_as_float(vd[q * 4 + 2]), s_bn[128 + cc + 2], s_bn[192 + cc + 2]), 0.f);
-            d.w = fmaxf(fmaf(__uint_as_float(vd[q * 4 + 3]), s_bn[128 + cc + 3], s_bn[192 + cc + 3]), 0.f);
-            r.x += d.x; r.y += d.y; r.z += d.z; r.w += d.w;      // rgb + depth (model_skip_mod_globalgate.py:258)
-            const uint32_t off = tile_off(row, hh * 8 + q * 4);
-            *reinterpret_cast<float4*>(s_fuse + off) = r;
-            *reinterpret_cast<float4*>(s_dep + off) = d;
-          }
+        if (row < kRows) {
+          const float4 sr = *reinterpret_cast<const float4*>(s_bn + c), br = *reinterpret_cast<const float4*>(s_bn + 64 + c);
+          const float4 sd = *reinterpret_cast<const float4*>(s_bn + 128 + c), bd = *reinterpret_cast<const float4*>(s_bn + 192 + c);
+          float4 r, d;
+          r.x = fmaxf(fmaf(__uint_as_float(vr[0]), sr.x, br.x), 0.f);
+          r.y = fmaxf(fmaf(__uint_as_float(vr[1]), sr.y, br.y), 0.f);
+          r.z = fmaxf(fmaf(__uint_as_float(vr[2]), sr.z, br.z), 0.f);
+          r.w = fmaxf(fmaf(__uint_as_float(vr[3]), sr.w, br.w), 0.f);
+          d.x = fmaxf(fmaf(__uint_as_float(vd[0]), sd.x, bd.x), 0.f);
+          d.y = fmaxf(fmaf(__uint_as_float(vd[1]), sd.y, bd.y), 0.f);
+          d.z = fmaxf(fmaf(__uint_as_float(vd[2]), sd.z, bd.z), 0.f);
+          d.w = fmaxf(fmaf(__uint_as_float(vd[3]), sd.w, bd.w), 0.f);
+          r.x += d.x; r.y += d.y; r.z += d.z; r.w += d.w;      // rgb + depth (model_skip_mod_globalgate.py:258)
+          const uint32_t off = tile_off(row, half * 4);
+          *reinterpret_cast<float4*>(s_fuse + off) = r;
+          *reinterpret_cast<float4*>(s_dep + off) = d;
         }
-        named_barrier(1, 32 * kEpiWarps);
-        // 3x3 / stride 2 / pad 1 max-pool of both tiles, 16 channels of 25 pooled pixels
-        for (int i = et; i < kPT * kPT * kPassCh; i += 32 * kEpiWarps) {
-          const int pp = i >> 4, ch = i & 15;
-          const int ly = pp / kPT, lx = pp % kPT;
-          const int py = py0 + ly, px = px0 + lx;
-          if (py >= Hp || px >= Wp) continue;
-          float mf = -INFINITY, md = -INFINITY;
+        named_barrier(1 + g, 32 * kGroupWarps);
+        // 3x3 / stride 2 / pad 1 max-pool of both tiles: 21 pooled pixels x 2 channel quads
+        if (item) {
+          float4 mf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), md = mf;
+          if (interior) {
 #pragma unroll
-          for (int dy = 0; dy < 3; ++dy) {
-            const int gy = sy0 + 2 * ly + dy;
-            if (gy < 0 || gy >= Hs) continue;
+            for (int t = 0; t < 9; ++t) {
+              const float4 a = *reinterpret_cast<const float4*>(s_fuse + woff[t]);
+              const float4 b = *reinterpret_cast<const float4*>(s_dep + woff[t]);
+              mf.x = fmaxf(mf.x, a.x); mf.y = fmaxf(mf.y, a.y); mf.z = fmaxf(mf.z, a.z); mf.w = fmaxf(mf.w, a.w);
+              md.x = fmaxf(md.x, b.x); md.y = fmaxf(md.y, b.y); md.z = fmaxf(md.z, b.z); md.w = fmaxf(md.w, b.w);
+            }
+          } else {
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-              const int gx = sx0 + 2 * lx + dx;
-              if (gx < 0 || gx >= Ws) continue;
-              const uint32_t off = tile_off((2 * ly + dy) * kST + 2 * lx + dx, ch);
-              mf = fmaxf(mf, *reinterpret_cast<const float*>(s_fuse + off));
-              md = fmaxf(md, *reinterpret_cast<const float*>(s_dep + off));
+            for (int dy = 0; dy < 3; ++dy) {
+              const int gy = sy0 + 2 * ply + dy;
+              if (gy < 0 || gy >= Hs) continue;
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                const int gx = sx0 + 2 * plx + dx;
+                if (gx < 0 || gx >= Ws) continue;
+                const float4 a = *reinterpret_cast<const float4*>(s_fuse + woff[dy * 3 + dx]);
+                const float4 b = *reinterpret_cast<const float4*>(s_dep + woff[dy * 3 + dx]);
+                mf.x = fmaxf(mf.x, a.x); mf.y = fmaxf(mf.y, a.y); mf.z = fmaxf(mf.z, a.z); mf.w = fmaxf(mf.w, a.w);
+                md.x = fmaxf(md.x, b.x); md.y = fmaxf(md.y, b.y); md.z = fmaxf(md.z, b.z); md.w = fmaxf(md.w, b.w);
+              }
             }
           }
-          const size_t o = ((static_cast<size_t>(n) * Hp + py) * Wp + px) * 64 + pass * kPassCh + ch;
-          if (rgb_f32) rgb_f32[o] = mf;
-          if (depth_f32) depth_f32[o] = md;
-          if (rgb_bf16) rgb_bf16[o] = __float2bfloat16_rn(mf);
-          if (depth_bf16) depth_bf16[o] = __float2bfloat16_rn(md);
+          const size_t o = ((static_cast<size_t>(n) * Hp + py) * Wp + px) * 64 + pass * kPassCh + c4;
+          if (rgb_f32) *reinterpret_cast<float4*>(rgb_f32 + o) = mf;
+          if (depth_f32) *reinterpret_cast<float4*>(depth_f32 + o) = md;
+          if (rgb_bf16) {
+            uint2 v;
+            v.x = pack_bf16(mf.x, mf.y);
+            v.y = pack_bf16(mf.z, mf.w);
+            *reinterpret_cast<uint2*>(rgb_bf16 + o) = v;
+          }
+          if (depth_bf16) {
+            uint2 v;
+            v.x = pack_bf16(md.x, md.y);
+            v.y = pack_bf16(md.z, md.w);
+            *reinterpret_cast<uint2*>(depth_bf16 + o) = v;
+          }
         }
-        named_barrier(1, 32 * kEpiWarps);       // the tiles are consumed before the next pass overwrites them
+        named_barrier(1 + g, 32 * kGroupWarps);   // the tiles are consumed before the next pass overwrites them
       }
     }
   }
@@ -398,7 +429,7 @@ extern "C" int dynmm_stem_s2d_fwd(const float* rgb, const float* depth, int b, i
   {
     const uint64_t dims[4] = {64, (uint64_t)Ws, (uint64_t)Hp2, (uint64_t)b};
     const uint64_t strides[3] = {32, (uint64_t)Wp2 * 32, (uint64_t)Hp2 * Wp2 * 32};
-    const uint32_t box[4] = {64, (uint32_t)kST, (uint32_t)kST, 1};
+    const uint32_t box[4] = {64, (uint32_t)kSW, (uint32_t)kFetchRows, 1};
     int rc = encode_map(&map_hi, p_hi, 4, dims, strides, box);
     if (rc) return rc;
     rc = encode_map(&map_lo, p_lo, 4, dims, strides, box);
@@ -417,7 +448,7 @@ extern "C" int dynmm_stem_s2d_fwd(const float* rgb, const float* depth, int b, i
   static cudaError_t attr_err =
       cudaFuncSetAttribute(stem_s2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   DYNMM_CUDA(attr_err);
-  const int tiles_x = ceil_div(Wp, kPT), tiles_y = ceil_div(Hp, kPT);
+  const int tiles_x = ceil_div(Wp, kPW), tiles_y = ceil_div(Hp, kPH);
   const long long total = 1LL * tiles_x * tiles_y * b;
   DYNMM_CHECK_ARG(total < (1LL << 30), "stem_s2d: too many tiles");
   const int grid = (int)(total < num_sms() ? total : num_sms());

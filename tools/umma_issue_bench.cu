@@ -9,6 +9,7 @@
 namespace dynmm { void set_error(const char*, ...) {} int num_sms() { return 148; } }
 using namespace dynmm;
 
+template <bool kElect>
 __global__ void __launch_bounds__(128, 1) bench_kernel(int n, int iters, int commit_every, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -22,7 +23,10 @@ __global__ void __launch_bounds__(128, 1) bench_kernel(int n, int iters, int com
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  if (threadIdx.x == 0) {
+  // kElect = false: one thread runs the whole loop (`if (lane == 0)`), the pattern of conv_igemm.cu before this
+  // measurement; kElect = true: the whole warp runs the loop converged and only the tcgen05 instructions sit under
+  // elect.sync (the CUTLASS pattern) -- the compiler then needs no ELECT/BRA.U.ANY loop around every UTCHMMA.
+  if (kElect ? (threadIdx.x < 32) : (threadIdx.x == 0)) {
     const uint32_t idesc = umma_idesc_bf16(128, n);
     const uint32_t sa = smem_u32(smem), sb = sa + 16384;
     uint32_t phase = 0;
@@ -30,19 +34,22 @@ __global__ void __launch_bounds__(128, 1) bench_kernel(int n, int iters, int com
     int since = 0;
     for (int it = 0; it < iters; ++it) {
       const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sb);
+      if (!kElect || elect_one()) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(tmem + (it & 1) * 256, da + k * 2, db + k * 2, idesc, 1);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem + (it & 1) * 256, da + k * 2, db + k * 2, idesc, 1);
+      }
+      if (kElect) __syncwarp();
       if (++since == commit_every) {
-        umma_commit(&bar);
+        if (!kElect || elect_one()) umma_commit(&bar);
         mbar_wait(&bar, phase);
         phase ^= 1;
         since = 0;
       }
     }
-    umma_commit(&bar);
+    if (!kElect || elect_one()) umma_commit(&bar);
     mbar_wait(&bar, phase);
     long long t1 = clock64();
-    out[blockIdx.x] = t1 - t0;
+    if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
   }
   tc_fence_before();
   __syncthreads();
@@ -52,12 +59,15 @@ __global__ void __launch_bounds__(128, 1) bench_kernel(int n, int iters, int com
 int main() {
   long long* d;
   cudaMalloc(&d, 148 * sizeof(long long));
-  cudaFuncSetAttribute(bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(bench_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(bench_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   const int iters = 2000;
+  for (int elect = 0; elect < 2; ++elect)
   for (int commit_every : {iters + 1, 8, 1}) {
     for (int n : {32, 64, 128, 256}) {
       for (int rep = 0; rep < 2; ++rep) {
-        bench_kernel<<<148, 128, 16384 + 32768 + 2048>>>(n, iters, commit_every, d);
+        if (elect) bench_kernel<true><<<148, 128, 16384 + 32768 + 2048>>>(n, iters, commit_every, d);
+        else bench_kernel<false><<<148, 128, 16384 + 32768 + 2048>>>(n, iters, commit_every, d);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
       }
@@ -67,7 +77,7 @@ int main() {
       for (long long v : h) avg += v;
       avg /= 148;
       const double per = avg / (iters * 4.0);
-      printf("N=%3d commit every %4d k-chunks: %.1f cycles per UMMA (128x%dx16), %.0f MAC/clk/SM = %.0f%% of 4096\n", n,
+      printf("%s N=%3d commit every %4d k-chunks: %.1f cycles per UMMA (128x%dx16), %.0f MAC/clk/SM = %.0f%% of 4096\n", elect ? "elect.sync" : "lane0     ", n,
              commit_every, per, n, 128.0 * n * 16 / per, 100.0 * 128.0 * n * 16 / per / 4096);
     }
   }
