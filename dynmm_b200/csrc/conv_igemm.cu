@@ -121,8 +121,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   if (threadIdx.x == 0) DYNMM_TRACE(1);
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------ TMA producer (whole warp converged, the TMA /
+    // mbarrier-arrive instructions under elect.sync: like the MMA issuer, a lone lane looping inside `if (lane == 0)`
+    // pays an ELECT / BRA.U.ANY loop around every UTMALDG)
+    {
       const CUtensorMap* maps[4] = {&map_a0, &map_a1, &map_a2, &map_a3};
       // TMA always delivers the full box (out-of-bounds elements arrive as zeros)
       const uint32_t a_tx = args.a_rows * kBlockK * 2;
@@ -140,26 +142,32 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           for (int kc = 0; kc < args.k_chunks; ++kc) {
             mbar_wait(&ctl->empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * args.stage_bytes;
-            mbar_expect_tx(&ctl->full[stage], tx_bytes);
-            tma_load_4d(sa, maps[gp.map], &ctl->full[stage], kc * kBlockK, t.x1 + gp.o1, t.x2 + gp.o2, n_in);
-            if (!args.b_resident)
-              tma_load_3d(sa + args.a_bytes, &map_b, &ctl->full[stage], kc * kBlockK, t.c0, g * args.tpg);
-            if (tile == (int)blockIdx.x && g == 0 && kc == 0) DYNMM_TRACE(2);
+            if (elect_one()) {
+              mbar_expect_tx(&ctl->full[stage], tx_bytes);
+              tma_load_4d(sa, maps[gp.map], &ctl->full[stage], kc * kBlockK, t.x1 + gp.o1, t.x2 + gp.o2, n_in);
+              if (!args.b_resident)
+                tma_load_3d(sa + args.a_bytes, &map_b, &ctl->full[stage], kc * kBlockK, t.c0, g * args.tpg);
+            }
+            __syncwarp();
+            if (lane == 0 && tile == (int)blockIdx.x && g == 0 && kc == 0) DYNMM_TRACE(2);
             if (++stage == args.stages) {
               stage = 0;
               phase ^= 1;
             }
           }
         }
-        if (tile == (int)blockIdx.x) DYNMM_TRACE(11);
+        if (lane == 0 && tile == (int)blockIdx.x) DYNMM_TRACE(11);
         // residual sub-tiles of this tile, consumed by the epilogue while the next tile's MMAs run
         if (aux_on && t.n0 + args.bn <= active) {
           const int n_res = args.res_map ? args.res_map[t.n0] : t.n0;
           for (int sub = 0; sub < n_sub; ++sub) {
             mbar_wait(&ctl->aux_empty[aux], aux_phase ^ 1);
-            mbar_expect_tx(&ctl->aux_full[aux], sub_tx);
-            tma_load_4d(smem_aux + aux * kSubBytes, &map_res, &ctl->aux_full[aux], t.c0 + sub * 64, t.x1, t.x2,
-                        n_res);
+            if (elect_one()) {
+              mbar_expect_tx(&ctl->aux_full[aux], sub_tx);
+              tma_load_4d(smem_aux + aux * kSubBytes, &map_res, &ctl->aux_full[aux], t.c0 + sub * 64, t.x1, t.x2,
+                          n_res);
+            }
+            __syncwarp();
             if (++aux == args.aux_slots) {
               aux = 0;
               aux_phase ^= 1;
@@ -293,10 +301,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
           if (leader && local == 0 && sub == 0) DYNMM_TRACE(14);
           fence_async_smem();                   // staging writes -> visible to the TMA engine
-          if (leader) bulk_wait_read<0>();      // the previous store (other buffer) has drained its smem
+          // bulk async-groups belong to the committing thread: the first epilogue warp's elected lane issues,
+          // commits and waits for every store (elect.sync under a converged warp: no ELECT loop around UTMASTG)
+          if (ewarp == 0 && elect_one()) bulk_wait_read<0>();   // the previous store (other buffer) has drained its smem
           named_barrier(1, 32 * kEpiWarps);
           if (leader && local == 0 && sub == 0) DYNMM_TRACE(15);
-          if (leader) {
+          if (ewarp == 0 && elect_one()) {
             tma_store_4d(&map_out, smem_stage_out + sbuf * kSubBytes, t.c0 + sub * 64, t.x1, t.x2, t.n0);
             bulk_commit();
           }
@@ -312,9 +322,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       if (lane == 0) mbar_arrive(&ctl->acc_empty[acc]);
       if (leader && local == 0) DYNMM_TRACE(6);
     }
+    if (leader) DYNMM_TRACE(7);
+    if (ewarp == 0 && elect_one()) bulk_wait<0>();
     if (leader) {
-      DYNMM_TRACE(7);
-      bulk_wait<0>();
       DYNMM_TRACE(8);
       if (args.trace) args.trace[blockIdx.x * 16 + 10] = local;
     }

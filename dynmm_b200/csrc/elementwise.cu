@@ -2,6 +2,8 @@
 // row compaction, layout conversion, learned 2x upsampling and pyramid pooling.
 // All kernels are coalesced, 16-byte vectorised where the layout allows, and sized
 // as a multiple of the SM count with grid-stride loops.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dynmm {
@@ -265,6 +267,83 @@ __global__ void upsample2x_dw_nhwc_kernel(const __nv_bfloat16* __restrict__ in, 
     *reinterpret_cast<uint4*>(out + o) = ov;
   }
 }
+// Strip variant of the NHWC kernel (used when c % 4 == 0): a thread owns 4 channels of one INPUT column and walks
+// down a strip of input rows with a 3x3 sliding window in registers.  Per input pixel it loads 3 x 8 bytes (the
+// new row), produces the 2x2 output block with the 16 parity stencils precombined from the 3x3 weights once per
+// thread (16 FMAs per channel instead of 36) and stores 4 x 8 bytes; the per-pixel kernel above re-loads 9 inputs
+// and 18 weight vectors for every 16-byte store.
+constexpr int kUpStripRows = 8;
+template <bool kSkip>
+__global__ void __launch_bounds__(256)
+upsample2x_dw_nhwc_strip_kernel(const __nv_bfloat16* __restrict__ in, int h, int w, int c,
+                                const float* __restrict__ wgt, const float* __restrict__ bias,
+                                const __nv_bfloat16* __restrict__ skip, __nv_bfloat16* __restrict__ out) {
+  const int cg = c >> 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= w * cg) return;
+  const int c4 = (idx % cg) * 4, x = idx / cg;
+  const int s = blockIdx.z;
+  const int y0 = blockIdx.y * kUpStripRows, y1 = min(y0 + kUpStripRows, h);
+  const int H = 2 * h, W = 2 * w;
+  // parity stencils (see upsample2x_dw_to_nchw_kernel): st[p][t][ch], p = 2*(Y&1) + (X&1), t = the 4 inputs of the block
+  float st[4][4][4], b4[4];
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    float k[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) k[t] = __ldg(wgt + t * c + c4 + ch);
+    b4[ch] = bias ? __ldg(bias + c4 + ch) : 0.f;
+    st[0][0][ch] = k[0];               st[0][1][ch] = k[1] + k[2];        st[0][2][ch] = k[3] + k[6];        st[0][3][ch] = (k[4] + k[5]) + (k[7] + k[8]);
+    st[1][0][ch] = k[0] + k[1];        st[1][1][ch] = k[2];               st[1][2][ch] = (k[3] + k[4]) + (k[6] + k[7]); st[1][3][ch] = k[5] + k[8];
+    st[2][0][ch] = k[0] + k[3];        st[2][1][ch] = (k[1] + k[2]) + (k[4] + k[5]); st[2][2][ch] = k[6];    st[2][3][ch] = k[7] + k[8];
+    st[3][0][ch] = (k[0] + k[1]) + (k[3] + k[4]); st[3][1][ch] = k[2] + k[5]; st[3][2][ch] = k[6] + k[7];    st[3][3][ch] = k[8];
+  }
+  const __nv_bfloat16* base = in + static_cast<size_t>(s) * h * w * c + c4;
+  auto load_row = [&](int y, float (&r)[3][4]) {        // columns x-1, x, x+1 of input row y (zeros outside)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int xx = x + j - 1;
+      uint2 v = make_uint2(0u, 0u);
+      if (y >= 0 && y < h && xx >= 0 && xx < w) v = __ldg(reinterpret_cast<const uint2*>(base + (static_cast<size_t>(y) * w + xx) * c));
+      r[j][0] = bf16_lo(v.x); r[j][1] = bf16_hi(v.x); r[j][2] = bf16_lo(v.y); r[j][3] = bf16_hi(v.y);
+    }
+  };
+  float up[3][4], mid[3][4], dn[3][4];
+  load_row(y0 - 1, up);
+  load_row(y0, mid);
+  for (int y = y0; y < y1; ++y) {
+    load_row(y + 1, dn);
+    float o[4][4];      // [parity][ch]
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      // (2y, 2x): (y-1,x-1) (y-1,x) (y,x-1) (y,x)      (2y, 2x+1): (y-1,x) (y-1,x+1) (y,x) (y,x+1)
+      o[0][ch] = fmaf(st[0][3][ch], mid[1][ch], fmaf(st[0][2][ch], mid[0][ch], fmaf(st[0][1][ch], up[1][ch], fmaf(st[0][0][ch], up[0][ch], b4[ch]))));
+      o[1][ch] = fmaf(st[1][3][ch], mid[2][ch], fmaf(st[1][2][ch], mid[1][ch], fmaf(st[1][1][ch], up[2][ch], fmaf(st[1][0][ch], up[1][ch], b4[ch]))));
+      // (2y+1, 2x): (y,x-1) (y,x) (y+1,x-1) (y+1,x)    (2y+1, 2x+1): (y,x) (y,x+1) (y+1,x) (y+1,x+1)
+      o[2][ch] = fmaf(st[2][3][ch], dn[1][ch], fmaf(st[2][2][ch], dn[0][ch], fmaf(st[2][1][ch], mid[1][ch], fmaf(st[2][0][ch], mid[0][ch], b4[ch]))));
+      o[3][ch] = fmaf(st[3][3][ch], dn[2][ch], fmaf(st[3][2][ch], dn[1][ch], fmaf(st[3][1][ch], mid[2][ch], fmaf(st[3][0][ch], mid[1][ch], b4[ch]))));
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const size_t oo = ((static_cast<size_t>(s) * H + 2 * y + (p >> 1)) * W + 2 * x + (p & 1)) * c + c4;
+      if (kSkip) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(skip + oo));
+        o[p][0] += bf16_lo(v.x); o[p][1] += bf16_hi(v.x); o[p][2] += bf16_lo(v.y); o[p][3] += bf16_hi(v.y);
+      }
+      uint2 ov;
+      ov.x = pack_bf16(o[p][0], o[p][1]);
+      ov.y = pack_bf16(o[p][2], o[p][3]);
+      *reinterpret_cast<uint2*>(out + oo) = ov;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        up[j][ch] = mid[j][ch];
+        mid[j][ch] = dn[j][ch];
+      }
+  }
+}
 // Final upsample: NHWC bf16 in -> NCHW fp32 out (the module's return layout; 393 MB of stores at
 // 8x40x480x640, the HBM-bound tail of the forward).  A CTA stages an 8x32 input tile (+1 halo) for
 // all channels in shared memory as fp32 [c][row][col]; then one warp per (channel, output row)
@@ -519,10 +598,26 @@ extern "C" int dynmm_upsample2x_dw3x3(const void* in, int n, int h, int w, int c
                   "upsample2x: either the NHWC output, or the NCHW logits and/or the arg-max labels");
   DYNMM_CHECK_ARG(!labels || c <= 256, "upsample2x: labels are uint8");
   if (out_nhwc_bf16) {
-    const long long total = 1LL * n * 4 * h * w * (c / 8);
-    upsample2x_dw_nhwc_kernel<<<grid_for(total, 256, 16), 256, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(in), n, h, w, c, weight, bias, static_cast<const __nv_bfloat16*>(skip),
-        static_cast<__nv_bfloat16*>(out_nhwc_bf16));
+    static const bool use_strip = [] {
+      const char* e = getenv("DYNMM_UPSAMPLE");
+      return !(e && e[0] == 'p');           // DYNMM_UPSAMPLE=pixel: the one-thread-per-output-pixel kernel
+    }();
+    if (use_strip && n <= 65535) {
+      dim3 grid(ceil_div(w * (c / 4), 256), ceil_div(h, kUpStripRows), n);
+      if (skip) {
+        upsample2x_dw_nhwc_strip_kernel<true><<<grid, 256, 0, stream>>>(
+            static_cast<const __nv_bfloat16*>(in), h, w, c, weight, bias, static_cast<const __nv_bfloat16*>(skip),
+            static_cast<__nv_bfloat16*>(out_nhwc_bf16));
+      } else {
+        upsample2x_dw_nhwc_strip_kernel<false><<<grid, 256, 0, stream>>>(
+            static_cast<const __nv_bfloat16*>(in), h, w, c, weight, bias, nullptr, static_cast<__nv_bfloat16*>(out_nhwc_bf16));
+      }
+    } else {
+      const long long total = 1LL * n * 4 * h * w * (c / 8);
+      upsample2x_dw_nhwc_kernel<<<grid_for(total, 256, 16), 256, 0, stream>>>(
+          static_cast<const __nv_bfloat16*>(in), n, h, w, c, weight, bias, static_cast<const __nv_bfloat16*>(skip),
+          static_cast<__nv_bfloat16*>(out_nhwc_bf16));
+    }
   } else {
     DYNMM_CHECK_ARG(!skip, "upsample2x: skip is only supported for the NHWC output");
     const int smem = (c * (kUpTy + 2) * (kUpTx + 3) + c * 16) * (int)sizeof(float);
