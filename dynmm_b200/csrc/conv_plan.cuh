@@ -320,10 +320,20 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
     tile_n = p->tile_n;
     if (tile_n == 0) {
       // multiples of 64 channels (TMA epilogue); widest tile that still gives every SM a tile
+      // channel tile of 64, 128 or 256: fewest MMA cycles on the critical CTA.  A 128 x N x 16 UMMA takes ~64
+      // cycles for every N <= 128 and 128 cycles for N = 256 (tools/umma_issue_bench.cu), so the estimate is
+      // rounds x (1 or 2); ties go to the narrower tile (more CTAs busy, shorter epilogues).
       const int c64 = (c_out_pad + 63) / 64 * 64;
-      tile_n = c64 < 256 ? c64 : 256;
-      if (tile_n == 192) tile_n = 64;
-      while (tile_n > 64 && m_tiles * ceil_div(c_out_pad, tile_n) < sms) tile_n /= 2;
+      tile_n = 64;
+      long long best = -1;
+      for (int cand = 64; cand <= 256 && cand <= c64 && c64 != 192; cand *= 2) {
+        const long long tiles = 1LL * m_tiles * ceil_div(c_out_pad, cand);
+        const long long est = ceil_div_ll(tiles, sms) * (cand > 128 ? 2 : 1);
+        if (best < 0 || est < best) {
+          best = est;
+          tile_n = cand;
+        }
+      }
     }
     DYNMM_CHECK_ARG(tile_n >= 16 && tile_n <= 256 && tile_n % 16 == 0, "conv_igemm: tile_n %d", tile_n);
     a.tile_n = tile_n;
