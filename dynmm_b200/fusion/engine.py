@@ -391,13 +391,21 @@ class FusionEngine:
             weight = torch.zeros(b, 5)
             weight[range(b), idx] = 1
             weight = weight.to(self.dev)
-        else:
-            gw = self.gate
-            logits = ops.global_gate_logits(r32, d32, gw["w1"], gw["s1"], gw["b1"], gw["w2"], gw["s2"], gw["b2"],
-                                            gw["wfc"])
-            weight, _, _ = ops.diffsoftmax_fwd(logits, temp, hard_gate)
-            self.launches += 4
-        plan = ops.gate_plan(weight, hist=hist)
+        # The learned gate (GlobalGate + DiffSoftmax + plan, ~0.1 ms of small kernels) is only needed by the depth
+        # encoder and by the gated convolution that ENDS RGB stage 1: it runs at the head of the side stream, under
+        # the first RGB convolutions, instead of in front of both encoders.
+        gate_on_side = learned and not self.use_programs
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side if gate_on_side else main):
+            if learned:
+                gw = self.gate
+                logits = ops.global_gate_logits(r32, d32, gw["w1"], gw["s1"], gw["b1"], gw["w2"], gw["s2"], gw["b2"],
+                                                gw["wfc"])
+                weight, _, _ = ops.diffsoftmax_fwd(logits, temp, hard_gate)
+                self.launches += 4
+            plan = ops.gate_plan(weight, hist=hist)
         self.launches += 1
         keep += [r32, d32, r16, d16, weight, plan]
 
@@ -409,9 +417,10 @@ class FusionEngine:
             fused, skips = self._encoder_program(r16, d16, plan, cat, keep)
         else:
             # ---- depth encoder on the side stream, in slot order, prefix-counted
-            fork = torch.cuda.Event()
-            fork.record(main)
-            side.wait_event(fork)
+            if not gate_on_side:
+                fork = torch.cuda.Event()
+                fork.record(main)
+                side.wait_event(fork)
             done = [torch.cuda.Event() for _ in range(4)]
             depth_out = []
             with torch.cuda.stream(side):

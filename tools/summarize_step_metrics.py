@@ -37,12 +37,12 @@ out.append("")
 out.append(f"conv_igemm_kernel (all variants): {conv['n']} launches, {conv['t']*1e6:.1f} us ({100*conv['t']/tot:.1f}% of GPU time), "
            f"DRAM {conv['rd']/1e6:.1f} MB read + {conv['wr']/1e6:.1f} MB written = {(conv['rd']+conv['wr'])/conv['n']/1e6:.2f} MB per launch, "
            f"L2 traffic {conv['l2']/1e6:.0f} MB, time-weighted tensor pipe active {conv['tw']/conv['t']:.1f}%")
-open("profiles/r1_step_metrics_summary.txt", "w").write("\n".join(out) + "\n")
+open(src.replace(".csv", "_summary.txt"), "w").write("\n".join(out) + "\n")
 json.dump({"kernel": "conv_igemm_kernel", "launches_per_step": conv["n"], "dram_bytes_per_launch": (conv["rd"] + conv["wr"]) / conv["n"],
            "dram_read_bytes_per_step": conv["rd"], "dram_write_bytes_per_step": conv["wr"], "l2_bytes_per_step": conv["l2"],
            "tensor_pipe_active_pct_time_weighted": conv["tw"] / conv["t"], "kernel_time_s_per_step_serialized": conv["t"],
            "share_of_gpu_time": conv["t"] / tot,
-           "source": "profiles/r1_step_metrics.csv (ncu --metrics gpu__time_duration.sum,dram__bytes_*,lts__t_bytes,sm__pipe_tensor_cycles_active; "
+           "source": src + " (ncu --metrics gpu__time_duration.sum,dram__bytes_*,lts__t_bytes,sm__pipe_tensor_cycles_active; "
                      "one steady-state step of the bench workload, eager launches, B=8 480x640, branches [0,4,0,0,4,4,4,0])"},
-          open("profiles/r1_conv_traffic.json", "w"), indent=1)
+          open(src.replace("step_metrics.csv", "conv_traffic.json"), "w"), indent=1)
 print("\n".join(out))
