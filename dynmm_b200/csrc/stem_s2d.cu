@@ -24,8 +24,8 @@
 //
 // Persistent warp-specialised CTAs: warp 0 TMA producer (2 x 20 KiB per tile, 2 tiles in flight), warp 1 MMA issuer (48 UMMAs
 // 128x128x16 per tile, the CTA owns the whole TMEM, base 0), two groups of 8 epilogue warps, one per accumulator buffer
-// (TMEM -> BN + ReLU -> fuse -> shared memory -> max-pool -> NHWC stores, 8 channels at a time), so the epilogues of
-// tiles i and i+1 and the MMAs of tile i+2 overlap.  The split weights (128 KiB) stay in
+// (TMEM -> BN + ReLU -> fuse -> horizontal 3-max by warp shuffles -> 7x7 row maxima in shared memory -> vertical 3-max ->
+// NHWC stores, 16 channels at a time), so the epilogues of tiles i and i+1 and the MMAs of tile i+2 overlap.  The split weights (128 KiB) stay in
 // shared memory for the kernel's lifetime.
 #include "common.cuh"
 #include "tma_host.cuh"
@@ -44,13 +44,13 @@ constexpr int kWSlab = 128 * 128;           // one [128 n][64 k] weight slab (16
 constexpr int kRing = 2;                    // tiles in flight
 constexpr int kEpiWarps = 16;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
-constexpr int kPassCh = 8;                  // channels per epilogue pass
+constexpr int kPassCh = 16;                 // channels per epilogue pass
 constexpr int kGroupWarps = kEpiWarps / 2;  // two epilogue groups, one per accumulator buffer, work on alternate tiles
 // shared memory layout (after 1024-byte alignment)
 constexpr int kOffW = 0;                                   // [4 qy][hi, lo][128 n][128 B]
 constexpr int kOffA = kOffW + 8 * kWSlab;                  // [kRing][hi, lo][160 rows][128 B]
-constexpr int kOffTile = kOffA + kRing * kStage;           // per group: s_fuse, s_dep: [112][8] fp32 each (swizzled)
-constexpr int kTileBytes = kRows * kPassCh * 4;            // 3584
+constexpr int kOffTile = kOffA + kRing * kStage;           // per group: row-maxima of the fused / depth maps,
+constexpr int kTileBytes = kSH * kPW * kPassCh * 4;        // [7 stem rows][7 pooled cols][16 ch] fp32 = 3136 B each
 constexpr int kOffBn = kOffTile + 4 * kTileBytes;          // scale_rgb, shift_rgb, scale_d, shift_d (64 each)
 constexpr int kOffCtl = kOffBn + 256 * 4;
 constexpr int kSmemBytes = 1024 + kOffCtl + 256;
@@ -136,10 +136,14 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
                : "r"(taddr)
                : "memory");
 }
-// byte offset of (row, ch) in a [112][8] fp32 tile (32 B per row); the two 16-byte halves swap every 4 rows so that
-// 8 consecutive rows writing the same half hit 8 different bank groups
-__device__ __forceinline__ uint32_t tile_off(int row, int ch) {
-  return row * 32 + ((((ch >> 2) ^ ((row >> 2) & 1)) << 4) | ((ch & 3) << 2));
+// byte offset of (stem row ly, pooled column plx, channel ch) in a [7][7][16] fp32 tile of horizontal maxima
+__device__ __forceinline__ uint32_t h_off(int ly, int plx, int ch) { return ((ly * kPW + plx) * kPassCh + ch) * 4; }
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -256,26 +260,24 @@ stem_s2d_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue: 2 groups x 8 warps.  Group g owns
-    // accumulator buffer g, i.e. every other tile of this CTA, with its own staging tiles and named barrier: the
-    // barrier / TMEM-load / store latencies of one group hide behind the other group's work.
+    // ------------------------------------------------------------ epilogue: 2 groups x 8 warps.  Group g owns the
+    // tiles with local index = g (mod 2) (accumulators g and g + 2), with its own staging tiles and named barrier.
+    // The 3x3 / stride-2 max-pool is separable: a warp holds two stem rows of 16 columns (TMEM lane = ly * 16 + lx),
+    // so the horizontal 3-max is two shuffles; only the 7 x 7 row-maxima per channel go through shared memory and the
+    // pooling threads read 3 values per output instead of 9.
     const int ewarp = warp - 2;
-    const int g = ewarp / kGroupWarps;            // group g: tiles with local index = g (mod 2)
+    const int g = ewarp / kGroupWarps;
     const int gt = tid - 64 - g * 32 * kGroupWarps;   // 0..255 inside the group
     const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31
-    const int half = (ewarp % kGroupWarps) >> 2;  // which 4 of the 8 channels of a pass
+    const int half = (ewarp % kGroupWarps) >> 2;  // which 8 of the 16 channels of a pass
     const int row = quarter * 32 + lane;          // GEMM row = stem position ly * 16 + lx
-    uint8_t* s_fuse = smem + kOffTile + g * 2 * kTileBytes;
-    uint8_t* s_dep = s_fuse + kTileBytes;
-    // pooling: the first 42 threads of the group own (pooled pixel pp = gt >> 1 < 21) x (channel quad c4 of the pass);
-    // the nine window offsets inside the swizzled tiles never change
-    const int pp = gt >> 1, c4 = (gt & 1) * 4;
+    const int ly = row >> 4, lx = row & 15;
+    const bool writer = ly < kSH && (lx & 1) == 0 && lx <= 2 * (kPW - 1);
+    uint8_t* s_hf = smem + kOffTile + g * 2 * kTileBytes;     // horizontal maxima of rgb + depth
+    uint8_t* s_hd = s_hf + kTileBytes;                        // ... of depth
+    // pooling: the first 84 threads of the group own (pooled pixel pp = gt >> 2 < 21) x (channel quad c4 of the pass)
+    const int pp = gt >> 2, c4 = (gt & 3) * 4;
     const int ply = pp / kPW, plx = pp - ply * kPW;
-    uint32_t woff[9];
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) woff[dy * 3 + dx] = tile_off(min((2 * ply + dy) * kSW + 2 * plx + dx, kRows - 1), c4);
     const uint32_t t_lane = static_cast<uint32_t>(quarter * 32) << 16;
     for (int local = g; blockIdx.x + static_cast<long long>(local) * gridDim.x < total_tiles; local += 2) {
       const int tile = blockIdx.x + local * gridDim.x;
@@ -284,18 +286,19 @@ stem_s2d_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
       const int sy0 = 2 * py0 - 1, sx0 = 2 * px0 - 1;
       const int py = py0 + ply, px = px0 + plx;
       const bool item = pp < kPW * kPH && py < Hp && px < Wp;
-      // every pooling window of the tile lies inside the stem map: no bounds logic in the hot path
-      const bool interior = sy0 >= 0 && sy0 + kSH <= Hs && sx0 >= 0 && sx0 + 2 * kPW + 1 <= Ws;
+      // stem positions outside the map (or the unused 8th row / 16th column) never win a maximum
+      const int gy = sy0 + ly, gx = sx0 + lx;
+      const bool inside = ly < kSH && gy >= 0 && gy < Hs && gx >= 0 && gx < Ws;
       const uint32_t acc = local & 3;             // group g reads buffers g and g + 2
       mbar_wait(&ctl->acc_full[acc], (local >> 2) & 1);
       tc_fence_after();
       const uint32_t t_row = t_lane + acc * 128;
 #pragma unroll 1
       for (int pass = 0; pass < 64 / kPassCh; ++pass) {
-        const int c = pass * kPassCh + half * 4;  // first of this thread's 4 channels
-        uint32_t vr[4], vd[4];
-        tmem_ld4(t_row + c, vr);
-        tmem_ld4(t_row + 64 + c, vd);
+        const int c = pass * kPassCh + half * 8;  // first of this thread's 8 channels
+        uint32_t vr[8], vd[8];
+        tmem_ld8(t_row + c, vr);
+        tmem_ld8(t_row + 64 + c, vd);
         tmem_ld_wait();
         if (pass == 64 / kPassCh - 1) {
           // accumulator fully read: the MMAs of the tile after next may start
@@ -303,50 +306,49 @@ stem_s2d_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive(&ctl->acc_empty[acc]);
         }
-        if (row < kRows) {
-          const float4 sr = *reinterpret_cast<const float4*>(s_bn + c), br = *reinterpret_cast<const float4*>(s_bn + 64 + c);
-          const float4 sd = *reinterpret_cast<const float4*>(s_bn + 128 + c), bd = *reinterpret_cast<const float4*>(s_bn + 192 + c);
-          float4 r, d;
-          r.x = fmaxf(fmaf(__uint_as_float(vr[0]), sr.x, br.x), 0.f);
-          r.y = fmaxf(fmaf(__uint_as_float(vr[1]), sr.y, br.y), 0.f);
-          r.z = fmaxf(fmaf(__uint_as_float(vr[2]), sr.z, br.z), 0.f);
-          r.w = fmaxf(fmaf(__uint_as_float(vr[3]), sr.w, br.w), 0.f);
-          d.x = fmaxf(fmaf(__uint_as_float(vd[0]), sd.x, bd.x), 0.f);
-          d.y = fmaxf(fmaf(__uint_as_float(vd[1]), sd.y, bd.y), 0.f);
-          d.z = fmaxf(fmaf(__uint_as_float(vd[2]), sd.z, bd.z), 0.f);
-          d.w = fmaxf(fmaf(__uint_as_float(vd[3]), sd.w, bd.w), 0.f);
-          r.x += d.x; r.y += d.y; r.z += d.z; r.w += d.w;      // rgb + depth (model_skip_mod_globalgate.py:258)
-          const uint32_t off = tile_off(row, half * 4);
-          *reinterpret_cast<float4*>(s_fuse + off) = r;
-          *reinterpret_cast<float4*>(s_dep + off) = d;
+        float f[8], d[8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float4 sr = *reinterpret_cast<const float4*>(s_bn + c + 4 * q), br = *reinterpret_cast<const float4*>(s_bn + 64 + c + 4 * q);
+          const float4 sd = *reinterpret_cast<const float4*>(s_bn + 128 + c + 4 * q), bd = *reinterpret_cast<const float4*>(s_bn + 192 + c + 4 * q);
+          d[4 * q + 0] = fmaxf(fmaf(__uint_as_float(vd[4 * q + 0]), sd.x, bd.x), 0.f);
+          d[4 * q + 1] = fmaxf(fmaf(__uint_as_float(vd[4 * q + 1]), sd.y, bd.y), 0.f);
+          d[4 * q + 2] = fmaxf(fmaf(__uint_as_float(vd[4 * q + 2]), sd.z, bd.z), 0.f);
+          d[4 * q + 3] = fmaxf(fmaf(__uint_as_float(vd[4 * q + 3]), sd.w, bd.w), 0.f);
+          // rgb + depth (model_skip_mod_globalgate.py:258)
+          f[4 * q + 0] = fmaxf(fmaf(__uint_as_float(vr[4 * q + 0]), sr.x, br.x), 0.f) + d[4 * q + 0];
+          f[4 * q + 1] = fmaxf(fmaf(__uint_as_float(vr[4 * q + 1]), sr.y, br.y), 0.f) + d[4 * q + 1];
+          f[4 * q + 2] = fmaxf(fmaf(__uint_as_float(vr[4 * q + 2]), sr.z, br.z), 0.f) + d[4 * q + 2];
+          f[4 * q + 3] = fmaxf(fmaf(__uint_as_float(vr[4 * q + 3]), sr.w, br.w), 0.f) + d[4 * q + 3];
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (!inside) {
+            f[e] = -INFINITY;
+            d[e] = -INFINITY;
+          }
+          // horizontal 3-max over columns lx, lx+1, lx+2 (16-lane segments = one stem row)
+          f[e] = fmaxf(f[e], fmaxf(__shfl_down_sync(0xffffffffu, f[e], 1, 16), __shfl_down_sync(0xffffffffu, f[e], 2, 16)));
+          d[e] = fmaxf(d[e], fmaxf(__shfl_down_sync(0xffffffffu, d[e], 1, 16), __shfl_down_sync(0xffffffffu, d[e], 2, 16)));
+        }
+        if (writer) {
+          const uint32_t off = h_off(ly, lx >> 1, half * 8);
+          *reinterpret_cast<float4*>(s_hf + off) = make_float4(f[0], f[1], f[2], f[3]);
+          *reinterpret_cast<float4*>(s_hf + off + 16) = make_float4(f[4], f[5], f[6], f[7]);
+          *reinterpret_cast<float4*>(s_hd + off) = make_float4(d[0], d[1], d[2], d[3]);
+          *reinterpret_cast<float4*>(s_hd + off + 16) = make_float4(d[4], d[5], d[6], d[7]);
         }
         named_barrier(1 + g, 32 * kGroupWarps);
-        // 3x3 / stride 2 / pad 1 max-pool of both tiles: 21 pooled pixels x 2 channel quads
+        // vertical 3-max over stem rows 2*ply .. 2*ply+2: 21 pooled pixels x 4 channel quads
         if (item) {
-          float4 mf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), md = mf;
-          if (interior) {
+          float4 mf = *reinterpret_cast<const float4*>(s_hf + h_off(2 * ply, plx, c4));
+          float4 md = *reinterpret_cast<const float4*>(s_hd + h_off(2 * ply, plx, c4));
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-              const float4 a = *reinterpret_cast<const float4*>(s_fuse + woff[t]);
-              const float4 b = *reinterpret_cast<const float4*>(s_dep + woff[t]);
-              mf.x = fmaxf(mf.x, a.x); mf.y = fmaxf(mf.y, a.y); mf.z = fmaxf(mf.z, a.z); mf.w = fmaxf(mf.w, a.w);
-              md.x = fmaxf(md.x, b.x); md.y = fmaxf(md.y, b.y); md.z = fmaxf(md.z, b.z); md.w = fmaxf(md.w, b.w);
-            }
-          } else {
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-              const int gy = sy0 + 2 * ply + dy;
-              if (gy < 0 || gy >= Hs) continue;
-#pragma unroll
-              for (int dx = 0; dx < 3; ++dx) {
-                const int gx = sx0 + 2 * plx + dx;
-                if (gx < 0 || gx >= Ws) continue;
-                const float4 a = *reinterpret_cast<const float4*>(s_fuse + woff[dy * 3 + dx]);
-                const float4 b = *reinterpret_cast<const float4*>(s_dep + woff[dy * 3 + dx]);
-                mf.x = fmaxf(mf.x, a.x); mf.y = fmaxf(mf.y, a.y); mf.z = fmaxf(mf.z, a.z); mf.w = fmaxf(mf.w, a.w);
-                md.x = fmaxf(md.x, b.x); md.y = fmaxf(md.y, b.y); md.z = fmaxf(md.z, b.z); md.w = fmaxf(md.w, b.w);
-              }
-            }
+          for (int dy = 1; dy < 3; ++dy) {
+            const float4 a = *reinterpret_cast<const float4*>(s_hf + h_off(2 * ply + dy, plx, c4));
+            const float4 b = *reinterpret_cast<const float4*>(s_hd + h_off(2 * ply + dy, plx, c4));
+            mf.x = fmaxf(mf.x, a.x); mf.y = fmaxf(mf.y, a.y); mf.z = fmaxf(mf.z, a.z); mf.w = fmaxf(mf.w, a.w);
+            md.x = fmaxf(md.x, b.x); md.y = fmaxf(md.y, b.y); md.z = fmaxf(md.z, b.z); md.w = fmaxf(md.w, b.w);
           }
           const size_t o = ((static_cast<size_t>(n) * Hp + py) * Wp + px) * 64 + pass * kPassCh + c4;
           if (rgb_f32) *reinterpret_cast<float4*>(rgb_f32 + o) = mf;
@@ -364,7 +366,7 @@ stem_s2d_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
             *reinterpret_cast<uint2*>(depth_bf16 + o) = v;
           }
         }
-        named_barrier(1 + g, 32 * kGroupWarps);   // the tiles are consumed before the next pass overwrites them
+        named_barrier(1 + g, 32 * kGroupWarps);   // the row maxima are consumed before the next pass overwrites them
       }
     }
   }
