@@ -123,12 +123,13 @@ def measured_peaks():
 
 
 def conv_traffic():
-    """DRAM bytes per conv launch from the committed ncu capture (profiles/r1_conv_traffic.json)."""
-    p = os.path.join(ROOT, "profiles", "r1_conv_traffic.json")
-    try:
-        return json.load(open(p))["dram_bytes_per_launch"]
-    except Exception:
-        return None
+    """DRAM bytes per conv launch from the committed ncu capture (profiles/r1b_conv_traffic.json)."""
+    for name in ("r1b_conv_traffic.json", "r1_conv_traffic.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", name)))["dram_bytes_per_launch"]
+        except Exception:
+            continue
+    return None
 
 
 def cpu_reference_images_per_s(state_dict, batch: int, warmup: int, steps: int, threads: int):
@@ -317,7 +318,7 @@ def main():
                     "note": "kernel_s_per_step = sum over the step's conv launches of their device time (each launch "
                             "replayed 4x from a CUDA graph between events on its own stream); the RGB and depth "
                             "encoder streams overlap in the timed step, so this sum is not a share of ms_per_step. "
-                            "Kernel shares of the step: profiles/r1_step_metrics_summary.txt (ncu).",
+                            "Kernel shares of the step: profiles/r1b_step_metrics_summary.txt (ncu).",
                     "step_s": step_s}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
