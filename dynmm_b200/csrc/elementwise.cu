@@ -272,18 +272,18 @@ __global__ void upsample2x_dw_nhwc_kernel(const __nv_bfloat16* __restrict__ in, 
 // new row), produces the 2x2 output block with the 16 parity stencils precombined from the 3x3 weights once per
 // thread (16 FMAs per channel instead of 36) and stores 4 x 8 bytes; the per-pixel kernel above re-loads 9 inputs
 // and 18 weight vectors for every 16-byte store.
-constexpr int kUpStripRows = 8;
+constexpr int kUpStripRows = 8;      // longest strip; short maps use shorter strips so that the grid still fills the GPU
 template <bool kSkip>
 __global__ void __launch_bounds__(256)
 upsample2x_dw_nhwc_strip_kernel(const __nv_bfloat16* __restrict__ in, int h, int w, int c,
                                 const float* __restrict__ wgt, const float* __restrict__ bias,
-                                const __nv_bfloat16* __restrict__ skip, __nv_bfloat16* __restrict__ out) {
+                                const __nv_bfloat16* __restrict__ skip, __nv_bfloat16* __restrict__ out, int strip_rows) {
   const int cg = c >> 2;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= w * cg) return;
   const int c4 = (idx % cg) * 4, x = idx / cg;
   const int s = blockIdx.z;
-  const int y0 = blockIdx.y * kUpStripRows, y1 = min(y0 + kUpStripRows, h);
+  const int y0 = blockIdx.y * strip_rows, y1 = min(y0 + strip_rows, h);
   const int H = 2 * h, W = 2 * w;
   // parity stencils (see upsample2x_dw_to_nchw_kernel): st[p][t][ch], p = 2*(Y&1) + (X&1), t = the 4 inputs of the block
   float st[4][4][4], b4[4];
@@ -603,14 +603,17 @@ extern "C" int dynmm_upsample2x_dw3x3(const void* in, int n, int h, int w, int c
       return !(e && e[0] == 'p');           // DYNMM_UPSAMPLE=pixel: the one-thread-per-output-pixel kernel
     }();
     if (use_strip && n <= 65535) {
-      dim3 grid(ceil_div(w * (c / 4), 256), ceil_div(h, kUpStripRows), n);
+      int rows = kUpStripRows;       // a thread walks `rows` input rows: halve until there are >= 4 CTAs per SM
+      while (rows > 1 && 1LL * ceil_div(w * (c / 4), 256) * ceil_div(h, rows) * n < 4LL * num_sms()) rows >>= 1;
+      dim3 grid(ceil_div(w * (c / 4), 256), ceil_div(h, rows), n);
       if (skip) {
         upsample2x_dw_nhwc_strip_kernel<true><<<grid, 256, 0, stream>>>(
             static_cast<const __nv_bfloat16*>(in), h, w, c, weight, bias, static_cast<const __nv_bfloat16*>(skip),
-            static_cast<__nv_bfloat16*>(out_nhwc_bf16));
+            static_cast<__nv_bfloat16*>(out_nhwc_bf16), rows);
       } else {
         upsample2x_dw_nhwc_strip_kernel<false><<<grid, 256, 0, stream>>>(
-            static_cast<const __nv_bfloat16*>(in), h, w, c, weight, bias, nullptr, static_cast<__nv_bfloat16*>(out_nhwc_bf16));
+            static_cast<const __nv_bfloat16*>(in), h, w, c, weight, bias, nullptr, static_cast<__nv_bfloat16*>(out_nhwc_bf16),
+            rows);
       }
     } else {
       const long long total = 1LL * n * 4 * h * w * (c / 8);
