@@ -464,6 +464,40 @@ __global__ void adaptive_avgpool_kernel(const __nv_bfloat16* __restrict__ in, in
     out[((1LL * s * bins + by) * bins + bx) * c + ch] = __float2bfloat16_rn(t / (float)npix);
   }
 }
+// 16-byte variant (c, ld multiples of 8): 32 pixel lanes x 8 channel octets per block, ~10 independent loads per
+// thread for the 15x20 global-pool window instead of 75 dependent 2-byte ones; fixed-order reduction.
+__global__ void __launch_bounds__(256)
+adaptive_avgpool_v8_kernel(const __nv_bfloat16* __restrict__ in, int h, int w, int c, int ld, int bins,
+                           __nv_bfloat16* __restrict__ out) {
+  __shared__ float s_part[32][64 + 4];
+  const int by = blockIdx.x / bins, bx = blockIdx.x % bins, s = blockIdx.y;
+  const int y0 = (by * h) / bins, y1 = ((by + 1) * h + bins - 1) / bins;
+  const int x0 = (bx * w) / bins, x1 = ((bx + 1) * w + bins - 1) / bins;
+  const int ww = x1 - x0, npix = (y1 - y0) * ww;
+  const int oct = threadIdx.x & 7, lane_p = threadIdx.x >> 3;
+  const int ch0 = blockIdx.z * 64 + oct * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (ch0 < c) {
+    for (int p = lane_p; p < npix; p += 32) {
+      const int y = y0 + p / ww, x = x0 + p % ww;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + ((1LL * s * h + y) * w + x) * ld + ch0));
+      acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+      acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s_part[lane_p][oct * 8 + e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int ch = blockIdx.z * 64 + threadIdx.x;
+    if (ch < c) {
+      float t = 0.f;
+#pragma unroll
+      for (int l = 0; l < 32; ++l) t += s_part[l][threadIdx.x];
+      out[((1LL * s * bins + by) * bins + bx) * c + ch] = __float2bfloat16_rn(t / (float)npix);
+    }
+  }
+}
 __global__ void nearest_resize_into_kernel(const __nv_bfloat16* __restrict__ src, int n, int hs, int ws, int c,
                                            __nv_bfloat16* __restrict__ dst, int h, int w, int ld, int c_off) {
   const int cv = c >> 3;
@@ -642,8 +676,13 @@ extern "C" int dynmm_adaptive_avgpool(const void* in, int n, int h, int w, int c
                                       void* stream) {
   DYNMM_CHECK_ARG(in && out && n >= 1 && h >= 1 && w >= 1 && c >= 1 && ld >= c && bins >= 1 && bins <= 64,
                   "avgpool: bad args");
-  adaptive_avgpool_kernel<<<dim3(bins * bins, n, ceil_div(c, 64)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(in), h, w, c, ld, bins, static_cast<__nv_bfloat16*>(out));
+  if (c % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    adaptive_avgpool_v8_kernel<<<dim3(bins * bins, n, ceil_div(c, 64)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(in), h, w, c, ld, bins, static_cast<__nv_bfloat16*>(out));
+  } else {
+    adaptive_avgpool_kernel<<<dim3(bins * bins, n, ceil_div(c, 64)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(in), h, w, c, ld, bins, static_cast<__nv_bfloat16*>(out));
+  }
   DYNMM_LAUNCH_CHECK();
   return DYNMM_OK;
 }
