@@ -82,6 +82,30 @@ static_assert(kOffPhase + kMaxPhases * sizeof(PhaseCtl) <= kCtlBytes, "phase tab
 inline size_t briefs_offset() { return kHeaderBytes; }
 inline size_t plans_offset(int n_jobs) { return kHeaderBytes + ((size_t)n_jobs * sizeof(JobBrief) + 127) / 128 * 128; }
 
+// epilogue_chunk with the flag combinations the network uses folded at compile time (as in the one-launch kernel,
+// where they are a template parameter); anything else takes the run-time path
+template <bool kTma>
+__device__ __forceinline__ void epilogue_chunk_sw(int flags, const KernelArgs& args, const uint32_t (&v)[32], int c_first,
+                                                  int cols_left, bool valid, uint32_t res_smem, uint32_t out_smem,
+                                                  uint32_t chunk0, uint32_t swz, size_t pix, size_t rpix, size_t gpix,
+                                                  float g, const float* shift_smem) {
+#define DYNMM_EPI_CASE(F)                                                                                             \
+  case (F):                                                                                                           \
+    epilogue_chunk<kTma, true>((F), args, v, c_first, cols_left, valid, res_smem, out_smem, chunk0, swz, pix, rpix, gpix, \
+                               g, shift_smem);                                                                        \
+    break;
+  switch (flags) {
+    DYNMM_EPI_CASE(kFlagRelu)
+    DYNMM_EPI_CASE(kFlagRelu | kFlagRes)
+    DYNMM_EPI_CASE(kFlagRelu | kFlagRes | kFlagGated)
+    DYNMM_EPI_CASE(0)
+    default:
+      epilogue_chunk<kTma, true>(flags, args, v, c_first, cols_left, valid, res_smem, out_smem, chunk0, swz, pix, rpix,
+                                 gpix, g, shift_smem);
+  }
+#undef DYNMM_EPI_CASE
+}
+
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
   unsigned spins = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -312,66 +336,80 @@ conv_program_kernel(const __grid_constant__ ProgramParams params, const uint8_t*
     }
     __syncthreads();
 
-    // Tile k (k-th tile of this CTA in the phase) belongs to issuer k & 1: accumulator buffer k & 1, and the stage
-    // ring is split in two halves, ring r = slots [r * half, (r + 1) * half), filled by the producer for the
-    // tiles of issuer r only -- every mbarrier keeps exactly one producer and one consumer.
+    // Accumulator buffer of the CTA's k-th tile in the phase: k & 1.  DUAL mode (>= 2 tiles and >= 4 stages): tile k
+    // belongs to issuer k & 1 and the stage ring is split in two halves, ring r = slots [r * half, (r + 1) * half),
+    // filled by the producer for issuer r's tiles only.  SINGLE mode (one tile, or too few stages to split -- the
+    // deep layers with K = 1536 need the whole ring as prefetch depth): issuer 0 works through all tiles on the whole
+    // ring.  Either way every mbarrier has exactly one producer and one consumer per phase.
     const int n_my = my_tiles ? (total_tiles - pc.cta_local + pc.ctas_job - 1) / pc.ctas_job : 0;
+    const bool dual = busy && args.stages >= 4 && n_my >= 2;
     auto mma_role = [&](const uint32_t me) {
       const MmaJob& mj = params.jobs[pc.job];
-      const int half = mj.stages >> 1;
-      const int slot0 = me * half;
-      int slot = 0;
+      const int ring = dual ? (mj.stages >> 1) : mj.stages;
+      const int slot0 = dual ? me * ring : 0;
       if (mj.b_resident) {
         mbar_wait_wd(&ctl->b_full, bres_parity);
         bres_parity ^= 1u;
         tc_fence_after();
       }
-      for (int k = me; k < n_my; k += 2, ++acc_cnt0) {       // an issuer only counts the uses of ITS buffer
-        mbar_wait_wd(&ctl->acc_empty[me], (acc_cnt0 & 1u) ^ 1u);
-        tc_fence_after();
-        for (int it = 0; it < mj.k_iters; ++it) {
-          const int stage = slot0 + slot;
-          mbar_wait_wd(&ctl->full[stage], (full_bits >> stage) & 1u);
-          full_bits ^= 1u << stage;
+      if (dual || me == 0) {
+        int slot = 0;
+        for (int k = dual ? me : 0; k < n_my; k += dual ? 2 : 1) {
+          const uint32_t acc = k & 1;
+          const uint32_t uses_before = (acc ? acc_cnt1 : acc_cnt0) + (k >> 1);    // of this accumulator buffer
+          mbar_wait_wd(&ctl->acc_empty[acc], (uses_before & 1u) ^ 1u);
           tc_fence_after();
-          const uint32_t sa = smem_u + stage * mj.stage_bytes;
-          const uint32_t sb = mj.b_resident ? smem_u + mj.bres_off + it * mj.b_iter_bytes : sa + mj.a_bytes;
-          if (elect_one()) {       // the warp runs the loops converged; only the tcgen05 instructions are single-lane
-            if (me == 0) {
-              issue_kiter<0>(sa, sb, mj, it);
-            } else {
-              issue_kiter<kAccCols>(sa, sb, mj, it);
+          for (int it = 0; it < mj.k_iters; ++it) {
+            const int stage = slot0 + slot;
+            mbar_wait_wd(&ctl->full[stage], (full_bits >> stage) & 1u);
+            full_bits ^= 1u << stage;
+            tc_fence_after();
+            const uint32_t sa = smem_u + stage * mj.stage_bytes;
+            const uint32_t sb = mj.b_resident ? smem_u + mj.bres_off + it * mj.b_iter_bytes : sa + mj.a_bytes;
+            if (elect_one()) {       // the warp runs the loops converged; only the tcgen05 instructions are single-lane
+              if (acc == 0) {
+                issue_kiter<0>(sa, sb, mj, it);
+              } else {
+                issue_kiter<kAccCols>(sa, sb, mj, it);
+              }
+              umma_commit(&ctl->empty[stage]);
+              if (it == mj.k_iters - 1) umma_commit(&ctl->acc_full[acc]);
             }
-            umma_commit(&ctl->empty[stage]);
-            if (it == mj.k_iters - 1) umma_commit(&ctl->acc_full[me]);
+            __syncwarp();
+            if (++slot == ring) slot = 0;
           }
-          __syncwarp();
-          if (++slot == half) slot = 0;
         }
       }
-      // the other issuer's fills of ITS ring in this phase: the ring split changes from phase to phase, so each
-      // issuer keeps the parity of every stage barrier up to date
-      const uint32_t other = me ^ 1u;
-      const int uses = ((n_my + (other == 0 ? 1 : 0)) >> 1) * mj.k_iters;
-      for (int j = 0; j < half; ++j) {
-        const int cnt = uses / half + (j < uses % half ? 1 : 0);
-        if (cnt & 1) full_bits ^= 1u << (other * half + j);
+      // both issuers keep complete books: uses of the two accumulators, and the parity of the stage barriers the OTHER
+      // issuer consumed in this phase (the ring split changes from phase to phase)
+      acc_cnt0 += (n_my + 1) >> 1;
+      acc_cnt1 += n_my >> 1;
+      if (dual || me == 1) {
+        const uint32_t other = me ^ 1u;
+        const int other_tiles = dual ? ((n_my + (other == 0 ? 1 : 0)) >> 1) : n_my;
+        const int other_slot0 = dual ? other * ring : 0;
+        const int uses = other_tiles * mj.k_iters;
+        for (int j = 0; j < ring; ++j) {
+          const int cnt = uses / ring + (j < uses % ring ? 1 : 0);
+          if (cnt & 1) full_bits ^= 1u << (other_slot0 + j);
+        }
       }
     };
     if (busy && my_tiles) {
       if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        // ------------------------------------------------------------ TMA producer (whole warp converged, TMA and
+        // mbarrier-arrive instructions under elect.sync)
+        {
           const CUtensorMap* maps[4] = {&jd->maps[0], &jd->maps[1], &jd->maps[2], &jd->maps[3]};
           const uint32_t a_tx = args.a_rows * kBlockK * 2;
           const uint32_t tx_bytes = a_tx + (args.b_resident ? 0 : b_iter_bytes);
           const uint32_t sub_tx = args.b1 * args.b2 * args.bn * kBlockK * 2;
-          const int half = args.stages >> 1;
+          const int half = dual ? (args.stages >> 1) : args.stages;    // slots per ring (single mode: one ring)
           int slot[2] = {0, 0};
           int aux = 0;
-          for (int k = 0; k < n_my; k += 2) {
-            // the loads of a pair of tiles are interleaved k-iteration by k-iteration, so both issuers advance together
-            const int pair = min(2, n_my - k);
+          for (int k = 0; k < n_my; k += dual ? 2 : 1) {
+            // dual mode: the loads of a pair of tiles are interleaved k-iteration by k-iteration, so both issuers advance
+            const int pair = dual ? min(2, n_my - k) : 1;
             TileCoord t[2];
             int n_in[2];
 #pragma unroll
@@ -389,11 +427,14 @@ conv_program_kernel(const __grid_constant__ ProgramParams params, const uint8_t*
                     mbar_wait_wd(&ctl->empty[stage], ((empty_bits >> stage) & 1u) ^ 1u);
                     empty_bits ^= 1u << stage;
                     uint8_t* sa = smem + stage * args.stage_bytes;
-                    mbar_expect_tx(&ctl->full[stage], tx_bytes);
-                    tma_load_4d(sa, maps[gp.map], &ctl->full[stage], kc * kBlockK, t[r].x1 + gp.o1, t[r].x2 + gp.o2,
-                                n_in[r]);
-                    if (!args.b_resident)
-                      tma_load_3d(sa + args.a_bytes, &jd->map_b, &ctl->full[stage], kc * kBlockK, t[r].c0, g * args.tpg);
+                    if (elect_one()) {
+                      mbar_expect_tx(&ctl->full[stage], tx_bytes);
+                      tma_load_4d(sa, maps[gp.map], &ctl->full[stage], kc * kBlockK, t[r].x1 + gp.o1, t[r].x2 + gp.o2,
+                                  n_in[r]);
+                      if (!args.b_resident)
+                        tma_load_3d(sa + args.a_bytes, &jd->map_b, &ctl->full[stage], kc * kBlockK, t[r].c0, g * args.tpg);
+                    }
+                    __syncwarp();
                     if (++slot[r] == half) slot[r] = 0;
                   }
                 }
@@ -406,9 +447,12 @@ conv_program_kernel(const __grid_constant__ ProgramParams params, const uint8_t*
                 for (int sub = 0; sub < n_sub; ++sub) {
                   mbar_wait_wd(&ctl->aux_empty[aux], ((aux_empty_bits >> aux) & 1u) ^ 1u);
                   aux_empty_bits ^= 1u << aux;
-                  mbar_expect_tx(&ctl->aux_full[aux], sub_tx);
-                  tma_load_4d(smem_aux + aux * kSubBytes, &jd->map_res, &ctl->aux_full[aux], t[r].c0 + sub * 64, t[r].x1,
-                              t[r].x2, n_res);
+                  if (elect_one()) {
+                    mbar_expect_tx(&ctl->aux_full[aux], sub_tx);
+                    tma_load_4d(smem_aux + aux * kSubBytes, &jd->map_res, &ctl->aux_full[aux], t[r].c0 + sub * 64, t[r].x1,
+                                t[r].x2, n_res);
+                  }
+                  __syncwarp();
                   if (++aux == args.aux_slots) aux = 0;
                 }
               }
@@ -425,7 +469,6 @@ conv_program_kernel(const __grid_constant__ ProgramParams params, const uint8_t*
         mma_role(1);
       } else {
         // ------------------------------------------------------------ epilogue (8 warps)
-        const int flags = args.flags;
         const int ewarp = warp - 2;
         const int quarter = warp & 3;
         const int half = ewarp >> 2;
@@ -433,12 +476,12 @@ conv_program_kernel(const __grid_constant__ ProgramParams params, const uint8_t*
         const int i1 = row % args.b1;
         const int i2 = (row / args.b1) % args.b2;
         const int nl = row / (args.b1 * args.b2);
-        const bool leader = (threadIdx.x == 64);
         const uint32_t row_off = row * 128;
         const uint32_t swz = row & 7;
         const uint32_t aux_base = smem_u32(smem_aux) + row_off;
         const uint32_t out_base = smem_u32(smem_stage_out) + row_off;
         int aux = 0;
+        const int flags = args.flags;
         for (int k = 0; k < n_my; ++k) {
           const int tile = pc.cta_local + k * pc.ctas_job;
           const int acc = k & 1;
@@ -486,7 +529,7 @@ conv_program_kernel(const __grid_constant__ ProgramParams params, const uint8_t*
               }
               const uint32_t out_smem = out_base + sbuf * kSubBytes;
               if (cols_live) {
-                epilogue_chunk<true, true>(flags, args, v, t.c0 + cb, args.tile_n - cb, valid, res_smem, out_smem,
+                epilogue_chunk_sw<true>(flags, args, v, t.c0 + cb, args.tile_n - cb, valid, res_smem, out_smem,
                                            half * 4, swz, pix, rpix, gpix, g, smem_shift);
               }
               if (aux_on) {
@@ -495,15 +538,15 @@ conv_program_kernel(const __grid_constant__ ProgramParams params, const uint8_t*
                 if (++aux == args.aux_slots) aux = 0;
               }
               fence_async_smem();
-              if (leader) bulk_wait_read<0>();
+              if (ewarp == 0 && elect_one()) bulk_wait_read<0>();
               named_barrier(1, 32 * kEpiWarps);
-              if (leader) {
+              if (ewarp == 0 && elect_one()) {
                 tma_store_4d(&jd->map_out, smem_stage_out + sbuf * kSubBytes, t.c0 + sub * 64, t.x1, t.x2, t.n0);
                 bulk_commit();
               }
               sbuf ^= 1;
             } else if (cols_live) {
-              epilogue_chunk<false, true>(flags, args, v, t.c0 + cb, args.tile_n - cb, valid, 0, 0, 0, 0, pix, rpix,
+              epilogue_chunk_sw<false>(flags, args, v, t.c0 + cb, args.tile_n - cb, valid, 0, 0, 0, 0, pix, rpix,
                                           gpix, g, smem_shift);
             }
           }
@@ -513,7 +556,7 @@ conv_program_kernel(const __grid_constant__ ProgramParams params, const uint8_t*
         }
         // this phase's outputs must be complete before the CTA reports at the grid barrier:
         // TMA stores fully written (not just read out of shared memory), direct stores ordered before later TMA reads
-        if (leader) bulk_wait<0>();
+        if (ewarp == 0 && elect_one()) bulk_wait<0>();
         fence_proxy_async_all();
       }
     }
