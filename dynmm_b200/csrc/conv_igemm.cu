@@ -85,7 +85,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     }
     mbar_init(&ctl->b_full, 1);
     fence_mbar_init();
-    if (args.b_resident) {
+  }
+  if (warp == 0) {
+    __syncwarp();
+    if (args.b_resident && elect_one()) {
       // weights are constants: fetch them before waiting on the previous kernel (c_tiles == 1)
       mbar_expect_tx(&ctl->b_full, k_iters * b_iter_bytes);
       for (int g = 0; g < args.num_groups; ++g)
@@ -93,6 +96,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           tma_load_3d(smem_bres + (g * args.k_chunks + kc) * b_iter_bytes, &map_b, &ctl->b_full, kc * kBlockK, 0,
                       g * args.tpg);
     }
+    __syncwarp();
   }
   if (warp == 1) {
     tmem_alloc(&ctl->tmem_base, 512);

@@ -122,8 +122,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   const uint32_t tmem_base = ctl->tmem_base;
   const int dy_bytes = 2 * kAtomBytes;           // the A view always spans two atoms (M = 128)
 
+  // Producer and MMA issuer: the whole warp runs the loop converged, the TMA / tcgen05 instructions sit under
+  // elect.sync (a lone lane inside `if (lane == 0)` pays an ELECT / BRA.U.ANY loop per instruction: >= 90 cycles per
+  // UMMA, tools/umma_issue_bench.cu).
   if (warp == 0) {
-    if (lane == 0) {
+    {
       const CUtensorMap* maps[4] = {&map_x0, &map_x1, &map_x2, &map_x3};
       const uint32_t box_bytes = args.rows * 128;
       const uint32_t tx = (m_atoms + args.tpu * n_atoms) * box_bytes;
@@ -137,14 +140,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         const int x1 = tw * args.bw, x2 = th * args.bh, n0 = tn * args.bn;
         mbar_wait(&ctl->empty[stage], phase ^ 1);
         uint8_t* sa = smem + stage * args.stage_bytes;
-        mbar_expect_tx(&ctl->full[stage], tx);
-        for (int a = 0; a < m_atoms; ++a) tma_load_4d(sa + a * kAtomBytes, &map_dy, &ctl->full[stage], co0 + a * 64, x1, x2, n0);
-        for (int t = 0; t < args.tpu; ++t) {
-          const TapW tp = args.tap[tg * args.tpu + t];
-          for (int b = 0; b < n_atoms; ++b)
-            tma_load_4d(sa + dy_bytes + (t * args.n_atoms + b) * kAtomBytes, maps[tp.map], &ctl->full[stage],
-                        ci0 + b * 64, x1 + tp.o1, x2 + tp.o2, n0);
+        if (elect_one()) {
+          mbar_expect_tx(&ctl->full[stage], tx);
+          for (int a = 0; a < m_atoms; ++a) tma_load_4d(sa + a * kAtomBytes, &map_dy, &ctl->full[stage], co0 + a * 64, x1, x2, n0);
+          for (int t = 0; t < args.tpu; ++t) {
+            const TapW tp = args.tap[tg * args.tpu + t];
+            for (int b = 0; b < n_atoms; ++b)
+              tma_load_4d(sa + dy_bytes + (t * args.n_atoms + b) * kAtomBytes, maps[tp.map], &ctl->full[stage],
+                          ci0 + b * 64, x1 + tp.o1, x2 + tp.o2, n0);
+          }
         }
+        __syncwarp();
         if (++stage == args.stages) {
           stage = 0;
           phase ^= 1;
@@ -152,7 +158,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = umma_idesc_bf16_mn(128, args.n_tile);
       int stage = 0;
       uint32_t phase = 0;
@@ -160,22 +166,26 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         mbar_wait(&ctl->full[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * args.stage_bytes);
-        for (int t = 0; t < args.tpu; ++t) {
-          const uint32_t sb = sa + dy_bytes + t * args.n_atoms * kAtomBytes;
-          for (int ks = 0; ks < args.k_steps; ++ks) {
-            // 16 pixels = two 8-pixel groups = 2048 bytes further along K
-            const uint64_t da = umma_desc_sw128_mn(sa + ks * 2048, kAtomBytes);
-            const uint64_t db = umma_desc_sw128_mn(sb + ks * 2048, kAtomBytes);
-            umma_bf16(tmem_base + t * args.n_tile, da, db, idesc, (kt > k0 || ks > 0) ? 1u : 0u);
+        if (elect_one()) {
+          for (int t = 0; t < args.tpu; ++t) {
+            const uint32_t sb = sa + dy_bytes + t * args.n_atoms * kAtomBytes;
+            for (int ks = 0; ks < args.k_steps; ++ks) {
+              // 16 pixels = two 8-pixel groups = 2048 bytes further along K
+              const uint64_t da = umma_desc_sw128_mn(sa + ks * 2048, kAtomBytes);
+              const uint64_t db = umma_desc_sw128_mn(sb + ks * 2048, kAtomBytes);
+              umma_bf16(tmem_base + t * args.n_tile, da, db, idesc, (kt > k0 || ks > 0) ? 1u : 0u);
+            }
           }
+          umma_commit(&ctl->empty[stage]);
         }
-        umma_commit(&ctl->empty[stage]);
+        __syncwarp();
         if (++stage == args.stages) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit(&ctl->acc_full);
+      if (elect_one()) umma_commit(&ctl->acc_full);
+      __syncwarp();
     }
   } else {
     // epilogue: TMEM lane = output channel, column = (tap, input channel)
