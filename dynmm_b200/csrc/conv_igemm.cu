@@ -41,8 +41,8 @@ using namespace convk;
     if (args.trace) args.trace[blockIdx.x * 16 + (slot)] = (unsigned long long)clock64(); \
   } while (0)
 
-template <int kFlags>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int kFlags, int kPerSm>
+__global__ void __launch_bounds__(kThreads, kPerSm)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                   const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
                   const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_res,
@@ -99,7 +99,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     __syncwarp();
   }
   if (warp == 1) {
-    tmem_alloc(&ctl->tmem_base, 512);
+    tmem_alloc(&ctl->tmem_base, kPerSm == 1 ? 512 : args.tmem_cols);
     tmem_relinquish();
   }
   if (warp >= 2) {   // epilogue warps stage the shift vector once: no global loads inside the tile loop
@@ -108,11 +108,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  // The CTA owns all 512 TMEM columns, so the allocation starts at column 0 / lane 0: using the CONSTANT keeps
-  // every tcgen05.mma operand in uniform registers (a base read back from shared memory forces an
-  // ELECT / R2UR / branch sequence around each MMA: ~70 issue cycles per 32-cycle UMMA at N = 64).
-  if (ctl->tmem_base != 0) __trap();
-  constexpr uint32_t tmem_base = 0;
+  // One CTA per SM owns all 512 TMEM columns, so the allocation starts at column 0 / lane 0: using the CONSTANT
+  // keeps every tcgen05.mma operand in uniform registers.  Two CTAs per SM allocate what they need (2 x 64 columns)
+  // and carry the base in a register.
+  if (kPerSm == 1 && ctl->tmem_base != 0) __trap();
+  const uint32_t tmem_base = kPerSm == 1 ? 0u : ctl->tmem_base;
   // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch, shift
   // staging, resident weights -- constants only) overlapped the tail of the previous kernel in the
   // stream.  From here on we touch tensors it produced, so wait for it; then let OUR dependent
@@ -338,7 +338,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, kPerSm == 1 ? 512 : args.tmem_cols);
   }
   if (threadIdx.x == 0) DYNMM_TRACE(9);
 }
@@ -353,24 +353,35 @@ extern "C" int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int sms = num_sms();
   ConvPlan plan;
-  int rc = plan_conv(p, &plan, sms);
+  static const bool allow_two = [] {
+    const char* e = getenv("DYNMM_CONV_2CTA");
+    return !(e && e[0] == '0');
+  }();
+  int rc = plan_conv(p, &plan, sms, kSmemBudget, allow_two);
   if (rc) return rc;
   const KernelArgs& a = plan.a;
-  int grid = p->max_ctas > 0 ? p->max_ctas : sms;
+  int grid = p->max_ctas > 0 ? p->max_ctas : (a.two_per_sm ? 2 * sms : sms);
   if (grid > plan.max_tiles) grid = plan.max_tiles;
   const int flags = a.flags;
   typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap,
                            KernelArgs);
-  static const KernelFn table[16] = {
-      conv_igemm_kernel<0>,  conv_igemm_kernel<1>,  conv_igemm_kernel<2>,  conv_igemm_kernel<3>,
-      conv_igemm_kernel<4>,  conv_igemm_kernel<5>,  conv_igemm_kernel<6>,  conv_igemm_kernel<7>,
-      conv_igemm_kernel<8>,  conv_igemm_kernel<9>,  conv_igemm_kernel<10>, conv_igemm_kernel<11>,
-      conv_igemm_kernel<12>, conv_igemm_kernel<13>, conv_igemm_kernel<14>, conv_igemm_kernel<15>};
+  static const KernelFn table[32] = {
+      conv_igemm_kernel<0, 1>,  conv_igemm_kernel<1, 1>,  conv_igemm_kernel<2, 1>,  conv_igemm_kernel<3, 1>,
+      conv_igemm_kernel<4, 1>,  conv_igemm_kernel<5, 1>,  conv_igemm_kernel<6, 1>,  conv_igemm_kernel<7, 1>,
+      conv_igemm_kernel<8, 1>,  conv_igemm_kernel<9, 1>,  conv_igemm_kernel<10, 1>, conv_igemm_kernel<11, 1>,
+      conv_igemm_kernel<12, 1>, conv_igemm_kernel<13, 1>, conv_igemm_kernel<14, 1>, conv_igemm_kernel<15, 1>,
+      conv_igemm_kernel<0, 2>,  conv_igemm_kernel<1, 2>,  conv_igemm_kernel<2, 2>,  conv_igemm_kernel<3, 2>,
+      conv_igemm_kernel<4, 2>,  conv_igemm_kernel<5, 2>,  conv_igemm_kernel<6, 2>,  conv_igemm_kernel<7, 2>,
+      conv_igemm_kernel<8, 2>,  conv_igemm_kernel<9, 2>,  conv_igemm_kernel<10, 2>, conv_igemm_kernel<11, 2>,
+      conv_igemm_kernel<12, 2>, conv_igemm_kernel<13, 2>, conv_igemm_kernel<14, 2>, conv_igemm_kernel<15, 2>};
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    for (int i = 0; i < 16 && attr_err == cudaSuccess; ++i)
-      attr_err = cudaFuncSetAttribute(table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    for (int i = 0; i < 32 && attr_err == cudaSuccess; ++i) {
+      attr_err = cudaFuncSetAttribute(table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, i < 16 ? kSmemBudget : 113 * 1024);
+      if (attr_err == cudaSuccess && i >= 16)
+        attr_err = cudaFuncSetAttribute(table[i], cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    }
   });
   DYNMM_CUDA(attr_err);
   static const bool use_pdl = [] {
@@ -387,7 +398,7 @@ extern "C" int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream_) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl ? 1 : 0;
-  DYNMM_CUDA(cudaLaunchKernelEx(&cfg, table[flags], plan.maps[0], plan.maps[1], plan.maps[2], plan.maps[3], plan.map_b,
+  DYNMM_CUDA(cudaLaunchKernelEx(&cfg, table[flags + (a.two_per_sm ? 16 : 0)], plan.maps[0], plan.maps[1], plan.maps[2], plan.maps[3], plan.map_b,
                                 plan.map_res, plan.map_out, a));
   return DYNMM_OK;
 }

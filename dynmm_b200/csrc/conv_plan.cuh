@@ -46,6 +46,7 @@ struct KernelArgs {
   int tma_epi;                      // 1: TMA residual loads + TMA stores (tile_n % 64 == 0)
   int aux_slots;                    // residual ring slots (0 without residual)
   int b_resident;                   // 1: all weights live in smem for the kernel's lifetime
+  int two_per_sm;                   // 1: shared memory / TMEM sized so that two CTAs share an SM (C = 64 layers)
   int swap;                         // 1: d1 = H, d2 = W
   Group groups[kMaxGroups];
   // problem
@@ -240,7 +241,8 @@ struct ConvPlan {
 
 // `sms`: CTAs this convolution can expect to run on (the tile width is chosen to give each of them a tile);
 // `smem_budget`: dynamic shared memory the kernel may use for this convolution
-inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int smem_budget = kSmemBudget) {
+inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int smem_budget = kSmemBudget,
+                     bool allow_two_per_sm = false) {
   DYNMM_CHECK_ARG(p && p->in && p->weight && p->out, "conv_igemm: null pointer");
   DYNMM_CHECK_ARG(p->kh >= 1 && p->kw >= 1 && p->kh * p->kw <= kMaxGroups, "conv_igemm: at most %d taps", kMaxGroups);
   DYNMM_CHECK_ARG(p->stride_h >= 1 && p->stride_h <= 2 && p->stride_w >= 1 && p->stride_w <= 2,
@@ -365,6 +367,23 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
       a.stages = (smem_budget - 2048 - epi_bytes - shift_bytes) / a.stage_bytes;
     }
     if (a.stages > kMaxStages) a.stages = kMaxStages;
+    // Large C = 64 layers (24 KiB of resident weights, 18 KiB stages): a single CTA per SM leaves the tensor pipe, the
+    // TMA engine and the epilogue warps idle in turn; with <= 113 KiB per CTA two CTAs share the SM and fill each
+    // other's bubbles.  One residual slot and at most 4 stages per CTA.
+    a.two_per_sm = 0;
+    if (allow_two_per_sm && halo && a.b_resident && tile_n == 64 && a.c_tiles == 1 && a.tma_epi && !p->trace &&
+        m_tiles >= 4 * sms) {
+      const int aux2 = a.aux_slots ? 1 : 0;
+      const int epi2 = 2 * kSubBytes + aux2 * kSubBytes;
+      int st2 = (113 * 1024 - 2048 - epi2 - shift_bytes - b_total) / a.stage_bytes;
+      if (st2 > 4) st2 = 4;
+      if (st2 >= 2) {
+        a.two_per_sm = 1;
+        a.aux_slots = aux2;
+        epi_bytes = epi2;
+        a.stages = st2;
+      }
+    }
     if (a.stages >= 2 || !halo) break;
   }
   DYNMM_CHECK_ARG(a.stages >= 2, "conv_igemm: not enough shared memory for 2 stages");
