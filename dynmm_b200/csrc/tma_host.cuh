@@ -1,6 +1,8 @@
 // Host-side TMA descriptor helpers shared by the tensor-core kernels.
 #pragma once
 
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -50,9 +52,19 @@ inline int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t
     estr[i] = 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
+  // L2 promotion of the TMA requests: 128 B by default; DYNMM_TMA_L2=256 / 64 / 0 selects another granularity
+  static const CUtensorMapL2promotion promo = [] {
+    const char* e = getenv("DYNMM_TMA_L2");
+    if (!e) return CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    switch (atoi(e)) {
+      case 256: return CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+      case 64: return CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+      case 0: return CU_TENSOR_MAP_L2_PROMOTION_NONE;
+      default: return CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    }
+  }();
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with %d (rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u)", (int)r, rank,
               (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],

@@ -86,3 +86,23 @@ def test_build_model_signature():
     with pytest.raises(NotImplementedError):
         from dynmm_b200.fusion import SkipGateESANet
         SkipGateESANet(encoder_rgb="vgg16")
+
+
+def test_conv_program_recorder_phases():
+    """ConvProgram (host side of dynmm_conv_program_*): phases are numbered without gaps, at most 4 jobs each."""
+    import pytest
+    from dynmm_b200 import ops, _lib
+    prog = ops.ConvProgram()
+    prog.next_phase()                      # an empty phase is not numbered
+    assert prog.phase == 0
+    for _ in range(3):
+        prog._record(_lib.ConvParams(), (None,) * 12)
+    assert prog.jobs_in_phase() == 3
+    prog.next_phase()
+    prog.next_phase()                      # second call: the new phase is still empty
+    assert prog.phase == 1
+    for _ in range(4):
+        prog._record(_lib.ConvParams(), (None,) * 12)
+    with pytest.raises(_lib.DynmmError):
+        prog._record(_lib.ConvParams(), (None,) * 12)
+    assert prog.phases == [0, 0, 0, 1, 1, 1, 1]
