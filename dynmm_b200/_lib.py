@@ -36,6 +36,16 @@ class ConvParams(Structure):
     ]
 
 
+class ConvPairParams(Structure):
+    """Mirror of ``dynmm_conv_pair_params`` (include/dynmm_b200.h)."""
+    _fields_ = [
+        ("in_", c_void_p), ("w1", c_void_p), ("shift1", c_void_p), ("w2", c_void_p), ("shift2", c_void_p),
+        ("residual", c_void_p), ("out", c_void_p), ("count", c_void_p), ("in_map", c_void_p), ("res_map", c_void_p),
+        ("n", c_int32), ("n_in", c_int32), ("h", c_int32), ("w", c_int32),
+        ("in_ld", c_int32), ("out_ld", c_int32), ("res_ld", c_int32), ("relu2", c_int32),
+    ]
+
+
 class WgradParams(Structure):
     """Mirror of ``dynmm_wgrad_params`` (include/dynmm_b200.h)."""
     _fields_ = [
@@ -73,6 +83,7 @@ SIGNATURES = {
                                     c_int, c_int, c_void_p, c_void_p]),
     "dynmm_conv_igemm_fwd": (c_int, [POINTER(ConvParams), c_void_p]),
     "dynmm_conv_direct_fwd": (c_int, [POINTER(ConvParams), c_void_p]),
+    "dynmm_conv_pair_fwd": (c_int, [POINTER(ConvPairParams), c_void_p]),
     "dynmm_conv_program_bytes": (c_longlong, [c_int]),
     "dynmm_conv_program_build": (c_int, [POINTER(ConvParams), POINTER(c_int32), c_int, c_void_p, c_longlong,
                                          POINTER(c_int32)]),

@@ -215,11 +215,42 @@ class FusionEngine:
         # batch 8 in round 1 (profiles/r1_program_*), so the per-launch path stays the default.
         self.use_programs = cfg.fuse == "add" and os.environ.get("DYNMM_PROGRAM", "0") == "1"
         self.programs: list = []   # ConvPrograms of the last forward (a captured graph must keep them alive)
+        # 64-channel NonBottleneck1D blocks: each 3x1 -> 1x3 pair as ONE fused kernel (dynmm_conv_pair_fwd, bit-identical
+        # to the two launches); DYNMM_PAIR=0 keeps one launch per convolution
+        self.use_pairs = os.environ.get("DYNMM_PAIR", "1") != "0"
 
     # ------------------------------------------------------------------ blocks
+    @staticmethod
+    def _pairable(blk: Block) -> bool:
+        """NonBottleneck1D block whose two 3x1 -> 1x3 pairs fit dynmm_conv_pair_fwd (64 channels, stride 1)."""
+        if blk.downsample is not None or len(blk.convs) != 4:
+            return False
+        shapes = [(3, 1), (1, 3), (3, 1), (1, 3)]
+        return all(c.c_in == 64 and c.c_out == 64 and (c.kh, c.kw) == k and c.stride == (1, 1) and c.scale is None
+                   and c.relu for c, k in zip(blk.convs, shapes))
+
     def _block(self, x: Tensor, blk: Block, keep: list, *, count=None, in_map=None, before_last: Callable = None,
                last_kw: Optional[dict] = None) -> Tensor:
         n_out = x.shape[0]
+        if self.use_pairs and self._pairable(blk):
+            c0, c1, c2, c3 = blk.convs
+            y = ops.conv_pair(x, c0.weight, c0.shift, c1.weight, c1.shift, relu2=True, count=count, in_map=in_map,
+                              n_out=n_out)
+            keep.append(y)
+            self.launches += 1
+            if before_last is not None:
+                before_last()
+            if last_kw:                # gated add / redirected output: the second pair stays two launches
+                y = c2(y, count=count, n_out=n_out)
+                out = c3(y, residual=x, res_map=in_map, count=count, n_out=n_out, **last_kw)
+                keep += [y, out]
+                self.launches += 2
+            else:
+                out = ops.conv_pair(y, c2.weight, c2.shift, c3.weight, c3.shift, residual=x, res_map=in_map, relu2=True,
+                                    count=count, n_out=n_out)
+                keep.append(out)
+                self.launches += 1
+            return out
         y = x
         for i, cv in enumerate(blk.convs[:-1]):
             y = cv(y, count=count, in_map=in_map if i == 0 else None, n_out=n_out)

@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import ConvParams, WgradParams, check, ptr, stream_ptr
+from ._lib import ConvPairParams, ConvParams, WgradParams, check, ptr, stream_ptr
 
 Tensor = torch.Tensor
 
@@ -91,6 +91,29 @@ def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 
         CONV_PROFILER(p, lambda: check(fn(ctypes.byref(p), stream_ptr()), "conv_igemm"))
     else:
         check(fn(ctypes.byref(p), stream_ptr()), "conv_direct" if direct else "conv_igemm")
+    return out
+
+
+def conv_pair(x: Tensor, w1: Tensor, shift1: Optional[Tensor], w2: Tensor, shift2: Optional[Tensor], *,
+              residual: Optional[Tensor] = None, relu2: bool = True, count: Optional[Tensor] = None,
+              in_map: Optional[Tensor] = None, res_map: Optional[Tensor] = None, n_out: Optional[int] = None,
+              out: Optional[Tensor] = None) -> Tensor:
+    """conv3x1 + bias + ReLU -> conv1x3 + shift (+ residual) (+ ReLU) of a 64-channel NonBottleneck1D block in one
+    kernel (dynmm_conv_pair_fwd); bit-identical to the two :func:`conv` calls.  x NHWC bf16 [n_in, h, w, >= 64]."""
+    lib = _lib.load()
+    _cuda(x, w1, w2, shift1, shift2, residual, count, in_map, res_map, out)
+    n_in, h, w, in_ld = x.shape
+    n = n_in if n_out is None else n_out
+    if out is None:
+        out = torch.empty(n, h, w, 64, dtype=torch.bfloat16, device=x.device)
+    p = ConvPairParams()
+    p.in_, p.w1, p.shift1, p.w2, p.shift2 = ptr(x), ptr(w1), ptr(shift1), ptr(w2), ptr(shift2)
+    p.residual, p.out, p.count, p.in_map, p.res_map = ptr(residual), ptr(out), ptr(count), ptr(in_map), ptr(res_map)
+    p.n, p.n_in, p.h, p.w = n, n_in, h, w
+    p.in_ld, p.out_ld = in_ld, out.shape[3]
+    p.res_ld = residual.shape[3] if residual is not None else 0
+    p.relu2 = int(relu2)
+    check(lib.dynmm_conv_pair_fwd(ctypes.byref(p), stream_ptr()), "conv_pair")
     return out
 
 

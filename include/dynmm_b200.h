@@ -211,6 +211,27 @@ int dynmm_conv_program_build(const dynmm_conv_params* jobs, const int32_t* phase
 int dynmm_conv_program_launch(const void* device_image, const void* host_image, void* barrier, void* trace,
                               void* stream);
 
+/* Fused pair of a 64-channel NonBottleneck1D block (resnet.py:124-147): conv3x1(+bias)+ReLU followed by
+ * conv1x3(+folded BN shift)(+residual)(+ReLU) in ONE kernel; the intermediate stays in shared memory.  Same
+ * arithmetic and rounding as two dynmm_conv_igemm_fwd calls (bit-identical).  64 -> 64 -> 64 channels, stride 1.
+ * w1 / w2: packed bf16 [3][64][64] as for dynmm_conv_igemm_fwd.  in_map / res_map / count as in dynmm_conv_params. */
+typedef struct dynmm_conv_pair_params {
+  const void* in;         /* bf16 NHWC [n_in, h, w, in_ld] */
+  const void* w1;         /* 3x1 conv */
+  const float* shift1;    /* [64] or NULL */
+  const void* w2;         /* 1x3 conv */
+  const float* shift2;    /* [64] or NULL */
+  const void* residual;   /* bf16 NHWC [*, h, w, res_ld] or NULL */
+  void* out;              /* bf16 NHWC [n, h, w, out_ld] */
+  const int32_t* count;
+  const int32_t* in_map;
+  const int32_t* res_map;
+  int32_t n, n_in, h, w;
+  int32_t in_ld, out_ld, res_ld;
+  int32_t relu2;
+} dynmm_conv_pair_params;
+int dynmm_conv_pair_fwd(const dynmm_conv_pair_params* p, void* stream);
+
 /* Same contract, one thread per output element, CUDA cores.  Test comparator
  * for the tensor-core kernel at sizes the CPU oracle cannot reach; never used
  * by the product path. */
