@@ -180,7 +180,7 @@ def profile_conv_kernel(model, rgb, depth):
     recs = []
     REP = 4
 
-    def prof(p, launch):
+    def prof(launch, macs_per_sample, n, count):
         launch()                                        # the real launch of the forward
         s = torch.cuda.current_stream()
         g = torch.cuda.CUDAGraph()
@@ -192,8 +192,7 @@ def profile_conv_kernel(model, rgb, depth):
         e0.record(s)
         g.replay()
         e1.record(s)
-        macs_per_sample = p.h_out * p.w_out * p.c_out * p.c_in * p.kh * p.kw
-        recs.append((e0, e1, macs_per_sample, p.n, p.count, g))
+        recs.append((e0, e1, macs_per_sample, n, count, g))
     eng = model.engine(rgb.device)
     with torch.no_grad():
         eng.forward(rgb, depth, temp=1.0, hard_gate=True)
@@ -299,19 +298,15 @@ def main():
         model.use_cuda_graph = False
         t_conv, n_conv, wgt, recs = profile_conv_kernel(model, *batches[0])
         model.use_cuda_graph = not args.no_graph
-        branches = wgt.argmax(1).tolist()
-        # executed FLOPs of the tensor-core conv launches: dense launches count n samples, depth-stage
-        # launches count the samples the gate kept (count[s] = #samples with branch >= s)
-        kept = [sum(1 for k in branches if k >= s) for s in (1, 2, 3, 4)]
-        count_ptrs = sorted({r[4] for r in recs if r[4]})
-        ptr_to_kept = {p: kept[i] for i, p in enumerate(count_ptrs)} if len(count_ptrs) == 4 else {}
+        # executed FLOPs of the tensor-core conv launches (single convolutions and fused pairs): depth-stage launches
+        # count the samples the gate kept (their device-side `count`), everything else its n samples
         gflop = 0.0
-        for _, _, macs, n, cptr in recs:
-            active = ptr_to_kept.get(cptr, n) if cptr else n
+        for _, _, macs, n, count in recs:
+            active = min(int(count.item()), n) if count is not None else n
             gflop += 2.0 * macs * active / 1e9
         achieved = gflop / 1e3 / t_conv if t_conv > 0 else 0.0
         step_s = t_dev / args.steps
-        roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, all launches of a step)",
+        roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel + conv_pair_kernel (tcgen05 implicit GEMM; all conv launches of a step)",
                     "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s", "frac": achieved / tf_sust,
                     "peak_source": f"{src} (bf16 sustained; burst {tf_burst})", "traffic": conv_traffic(),
                     "launches_per_step": n_conv, "gflop_per_step": gflop, "kernel_s_per_step": t_conv,

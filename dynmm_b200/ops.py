@@ -88,7 +88,9 @@ def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 
         return out
     fn = lib.dynmm_conv_direct_fwd if direct else lib.dynmm_conv_igemm_fwd
     if CONV_PROFILER is not None and not direct:
-        CONV_PROFILER(p, lambda: check(fn(ctypes.byref(p), stream_ptr()), "conv_igemm"))
+        # (launch closure, MACs per output sample, output sample slots, device count tensor or None)
+        CONV_PROFILER(lambda: check(fn(ctypes.byref(p), stream_ptr()), "conv_igemm"),
+                      h_out * w_out * c_out * c_in * kh * kw, n, count)
     else:
         check(fn(ctypes.byref(p), stream_ptr()), "conv_direct" if direct else "conv_igemm")
     return out
@@ -113,7 +115,11 @@ def conv_pair(x: Tensor, w1: Tensor, shift1: Optional[Tensor], w2: Tensor, shift
     p.in_ld, p.out_ld = in_ld, out.shape[3]
     p.res_ld = residual.shape[3] if residual is not None else 0
     p.relu2 = int(relu2)
-    check(lib.dynmm_conv_pair_fwd(ctypes.byref(p), stream_ptr()), "conv_pair")
+    if CONV_PROFILER is not None:
+        CONV_PROFILER(lambda: check(lib.dynmm_conv_pair_fwd(ctypes.byref(p), stream_ptr()), "conv_pair"),
+                      2 * h * w * 64 * 64 * 3, n, count)
+    else:
+        check(lib.dynmm_conv_pair_fwd(ctypes.byref(p), stream_ptr()), "conv_pair")
     return out
 
 
