@@ -4,3 +4,4 @@ from .modules import (BasicBlock, Bottleneck, ConvBNAct, Decoder, DecoderModule,
                       SqueezeAndExcitation, SqueezeAndExciteFusionAdd, Upsample, get_context_module)
 from .build import build_model  # noqa: F401,E402
 from .pipeline import EvalPipeline  # noqa: F401,E402
+from .loss import CrossEntropyLoss2d  # noqa: F401,E402

@@ -102,3 +102,31 @@ def test_flop_tables_are_reproduced():
         assert abs(cum / 1e9 - table[s + 1]) / table[s + 1] < 0.02, (s, cum / 1e9, table[s + 1])
     # each 3x1 / 1x3 conv of a stage-1 block is 235.9 MMAC
     assert m["encoder_rgb.stage1"] == 3 * 4 * 64 * 64 * 3 * 120 * 160
+
+
+def test_multiscale_cross_entropy_oracle_and_module_match_reference_vectors(golden_dir):
+    """CrossEntropyLoss2d (utils.py:18-50).  The numpy oracle and the drop-in module against losses and
+    logit gradients produced by the reference class (oracle/make_golden_loss.py)."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import loss_oracle as lo
+    from dynmm_b200.fusion import CrossEntropyLoss2d
+    gold = np.load(os.path.join(golden_dir, "loss_ce2d.npz"))
+    weight = gold["weight"]
+    logits = [gold[f"logits{i}"] for i in range(4)]
+    targets = [gold[f"targets{i}"] for i in range(4)]
+    ref = [float(gold[f"loss{i}"]) for i in range(4)]
+    got = lo.ce2d(logits, targets, weight)
+    np.testing.assert_allclose(got, ref, rtol=2e-6)
+    np.testing.assert_allclose(lo.ce2d_scale(gold["edge_logits"], gold["edge_targets"], weight), float(gold["edge_loss"]),
+                               rtol=2e-6)
+    loss_fn = CrossEntropyLoss2d(torch.device("cpu"), weight)
+    xs = [torch.from_numpy(x).requires_grad_(True) for x in logits]
+    losses = loss_fn(xs, [torch.from_numpy(t) for t in targets])
+    np.testing.assert_allclose([l.item() for l in losses], ref, rtol=2e-6)
+    sum(losses).backward()
+    for i, x in enumerate(xs):
+        np.testing.assert_allclose(x.grad.numpy(), gold[f"grad{i}"], rtol=1e-5, atol=1e-9)
+    edge = loss_fn([torch.from_numpy(gold["edge_logits"])], [torch.from_numpy(gold["edge_targets"])])[0].item()
+    np.testing.assert_allclose(edge, float(gold["edge_loss"]), rtol=2e-6)
