@@ -162,34 +162,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// Four UMMAs (the 4 k-steps of one 64-element K chunk) in ONE asm statement.  Operands that the compiler holds
-// in ordinary registers must be moved to uniform registers behind an ELECT / R2UR / branch sequence before
-// every tcgen05.mma (~70 issue cycles); here that price is paid once per four MMAs: the descriptors are
-// rebuilt inside the block from their low words (the high word of a K-major SWIZZLE_128B descriptor is the
-// constant 0x40004040: SBO 1024 B, version 1, swizzle mode 2) and advanced by 32 bytes (+2) per k-step.
-//   kTmemCol: accumulator TMEM column (lane 0), compile-time;  a_lo / b_lo: ((smem_addr & 0x3FFFF) >> 4) | 0x10000
-template <uint32_t kTmemCol>
-__device__ __forceinline__ void umma_bf16_x4(uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, t;\n\t.reg .b64 da, db;\n\t.reg .b32 td;\n\t"
-      "setp.ne.b32 p, %3, 0;\n\t"
-      "setp.eq.b32 t, 0, 0;\n\t"
-      "mov.b32 td, %4;\n\t"
-      "mov.b64 da, {%0, 0x40004040};\n\t"
-      "mov.b64 db, {%1, 0x40004040};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [td], da, db, %2, p;\n\t"
-      "add.s64 da, da, 2;\n\tadd.s64 db, db, 2;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [td], da, db, %2, t;\n\t"
-      "add.s64 da, da, 2;\n\tadd.s64 db, db, 2;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [td], da, db, %2, t;\n\t"
-      "add.s64 da, da, 2;\n\tadd.s64 db, db, 2;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [td], da, db, %2, t;\n\t}\n" ::"r"(a_lo),
-      "r"(b_lo), "r"(idesc), "r"(accumulate), "n"(kTmemCol)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t umma_desc_lo_sw128(uint32_t smem_addr) {
-  return ((smem_addr & 0x3FFFF) >> 4) | 0x10000u;
-}
 // all previously issued MMAs of this thread arrive on `bar` when complete
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
