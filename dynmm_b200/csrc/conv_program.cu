@@ -16,9 +16,10 @@
 //   * tensors written in one phase and read in the next stay in L2 (ld.global.cg / TMA, never the
 //     non-coherent path).
 //
-// The per-tile work (TMA producer, single-thread MMA issue, 8 epilogue warps) is the code of conv_igemm.cu,
-// reading its KernelArgs from shared memory and its tensor maps from the device-resident program image;
-// a convolution run through a program is bit-identical to the same convolution launched on its own.
+// The per-tile work (TMA producer, MMA issue, 8 epilogue warps) is the code of conv_igemm.cu, reading its KernelArgs
+// from shared memory and its tensor maps from the device-resident program image; two MMA-issuing warps work on
+// alternate tiles when a CTA has several tiles and enough stages (dual mode).  A convolution run through a program
+// is bit-identical to the same convolution launched on its own.
 #include <string.h>
 
 #include "conv_plan.cuh"
@@ -50,11 +51,9 @@ static_assert(sizeof(ProgramHeader) <= kHeaderBytes, "program header");
 static_assert(sizeof(JobBrief) == 32, "JobBrief");
 static_assert(sizeof(ConvPlan) % 64 == 0, "tensor maps need 64-byte alignment");
 
-// What the MMA-issuing thread needs to know about a job.  These travel as KERNEL PARAMETERS (constant bank)
-// and are indexed by a warp-uniform loop counter, so that shared-memory / TMEM addresses, descriptors and the
-// instruction descriptor of every tcgen05.mma are computed in uniform registers: values loaded from shared
-// or global memory would cost an ELECT + 7 x R2UR + branch sequence per MMA (measured: the issue thread was
-// busy 77 % of the time and the tensor pipe waited for it).
+// What the MMA-issuing warps need to know about a job, as KERNEL PARAMETERS (constant bank) next to the device
+// image.  (The job index of a CTA is data dependent, so these values still arrive in ordinary registers; what keeps
+// the issue rate up is the converged-warp / elect.sync pattern of the issuers, see conv_igemm.cu.)
 constexpr int kMaxJobs = 160;
 struct MmaJob {
   uint32_t idesc;
