@@ -331,7 +331,12 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
       for (int cand = 64; cand <= 256 && cand <= c64 && c64 != 192; cand *= 2) {
         const long long tiles = 1LL * m_tiles * ceil_div(c_out_pad, cand);
         const long long est = ceil_div_ll(tiles, sms) * (cand > 128 ? 2 : 1);
-        if (best < 0 || est < best) {
+        // DYNMM_CONV_WIDE=1 (experiment, default off): ties go to the WIDER tile (one round of 256 instead of two of 128)
+        static const bool prefer_wide = [] {
+          const char* e = getenv("DYNMM_CONV_WIDE");
+          return e && e[0] == '1';
+        }();
+        if (best < 0 || est < best || (prefer_wide && est == best)) {
           best = est;
           tile_n = cand;
         }
