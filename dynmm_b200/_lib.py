@@ -105,6 +105,10 @@ SIGNATURES = {
     "dynmm_compact_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dynmm_argmax_confusion": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dynmm_miou": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "dynmm_ce2d_workspace": (c_longlong, [c_int, c_int, c_int, c_int]),
+    "dynmm_ce2d_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_longlong,
+                               c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dynmm_ce2d_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dynmm_nchw_f32_to_nhwc_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dynmm_nhwc_bf16_to_nchw_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dynmm_upsample2x_dw3x3": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -629,3 +629,33 @@ def miou(cm: Tensor):
     m = torch.empty(1, dtype=torch.float64, device=cm.device)
     check(lib.dynmm_miou(ptr(cm), c, ptr(iou), ptr(m), stream_ptr()), "miou")
     return m, iou
+
+
+# ------------------------------------------------------------------ training loss (experimental)
+
+def ce2d_fwd(logits: Tensor, targets: Tensor, weight: Tensor):
+    """One scale of CrossEntropyLoss2d (dynmm_ce2d_fwd): logits fp32 NCHW, targets int32 [n,h,w] (0 = void).
+    -> (loss [1], lse [n,h,w], divisor [1])."""
+    lib = _lib.load()
+    _cuda(logits, targets, weight)
+    n, c, h, w = logits.shape
+    need = lib.dynmm_ce2d_workspace(n, c, h, w)
+    if need < 0:
+        raise _lib.DynmmError("ce2d: 1..255 classes")
+    ws = torch.empty(need, dtype=torch.uint8, device=logits.device)
+    lse = torch.empty(n, h, w, dtype=torch.float32, device=logits.device)
+    loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+    divisor = torch.empty(1, dtype=torch.float32, device=logits.device)
+    check(lib.dynmm_ce2d_fwd(ptr(logits), ptr(targets), ptr(weight), n, c, h, w, ptr(ws), need, ptr(lse), ptr(loss),
+                             ptr(divisor), stream_ptr()), "ce2d_fwd")
+    return loss, lse, divisor
+
+
+def ce2d_bwd(logits: Tensor, targets: Tensor, weight: Tensor, lse: Tensor, divisor: Tensor, grad_out: Tensor) -> Tensor:
+    lib = _lib.load()
+    _cuda(logits, targets, weight, lse, divisor, grad_out)
+    n, c, h, w = logits.shape
+    grad = torch.empty_like(logits)
+    check(lib.dynmm_ce2d_bwd(ptr(logits), ptr(targets), ptr(weight), ptr(lse), ptr(divisor), ptr(grad_out), n, c, h, w,
+                             ptr(grad), stream_ptr()), "ce2d_bwd")
+    return grad

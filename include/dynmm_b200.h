@@ -324,6 +324,20 @@ int dynmm_argmax_confusion(const float* logits, const uint8_t* label_orig, int n
  * miou = mean(iou).  iou (double[c]) optional. */
 int dynmm_miou(const long long* cm, int c, double* iou, double* miou, void* stream);
 
+/* ------------------------------------------------------ training loss
+ *
+ * One scale of CrossEntropyLoss2d (FusionDynMM/src/utils.py:34-50): logits fp32 NCHW [n,c,h,w], targets int32 [n,h,w]
+ * with 0 = void and 1..c = class + 1, weight [c].  loss = sum w[t] (logsumexp(x) - x[t]) / sum_c n_c w[c];
+ * `lse` [n,h,w] and `divisor` (device scalars / buffers) are kept for the backward, which writes
+ * grad_logits = grad_out * w[t] (softmax(x) - onehot(t)) / divisor.  workspace: dynmm_ce2d_workspace() bytes.
+ * EXPERIMENTAL in round 1 (not yet validated on a GPU; DYNMM_CE_CUDA=1 enables it in the module). */
+long long dynmm_ce2d_workspace(int n, int c, int h, int w);
+int dynmm_ce2d_fwd(const float* logits, const int32_t* targets, const float* weight, int n, int c, int h, int w,
+                   void* workspace, long long workspace_bytes, float* lse, float* loss, float* divisor, void* stream);
+int dynmm_ce2d_bwd(const float* logits, const int32_t* targets, const float* weight, const float* lse,
+                   const float* divisor, const float* grad_out, int n, int c, int h, int w, float* grad_logits,
+                   void* stream);
+
 /* layout / dtype plumbing */
 int dynmm_nchw_f32_to_nhwc_bf16(const float* in, int n, int c, int h, int w, void* out, void* stream);
 int dynmm_nhwc_bf16_to_nchw_f32(const void* in, int n, int c, int h, int w, int ld, float* out, void* stream);
