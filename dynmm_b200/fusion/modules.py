@@ -595,10 +595,11 @@ class SkipGateESANet(nn.Module):
         return eng.forward(rgb, depth, **modes)
 
     @torch.no_grad()
-    def predict_labels(self, rgb, depth, out=None):
+    def predict_labels(self, rgb, depth, out=None, return_weight=False):
         """argmax_c(self(rgb, depth, True)) as uint8 [B,H,W] -- what eval.py:109-120 computes per batch --
         produced by the final upsampling kernel itself, so the 40-channel full-resolution logits are
-        never written to memory.  Eval mode, CUDA tensors."""
+        never written to memory.  Eval mode, CUDA tensors.  ``return_weight``: also the gate weights [B,5]
+        (like ``forward(..., test=True, return_weight=True)``)."""
         if self.training or not rgb.is_cuda:
             raise RuntimeError("predict_labels runs the CUDA engine: call model.eval() and pass CUDA tensors")
         labels, weight = self._forward_engine(rgb, depth, labels_only=True)
@@ -606,8 +607,8 @@ class SkipGateESANet(nn.Module):
             self._pending_weights.append(weight.detach().clone())
         if out is not None:
             out.copy_(labels)
-            return out
-        return labels
+            labels = out
+        return (labels, weight) if return_weight else labels
 
     # ------------------------------------------------------------------ forward
     def forward(self, rgb, depth, test=False, return_weight=False):      # :255-322
