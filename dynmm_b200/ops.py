@@ -631,7 +631,7 @@ def miou(cm: Tensor):
     return m, iou
 
 
-# ------------------------------------------------------------------ training loss (experimental)
+# ------------------------------------------------------------------ training loss
 
 def ce2d_fwd(logits: Tensor, targets: Tensor, weight: Tensor):
     """One scale of CrossEntropyLoss2d (dynmm_ce2d_fwd): logits fp32 NCHW, targets int32 [n,h,w] (0 = void).

@@ -330,7 +330,7 @@ int dynmm_miou(const long long* cm, int c, double* iou, double* miou, void* stre
  * with 0 = void and 1..c = class + 1, weight [c].  loss = sum w[t] (logsumexp(x) - x[t]) / sum_c n_c w[c];
  * `lse` [n,h,w] and `divisor` (device scalars / buffers) are kept for the backward, which writes
  * grad_logits = grad_out * w[t] (softmax(x) - onehot(t)) / divisor.  workspace: dynmm_ce2d_workspace() bytes.
- * EXPERIMENTAL in round 1 (not yet validated on a GPU; DYNMM_CE_CUDA=1 enables it in the module). */
+ * Used by dynmm_b200.fusion.CrossEntropyLoss2d for CUDA logits (DYNMM_CE_CUDA=0 selects the PyTorch statement). */
 long long dynmm_ce2d_workspace(int n, int c, int h, int w);
 int dynmm_ce2d_fwd(const float* logits, const int32_t* targets, const float* weight, int n, int c, int h, int w,
                    void* workspace, long long workspace_bytes, float* lse, float* loss, float* divisor, void* stream);
