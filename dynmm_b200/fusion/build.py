@@ -1,5 +1,6 @@
 """``build_model(args, n_classes)`` -- drop-in for FusionDynMM/src/build_model.py:18-218
-restricted to the path this package accelerates (``--dynamic --global-gate``)."""
+restricted to the dynamic models this package provides: ``--dynamic --global-gate`` (``SkipGateESANet``, the
+accelerated path) and ``--dynamic`` alone (``SkipESANet``, the local-gate variant, build_model.py:76-95)."""
 from __future__ import annotations
 
 import warnings
@@ -7,13 +8,14 @@ import warnings
 import torch
 from torch import nn
 
+from .local_gate import SkipESANet
 from .modules import SkipGateESANet
 
 
 def build_model(args, n_classes):
-    if not getattr(args, "dynamic", False) or not getattr(args, "global_gate", False):
-        raise NotImplementedError("dynmm_b200 provides the global-gate dynamic model (--dynamic --global-gate); "
-                                  "the static / local-gate ESANet variants are outside the accelerated path")
+    if not getattr(args, "dynamic", False):
+        raise NotImplementedError("dynmm_b200 provides the dynamic models (--dynamic [--global-gate]); the static "
+                                  "ESANet / one-modality variants are outside the gated path")
     if getattr(args, "pretrained_on_imagenet", False) and not getattr(args, "last_ckpt", "") and \
             getattr(args, "pretrained_scenenet", "") == "":
         warnings.warn("ImageNet checkpoints are not reachable offline: building with random init")
@@ -28,7 +30,8 @@ def build_model(args, n_classes):
     assert len(block_rule) == 4
     if args.encoder_depth in (None, "None"):
         args.encoder_depth = args.encoder
-    model = SkipGateESANet(
+    cls = SkipGateESANet if getattr(args, "global_gate", False) else SkipESANet      # build_model.py:54-95
+    model = cls(
         height=args.height, width=args.width, num_classes=n_classes, pretrained_on_imagenet=False,
         pretrained_dir=getattr(args, "pretrained_dir", None), encoder_rgb=args.encoder,
         encoder_depth=args.encoder_depth, encoder_block=args.encoder_block, activation=args.activation,

@@ -80,7 +80,10 @@ def test_build_model_signature():
                               pretrained_scenenet="", pretrained_dir="", he_init=True, finetune=None)
     model, device = build_model(args, n_classes=40)
     assert isinstance(device, torch.device) and model.decoder.conv_out.out_channels == 40
-    args.global_gate = False
+    args.global_gate = False                                   # build_model.py:76-95: the local-gate variant
+    from dynmm_b200.fusion import SkipESANet
+    assert isinstance(build_model(args, 40)[0], SkipESANet)
+    args.dynamic = False                                       # static / one-modality ESANets are not provided
     with pytest.raises(NotImplementedError):
         build_model(args, 40)
     with pytest.raises(NotImplementedError):

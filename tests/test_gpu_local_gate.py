@@ -1,0 +1,113 @@
+"""Local-gate dynamic ESANet on the GPU.
+
+* The Gumbel gate op (noise drawn like ``F.gumbel_softmax`` draws it + the ``diff_softmax`` CUDA kernel) makes the
+  SAME decisions as ``F.gumbel_softmax`` on the same device and seed, soft values to 1e-6, and has its gradient.
+* With the random policy (CPU ``torch.randint``, rgb_depth_fusion.py:36-40) nothing depends on the device generator, so
+  the reference's own vectors (tests/golden/local_gate_*.npz) apply: decisions bit-exact, logits within the fp32 /
+  stated bf16 tolerance -- the fp32 graph uses the ``gated_add`` kernel for the blends, ``train_precision='bf16'``
+  additionally runs every stage convolution on the tcgen05 kernels.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = [pytest.mark.gpu, pytest.mark.first_run]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _setup():
+    from dynmm_b200 import _lib
+    _lib.require_device()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+@pytest.mark.parametrize("hard", [True, False])
+def test_gumbel_gate_equals_torch_gumbel_softmax_on_device(hard):
+    from dynmm_b200.fusion.local_gate import gumbel_softmax
+    g = torch.Generator().manual_seed(9)
+    logits = (torch.rand(64, 2, generator=g) / 0.7).cuda()
+    torch.manual_seed(123)
+    ref = F.gumbel_softmax(logits, tau=1, hard=hard)
+    torch.manual_seed(123)
+    x = logits.clone().requires_grad_(True)
+    got = gumbel_softmax(x, hard)
+    if hard:
+        assert torch.equal(got.detach().argmax(1), ref.argmax(1))            # decisions bit-exact
+        torch.testing.assert_close(got.detach(), ref, rtol=0, atol=2e-7)     # one-hot up to (1 - s) + s rounding
+    else:
+        torch.testing.assert_close(got.detach(), ref, rtol=1e-5, atol=1e-6)
+    # straight-through / soft gradient = Jacobian of the softmax of the noisy logits
+    torch.manual_seed(123)
+    y = logits.clone().requires_grad_(True)
+    up = torch.randn(64, 2, generator=g).cuda()
+    (F.gumbel_softmax(y, tau=1, hard=hard) * up).sum().backward()
+    (got * up).sum().backward()
+    torch.testing.assert_close(x.grad, y.grad, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["local_gate_r18_basic_64x64", "local_gate_r34_nbt1d_64x96"])
+def test_random_policy_matches_reference_vectors(name, golden_dir):
+    from dynmm_b200.fusion import SkipESANet
+    from oracle.make_golden_local import CASES, MODES, apply_mode, sample_inputs, seeded_state
+    kw, seed, b = CASES[name]
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    model = SkipESANet(pretrained_on_imagenet=False, **kw)
+    model.load_state_dict(seeded_state(model.state_dict(), seed), strict=True)
+    model = model.cuda().eval()
+    rgb, depth = (t.cuda() for t in sample_inputs(seed + 100, b, kw["height"], kw["width"]))
+    tag, rule, attrs, test, fseed = next(m for m in MODES if m[0] == "random")
+    ref = torch.from_numpy(gold[f"{tag}_out"])
+    for precision, tol in (("fp32", 2e-3), ("bf16", 2e-2)):
+        model.train_precision = precision
+        apply_mode(model, rule, attrs)
+        model.start_weight()
+        torch.manual_seed(fseed)
+        with torch.no_grad():
+            out = model(rgb, depth, test)
+        model._flush_weights()
+        for i in range(4):
+            np.testing.assert_array_equal(model.weight_list[i].numpy(), gold[f"{tag}_weight{i}"])
+        model.end_weight()
+        got = out[:, :, ::4, ::4].float().cpu()
+        err = ((got.double() - ref.double()).norm() / ref.double().norm()).item()
+        assert err <= tol, f"{name}/{precision}: relative L2 error {err:.5f}"
+    # static rules (no gate in the data path): 1111 = plain ESANet-style add fusion
+    tag, rule, attrs, test, fseed = next(m for m in MODES if m[0] == "static1111")
+    model.train_precision = "fp32"
+    apply_mode(model, rule, attrs)
+    torch.manual_seed(fseed)
+    with torch.no_grad():
+        out = model(rgb, depth, test)
+    ref = torch.from_numpy(gold[f"{tag}_out"])
+    err = ((out[:, :, ::4, ::4].cpu().double() - ref.double()).norm() / ref.double().norm()).item()
+    assert err <= 2e-3, err
+
+
+def test_hard_chain_is_monotone_on_device():
+    """Chained hard gates (prev_weight, model_skip_mod.py:259,277,295): once a site is closed every later one is."""
+    from dynmm_b200.fusion import SkipESANet
+    from oracle.make_golden_local import CASES, apply_mode, sample_inputs, seeded_state
+    kw, seed, b = CASES["local_gate_r18_basic_64x64"]
+    model = SkipESANet(pretrained_on_imagenet=False, **kw)
+    model.load_state_dict(seeded_state(model.state_dict(), seed), strict=True)
+    model = model.cuda().eval()
+    rgb, depth = (t.cuda() for t in sample_inputs(seed + 100, 8, kw["height"], kw["width"]))
+    apply_mode(model, [2, 2, 2, 2], dict(hard_gate=True))
+    model.start_weight()
+    with torch.no_grad():
+        for s in range(4):
+            torch.manual_seed(s)
+            out = model(rgb, depth, True)
+            assert torch.isfinite(out).all()
+    model._flush_weights()
+    w = torch.stack([model.weight_list[i][:, 1] for i in range(4)])            # [site, samples]
+    assert (w - w.round()).abs().max().item() <= 1e-6            # one-hot up to the (1 - s) + s rounding of the ST form
+    w = w.round()
+    assert (w[1:] <= w[:-1]).all()
+    assert 0 < w.sum() < w.numel()
+    model.end_weight()
