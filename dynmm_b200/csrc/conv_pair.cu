@@ -17,6 +17,8 @@
 // Persistent CTA per SM: warp 0 TMA producer, warp 1 MMA issuer, 8 warps for epilogue 1 and 8 warps for epilogue 2
 // (the epilogues, not the MMAs, bound the kernel); X ring of 3, double-buffered Y / accumulators / staging; both
 // weight sets (2 x 24 KiB) resident.  MMA 1 of tile i+1 is issued before MMA 2 of tile i.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tma_host.cuh"
 
@@ -76,6 +78,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
                : "memory");
 }
 
+template <bool kRot>      // kRot: experimental conflict-avoiding chunk order in epilogue 1 (DYNMM_PAIR_ROT=1)
 __global__ void __launch_bounds__(kThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                  const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_res,
@@ -260,18 +263,53 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       const int yrow = ww * kTH + hh;
       const uint32_t dst = s_base + kOffY + b * kYBytes + yrow * 128;
       const uint32_t swz = yrow & 7;
+      if constexpr (!kRot) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        float f[8];
+        for (int j = 0; j < 32; j += 8) {
+          float f[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(v[j + e]) + sh1[j + e], 0.f);
-        uint4 o;
-        o.x = pack_bf16(f[0], f[1]);
-        o.y = pack_bf16(f[2], f[3]);
-        o.z = pack_bf16(f[4], f[5]);
-        o.w = pack_bf16(f[6], f[7]);
-        if (zero) o = make_uint4(0u, 0u, 0u, 0u);
-        sts128(dst + ((((half * 4 + (j >> 3)) ^ swz)) << 4), o);
+          for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(v[j + e]) + sh1[j + e], 0.f);
+          uint4 o;
+          o.x = pack_bf16(f[0], f[1]);
+          o.y = pack_bf16(f[2], f[3]);
+          o.z = pack_bf16(f[4], f[5]);
+          o.w = pack_bf16(f[6], f[7]);
+          if (zero) o = make_uint4(0u, 0u, 0u, 0u);
+          sts128(dst + ((((half * 4 + (j >> 3)) ^ swz)) << 4), o);
+        }
+      } else {
+        // EXPERIMENT (DYNMM_PAIR_ROT=1, not yet run on a GPU).  The 8 lanes of a quarter-warp write Y rows 8 apart
+        // (ww consecutive, same hh): 1024-byte stride and the same swizzle term, i.e. the same 4 banks for a given
+        // chunk -> 8-way conflicts on every 16-byte store above.  Here lane ww writes its four chunks in the order
+        // (i + ww) & 3, so a quarter-warp covers all four chunk positions in every store (2-way instead of 8-way).
+        // Same bytes at the same addresses: the result is unchanged.
+        uint4 o[4];
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(v[j + e]) + sh1[j + e], 0.f);
+          o[j >> 3].x = pack_bf16(f[0], f[1]);
+          o[j >> 3].y = pack_bf16(f[2], f[3]);
+          o[j >> 3].z = pack_bf16(f[4], f[5]);
+          o[j >> 3].w = pack_bf16(f[6], f[7]);
+          if (zero) o[j >> 3] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        const uint32_t r = ww & 3;
+        const bool r1 = r & 1, r2 = r & 2;
+        uint4 p[4], q[4];
+        auto sel = [](bool c, const uint4& a, const uint4& b) {
+          return make_uint4(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z, c ? a.w : b.w);
+        };
+#pragma unroll
+        for (int k = 0; k < 4; ++k) p[k] = sel(r1, o[(k + 1) & 3], o[k]);        // rotate by (r & 1)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) q[k] = sel(r2, p[(k + 2) & 3], p[k]);        // then by (r & 2): q[k] = o[(k + r) & 3]
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t c = (i + r) & 3;
+          sts128(dst + ((((half * 4 + c) ^ swz)) << 4), q[i]);
+        }
       }
       fence_async_smem();                                // generic writes -> visible to the tensor core (async proxy)
       __syncwarp();
@@ -404,6 +442,10 @@ extern "C" int dynmm_conv_pair_fwd(const dynmm_conv_pair_params* p, void* stream
   a.tiles_w = ceil_div(p->w, kTW);
   a.relu2 = p->relu2;
   a.has_res = p->residual ? 1 : 0;
+  static const bool rot = [] {
+    const char* e = getenv("DYNMM_PAIR_ROT");
+    return e && e[0] == '1';
+  }();
   a.shift1 = p->shift1;
   a.shift2 = p->shift2;
   a.count = p->count;
@@ -411,7 +453,10 @@ extern "C" int dynmm_conv_pair_fwd(const dynmm_conv_pair_params* p, void* stream
   a.res_map = p->res_map;
   const long long max_tiles = 1LL * p->n * a.tiles_h * a.tiles_w;
   DYNMM_CHECK_ARG(max_tiles < (1LL << 30), "conv_pair: too many tiles");
-  static cudaError_t attr_err = cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  static cudaError_t attr_err = [] {
+    cudaError_t e = cudaFuncSetAttribute(conv_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    return e != cudaSuccess ? e : cudaFuncSetAttribute(conv_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  }();
   DYNMM_CUDA(attr_err);
   int grid = num_sms();
   if (grid > max_tiles) grid = (int)max_tiles;
@@ -425,6 +470,10 @@ extern "C" int dynmm_conv_pair_fwd(const dynmm_conv_pair_params* p, void* stream
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DYNMM_CUDA(cudaLaunchKernelEx(&cfg, conv_pair_kernel, map_x, map_w1, map_w2, map_res, map_out, a));
+  if (rot) {
+    DYNMM_CUDA(cudaLaunchKernelEx(&cfg, conv_pair_kernel<true>, map_x, map_w1, map_w2, map_res, map_out, a));
+  } else {
+    DYNMM_CUDA(cudaLaunchKernelEx(&cfg, conv_pair_kernel<false>, map_x, map_w1, map_w2, map_res, map_out, a));
+  }
   return DYNMM_OK;
 }

@@ -54,3 +54,19 @@ def test_pair_count_and_maps():
                             n_out=n, out=torch.zeros(n, h, w, 64, dtype=torch.bfloat16, device="cuda"))
         torch.cuda.synchronize()
         assert torch.equal(ref, got), f"active={active}"
+
+
+@pytest.mark.first_run
+def test_pair_rotated_store_order_is_bit_identical():
+    """DYNMM_PAIR_ROT=1 (conflict-avoiding chunk order in epilogue 1, written after round 1's GPU budget was spent): the
+    switch is read once per process, so the bit-identity tests above are re-run in a child process with it set."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, DYNMM_PAIR_ROT="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_pair.py"), "-q", "-x",
+                        "-m", "gpu", "-k", "bit_identical and not rotated or count_and_maps", "-p", "no:cacheprovider"],
+                       env=env, cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "passed" in r.stdout

@@ -9,6 +9,9 @@ timeout 300 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err
 timeout 200 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference.json 2> $O/bench_reference.err
 timeout 300 python bench.py --batch 32 --steps 60 --no-cpu-baseline > $O/bench_b32.json 2> $O/bench_b32.err
 DYNMM_CONV_WIDE=1 timeout 200 python bench.py --no-cpu-baseline --steps 100 > $O/bench_conv_wide.json 2> $O/bench_conv_wide.err
+timeout 60 python tools/pair_bench.py > $O/pair_bench.txt 2>&1
+DYNMM_PAIR_ROT=1 timeout 60 python tools/pair_bench.py > $O/pair_bench_rot.txt 2>&1
+DYNMM_PAIR_ROT=1 timeout 200 python bench.py --no-cpu-baseline --steps 100 > $O/bench_pair_rot.json 2> $O/bench_pair_rot.err
 timeout 120 python tools/ce_bench.py > $O/ce_bench.txt 2>&1
 timeout 200 python tools/noise_sweep.py --batches 24 > $O/noise_sweep.txt 2>&1
 timeout 200 python tools/noise_sweep.py --batches 24 --labels > $O/noise_sweep_labels.txt 2>&1
