@@ -3,8 +3,8 @@
 ``install_aliases()`` registers
   unimodals.common_models, fusions.common_fusions, training_structures.Supervised_Learning
 (the MultiBench paths imported at imdb_dyn.py:10-13 / affect_dyn.py:12-15) and
-  src.models.model_skip_mod_globalgate
-(imported by FusionDynMM/src/build_model.py) in ``sys.modules``.
+  src.models.model_skip_mod_globalgate, src.models.model_skip_mod
+(imported by FusionDynMM/src/build_model.py:11-12) in ``sys.modules``.
 """
 from __future__ import annotations
 
@@ -14,6 +14,7 @@ import types
 
 def install_aliases() -> None:
     from . import common_models, supervised
+    from ..fusion import local_gate as fusion_local_gate
     from ..fusion import modules as fusion_modules
 
     def alias(name, module):
@@ -31,3 +32,4 @@ def install_aliases() -> None:
     alias("fusions.common_fusions", fusions)
     alias("training_structures.Supervised_Learning", supervised)
     alias("src.models.model_skip_mod_globalgate", fusion_modules)
+    alias("src.models.model_skip_mod", fusion_local_gate)

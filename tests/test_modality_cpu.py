@@ -86,6 +86,8 @@ def test_multibench_import_aliases_and_pickle_roundtrip(tmp_path):
     from unimodals.common_models import MLP, MaxOut_MLP           # noqa: F401  (MultiBench import path)
     from fusions.common_fusions import Concat                      # noqa: F401
     from training_structures.Supervised_Learning import MMDL       # noqa: F401
+    from src.models.model_skip_mod_globalgate import SkipGateESANet  # noqa: F401  (build_model.py:11-12)
+    from src.models.model_skip_mod import SkipESANet               # noqa: F401
     model = DynMMNet(pretrain=False, freeze=False)
     path = tmp_path / "m.pt"
     torch.save(model, path)                                        # Supervised_Learning.py:208 saves whole modules
