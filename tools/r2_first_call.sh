@@ -13,6 +13,7 @@ timeout 60 python tools/pair_bench.py > $O/pair_bench.txt 2>&1
 DYNMM_PAIR_ROT=1 timeout 60 python tools/pair_bench.py > $O/pair_bench_rot.txt 2>&1
 DYNMM_PAIR_ROT=1 timeout 200 python bench.py --no-cpu-baseline --steps 100 > $O/bench_pair_rot.json 2> $O/bench_pair_rot.err
 timeout 120 python tools/ce_bench.py > $O/ce_bench.txt 2>&1
+timeout 200 python tools/modality_bench.py > $O/modality_bench.txt 2>&1
 timeout 200 python tools/noise_sweep.py --batches 24 > $O/noise_sweep.txt 2>&1
 timeout 200 python tools/noise_sweep.py --batches 24 --labels > $O/noise_sweep_labels.txt 2>&1
 timeout 300 ncu --profile-from-start off --clock-control none --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --csv --log-file $O/step_metrics.csv python tools/one_step.py > $O/one_step.log 2>&1
