@@ -17,5 +17,8 @@ timeout 200 python tools/modality_bench.py > $O/modality_bench.txt 2>&1
 timeout 200 python tools/noise_sweep.py --batches 24 > $O/noise_sweep.txt 2>&1
 timeout 200 python tools/noise_sweep.py --batches 24 --labels > $O/noise_sweep_labels.txt 2>&1
 timeout 300 ncu --profile-from-start off --clock-control none --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --csv --log-file $O/step_metrics.csv python tools/one_step.py > $O/one_step.log 2>&1
+timeout 200 python tools/train_profile.py > $O/train_profile_bf16.txt 2>&1
+TRAIN_PRECISION=bf16 timeout 150 python tools/train_step_dp.py > $O/train_bf16.log 2>&1
+PER_GPU_BATCH=32 TRAIN_PRECISION=bf16 timeout 200 python tools/train_step_dp.py > $O/train_bf16_b32.log 2>&1
 tail -n 3 $O/pytest_gpu.log $O/pytest_first_run.log
 cat $O/bench_n1.json | cut -c1-400
