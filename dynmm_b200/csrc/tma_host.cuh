@@ -29,6 +29,11 @@ inline EncodeTiledFn get_encode_fn() {
 
 inline int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                const uint32_t* box) {
+#ifdef DYNMM_PLAN_DRYRUN
+  // host-only planner report (tools/plan_report.cu): no driver, no descriptors -- only the tiling decisions matter
+  (void)m; (void)base; (void)rank; (void)dims; (void)strides_bytes; (void)box;
+  return DYNMM_OK;
+#endif
   EncodeTiledFn fn = get_encode_fn();
   // The encoder is a DRIVER entry point: it needs the primary context bound to the calling thread.
   // Threads that have not made a runtime call yet (e.g. an autograd worker running our backward)
