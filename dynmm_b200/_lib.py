@@ -32,7 +32,8 @@ class ConvParams(Structure):
         ("res_ld", c_int32), ("gated_ld", c_int32),
         ("kh", c_int32), ("kw", c_int32), ("stride_h", c_int32), ("stride_w", c_int32),
         ("pad_h", c_int32), ("pad_w", c_int32),
-        ("relu", c_int32), ("tile_n", c_int32), ("max_ctas", c_int32), ("trace", c_void_p),
+        ("relu", c_int32), ("tile_n", c_int32), ("max_ctas", c_int32), ("flags", c_int32),
+        ("trace", c_void_p),
     ]
 
 
@@ -92,6 +93,10 @@ SIGNATURES = {
     "dynmm_conv_wgrad": (c_int, [POINTER(WgradParams), c_void_p]),
     "dynmm_conv_wgrad_direct": (c_int, [POINTER(WgradParams), c_void_p]),
     "dynmm_pack_conv_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "dynmm_fold_pack_conv": (c_int, [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 5 + [c_float, c_void_p, c_void_p,
+                                                                                           c_void_p]),
+    "dynmm_fold_bn": (c_int, [c_int] + [c_void_p] * 5 + [c_float, c_void_p, c_void_p, c_void_p]),
+    "dynmm_permute3d_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dynmm_channel_sum_workspace": (c_longlong, [c_longlong, c_int]),
     "dynmm_channel_sum": (c_int, [c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p, c_longlong, c_int,
                                   c_void_p]),

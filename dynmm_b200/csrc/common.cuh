@@ -7,6 +7,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <mutex>
+
 #include "../../include/dynmm_b200.h"
 
 namespace dynmm {
@@ -35,6 +37,25 @@ void set_error(const char* fmt, ...);
 #define DYNMM_LAUNCH_CHECK() DYNMM_CUDA(cudaPeekAtLastError())
 
 int num_sms();
+
+// cudaFuncSetAttribute is PER DEVICE: every kernel that needs more than 48 KiB of dynamic shared memory is configured
+// once on each device it is launched on (not once per process).  `f` returns a cudaError_t.
+struct PerDeviceOnce {
+  std::mutex mu;
+  bool done[64] = {};
+  template <class F>
+  cudaError_t run(F&& f) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> g(mu);
+    if (done[dev]) return cudaSuccess;
+    e = f();
+    if (e == cudaSuccess) done[dev] = true;
+    return e;
+  }
+};
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }

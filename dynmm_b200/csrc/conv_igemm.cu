@@ -374,16 +374,15 @@ extern "C" int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream_) {
       conv_igemm_kernel<4, 2>,  conv_igemm_kernel<5, 2>,  conv_igemm_kernel<6, 2>,  conv_igemm_kernel<7, 2>,
       conv_igemm_kernel<8, 2>,  conv_igemm_kernel<9, 2>,  conv_igemm_kernel<10, 2>, conv_igemm_kernel<11, 2>,
       conv_igemm_kernel<12, 2>, conv_igemm_kernel<13, 2>, conv_igemm_kernel<14, 2>, conv_igemm_kernel<15, 2>};
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    for (int i = 0; i < 32 && attr_err == cudaSuccess; ++i) {
-      attr_err = cudaFuncSetAttribute(table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, i < 16 ? kSmemBudget : 113 * 1024);
-      if (attr_err == cudaSuccess && i >= 16)
-        attr_err = cudaFuncSetAttribute(table[i], cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  static PerDeviceOnce attr_once;
+  DYNMM_CUDA(attr_once.run([] {
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 32 && e == cudaSuccess; ++i) {
+      e = cudaFuncSetAttribute(table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, i < 16 ? kSmemBudget : 113 * 1024);
+      if (e == cudaSuccess && i >= 16) e = cudaFuncSetAttribute(table[i], cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     }
-  });
-  DYNMM_CUDA(attr_err);
+    return e;
+  }));
   static const bool use_pdl = [] {
     const char* e = getenv("DYNMM_PDL");
     return !(e && e[0] == '0');
@@ -397,7 +396,7 @@ extern "C" int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream_) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl ? 1 : 0;
+  cfg.numAttrs = (use_pdl && !(p->flags & DYNMM_CONV_VOLATILE_WEIGHTS)) ? 1 : 0;
   DYNMM_CUDA(cudaLaunchKernelEx(&cfg, table[flags + (a.two_per_sm ? 16 : 0)], plan.maps[0], plan.maps[1], plan.maps[2], plan.maps[3], plan.map_b,
                                 plan.map_res, plan.map_out, a));
   return DYNMM_OK;

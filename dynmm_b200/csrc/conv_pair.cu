@@ -78,7 +78,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
                : "memory");
 }
 
-template <bool kRot>      // kRot: experimental conflict-avoiding chunk order in epilogue 1 (DYNMM_PAIR_ROT=1)
+template <bool kRot>      // kRot: conflict-avoiding chunk order in epilogue 1 (default; DYNMM_PAIR_ROT=0 turns it off)
 __global__ void __launch_bounds__(kThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                  const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_res,
@@ -278,7 +278,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           sts128(dst + ((((half * 4 + (j >> 3)) ^ swz)) << 4), o);
         }
       } else {
-        // EXPERIMENT (DYNMM_PAIR_ROT=1, not yet run on a GPU).  The 8 lanes of a quarter-warp write Y rows 8 apart
+        // Default since round 2 (measured 20.3 -> 17.8 us per pair, bit-identical).  The 8 lanes of a quarter-warp write Y rows 8 apart
         // (ww consecutive, same hh): 1024-byte stride and the same swizzle term, i.e. the same 4 banks for a given
         // chunk -> 8-way conflicts on every 16-byte store above.  Here lane ww writes its four chunks in the order
         // (i + ww) & 3, so a quarter-warp covers all four chunk positions in every store (2-way instead of 8-way).
@@ -443,8 +443,10 @@ extern "C" int dynmm_conv_pair_fwd(const dynmm_conv_pair_params* p, void* stream
   a.relu2 = p->relu2;
   a.has_res = p->residual ? 1 : 0;
   static const bool rot = [] {
+    // rotated chunk order in epilogue 1: 20.3 -> 17.8 us per pair at B = 8 (gpurun_out/r2a, round 2); DYNMM_PAIR_ROT=0
+    // keeps the straight order for comparison
     const char* e = getenv("DYNMM_PAIR_ROT");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');
   }();
   a.shift1 = p->shift1;
   a.shift2 = p->shift2;
@@ -453,11 +455,11 @@ extern "C" int dynmm_conv_pair_fwd(const dynmm_conv_pair_params* p, void* stream
   a.res_map = p->res_map;
   const long long max_tiles = 1LL * p->n * a.tiles_h * a.tiles_w;
   DYNMM_CHECK_ARG(max_tiles < (1LL << 30), "conv_pair: too many tiles");
-  static cudaError_t attr_err = [] {
+  static PerDeviceOnce attr_once;
+  DYNMM_CUDA(attr_once.run([] {
     cudaError_t e = cudaFuncSetAttribute(conv_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     return e != cudaSuccess ? e : cudaFuncSetAttribute(conv_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-  }();
-  DYNMM_CUDA(attr_err);
+  }));
   int grid = num_sms();
   if (grid > max_tiles) grid = (int)max_tiles;
   cudaLaunchConfig_t cfg{};

@@ -653,9 +653,9 @@ extern "C" int dynmm_conv_program_launch(const void* image_dev, const void* imag
   DYNMM_CHECK_ARG(grid >= 1 && grid <= num_sms() && smem_bytes > 0 && smem_bytes <= kSmemBudget && n_jobs >= 1 &&
                       n_jobs <= kMaxJobs && hdr->n_phases >= 1 && hdr->n_phases <= kMaxPhases,
                   "conv_program_launch: not a program image (grid %d, smem %d, jobs %d)", grid, smem_bytes, n_jobs);
-  static cudaError_t attr_err =
-      cudaFuncSetAttribute(conv_program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
-  DYNMM_CUDA(attr_err);
+  static PerDeviceOnce attr_once;
+  DYNMM_CUDA(attr_once.run(
+      [] { return cudaFuncSetAttribute(conv_program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget); }));
   // the MMA thread's view of every job goes into the kernel parameters (constant bank -> uniform registers)
   static thread_local ProgramParams params;
   params.n_phases = hdr->n_phases;

@@ -418,12 +418,9 @@ extern "C" int dynmm_conv_wgrad(const dynmm_wgrad_params* p, void* stream_) {
     if (!used[m]) maps[m] = maps[first_used];
 
   const int smem_bytes = a.stages * a.stage_bytes + 1024 + (int)sizeof(SmemCtlW);
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudgetW);
-  });
-  DYNMM_CUDA(attr_err);
+  static PerDeviceOnce attr_once;
+  DYNMM_CUDA(attr_once.run(
+      [] { return cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudgetW); }));
   conv_wgrad_kernel<<<units * a.splits, kThreadsW, smem_bytes, stream>>>(map_dy, maps[0], maps[1], maps[2], maps[3], a);
   DYNMM_LAUNCH_CHECK();
   const long long plane = 1LL * p->c_out * p->c_in;

@@ -659,11 +659,10 @@ extern "C" int dynmm_upsample2x_dw3x3(const void* in, int n, int h, int w, int c
     DYNMM_CHECK_ARG(!skip, "upsample2x: skip is only supported for the NHWC output");
     const int smem = (c * (kUpTy + 2) * (kUpTx + 3) + c * 16) * (int)sizeof(float);
     DYNMM_CHECK_ARG(smem <= 200 * 1024, "upsample2x: too many channels for the NCHW output");
-    static int configured = 0;
-    if (smem > configured) {
-      DYNMM_CUDA(cudaFuncSetAttribute(upsample2x_dw_to_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      configured = smem;
-    }
+    static PerDeviceOnce attr_once;      // the limit checked above, so one setting serves every channel count
+    DYNMM_CUDA(attr_once.run([] {
+      return cudaFuncSetAttribute(upsample2x_dw_to_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    }));
     dim3 grid(ceil_div(w, kUpTx), ceil_div(h, kUpTy), n);
     upsample2x_dw_to_nchw_kernel<<<grid, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(in), h, w, c, weight,
                                                               bias, out_nchw_f32, labels);

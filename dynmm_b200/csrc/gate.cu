@@ -317,9 +317,10 @@ extern "C" int dynmm_global_gate_logits(const float* rgb, const float* depth, in
   const long long conv1_bytes = (1LL * b * h1 * w1 * kGateC * sizeof(float) + 255) / 256 * 256;
   float* partial = reinterpret_cast<float*>(static_cast<char*>(work) + conv1_bytes);
   const int smem1 = kGateC * kTaps * 128 * sizeof(float);
-  static cudaError_t attr_err =
-      cudaFuncSetAttribute(gate_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGateC * kTaps * 128 * 4);
-  DYNMM_CUDA(attr_err);
+  static PerDeviceOnce attr_once;
+  DYNMM_CUDA(attr_once.run([] {
+    return cudaFuncSetAttribute(gate_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGateC * kTaps * 128 * 4);
+  }));
   const long long items = 1LL * b * h1 * ceil_div(w1, kPx);
   int grid1 = 2 * num_sms();
   if (grid1 > ceil_div_ll(items, 8)) grid1 = (int)ceil_div_ll(items, 8);

@@ -447,9 +447,9 @@ extern "C" int dynmm_stem_s2d_fwd(const float* rgb, const float* depth, int b, i
   s2d_pack_kernel<<<pack_grid, 256, 0, stream>>>(rgb, depth, b, h, w, Hp2, Wp2, p_hi, p_lo);
   DYNMM_LAUNCH_CHECK();
 
-  static cudaError_t attr_err =
-      cudaFuncSetAttribute(stem_s2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-  DYNMM_CUDA(attr_err);
+  static PerDeviceOnce attr_once;
+  DYNMM_CUDA(attr_once.run(
+      [] { return cudaFuncSetAttribute(stem_s2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes); }));
   const int tiles_x = ceil_div(Wp, kPW), tiles_y = ceil_div(Hp, kPH);
   const long long total = 1LL * tiles_x * tiles_y * b;
   DYNMM_CHECK_ARG(total < (1LL << 30), "stem_s2d: too many tiles");

@@ -384,9 +384,9 @@ int stem_tc_launch(const float* rgb, const float* depth, int b, int h, int w, co
   using namespace stemtc;
   const int Hs = (h + 6 - 7) / 2 + 1, Ws = (w + 6 - 7) / 2 + 1;
   const int Hp = (Hs + 2 - 3) / 2 + 1, Wp = (Ws + 2 - 3) / 2 + 1;
-  static cudaError_t attr_err =
-      cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-  DYNMM_CUDA(attr_err);
+  static PerDeviceOnce attr_once;
+  DYNMM_CUDA(attr_once.run(
+      [] { return cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes); }));
   const int tiles_x = ceil_div(Wp, kPT), tiles_y = ceil_div(Hp, kPT);
   const long long total = 1LL * tiles_x * tiles_y * b;
   DYNMM_CHECK_ARG(total < (1LL << 30), "stem: too many tiles");

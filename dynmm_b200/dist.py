@@ -92,5 +92,8 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0) -> None:
     """Make replicas identical (parameters and buffers, e.g. BN running statistics)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return
-    for t in list(module.parameters()) + list(module.buffers()):
-        dist.broadcast(t.data, src)
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t, src)       # in-place on the tensor itself: bumps its version counter (engine cache key)
+    if hasattr(module, "invalidate_engine"):
+        module.invalidate_engine()

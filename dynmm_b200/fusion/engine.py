@@ -34,14 +34,22 @@ def pack_gate(sd: Dict[str, Tensor], prefix: str = "gate_layer.") -> Dict[str, T
     """GlobalGate parameters (model_skip_mod_globalgate.py:379-386) in the layout
     dynmm_global_gate_logits expects; conv bias + eval BN folded to scale/shift."""
     g = lambda k: sd[prefix + k].detach().float()
-    s1, b1 = ops.fold_bn(g("conv.1.weight"), g("conv.1.bias"), g("conv.1.running_mean"), g("conv.1.running_var"),
-                         1e-5, g("conv.0.bias"))
-    s2, b2 = ops.fold_bn(g("conv.4.weight"), g("conv.4.bias"), g("conv.4.running_mean"), g("conv.4.running_var"),
-                         1e-5, g("conv.3.bias"))
+    cuda = g("conv.0.weight").is_cuda
+    fold = ops.fold_bn_cuda if cuda else ops.fold_bn
+    s1, b1 = fold(g("conv.1.weight"), g("conv.1.bias"), g("conv.1.running_mean"), g("conv.1.running_var"),
+                  1e-5, g("conv.0.bias"))
+    s2, b2 = fold(g("conv.4.weight"), g("conv.4.bias"), g("conv.4.running_mean"), g("conv.4.running_var"),
+                  1e-5, g("conv.3.bias"))
+
+    def taps_last_channel(w):          # [o][c][kh][kw] -> [o][kh][kw][c]
+        o, c, kh, kw = w.shape
+        if cuda:
+            return ops.permute3d(w.reshape(o, c, kh * kw), (0, 2, 1)).view(o, kh, kw, c)
+        return w.permute(0, 2, 3, 1).contiguous()
     return {
-        "w1": g("conv.0.weight").permute(0, 2, 3, 1).contiguous(),   # [8][5][5][128]
+        "w1": taps_last_channel(g("conv.0.weight")),                 # [8][5][5][128]
         "s1": s1, "b1": b1,
-        "w2": g("conv.3.weight").permute(0, 2, 3, 1).contiguous(),   # [8][5][5][8]
+        "w2": taps_last_channel(g("conv.3.weight")),                 # [8][5][5][8]
         "s2": s2, "b2": b2,
         "wfc": g("fc.weight").reshape(g("fc.weight").shape[0], -1).contiguous(),
     }
@@ -79,19 +87,20 @@ class _Packer:
     def t(self, key):
         return self.sd[key].detach().float().to(self.dev)
 
+    def taps_major(self, key):
+        """depthwise 3x3 stencil [C][1][3][3] -> tap-major [9][C] (dynmm_upsample2x_dw3x3)."""
+        w = self.t(key)
+        return ops.permute3d(w.reshape(w.shape[0], 1, 9), (2, 1, 0)).view(9, w.shape[0])
+
     def conv(self, key, *, stride=(1, 1), pad=(0, 0), bn: Optional[str] = None, bn_eps=1e-5, relu=False) -> ConvLayer:
+        """BN scale folded into the fp32 weights before bf16 packing, the epilogue only adds `shift`: one launch of
+        dynmm_fold_pack_conv per convolution (no library element-wise kernels in the engine build)."""
         w = self.t(key + ".weight")
         bias = self.t(key + ".bias") if key + ".bias" in self.sd else None
-        if bn is not None:
-            scale, shift = ops.fold_bn(self.t(bn + ".weight"), self.t(bn + ".bias"), self.t(bn + ".running_mean"),
-                                       self.t(bn + ".running_var"), bn_eps, bias)
-            # the BN scale goes into the (fp32) weights before bf16 packing: the epilogue only adds `shift`
-            w = w * scale.view(-1, 1, 1, 1)
-            scale = None
-        else:
-            scale, shift = None, (bias.contiguous() if bias is not None else None)
+        bn_t = [self.t(bn + s) for s in (".weight", ".bias", ".running_mean", ".running_var")] if bn is not None else None
+        packed, shift = ops.fold_pack_conv(w, bias, bn_t, bn_eps)
         c_out, c_in, kh, kw = w.shape
-        return ConvLayer(ops.pack_conv_weight(w), scale, shift, c_in, c_out, kh, kw, tuple(stride), tuple(pad), relu)
+        return ConvLayer(packed, None, shift, c_in, c_out, kh, kw, tuple(stride), tuple(pad), relu)
 
     def nbt1d(self, key, stride=1) -> Block:
         """resnet.py:124-147: 3x1 -> ReLU -> 1x3 -> BN(1e-3) -> ReLU -> 3x1 -> ReLU -> 1x3 -> BN -> +id -> ReLU."""
@@ -145,6 +154,13 @@ class FusionEngine:
     """Packed weights + launch sequence for one ``state_dict``."""
 
     def __init__(self, sd: Dict[str, Tensor], cfg: EngineConfig, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.DynmmError("FusionEngine needs a CUDA device")
+        with torch.cuda.device(device):          # packing kernels, streams and kernel attributes are per device
+            self._build(sd, cfg, device)
+
+    def _build(self, sd: Dict[str, Tensor], cfg: EngineConfig, device):
         _lib.require_device()
         if cfg.activation.lower() != "relu":
             raise NotImplementedError("the CUDA engine fuses ReLU epilogues only; got activation=" + cfg.activation)
@@ -160,9 +176,10 @@ class FusionEngine:
         # stem: [7][7][cin][64] fp32 + folded BN
         self.stem = {}
         for enc in ("encoder_rgb", "encoder_depth"):
-            w = p.t(enc + ".conv1.weight").permute(2, 3, 1, 0).contiguous()
-            s, b = ops.fold_bn(p.t(enc + ".bn1.weight"), p.t(enc + ".bn1.bias"), p.t(enc + ".bn1.running_mean"),
-                               p.t(enc + ".bn1.running_var"), 1e-5)
+            w0 = p.t(enc + ".conv1.weight")                               # [64][cin][7][7] -> [7][7][cin][64]
+            w = ops.permute3d(w0.reshape(w0.shape[0], w0.shape[1], 49), (2, 1, 0)).view(7, 7, w0.shape[1], w0.shape[0])
+            s, b = ops.fold_bn_cuda(p.t(enc + ".bn1.weight"), p.t(enc + ".bn1.bias"), p.t(enc + ".bn1.running_mean"),
+                                    p.t(enc + ".bn1.running_var"), 1e-5)
             self.stem[enc] = (w, s, b)
         # plain `add` fusion: TMA-gathered stem (dynmm_stem_s2d_fwd); DYNMM_STEM=tc|fp32 selects the older kernels
         self.stem_packed = None
@@ -188,12 +205,12 @@ class FusionEngine:
             self.dec.append({
                 "conv3x3": p.conv_bn_act(dk + ".conv3x3", 3),
                 "blocks": [p.nbt1d(f"{dk}.decoder_blocks.{b}") for b in range(cfg.nr_decoder_blocks[i])],
-                "up_w": p.t(dk + ".upsample.conv.weight").reshape(-1, 9).t().contiguous(),   # [9][C]
+                "up_w": p.taps_major(dk + ".upsample.conv.weight"),                          # [9][C]
                 "up_b": p.t(dk + ".upsample.conv.bias").contiguous(),
             })
         self.conv_out = p.conv("decoder.conv_out", pad=(1, 1))
-        self.up = [(p.t(f"decoder.{u}.conv.weight").reshape(-1, 9).t().contiguous(),
-                    p.t(f"decoder.{u}.conv.bias").contiguous()) for u in ("upsample1", "upsample2")]
+        self.up = [(p.taps_major(f"decoder.{u}.conv.weight"), p.t(f"decoder.{u}.conv.bias").contiguous())
+                   for u in ("upsample1", "upsample2")]
         # SE-add fusion: the 1x1 convs of SqueezeAndExcitation as fp32 matrices (model_utils.py:40-45)
         self.se = None
         if cfg.fuse == "SE-add":
@@ -374,10 +391,16 @@ class FusionEngine:
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
-    def forward(self, rgb: Tensor, depth: Tensor, *, temp: float = 1.0, hard_gate: bool = False,
-                baseline: bool = False, ini_stage: bool = False, weight: Optional[Tensor] = None,
-                out: Optional[Tensor] = None, hist: Optional[Tensor] = None, labels: Optional[Tensor] = None,
-                want_logits: bool = True):
+    def forward(self, rgb: Tensor, depth: Tensor, **kw):
+        """See :meth:`_forward`; runs with the engine's device current (kernel attributes, streams and launches
+        are per device)."""
+        with torch.cuda.device(self.dev):
+            return self._forward(rgb, depth, **kw)
+
+    def _forward(self, rgb: Tensor, depth: Tensor, *, temp: float = 1.0, hard_gate: bool = False,
+                 baseline: bool = False, ini_stage: bool = False, weight: Optional[Tensor] = None,
+                 out: Optional[Tensor] = None, hist: Optional[Tensor] = None, labels: Optional[Tensor] = None,
+                 want_logits: bool = True):
         """rgb [B,3,H,W], depth [B,1,H,W] fp32 NCHW on the GPU ->
         (logits [B,classes,H,W] fp32 NCHW, gate weight [B,5] fp32).
         ``labels`` (uint8 [B,H,W]): also emit argmax_c(logits) from the final kernel (eval.py:120);

@@ -549,17 +549,17 @@ class SkipGateESANet(nn.Module):
         return out
 
     def _state_version(self):
-        # cheap tripwire for in-place edits: version counters of the first / last tensors
-        ps = self._version_probe
-        return tuple(p._version for p in ps)
+        # tripwire for in-place edits while in eval mode: the version counters of EVERY parameter and buffer
+        # (~500 ints, negligible next to a forward).  Writes through ``.data`` do not bump them: call
+        # invalidate_engine() after those.
+        return tuple(p._version for p in self._version_probe)
 
     def engine(self, device=None):
         """The packed CUDA engine for the current weights (rebuilt when they change)."""
         from .engine import EngineConfig, FusionEngine
         device = device or next(self.parameters()).device
         if not hasattr(self, "_version_probe") or self._engine is None:
-            params = list(self.parameters())
-            self._version_probe = [params[0], params[len(params) // 2], params[-1]]
+            self._version_probe = list(self.parameters()) + list(self.buffers())
         key = (str(device), self._state_version())
         if self._engine is None or self._engine_key != key:
             c = self._cfg
@@ -611,13 +611,32 @@ class SkipGateESANet(nn.Module):
         return (labels, weight) if return_weight else labels
 
     # ------------------------------------------------------------------ forward
+    def _forward_eval_cuda(self, rgb, depth):
+        """Eval forward on CUDA tensors: the engine.  A CONFIGURATION the engine does not implement (swish, ppm-1-2-4-8,
+        bilinear upsampling, mixed encoders, input not a multiple of 32, ...) is a NotImplementedError from the engine:
+        such a model trained on the differentiable graph, so validation uses that graph too (one warning).  A missing
+        library / wrong device is a DynmmError and always propagates -- there is no silent CPU or library fallback."""
+        reason = getattr(self, "_engine_unsupported", None)
+        if reason is None and (rgb.shape[2] % 32 or rgb.shape[3] % 32):
+            if not getattr(self, "_warned_shape", False):
+                self._warned_shape = True
+                warnings.warn(f"dynmm_b200: input {tuple(rgb.shape[2:])} is not a multiple of 32; this eval forward runs "
+                              f"the PyTorch graph instead of the CUDA engine")
+            return self._forward_torch(rgb, depth)
+        if reason is None:
+            try:
+                return self._forward_engine(rgb, depth)
+            except NotImplementedError as e:
+                reason = self._engine_unsupported = str(e) or "unsupported configuration"
+                warnings.warn("dynmm_b200: the CUDA engine does not implement this configuration (" + reason +
+                              "); eval forwards run the PyTorch graph instead")
+        return self._forward_torch(rgb, depth)
+
     def forward(self, rgb, depth, test=False, return_weight=False):      # :255-322
-        if rgb.is_cuda and not self.training and not torch.is_grad_enabled():
-            out, weight = self._forward_engine(rgb, depth)
-        elif rgb.is_cuda and not self.training:
-            # eval mode with autograd enabled (the reference's validate() wraps in no_grad; be safe)
+        if rgb.is_cuda and not self.training:
+            # (the reference's validate() wraps in no_grad; be safe when it is not)
             with torch.no_grad():
-                out, weight = self._forward_engine(rgb, depth)
+                out, weight = self._forward_eval_cuda(rgb, depth)
         else:
             out, weight = self._forward_torch(rgb, depth)
         if self.save_weight_info:

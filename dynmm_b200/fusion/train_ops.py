@@ -73,7 +73,7 @@ class _Conv2dFn(torch.autograd.Function):
         out = torch.empty((b, co, h_out, w_out), dtype=torch.bfloat16, device=x.device,
                           memory_format=torch.channels_last)
         ops.conv(xn, wf, c_out=co, kh=kh, kw=kw, stride=stride, pad=padding, shift=shift,
-                 out=out.permute(0, 2, 3, 1))
+                 out=out.permute(0, 2, 3, 1), volatile_weights=True)
         ctx.save_for_backward(xn, weight)
         ctx.geom = (tuple(stride), tuple(padding), bias is not None)
         return out
@@ -97,7 +97,7 @@ class _Conv2dFn(torch.autograd.Function):
             gx = torch.empty((b, ci, h_in, w_in), dtype=torch.bfloat16, device=gyn.device,
                              memory_format=torch.channels_last)
             ops.conv(up, wd, c_out=ci, kh=kh, kw=kw, stride=(1, 1), pad=(kh - 1 - padding[0], kw - 1 - padding[1]),
-                     out=gx.permute(0, 2, 3, 1))
+                     out=gx.permute(0, 2, 3, 1), volatile_weights=True)
         if ctx.needs_input_grad[1]:
             gw = ops.conv_wgrad(xn, gyn, kh=kh, kw=kw, stride=stride, pad=padding, c_in=ci, c_out=co)
             gw = gw.to(weight.dtype)

@@ -19,9 +19,19 @@ Tensor = torch.Tensor
 
 
 def _cuda(*ts):
+    """Every launch goes to the CURRENT device's current stream: reject tensors that live elsewhere (a kernel launched
+    on cuda:0 with cuda:1 pointers faults asynchronously) -- callers enter ``torch.cuda.device(t.device)`` first."""
+    cur = None
     for t in ts:
-        if t is not None and not (t.is_cuda and t.is_contiguous()):
+        if t is None:
+            continue
+        if not (t.is_cuda and t.is_contiguous()):
             raise _lib.DynmmError("dynmm ops need contiguous CUDA tensors")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise _lib.DynmmError(f"dynmm ops launch on the current device (cuda:{cur}) but got a tensor on {t.device}; "
+                                  f"wrap the call in `with torch.cuda.device(tensor.device):`")
 
 
 # ------------------------------------------------------------------ weights
@@ -44,6 +54,51 @@ def fold_bn(bn_w, bn_b, bn_m, bn_v, eps, conv_bias=None):
     return scale.float().contiguous(), shift.float().contiguous()
 
 
+def _f32(t: Optional[Tensor]) -> Optional[Tensor]:
+    return None if t is None else t.detach().float().contiguous()
+
+
+def fold_pack_conv(w: Tensor, bias: Optional[Tensor] = None, bn: Optional[Sequence[Tensor]] = None, eps: float = 1e-5):
+    """One launch (dynmm_fold_pack_conv): eval-mode BatchNorm ``bn = (weight, bias, running_mean, running_var)`` and
+    the conv bias folded, weights packed like :func:`pack_conv_weight`.  -> (packed bf16, shift fp32 [c_out] or None);
+    bit-identical to ``pack_conv_weight(w * scale.view(-1,1,1,1))`` with :func:`fold_bn`'s scale / shift."""
+    lib = _lib.load()
+    w = _f32(w)
+    bias = _f32(bias)
+    bn = [_f32(t) for t in bn] if bn is not None else [None] * 4
+    _cuda(w, bias, *bn)
+    c_out, c_in, kh, kw = w.shape
+    packed = torch.empty(kh * kw, (c_out + 15) // 16 * 16, c_in, dtype=torch.bfloat16, device=w.device)
+    shift = torch.empty(c_out, dtype=torch.float32, device=w.device) if (bias is not None or bn[0] is not None) else None
+    check(lib.dynmm_fold_pack_conv(ptr(w), c_out, c_in, kh, kw, ptr(bias), ptr(bn[0]), ptr(bn[1]), ptr(bn[2]), ptr(bn[3]),
+                                   float(eps), ptr(packed), ptr(shift), stream_ptr()), "fold_pack_conv")
+    return packed, shift
+
+
+def fold_bn_cuda(bn_w: Tensor, bn_b: Tensor, bn_m: Tensor, bn_v: Tensor, eps: float, conv_bias: Optional[Tensor] = None):
+    """:func:`fold_bn` as one launch of our own kernel (same roundings, bit-identical)."""
+    lib = _lib.load()
+    bn_w, bn_b, bn_m, bn_v, conv_bias = _f32(bn_w), _f32(bn_b), _f32(bn_m), _f32(bn_v), _f32(conv_bias)
+    _cuda(bn_w, bn_b, bn_m, bn_v, conv_bias)
+    c = bn_w.numel()
+    scale = torch.empty(c, dtype=torch.float32, device=bn_w.device)
+    shift = torch.empty(c, dtype=torch.float32, device=bn_w.device)
+    check(lib.dynmm_fold_bn(c, ptr(conv_bias), ptr(bn_w), ptr(bn_b), ptr(bn_m), ptr(bn_v), float(eps), ptr(scale),
+                            ptr(shift), stream_ptr()), "fold_bn")
+    return scale, shift
+
+
+def permute3d(x: Tensor, perm: Sequence[int]) -> Tensor:
+    """``x.permute(perm).contiguous()`` of a 3-D fp32 CUDA tensor in one launch of our own kernel."""
+    lib = _lib.load()
+    x = _f32(x)
+    _cuda(x)
+    d = x.shape
+    out = torch.empty(d[perm[0]], d[perm[1]], d[perm[2]], dtype=torch.float32, device=x.device)
+    check(lib.dynmm_permute3d_f32(ptr(x), d[0], d[1], d[2], perm[0], perm[1], perm[2], ptr(out), stream_ptr()), "permute3d")
+    return out
+
+
 # ------------------------------------------------------------------ conv
 
 def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 1), pad=(0, 0),
@@ -53,7 +108,7 @@ def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 
          count: Optional[Tensor] = None,
          out: Optional[Tensor] = None, n_out: Optional[int] = None, c_in: Optional[int] = None,
          out_c_off: int = 0, tile_n: int = 0, max_ctas: int = 0, direct: bool = False,
-         trace: Optional[Tensor] = None) -> Tensor:
+         trace: Optional[Tensor] = None, volatile_weights: bool = False) -> Tensor:
     """Fused conv + scale/shift + residual + ReLU + gated add (see dynmm_conv_igemm_fwd).
 
     x: NHWC bf16 [n_in, h, w, in_ld] (``c_in`` <= in_ld selects a channel prefix);
@@ -81,6 +136,7 @@ def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 
     p.gated_ld = gated.shape[3] if gated is not None else 0
     p.kh, p.kw, p.stride_h, p.stride_w, p.pad_h, p.pad_w = kh, kw, stride[0], stride[1], pad[0], pad[1]
     p.relu, p.tile_n, p.max_ctas = int(relu), tile_n, max_ctas
+    p.flags = 1 if volatile_weights else 0       # DYNMM_CONV_VOLATILE_WEIGHTS: packed on this stream just before
     p.trace = ptr(trace)
     if CONV_RECORDER is not None and not direct:
         # inside `with ConvProgram()`: the convolution becomes a job of the program's current phase

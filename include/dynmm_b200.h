@@ -181,8 +181,16 @@ typedef struct dynmm_conv_params {
   int32_t relu;
   int32_t tile_n;         /* 0 = choose; else 16..256 output channels per CTA tile */
   int32_t max_ctas;       /* 0 = one per SM */
+  int32_t flags;          /* DYNMM_CONV_* bits (fills the padding in front of `trace`: the layout is unchanged) */
   void* trace;            /* debug: device uint64[16 * ctas] in-kernel cycle stamps, or NULL */
 } dynmm_conv_params;
+
+/* dynmm_conv_params.flags: `weight` / `scale` / `shift` were WRITTEN by earlier work on the same stream (training:
+ * the bf16 weights are re-packed every optimizer step right before the convolution).  The kernel normally fetches
+ * them in its prologue, before the programmatic-dependent-launch wait, because for inference they are constants;
+ * with this flag the launch is ordinary stream-ordered (no programmatic early start), so the prologue cannot run
+ * ahead of the producer. */
+#define DYNMM_CONV_VOLATILE_WEIGHTS 1
 
 int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream);
 /* ------------------------------------------------- convolution programs
@@ -272,6 +280,22 @@ long long dynmm_conv_wgrad_workspace(const dynmm_wgrad_params* p);
 int dynmm_conv_wgrad(const dynmm_wgrad_params* p, void* stream);
 /* CUDA-core comparator with the same contract (tests only; no workspace needed). */
 int dynmm_conv_wgrad_direct(const dynmm_wgrad_params* p, void* stream);
+
+/* Engine build (FusionEngine.__init__), one launch per convolution: eval-mode BatchNorm (and an optional conv bias)
+ * folded into the weights, then packed to the bf16 operand layout of dynmm_conv_params.weight:
+ *   scale = bn_weight / sqrt(bn_var + eps);  shift = bn_bias - bn_mean * scale (+ bias * scale)
+ *   packed [kh*kw][c_out_pad16][c_in] = bf16(w * scale)            (padding rows zero)
+ * bn_* all NULL: no BatchNorm (packed = bf16(w), shift = bias).  shift may be NULL only without bias and BatchNorm.
+ * Every operation is rounded separately -- bit-identical to the fp32 PyTorch expression (conv + BatchNorm2d of
+ * FusionDynMM/src/models/resnet.py:124-147, model_utils.py:11-23 in eval mode). */
+int dynmm_fold_pack_conv(const float* w, int c_out, int c_in, int kh, int kw, const float* bias, const float* bn_weight,
+                         const float* bn_bias, const float* bn_mean, const float* bn_var, float eps, void* packed,
+                         float* shift, void* stream);
+/* scale / shift [c] of an eval-mode BatchNorm (+ preceding conv bias), as above (stem, gate: fp32 epilogues). */
+int dynmm_fold_bn(int c, const float* bias, const float* bn_weight, const float* bn_bias, const float* bn_mean,
+                  const float* bn_var, float eps, float* scale, float* shift, void* stream);
+/* out = in.permute(p0, p1, p2).contiguous() of an fp32 tensor [d0][d1][d2] (weight layout changes of the engine build). */
+int dynmm_permute3d_f32(const float* in, int d0, int d1, int d2, int p0, int p1, int p2, float* out, void* stream);
 
 /* fp32 master weight [c_out][c_in][kh][kw] -> the bf16 operand layouts, in one pass (either may be NULL):
  *   fwd   [kh*kw][c_out_pad16][c_in]   (dynmm_conv_params.weight of the forward convolution)

@@ -91,6 +91,36 @@ def test_build_model_signature():
         SkipGateESANet(encoder_rgb="vgg16")
 
 
+def test_he_init_follows_the_reference_rules():
+    """build_model.py:152-178: output layers, SE convs followed by a Sigmoid and depthwise convs keep their init, no
+    bias is touched, encoders and gate ARE re-initialised (no ImageNet weights), BatchNorm -> (1, 0)."""
+    from dynmm_b200.fusion import SkipGateESANet
+    from dynmm_b200.fusion.build import he_init
+    torch.manual_seed(3)
+    model = SkipGateESANet(height=64, width=64, num_classes=40, encoder_rgb="resnet18", encoder_depth="resnet18",
+                           encoder_block="BasicBlock", fuse_depth_in_rgb_encoder="SE-add")
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.fill_(0.5)
+                m.bias.fill_(0.25)
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    he_init(model, 40, pretrained_on_imagenet=False)
+    after = model.state_dict()
+    same = lambda k: torch.equal(before[k], after[k])
+    assert same("decoder.conv_out.weight") and same("decoder.decoder_module_1.side_output.weight")       # out == n_classes
+    assert same("se_layer1.se_rgb.fc.2.weight") and not same("se_layer1.se_rgb.fc.0.weight")            # before Sigmoid
+    assert same("decoder.upsample1.conv.weight") and same("decoder.decoder_module_1.upsample.conv.weight")   # depthwise
+    conv_biases = [n + ".bias" for n, m in model.named_modules() if isinstance(m, torch.nn.Conv2d) and m.bias is not None]
+    assert len(conv_biases) > 10 and all(same(k) for k in conv_biases), "conv biases must not be touched"
+    assert not same("encoder_rgb.layer1.0.conv1.weight") and not same("gate_layer.conv.0.weight")
+    assert not same("gate_layer.fc.weight")        # last module: the reference's unguarded index would raise here
+    assert float(after["encoder_depth.bn1.weight"].min()) == 1.0 and float(after["encoder_depth.bn1.bias"].abs().max()) == 0.0
+    before2 = {k: v.clone() for k, v in after.items()}
+    he_init(model, 40, pretrained_on_imagenet=True)      # ImageNet encoders are skipped
+    assert torch.equal(before2["encoder_rgb.layer1.0.conv1.weight"], model.state_dict()["encoder_rgb.layer1.0.conv1.weight"])
+
+
 def test_conv_program_recorder_phases():
     """ConvProgram (host side of dynmm_conv_program_*): phases are numbered without gaps, at most 4 jobs each."""
     import pytest

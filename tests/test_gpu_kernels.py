@@ -396,3 +396,42 @@ def test_se_fusion_kernels():
     ref = rgb.float() * (1 - gg + gg * sig.view(n, 1, 1, c)) + gg * sd_sel.view(n, 1, 1, c) * d_sel
     _bf16_close(out, ref, "se_gated_fuse")
     assert torch.isfinite(out.float()).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,has_bias,has_bn", [((64, 64, 3, 1), True, False), ((128, 64, 1, 3), True, True),
+                                                   ((40, 128, 3, 3), False, False), ((256, 128, 1, 1), False, True),
+                                                   ((24, 16, 3, 3), True, True)])
+def test_fold_pack_conv_is_bit_identical_to_the_pytorch_expression(shape, has_bias, has_bn):
+    """dynmm_fold_pack_conv (engine build, one launch per convolution) == fold_bn + scale + pack_conv_weight done with
+    fp32 PyTorch ops (what the oracle folds: conv + eval BatchNorm, resnet.py:124-147), bit for bit."""
+    from dynmm_b200 import ops
+    g = torch.Generator().manual_seed(sum(shape))
+    co = shape[0]
+    w = (torch.randn(shape, generator=g) * 0.1).cuda()
+    bias = torch.randn(co, generator=g).cuda() if has_bias else None
+    bn = None
+    if has_bn:
+        bn = [(0.5 + torch.rand(co, generator=g)).cuda(), torch.randn(co, generator=g).cuda(),
+              (torch.randn(co, generator=g) * 0.2).cuda(), (0.3 + torch.rand(co, generator=g)).cuda()]
+    packed, shift = ops.fold_pack_conv(w, bias, bn, 1e-3)
+    if has_bn:
+        scale, ref_shift = ops.fold_bn(*bn, 1e-3, bias)
+        ref_packed = ops.pack_conv_weight(w * scale.view(-1, 1, 1, 1))
+        s2, b2 = ops.fold_bn_cuda(*bn, 1e-3, bias)
+        assert torch.equal(s2, scale) and torch.equal(b2, ref_shift)
+    else:
+        ref_packed, ref_shift = ops.pack_conv_weight(w), bias
+    assert torch.equal(packed.view(torch.int16), ref_packed.view(torch.int16))
+    if ref_shift is None:
+        assert shift is None
+    else:
+        assert torch.equal(shift, ref_shift)
+
+
+@pytest.mark.gpu
+def test_permute3d_matches_torch():
+    from dynmm_b200 import ops
+    x = torch.randn(7, 5, 9).cuda()
+    for perm in [(2, 1, 0), (0, 2, 1), (1, 0, 2), (0, 1, 2), (2, 0, 1), (1, 2, 0)]:
+        assert torch.equal(ops.permute3d(x, perm), x.permute(*perm).contiguous())

@@ -58,12 +58,13 @@ def test_pair_count_and_maps():
 
 @pytest.mark.first_run
 def test_pair_rotated_store_order_is_bit_identical():
-    """DYNMM_PAIR_ROT=1 (conflict-avoiding chunk order in epilogue 1, written after round 1's GPU budget was spent): the
-    switch is read once per process, so the bit-identity tests above are re-run in a child process with it set."""
+    """The conflict-avoiding chunk order in epilogue 1 is the default since round 2 (DYNMM_PAIR_ROT=0 selects the straight
+    order): the switch is read once per process, so the bit-identity tests above are re-run in a child process with the
+    OTHER setting -- both orders must give the bits of two separate convolutions."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, DYNMM_PAIR_ROT="1")
+    env = dict(os.environ, DYNMM_PAIR_ROT="0")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_pair.py"), "-q", "-x",
                         "-m", "gpu", "-k", "bit_identical and not rotated or count_and_maps", "-p", "no:cacheprovider"],

@@ -20,5 +20,6 @@ timeout 300 ncu --profile-from-start off --clock-control none --metrics gpu__tim
 timeout 200 python tools/train_profile.py > $O/train_profile_bf16.txt 2>&1
 TRAIN_PRECISION=bf16 timeout 150 python tools/train_step_dp.py > $O/train_bf16.log 2>&1
 PER_GPU_BATCH=32 TRAIN_PRECISION=bf16 timeout 200 python tools/train_step_dp.py > $O/train_bf16_b32.log 2>&1
+timeout 120 python tools/conv_shapes.py > $O/conv_shapes.txt 2>&1
 tail -n 3 $O/pytest_gpu.log $O/pytest_first_run.log
 cat $O/bench_n1.json | cut -c1-400
