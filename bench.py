@@ -30,6 +30,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 H, W, BATCH = 480, 640, 8
+WORKLOAD = "FusionDynMM ESANet RGB+D 480x640 batch=8, global-gate hard (configs[1])"
 METRIC = "NYUv2-shape RGB-D images/sec (FusionDynMM ESANet-R34-NBt1D 480x640, global gate hard, eval forward)"
 # algorithmic conv GFLOP per image by gate branch (2 x MAC, conv layers only)
 GFLOP_BY_BRANCH = (44.47, 50.13, 57.76, 69.16, 74.90)
@@ -151,27 +152,116 @@ def cpu_reference_images_per_s(state_dict, batch: int, warmup: int, steps: int, 
 
 
 def run_reference_arm(args, rank):
+    """`--impl reference`: the reference's own CPU path (the oracle port of its nn.Module graph: PyTorch fp32 on all
+    host cores) on the SAME workload -- batch 8 per step, the requested steps / warm-up up to caps that keep the run
+    within a few minutes (a step is ~0.7 s on 16 cores)."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     model = build_model()
-    # 2 images per forward: at least as fast per image as the workload's batch 8 on the host (build container, 8 vCPU,
-    # noisy: 2.5-3.5 images/s at batch 2, 3.2 at batch 4, 2.3-2.4 at batch 8) and 4x shorter per step
-    sample = 2
     steps = max(1, min(args.steps, 20))
-    v, per_step = cpu_reference_images_per_s(model.state_dict(), sample, min(args.warmup, 1), steps, threads)
+    warmup = max(1, min(args.warmup, 5))
+    v, per_step = cpu_reference_images_per_s(model.state_dict(), BATCH, warmup, steps, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": per_step * 1e3,
+        "steps": steps, "warmup": warmup, "ms_per_step": per_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "FusionDynMM ESANet RGB+D 480x640 batch=8, global-gate hard (configs[1])",
-                   "note": "reference algorithm (PyTorch CPU, fp32, all branches always computed) on host cores"},
+        "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH,
+                   "note": "reference algorithm (PyTorch CPU, fp32, all branches always computed) on host cores; "
+                           "steps capped at 20 and warm-up at 5 (0.7 s per step)"},
         "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": f"{steps} forwards of {sample} images (480x640, eval, hard gate, fp32) after "
-                                   f"{min(args.warmup, 1)} warm-up"},
+                         "sample": f"{steps} forwards of {BATCH} images (480x640, eval, hard gate, fp32) after "
+                                   f"{warmup} warm-up"},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def gpu_eager_baselines(model, rgb, depth, reps: int = 10):
+    """SURVEY section 2.3 / 8d "second baseline": the reference's nn.Module graph (same layer sequence, every branch
+    of every sample computed, separate conv / BatchNorm / ReLU / blend kernels) run by PyTorch eager + cuDNN on THIS
+    GPU -- (i) as the reference is written: fp32 NCHW (cuDNN TF32 convolutions allowed, PyTorch's default);
+    (ii) bf16 autocast + channels_last.  `model._forward_torch` is that graph (it is what trains; parity with the
+    reference module: tests/test_fusion_cpu.py against reference-generated vectors)."""
+    out = {}
+    b = rgb.shape[0]
+
+    def timed(fn):
+        with torch.no_grad():
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        return {"images_per_s": b / ms * 1e3, "ms_per_step": ms}
+
+    out["fp32"] = timed(lambda: model._forward_torch(rgb, depth))
+    out["fp32"]["note"] = "fp32 NCHW eager, cudnn.allow_tf32=%s (PyTorch default)" % torch.backends.cudnn.allow_tf32
+    cl_model = model.to(memory_format=torch.channels_last)
+    rgb_cl, depth_cl = rgb.contiguous(memory_format=torch.channels_last), depth.contiguous(memory_format=torch.channels_last)
+
+    def bf16():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return cl_model._forward_torch(rgb_cl, depth_cl)
+    out["bf16"] = timed(bf16)
+    out["bf16"]["note"] = "torch.autocast(bf16) + channels_last eager"
+    model.to(memory_format=torch.contiguous_format)
+    model.invalidate_engine()
+    out["kind"] = "port: the package's differentiable nn.Module graph = the reference's layer sequence, PyTorch eager/cuDNN"
+    out["batch"] = b
+    return out
+
+
+def train_leg(dev, rank, world, per_gpu: int, steps: int, with_exchange: bool = True):
+    """BASELINE configs[2]: one data-parallel TRAINING step (train.py:299-324: forward, 4-scale weighted CE +
+    FLOP regulariser, backward, gradient exchange, SGD-nesterov) with bf16 tcgen05 convolutions, the whole step one
+    CUDA graph; gradients live in flat buckets whose all-reduce is launched from autograd hooks during backward.
+    -> (seconds per step on this rank, loss)"""
+    import warnings
+    from dynmm_b200 import dist as ddp
+    from dynmm_b200.fusion.loss import CrossEntropyLoss2d
+    from dynmm_b200.fusion.train_graph import GraphedTrainStep
+    warnings.simplefilter("ignore")
+    model = build_model().to(dev)
+    model.train()
+    model.hard_gate = False
+    model.train_precision = "bf16"
+    ddp.broadcast_parameters(model)
+    params = list(model.parameters())
+    opt = torch.optim.SGD(params, lr=1e-3, momentum=0.9, nesterov=True, weight_decay=1e-4)
+    buckets = ddp.GradBuckets(params).attach()
+    rgb, depth = (t.to(dev) for t in synthetic_batch(7000 + rank, per_gpu))
+    g = torch.Generator().manual_seed(9000 + rank)
+    targets = [torch.randint(0, 41, (per_gpu, H // r, W // r), generator=g).to(dev) for r in (1, 8, 16, 32)]
+    ce = CrossEntropyLoss2d(dev, [1.0] * 40)
+
+    def loss_fn(out, tgt):
+        pred_scales, loss_flop = out
+        return sum(ce(pred_scales, targets)) + 1e-4 * loss_flop.float().clamp_min(0)
+    buckets.enabled = with_exchange                          # False: the same graph minus the collective
+    gstep = GraphedTrainStep(model, opt, loss_fn, rgb, depth, targets[0], buckets=buckets, warmup=2)
+    for _ in range(2):
+        loss = gstep(rgb, depth, targets[0])
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = gstep(rgb, depth, targets[0])
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3 / steps
+    out = (t, float(loss), len(buckets.buckets), buckets.launched_in_backward)
+    del gstep, model, opt, buckets
+    torch.cuda.empty_cache()
+    return out
 
 
 def profile_conv_kernel(model, rgb, depth):
@@ -218,13 +308,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-train", action="store_true", help="skip the data-parallel training-step leg (configs[2])")
+    ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager-on-this-GPU baseline")
+    ap.add_argument("--min-seconds", type=float, default=1.0,
+                    help="the timed region repeats the K-step block until it lasts at least this long")
     ap.add_argument("--batch", type=int, default=BATCH,
                     help="images per GPU and step; the default 8 is BASELINE.json configs[1] (the headline workload), "
                          "32 is the per-step batch of configs[2]")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     batch = args.batch
-    workload = ("FusionDynMM ESANet RGB+D 480x640 batch=8, global-gate hard (configs[1])" if batch == BATCH else
+    workload = (WORKLOAD if batch == BATCH else
                 f"FusionDynMM ESANet RGB+D 480x640 batch={batch}, global-gate hard (eval forward at the batch of "
                 f"configs[2] when 32; NOT the headline workload)")
 
@@ -256,20 +350,34 @@ def main():
         torch.cuda.synchronize()
 
     with torch.no_grad():
-        # ---------------- device-resident throughput ("value")
+        # ---------------- device-resident throughput ("value"): K steps between two events, the block repeated
+        # until the timed region lasts >= --min-seconds (K = 20 alone would be a 30 ms measurement)
         for i in range(args.warmup):
             model(*batches[i % 3], True)
-        sampler = ClockSampler(local_rank)
-        barrier()
-        sampler.start()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(args.steps):
-            out, wgt = model(*batches[i % 3], True, True)
+            model(*batches[i % 3], True, True)
+        e1.record()
+        torch.cuda.synchronize()
+        est = max(e0.elapsed_time(e1) * 1e-3, 1e-6)
+        repeats = max(1, min(int(args.min_seconds / est + 0.999), 200))
+        if world > 1:                                  # every rank must run the same number of steps
+            r = torch.tensor([repeats], device=dev)
+            dist.all_reduce(r, op=dist.ReduceOp.MAX)
+            repeats = int(r.item())
+        sampler = ClockSampler(local_rank)
+        barrier()
+        sampler.start()
+        e0.record()
+        for _ in range(repeats):
+            for i in range(args.steps):
+                out, wgt = model(*batches[i % 3], True, True)
         e1.record()
         barrier()
         clocks = sampler.stop()
-        t_dev = e0.elapsed_time(e1) * 1e-3
+        t_dev = e0.elapsed_time(e1) * 1e-3 / repeats         # seconds per K steps
         for i in range(3):                        # gate statistics of the workload (outside the timed region)
             _, wgt = model(*batches[i], True, True)
             hist += torch.bincount(wgt.argmax(1), minlength=5)
@@ -282,17 +390,44 @@ def main():
         pipe = EvalPipeline(model, batch, H, W, dev)
         for _ in pipe.run(host[i % 3] for i in range(args.warmup)):
             pass
+        e2e_steps = args.steps * max(1, min(repeats, 10))
         barrier()
         t0 = time.perf_counter()
         n_out = 0
-        for labels in pipe.run(host[i % 3] for i in range(args.steps)):
+        for labels in pipe.run(host[i % 3] for i in range(e2e_steps)):
             n_out += labels.shape[0]
         barrier()
-        t_e2e = time.perf_counter() - t0
-        assert n_out == batch * args.steps
+        t_e2e = (time.perf_counter() - t0) * args.steps / e2e_steps      # seconds per K steps
+        assert n_out == batch * e2e_steps
 
+        # ---------------- the same, returning the full fp32 LOGITS to the host (393 MB per step: PCIe-bound);
+        # a secondary figure -- eval.py consumes the arg-max (eval.py:109-129), which is what `e2e` returns
+        e2e_logits = None
+        if rank == 0 and world == 1:
+            lh = torch.empty(batch, 40, H, W, dtype=torch.float32).pin_memory()
+            r_d, d_d = torch.empty_like(batches[0][0]), torch.empty_like(batches[0][1])
+            n_l = 5
+            for k in range(n_l + 1):
+                if k == 1:
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                r_d.copy_(host[k % 3][0], non_blocking=True)
+                d_d.copy_(host[k % 3][1], non_blocking=True)
+                lg = model(r_d, d_d, True)
+                lh.copy_(lg, non_blocking=True)
+                torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / n_l
+            e2e_logits = {"value": batch / dt, "unit": "images/s", "ms_per_step": dt * 1e3,
+                          "h2d_bytes_per_step": batch * 4 * H * W * 4, "d2h_bytes_per_step": batch * 40 * H * W * 4,
+                          "note": "unpipelined: upload, forward, full fp32 logits back to pinned host memory"}
+
+    # ---------------- max over ranks, per-rank times (load imbalance: the gate makes per-rank work data dependent)
     t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
+    rank_ms = [t_dev / args.steps * 1e3]
     if world > 1:
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        rank_ms = [float(g[0]) / args.steps * 1e3 for g in gathered]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(hist)
     t_dev, t_e2e = t.tolist()
@@ -302,7 +437,7 @@ def main():
     launches = model.engine(dev).launches
 
     # ---------------- roofline of the dominant kernel (rank 0, N=1 style instrumented pass)
-    roofline, cpu_base = None, None
+    roofline, cpu_base, eager = None, None, None
     if rank == 0:
         hbm, tf_sust, tf_burst, src = measured_peaks()
         model.use_cuda_graph = False
@@ -323,14 +458,55 @@ def main():
                     "note": "kernel_s_per_step = sum over the step's conv launches of their device time (each launch "
                             "replayed 4x from a CUDA graph between events on its own stream); the RGB and depth "
                             "encoder streams overlap in the timed step, so this sum is not a share of ms_per_step. "
-                            "Kernel shares of the step: profiles/r1b_step_metrics_summary.txt (ncu).",
+                            "Kernel shares of the step: profiles/ (ncu launch list).",
                     "step_s": step_s}
-        if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            v, per = cpu_reference_images_per_s(model.state_dict(), 2, 1, 10, threads)
-            cpu_base = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
-                        "sample": "10 forwards of 2 images (480x640, eval, hard gate, fp32; per image at least as fast as "
-                                  "batch 8 on the host) after 1 warm-up"}
+        if world == 1 and not args.no_eager:
+            eager = gpu_eager_baselines(model, *batches[0])
+            eager["ours_over_bf16_eager"] = value / eager["bf16"]["images_per_s"]
+            eager["ours_over_fp32_eager"] = value / eager["fp32"]["images_per_s"]
+
+    # ---------------- configs[2]: data-parallel TRAINING step, global batch 32 (strong: 32/N per GPU) and 32 per GPU
+    # (weak), gradient all-reduce overlapped with backward; the eval model is released first
+    train = None
+    if not args.no_train:
+        sd_for_cpu = {k: v.detach().cpu() for k, v in model.state_dict().items()} if rank == 0 else None
+        del pipe, model
+        torch.cuda.empty_cache()
+        train = {}
+        t_steps = 8
+        legs = [("weak_32_per_gpu", 32)] + ([("strong_global_32", max(32 // world, 1))] if world > 1 else [])
+        for name, per_gpu in legs:
+            ts, loss, n_buckets, in_bwd = train_leg(dev, rank, world, per_gpu, t_steps)
+            tt = torch.tensor([ts], dtype=torch.float64, device=dev)
+            per_rank = [ts]
+            if world > 1:
+                gl = [torch.zeros_like(tt) for _ in range(world)]
+                dist.all_gather(gl, tt)
+                per_rank = [float(x) for x in gl]
+            t_max = max(per_rank)
+            entry = {"per_gpu_batch": per_gpu, "global_batch": per_gpu * world, "ms_step": t_max * 1e3,
+                     "img_s": per_gpu * world / t_max, "rank_time_max_over_mean": t_max / (sum(per_rank) / len(per_rank)),
+                     "grad_buckets": n_buckets, "buckets_launched_during_backward": in_bwd, "loss": loss}
+            if world > 1:
+                ts0, _, _, _ = train_leg(dev, rank, world, per_gpu, t_steps, with_exchange=False)
+                t0m = torch.tensor([ts0], dtype=torch.float64, device=dev)
+                dist.all_reduce(t0m, op=dist.ReduceOp.MAX)
+                entry["ms_step_without_exchange"] = float(t0m) * 1e3
+                entry["allreduce_exposed_ms"] = max(0.0, (t_max - float(t0m)) * 1e3)
+            else:
+                entry["allreduce_exposed_ms"] = 0.0
+            train[name] = entry
+        train["note"] = ("train.py:299-324 step: forward (train-mode BN), 4-scale weighted CE + FLOP regulariser, "
+                         "backward, bucketed fp32 gradient all-reduce launched from autograd hooks during backward "
+                         "(NCCL AVG), SGD-nesterov; convolutions fwd/dgrad/wgrad bf16 on tcgen05 kernels; one CUDA graph")
+    else:
+        sd_for_cpu = {k: v.detach().cpu() for k, v in model.state_dict().items()} if rank == 0 else None
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, per = cpu_reference_images_per_s(sd_for_cpu, BATCH, 1, 8, threads)
+        cpu_base = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
+                    "sample": "8 forwards of 8 images (480x640, eval, hard gate, fp32) after 1 warm-up"}
 
     if rank == 0:
         h = hist.tolist()
@@ -343,16 +519,24 @@ def main():
             "config": {"workload": workload,
                        "per_gpu_batch": batch, "global_batch": batch * world, "parallelism": f"dp{world} (replicas, no data-path collective in eval)",
                        "gate_path_dtype": "f32", "cuda_graph": not args.no_graph,
+                       "timed_region": f"{repeats} x {args.steps} steps between one pair of CUDA events (>= {args.min_seconds} s)",
                        "l2": "3 rotating resident batches; per-step working set > 126 MB L2, no explicit flush",
                        "gate_branch_histogram": h, "gate_skip_flop_savings_pct": 100.0 * saved},
+            "rank_ms_per_step": rank_ms,
+            "rank_time_max_over_mean": max(rank_ms) / (sum(rank_ms) / len(rank_ms)),
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": batch * 4 * H * W * 4,
                     "d2h_bytes_per_step": batch * H * W, "ms_per_step": t_e2e / args.steps * 1e3,
+                    "returns": "uint8 arg-max labels (what eval.py:109-129 consumes); the fp32 logits are never "
+                               "written in this mode -- see e2e_logits for the variant that returns them",
                     "api": "dynmm_b200.fusion.EvalPipeline: pinned host inputs -> SkipGateESANet.forward -> argmax -> "
                            "uint8 labels in pinned host memory, copies overlapped with compute (2 slots)"},
-            "gpu_launches": launches * args.steps,
+            "e2e_logits": e2e_logits,
+            "gpu_launches": launches * args.steps * repeats,
             "gpu_launches_per_step": launches,
             "clocks": clocks,
             "roofline": roofline,
+            "gpu_eager_baseline": eager,
+            "train": train,
             "cpu_baseline": cpu_base,
         }
         print(json.dumps(line))

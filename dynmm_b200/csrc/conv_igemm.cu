@@ -121,7 +121,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   const int active = args.count ? min(*args.count, args.n) : args.n;
   const int n_groups = (active + args.bn - 1) / args.bn;
-  const int total_tiles = n_groups * args.tiles2 * args.tiles1 * args.c_tiles;
+  // A work unit = `mt` consecutive pixel tiles x one channel tile (mt = 2: both tiles share every streamed weight
+  // tile).  unit -> channel tile ct = unit % c_tiles, pixel tiles m = (unit / c_tiles) * mt + w.
+  const int mt = args.mt;
+  const int m_tiles = n_groups * args.tiles2 * args.tiles1;
+  const int total_tiles = ((m_tiles + mt - 1) / mt) * args.c_tiles;          // work units
   if (threadIdx.x == 0) DYNMM_TRACE(1);
 
   if (warp == 0) {
@@ -132,15 +136,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       const CUtensorMap* maps[4] = {&map_a0, &map_a1, &map_a2, &map_a3};
       // TMA always delivers the full box (out-of-bounds elements arrive as zeros)
       const uint32_t a_tx = args.a_rows * kBlockK * 2;
-      const uint32_t tx_bytes = a_tx + (args.b_resident ? 0 : b_iter_bytes);
       const uint32_t sub_tx = args.b1 * args.b2 * args.bn * kBlockK * 2;
       int stage = 0;
       uint32_t phase = 0;
       int aux = 0;
       uint32_t aux_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(args, tile);
-        const int n_in = args.in_map ? args.in_map[t.n0] : t.n0;
+        const uint32_t q = fast_div(tile, args.m_c);
+        const int ct = tile - q * args.c_tiles;
+        const int nact = min(mt, m_tiles - (int)q * mt);            // pixel tiles of this unit (the last may be alone)
+        TileCoord t[2];
+        int n_in[2];
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          t[w] = decode_tile(args, (q * mt + (w < nact ? w : 0)) * args.c_tiles + ct);
+          n_in[w] = args.in_map ? args.in_map[t[w].n0] : t[w].n0;
+        }
+        const uint32_t tx_bytes = nact * a_tx + (args.b_resident ? 0 : b_iter_bytes);
         for (int g = 0; g < args.num_groups; ++g) {
           const Group gp = args.groups[g];
           for (int kc = 0; kc < args.k_chunks; ++kc) {
@@ -148,9 +160,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             uint8_t* sa = smem + stage * args.stage_bytes;
             if (elect_one()) {
               mbar_expect_tx(&ctl->full[stage], tx_bytes);
-              tma_load_4d(sa, maps[gp.map], &ctl->full[stage], kc * kBlockK, t.x1 + gp.o1, t.x2 + gp.o2, n_in);
+              tma_load_4d(sa, maps[gp.map], &ctl->full[stage], kc * kBlockK, t[0].x1 + gp.o1, t[0].x2 + gp.o2, n_in[0]);
+              if (nact > 1)
+                tma_load_4d(sa + args.a_bytes, maps[gp.map], &ctl->full[stage], kc * kBlockK, t[1].x1 + gp.o1,
+                            t[1].x2 + gp.o2, n_in[1]);
               if (!args.b_resident)
-                tma_load_3d(sa + args.a_bytes, &map_b, &ctl->full[stage], kc * kBlockK, t.c0, g * args.tpg);
+                tma_load_3d(sa + mt * args.a_bytes, &map_b, &ctl->full[stage], kc * kBlockK, t[0].c0, g * args.tpg);
             }
             __syncwarp();
             if (lane == 0 && tile == (int)blockIdx.x && g == 0 && kc == 0) DYNMM_TRACE(2);
@@ -161,20 +176,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
         }
         if (lane == 0 && tile == (int)blockIdx.x) DYNMM_TRACE(11);
-        // residual sub-tiles of this tile, consumed by the epilogue while the next tile's MMAs run
-        if (aux_on && t.n0 + args.bn <= active) {
-          const int n_res = args.res_map ? args.res_map[t.n0] : t.n0;
-          for (int sub = 0; sub < n_sub; ++sub) {
-            mbar_wait(&ctl->aux_empty[aux], aux_phase ^ 1);
-            if (elect_one()) {
-              mbar_expect_tx(&ctl->aux_full[aux], sub_tx);
-              tma_load_4d(smem_aux + aux * kSubBytes, &map_res, &ctl->aux_full[aux], t.c0 + sub * 64, t.x1, t.x2,
-                          n_res);
-            }
-            __syncwarp();
-            if (++aux == args.aux_slots) {
-              aux = 0;
-              aux_phase ^= 1;
+        // residual sub-tiles of this unit's tiles, consumed by the epilogue while the next unit's MMAs run
+        for (int w = 0; w < nact; ++w) {
+          if (aux_on && t[w].n0 + args.bn <= active) {
+            const int n_res = args.res_map ? args.res_map[t[w].n0] : t[w].n0;
+            for (int sub = 0; sub < n_sub; ++sub) {
+              mbar_wait(&ctl->aux_empty[aux], aux_phase ^ 1);
+              if (elect_one()) {
+                mbar_expect_tx(&ctl->aux_full[aux], sub_tx);
+                tma_load_4d(smem_aux + aux * kSubBytes, &map_res, &ctl->aux_full[aux], t[w].c0 + sub * 64, t[w].x1,
+                            t[w].x2, n_res);
+              }
+              __syncwarp();
+              if (++aux == args.aux_slots) {
+                aux = 0;
+                aux_phase ^= 1;
+              }
             }
           }
         }
@@ -202,21 +219,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         const uint32_t acc_phase = (local >> 1) & 1;
         mbar_wait(&ctl->acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * args.acc_stride;
+        // accumulator buffer `acc` holds the unit's mt tiles side by side: columns [acc * mt + w] * acc_stride
+        const uint32_t d_tmem = tmem_base + acc * mt * args.acc_stride;
+        const int nact = min(mt, m_tiles - (tile / args.c_tiles) * mt);
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(&ctl->full[stage], phase);
           tc_fence_after();
           if (lane == 0 && local == 0 && it == 0) DYNMM_TRACE(3);
           const uint32_t sa = smem_u32(smem + stage * args.stage_bytes);
-          const uint32_t sb = args.b_resident ? smem_u32(smem_bres + it * b_iter_bytes) : sa + args.a_bytes;
+          const uint32_t sb = args.b_resident ? smem_u32(smem_bres + it * b_iter_bytes) : sa + mt * args.a_bytes;
           if (elect_one()) {
             for (int tp = 0; tp < args.tpg; ++tp) {
-              const uint64_t da = umma_desc_sw128(sa + tp * tap_step);
               const uint64_t db = umma_desc_sw128(sb + tp * b_tile_bytes);
+              for (int w = 0; w < nact; ++w) {        // both pixel tiles against the same weight tile
+                const uint64_t da = umma_desc_sw128(sa + w * args.a_bytes + tp * tap_step);
 #pragma unroll
-              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                // advancing K inside the swizzle atom = +32 bytes on the (16-byte unit) start address
-                umma_bf16(d_tmem, da + (k * 2), db + (k * 2), idesc, (it | tp | k) != 0);
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                  // advancing K inside the swizzle atom = +32 bytes on the (16-byte unit) start address
+                  umma_bf16(d_tmem + w * args.acc_stride, da + (k * 2), db + (k * 2), idesc, (it | tp | k) != 0);
+                }
               }
             }
             umma_commit(&ctl->empty[stage]);          // frees the smem stage when these MMAs retire
@@ -253,7 +274,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      const TileCoord t = decode_tile(args, tile);
+      const uint32_t q = fast_div(tile, args.m_c);
+      const int ct = tile - q * args.c_tiles;
+      const int nact = min(mt, m_tiles - (int)q * mt);
+      mbar_wait(&ctl->acc_full[acc], acc_phase);
+      tc_fence_after();
+      if (leader && local == 0) DYNMM_TRACE(5);
+     for (int wt = 0; wt < nact; ++wt) {             // the unit's pixel tiles, one after the other
+      const TileCoord t = decode_tile(args, (q * mt + wt) * args.c_tiles + ct);
       const int n = t.n0 + nl;
       const int p1 = t.x1 + i1, p2 = t.x2 + i2;
       const int h = args.swap ? p1 : p2, w = args.swap ? p2 : p1;
@@ -271,10 +299,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         const int slot = args.gated_slot ? args.gated_slot[n] : n;
         gpix = (static_cast<size_t>(slot) * args.h_out + h) * args.w_out + w;
       }
-      mbar_wait(&ctl->acc_full[acc], acc_phase);
-      tc_fence_after();
-      if (leader && local == 0) DYNMM_TRACE(5);
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * args.acc_stride;
+      const uint32_t t_row =
+          tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (acc * mt + wt) * args.acc_stride;
       for (int sub = 0; sub < n_sub; ++sub) {
         const int cb = sub * 64 + half * 32;       // first of this thread's 32 columns inside the tile
         const bool cols_live = cb < args.acc_stride;
@@ -320,6 +346,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                                         smem_shift);
         }
       }
+     }
       // this warp is done reading the accumulator buffer
       tc_fence_before();
       __syncwarp();
@@ -357,7 +384,7 @@ extern "C" int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream_) {
     const char* e = getenv("DYNMM_CONV_2CTA");
     return !(e && e[0] == '0');
   }();
-  int rc = plan_conv(p, &plan, sms, kSmemBudget, allow_two);
+  int rc = plan_conv(p, &plan, sms, kSmemBudget, allow_two, /*allow_dual=*/p->trace == nullptr);
   if (rc) return rc;
   const KernelArgs& a = plan.a;
   int grid = p->max_ctas > 0 ? p->max_ctas : (a.two_per_sm ? 2 * sms : sms);

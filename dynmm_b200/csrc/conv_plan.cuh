@@ -47,6 +47,7 @@ struct KernelArgs {
   int aux_slots;                    // residual ring slots (0 without residual)
   int b_resident;                   // 1: all weights live in smem for the kernel's lifetime
   int two_per_sm;                   // 1: shared memory / TMEM sized so that two CTAs share an SM (C = 64 layers)
+  int mt;                           // M tiles per work unit: 2 = two pixel tiles share every streamed weight tile
   int swap;                         // 1: d1 = H, d2 = W
   Group groups[kMaxGroups];
   // problem
@@ -150,7 +151,7 @@ __device__ __forceinline__ void epilogue_chunk(const int kFlags, const KernelArg
       const uint32_t chunk = ((chunk0 + (j >> 3)) ^ swz) << 4;
       if (kFlags & kFlagRes) {
         uint4 r;
-        if (kTma) {
+        if (kTma && res_smem != 0) {
           r = lds128(res_smem + chunk);
         } else {
           r = valid ? ld_feat<kCg>(args.residual + rpix * args.res_ld + c) : make_uint4(0, 0, 0, 0);
@@ -236,13 +237,13 @@ struct ConvPlan {
   CUtensorMap map_b, map_res, map_out;
   KernelArgs a;
   int smem_bytes;
-  int max_tiles;            // tiles when every sample slot is active
+  int max_tiles;            // work units (mt pixel tiles x one channel tile) when every sample slot is active
 };
 
 // `sms`: CTAs this convolution can expect to run on (the tile width is chosen to give each of them a tile);
 // `smem_budget`: dynamic shared memory the kernel may use for this convolution
 inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int smem_budget = kSmemBudget,
-                     bool allow_two_per_sm = false) {
+                     bool allow_two_per_sm = false, bool allow_dual = false) {
   DYNMM_CHECK_ARG(p && p->in && p->weight && p->out, "conv_igemm: null pointer");
   DYNMM_CHECK_ARG(p->kh >= 1 && p->kw >= 1 && p->kh * p->kw <= kMaxGroups, "conv_igemm: at most %d taps", kMaxGroups);
   DYNMM_CHECK_ARG(p->stride_h >= 1 && p->stride_h <= 2 && p->stride_w >= 1 && p->stride_w <= 2,
@@ -392,9 +393,38 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
     if (a.stages >= 2 || !halo) break;
   }
   DYNMM_CHECK_ARG(a.stages >= 2, "conv_igemm: not enough shared memory for 2 stages");
+  // Dual-M work units (streamed weights, C >= 256): the stage-3/4 layers are bound by operand streaming from L2
+  // (a 128 x 128 tile with K = 768 pulls 272 KB, 72 % of it weights, for 3072 cycles of UMMAs -- DESIGN.md 5b(f)).
+  // Two pixel tiles of the same channel tile share every weight tile: a stage holds A0, A1 and B, the MMA warp issues
+  // both tiles' UMMAs against the same B descriptors into two accumulators.  Half the weight traffic per output, half
+  // the CTAs per layer (the RGB and the depth launch of a stage then fit on the chip side by side).
+  a.mt = 1;
+  static const int dual_mode = [] {       // DYNMM_CONV_DUAL=0 off, 1 (default) heuristic, 2 whenever possible
+    const char* e = getenv("DYNMM_CONV_DUAL");
+    return e ? atoi(e) : 1;
+  }();
+  const bool force_dual = (p->flags & DYNMM_CONV_FORCE_DUAL) || dual_mode > 1;
+  if (allow_dual && dual_mode > 0 && !(p->flags & DYNMM_CONV_NO_DUAL) && !a.b_resident && a.tma_epi && tile_n <= 128 &&
+      m_tiles >= 2 && !a.two_per_sm && (force_dual || 4LL * m_tiles * a.c_tiles > 3LL * sms)) {
+    const int stage2 = 2 * a.a_bytes + a.tpg * b_tile_bytes;
+    for (int aux2 = a.aux_slots > 2 ? 2 : a.aux_slots; aux2 >= 0; --aux2) {
+      // a residual without a free aux slot is read by the epilogue threads straight from global memory
+      const int epi2 = 2 * kSubBytes + aux2 * kSubBytes;
+      int st2 = (smem_budget - 1024 - 256 - epi2 - shift_bytes) / stage2;
+      if (st2 > kMaxStages) st2 = kMaxStages;
+      if (st2 >= 2) {
+        a.mt = 2;
+        a.aux_slots = aux2;
+        epi_bytes = epi2;
+        a.stage_bytes = stage2;
+        a.stages = st2;
+        break;
+      }
+    }
+  }
   a.acc_stride = (tile_n + 31) / 32 * 32;
   a.tmem_cols = 32;
-  while (a.tmem_cols < 2 * a.acc_stride) a.tmem_cols *= 2;
+  while (a.tmem_cols < 2 * a.mt * a.acc_stride) a.tmem_cols *= 2;
   a.n = p->n;
   a.h_out = p->h_out;
   a.w_out = p->w_out;
@@ -497,8 +527,9 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
   const int smem_bytes = a.stages * a.stage_bytes + (a.b_resident ? b_total : 0) + epi_bytes + 1024 /*align*/ +
                          (int)sizeof(SmemCtl) + shift_bytes;
   DYNMM_CHECK_ARG(smem_bytes <= smem_budget, "conv_igemm: internal smem accounting error (%d bytes)", smem_bytes);
-  const int max_tiles = m_tiles * a.c_tiles;
-  DYNMM_CHECK_ARG((long long)max_tiles * a.c_tiles < (1LL << 31) && max_tiles < (1 << 20), "conv_igemm: too many tiles");
+  const int max_tiles = ceil_div(m_tiles, a.mt) * a.c_tiles;       // work units when every sample slot is active
+  DYNMM_CHECK_ARG((long long)m_tiles * a.c_tiles * a.c_tiles < (1LL << 31) && m_tiles * a.c_tiles < (1 << 20),
+                  "conv_igemm: too many tiles");
   plan->smem_bytes = smem_bytes;
   plan->max_tiles = max_tiles;
   a.flags = (p->residual ? kFlagRes : 0) | (p->gated ? kFlagGated : 0) | (p->relu ? kFlagRelu : 0) |

@@ -49,12 +49,18 @@ class GraphedTrainStep:
                 del p._dynmm_pack
 
     def _step(self) -> Tensor:
-        self.optimizer.zero_grad(set_to_none=False)
+        attached = self.buckets is not None and getattr(self.buckets, "_attached", False)
+        if attached:
+            self.buckets.zero()               # gradients are views into the flat buckets: one memset per bucket
+        else:
+            self.optimizer.zero_grad(set_to_none=False)
         with torch.autocast("cuda", dtype=self.autocast or torch.bfloat16, enabled=self.autocast is not None):
             out = self.model(self.rgb, self.depth)
         loss = self.loss_fn(out, self.target)
         loss.backward()
         if self.buckets is not None:
+            # attached buckets: the hooks already launched every bucket's all-reduce during backward (overlapped);
+            # this only makes the stream wait for them.  Otherwise: the simple post-backward exchange.
             self.buckets.allreduce(average=True)
         self.optimizer.step()
         return loss.detach()

@@ -108,7 +108,7 @@ def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 
          count: Optional[Tensor] = None,
          out: Optional[Tensor] = None, n_out: Optional[int] = None, c_in: Optional[int] = None,
          out_c_off: int = 0, tile_n: int = 0, max_ctas: int = 0, direct: bool = False,
-         trace: Optional[Tensor] = None, volatile_weights: bool = False) -> Tensor:
+         trace: Optional[Tensor] = None, volatile_weights: bool = False, dual: Optional[bool] = None) -> Tensor:
     """Fused conv + scale/shift + residual + ReLU + gated add (see dynmm_conv_igemm_fwd).
 
     x: NHWC bf16 [n_in, h, w, in_ld] (``c_in`` <= in_ld selects a channel prefix);
@@ -137,6 +137,8 @@ def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 
     p.kh, p.kw, p.stride_h, p.stride_w, p.pad_h, p.pad_w = kh, kw, stride[0], stride[1], pad[0], pad[1]
     p.relu, p.tile_n, p.max_ctas = int(relu), tile_n, max_ctas
     p.flags = 1 if volatile_weights else 0       # DYNMM_CONV_VOLATILE_WEIGHTS: packed on this stream just before
+    if dual is not None:                         # DYNMM_CONV_NO_DUAL / DYNMM_CONV_FORCE_DUAL (default: the planner decides)
+        p.flags |= 4 if dual else 2
     p.trace = ptr(trace)
     if CONV_RECORDER is not None and not direct:
         # inside `with ConvProgram()`: the convolution becomes a job of the program's current phase

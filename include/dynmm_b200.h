@@ -191,6 +191,11 @@ typedef struct dynmm_conv_params {
  * with this flag the launch is ordinary stream-ordered (no programmatic early start), so the prologue cannot run
  * ahead of the producer. */
 #define DYNMM_CONV_VOLATILE_WEIGHTS 1
+/* Work-unit shape of streamed-weight layers (C >= 256): by default the planner decides whether two pixel tiles share
+ * every weight tile ("dual-M" units: half the L2->SM weight traffic, half the CTAs); these bits force the choice
+ * (tests, experiments).  Results are bit-identical either way. */
+#define DYNMM_CONV_NO_DUAL 2
+#define DYNMM_CONV_FORCE_DUAL 4
 
 int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream);
 /* ------------------------------------------------- convolution programs

@@ -64,3 +64,55 @@ def test_two_rank_gradients_match_single_process():
     mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
     assert ret["err"] < 1e-5, ret["err"]
     assert ret["hist"] == [3, 0, 0, 0, 2]
+
+
+def _worker_overlap(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dynmm_b200 import dist as ddp
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(12, 32), torch.nn.Tanh(), torch.nn.Linear(32, 32), torch.nn.Tanh(),
+                                    torch.nn.Linear(32, 4))
+        extra = torch.nn.Parameter(torch.zeros(3))            # never receives a gradient: finish() must still reduce it
+        ddp.broadcast_parameters(model, 0)
+        g = torch.Generator().manual_seed(5)
+        x, y = torch.randn(8, 12, generator=g), torch.randn(8, 4, generator=g)
+        buckets = ddp.GradBuckets(list(model.parameters()) + [extra], bucket_bytes=256).attach()
+        assert len(buckets.buckets) >= 3
+        opt = torch.optim.SGD(list(model.parameters()) + [extra], lr=0.1)
+        ref = torch.nn.Sequential(torch.nn.Linear(12, 32), torch.nn.Tanh(), torch.nn.Linear(32, 32), torch.nn.Tanh(),
+                                  torch.nn.Linear(32, 4))
+        ref.load_state_dict(model.state_dict())
+        ref_opt = torch.optim.SGD(ref.parameters(), lr=0.1)
+        launched = []
+        for step in range(3):                                  # several steps: zero() must re-arm the hooks
+            buckets.zero()
+            loss = ((model(ddp.shard(x)) - ddp.shard(y)) ** 2).mean()
+            loss.backward()
+            launched.append(buckets.launched_in_backward)
+            buckets.finish()
+            assert all(p.grad.data_ptr() == v.data_ptr() for p, v in
+                       zip(buckets.buckets[0], [buckets.buckets[0][0].grad])), "gradients must stay bucket views"
+            opt.step()
+            ref_opt.zero_grad()
+            ((ref(x) - y) ** 2).mean().backward()
+            ref_opt.step()
+        err = max((a - b).abs().max().item() for a, b in zip(model.state_dict().values(), ref.state_dict().values()))
+        if rank == 0:
+            ret["err"] = err
+            ret["launched"] = launched
+            ret["n_buckets"] = len(buckets.buckets)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_overlapped_buckets_match_single_process():
+    """attach(): p.grad are views into the flat buckets, every bucket that received all its gradients is reduced from
+    a hook DURING backward, finish() reduces the rest; three SGD steps on 2 ranks == the single-process steps."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_overlap, args=(2, _free_port(), ret), nprocs=2, join=True)
+    assert ret["err"] < 1e-6, ret["err"]
+    # every bucket except the one holding the gradient-less parameter is launched from a hook, in every step
+    assert all(n == ret["n_buckets"] - 1 for n in ret["launched"]), (ret["launched"], ret["n_buckets"])

@@ -435,3 +435,59 @@ def test_permute3d_matches_torch():
     x = torch.randn(7, 5, 9).cuda()
     for perm in [(2, 1, 0), (0, 2, 1), (1, 0, 2), (0, 1, 2), (2, 0, 1), (1, 2, 0)]:
         assert torch.equal(ops.permute3d(x, perm), x.permute(*perm).contiguous())
+
+
+DUAL_CASES = [
+    # name, n, h, w, cin, cout, kh, kw, stride, pad  (streamed-weight layers: C >= 256)
+    ("s3_1x3_c256", 8, 30, 40, 256, 256, 1, 3, (1, 1), (0, 1)),
+    ("s3_3x1_c256", 8, 30, 40, 256, 256, 3, 1, (1, 1), (1, 0)),
+    ("s4_1x3_c512", 8, 15, 20, 512, 512, 1, 3, (1, 1), (0, 1)),
+    ("s4_3x1_c512_n5", 5, 15, 20, 512, 512, 3, 1, (1, 1), (1, 0)),          # odd number of pixel tiles
+    ("s3_3x1_s2_128to256", 3, 60, 80, 128, 256, 3, 1, (2, 1), (1, 0)),      # strided: per-tap loads
+    ("s4_1x1_s2_ds", 8, 30, 40, 256, 512, 1, 1, (2, 2), (0, 0)),
+    ("ppm_1x1_c768", 8, 15, 20, 768, 128, 1, 1, (1, 1), (0, 0)),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", DUAL_CASES, ids=[c[0] for c in DUAL_CASES])
+def test_conv_dual_units_are_bit_identical(case):
+    """Dual-M work units (two pixel tiles share every streamed weight tile; DYNMM_CONV_FORCE_DUAL) give the bits of the
+    one-tile units (DYNMM_CONV_NO_DUAL): same UMMA sequence per tile.  Full epilogue (shift, residual through res_map,
+    ReLU, gated add), sample indirection and every device-side count, and the fp32 reference on top."""
+    from dynmm_b200 import ops
+    name, n, h, w, cin, cout, kh, kw, stride, pad = case
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(len(name) + n)
+    x = torch.randn(n, h, w, cin, device=dev, generator=g).to(torch.bfloat16)
+    wt = torch.randn(cout, cin, kh, kw, device=dev, generator=g) * (2.0 / (cin * kh * kw)) ** 0.5
+    packed = ops.pack_conv_weight(wt)
+    ho = (h + 2 * pad[0] - kh) // stride[0] + 1
+    wo = (w + 2 * pad[1] - kw) // stride[1] + 1
+    shift = torch.randn(cout, device=dev, generator=g) * 0.1
+    res = torch.randn(n, ho, wo, cout, device=dev, generator=g).to(torch.bfloat16)
+    gated = torch.randn(n, ho, wo, cout, device=dev, generator=g).to(torch.bfloat16)
+    gate = torch.rand(n, device=dev, generator=g)
+    gate[0] = 0.0
+    slot = torch.randperm(n, device=dev, generator=g).to(torch.int32)
+    perm = torch.randperm(n, device=dev, generator=g).to(torch.int32)
+    base = dict(c_out=cout, kh=kh, kw=kw, stride=stride, pad=pad, shift=shift, relu=True)
+    variants = [dict(), dict(residual=res), dict(residual=res, gated=gated, gate=gate, gated_slot=slot),
+                dict(in_map=perm, residual=res, res_map=perm)]
+    for kw_ in variants:
+        a = ops.conv(x, packed, dual=False, **base, **kw_)
+        b = ops.conv(x, packed, dual=True, **base, **kw_)
+        torch.cuda.synchronize()
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16)), (name, sorted(kw_))
+    ref = _ref_conv(x, wt, stride, pad, None, shift, res, True, gated, gate, slot)
+    _bf16_close(ops.conv(x, packed, dual=True, residual=res, gated=gated, gate=gate, gated_slot=slot, **base), ref, name)
+    for cnt in range(0, n + 1):
+        count = torch.tensor([cnt], dtype=torch.int32, device=dev)
+        outs = []
+        for dual in (False, True):
+            out = torch.full((n, ho, wo, cout), 7.0, dtype=torch.bfloat16, device=dev)
+            ops.conv(x, packed, dual=dual, count=count, in_map=perm, residual=res, res_map=perm, out=out, **base)
+            outs.append(out)
+        torch.cuda.synchronize()
+        assert torch.equal(outs[0].view(torch.int16), outs[1].view(torch.int16)), (name, cnt)
+        assert (outs[1][cnt:].float() == 7.0).all()

@@ -15,7 +15,11 @@ SHAPES = [
     ("s2 3x1 s2 64->128", 8, 120, 160, 64, 128, 3, 1, (2, 1), False),
     ("s3 1x3 c256", 8, 30, 40, 256, 256, 1, 3, (1, 1), False),
     ("s3 3x1 c256 +res", 8, 30, 40, 256, 256, 3, 1, (1, 1), True),
+    ("s3 1x3 c256 n6", 6, 30, 40, 256, 256, 1, 3, (1, 1), False),
     ("s4 1x3 c512", 8, 15, 20, 512, 512, 1, 3, (1, 1), False),
+    ("s4 1x3 c512 n6", 6, 15, 20, 512, 512, 1, 3, (1, 1), False),
+    ("s4 1x3 s2 512", 8, 15, 40, 512, 512, 1, 3, (1, 2), False),
+    ("s3 1x3 s2 256", 8, 30, 80, 256, 256, 1, 3, (1, 2), False),
     ("s4 3x1 c512 +res", 8, 15, 20, 512, 512, 3, 1, (1, 1), True),
     ("dec 3x3 c128 15x20", 8, 15, 20, 128, 128, 3, 3, (1, 1), False),
     ("dec 1x3 c128 120x160", 8, 120, 160, 128, 128, 1, 3, (1, 1), False),
@@ -39,11 +43,11 @@ def main():
         sc = torch.rand(cout, device=dev) + 0.5
         sh = torch.randn(cout, device=dev)
         out = torch.empty(n, ho, wo, cout, dtype=torch.bfloat16, device=dev)
-        for tn in tile_ns:
+        for tn, dual in [(t, d) for t in tile_ns for d in ((None, False, True) if cin >= 256 else (None,))]:
             if tn > (cout + 15) // 16 * 16:
                 continue
             kw_ = dict(c_out=cout, kh=kh, kw=kw, stride=stride, pad=(kh // 2, kw // 2), scale=sc, shift=sh,
-                       residual=r, relu=True, out=out, tile_n=tn)
+                       residual=r, relu=True, out=out, tile_n=tn, dual=dual)
             for _ in range(3):
                 ops.conv(x, wt, **kw_)
             torch.cuda.synchronize()
@@ -63,7 +67,7 @@ def main():
             us = e0.elapsed_time(e1) / R * 1e3
             flops = 2.0 * n * ho * wo * cout * cin * kh * kw
             byts = 2.0 * (x.numel() + out.numel() + (r.numel() if res else 0) + wt.numel())
-            print(f"{name:28s} tile_n={tn:3d}  {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s  {byts / us / 1e3:7.1f} GB/s")
+            print(f"{name:28s} tile_n={tn:3d} dual={str(dual):5s} {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s  {byts / us / 1e3:7.1f} GB/s")
 
 if __name__ == "__main__":
     main()

@@ -32,6 +32,8 @@ def main():
     ddp.broadcast_parameters(model)
     opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, nesterov=True, weight_decay=1e-4)
     buckets = ddp.GradBuckets(model.parameters())
+    if os.environ.get("OVERLAP", "1") != "0":
+        buckets.attach()      # gradients are bucket views, all-reduce launched from hooks during backward
     rgb, depth = (t.to(dev)[:per_gpu] for t in bench.synthetic_batch(7 + rank, max(per_gpu, 8)))
     target = torch.randint(0, 40, (per_gpu, bench.H, bench.W), device=dev)
     times = []
@@ -62,7 +64,10 @@ def main():
         for step in range(7):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            opt.zero_grad(set_to_none=True)
+            if buckets._attached:
+                buckets.zero()
+            else:
+                opt.zero_grad(set_to_none=True)
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(precision == "autocast")):
                 (out, o8, o16, o32), loss_flop = model(rgb, depth)
             loss = torch.nn.functional.cross_entropy(out.float(), target) + 1e-4 * loss_flop.float()
