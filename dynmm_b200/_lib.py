@@ -20,6 +20,12 @@ class DynmmError(RuntimeError):
     pass
 
 
+class TileFlags(Structure):
+    """Mirror of ``dynmm_tile_flags`` (include/dynmm_b200.h)."""
+    _fields_ = [("flags", c_void_p), ("box_n", c_int32), ("box_h", c_int32), ("box_w", c_int32),
+                ("tiles_h", c_int32), ("tiles_w", c_int32), ("need", c_int32)]
+
+
 class ConvParams(Structure):
     """Mirror of ``dynmm_conv_params`` (include/dynmm_b200.h)."""
     _fields_ = [
@@ -34,6 +40,7 @@ class ConvParams(Structure):
         ("pad_h", c_int32), ("pad_w", c_int32),
         ("relu", c_int32), ("tile_n", c_int32), ("max_ctas", c_int32), ("flags", c_int32),
         ("trace", c_void_p),
+        ("in_flags", TileFlags), ("res_flags", TileFlags), ("out_flags", TileFlags),
     ]
 
 
@@ -83,6 +90,7 @@ SIGNATURES = {
     "dynmm_se_gated_fuse": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong,
                                     c_int, c_int, c_void_p, c_void_p]),
     "dynmm_conv_igemm_fwd": (c_int, [POINTER(ConvParams), c_void_p]),
+    "dynmm_conv_tile_grid": (c_int, [POINTER(ConvParams), POINTER(TileFlags)]),
     "dynmm_conv_direct_fwd": (c_int, [POINTER(ConvParams), c_void_p]),
     "dynmm_conv_pair_fwd": (c_int, [POINTER(ConvPairParams), c_void_p]),
     "dynmm_conv_program_bytes": (c_longlong, [c_int]),

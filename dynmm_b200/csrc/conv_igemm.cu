@@ -117,7 +117,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   // staging, resident weights -- constants only) overlapped the tail of the previous kernel in the
   // stream.  From here on we touch tensors it produced, so wait for it; then let OUR dependent
   // start its prologue.
-  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+  // With tile-completion flags on the input (in_f) there is NO wait for the previous kernel as a whole: the loader
+  // waits per work unit for the producer tiles its window overlaps, so this CTA -- scheduled on an SM one of the
+  // previous layer's early finishers freed -- already works while that layer's last tiles are in flight.
+  if (args.in_f.flags == nullptr) asm volatile("griddepcontrol.wait;\n" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   const int active = args.count ? min(*args.count, args.n) : args.n;
   const int n_groups = (active + args.bn - 1) / args.bn;
@@ -153,6 +156,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           n_in[w] = args.in_map ? args.in_map[t[w].n0] : t[w].n0;
         }
         const uint32_t tx_bytes = nact * a_tx + (args.b_resident ? 0 : b_iter_bytes);
+        if (args.in_f.flags != nullptr) {
+          for (int w = 0; w < nact; ++w) wait_tile_inputs(args, t[w], active, lane);
+        }
         for (int g = 0; g < args.num_groups; ++g) {
           const Group gp = args.groups[g];
           for (int kc = 0; kc < args.k_chunks; ++kc) {
@@ -271,6 +277,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     int aux = 0;
     uint32_t aux_phase = 0;
     int sbuf = 0;
+    // tile-completion flags: a tile whose last TMA store has been committed is published one commit later (then
+    // `cp.async.bulk.wait_group 1` proves its stores are in memory without stalling on the store just issued)
+    const bool publish = args.out_f.flags != nullptr;
+    int pending = -1;
+    auto publish_flag = [&](int idx) {
+      fence_proxy_async_global();
+      __threadfence();
+      red_release_gpu_add(args.out_f.flags + idx, 1);
+    };
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
@@ -287,6 +302,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       const int h = args.swap ? p1 : p2, w = args.swap ? p2 : p1;
       const bool valid = nl < args.bn && n < active && h < args.h_out && w < args.w_out;
       const bool tile_tma = args.tma_epi && (t.n0 + args.bn <= active);   // uniform over the CTA
+      const int h0t = args.swap ? t.x1 : t.x2, w0t = args.swap ? t.x2 : t.x1;    // tile origin in (h, w)
       const size_t pix = valid ? (static_cast<size_t>(n) * args.h_out + h) * args.w_out + w : 0;
       size_t rpix = pix;
       if ((kFlags & kFlagRes) && valid && args.res_map) {
@@ -339,12 +355,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           if (ewarp == 0 && elect_one()) {
             tma_store_4d(&map_out, smem_stage_out + sbuf * kSubBytes, t.c0 + sub * 64, t.x1, t.x2, t.n0);
             bulk_commit();
+            if (pending >= 0) {
+              bulk_wait<1>();                   // every store but the one just committed is complete
+              publish_flag(pending);
+            }
           }
+          pending = (publish && sub == n_sub - 1) ? flag_index(args.out_f, t.n0, h0t, w0t) : -1;
           sbuf ^= 1;
         } else if (cols_live) {
           epilogue_chunk<false, false>(kFlags, args, v, t.c0 + cb, args.tile_n - cb, valid, 0, 0, 0, 0, pix, rpix, gpix, g,
                                         smem_shift);
         }
+      }
+      if (publish && !tile_tma) {
+        // direct stores by every epilogue thread: all of them must be ordered before the flag
+        __threadfence();
+        named_barrier(2, 32 * kEpiWarps);
+        if (leader) red_release_gpu_add(args.out_f.flags + flag_index(args.out_f, t.n0, h0t, w0t), 1);
       }
      }
       // this warp is done reading the accumulator buffer
@@ -354,7 +381,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       if (leader && local == 0) DYNMM_TRACE(6);
     }
     if (leader) DYNMM_TRACE(7);
-    if (ewarp == 0 && elect_one()) bulk_wait<0>();
+    if (ewarp == 0 && elect_one()) {
+      bulk_wait<0>();
+      if (pending >= 0) publish_flag(pending);
+    }
     if (leader) {
       DYNMM_TRACE(8);
       if (args.trace) args.trace[blockIdx.x * 16 + 10] = local;
@@ -384,7 +414,7 @@ extern "C" int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream_) {
     const char* e = getenv("DYNMM_CONV_2CTA");
     return !(e && e[0] == '0');
   }();
-  int rc = plan_conv(p, &plan, sms, kSmemBudget, allow_two, /*allow_dual=*/p->trace == nullptr);
+  int rc = plan_conv(p, &plan, sms, kSmemBudget, allow_two, /*allow_dual=*/true);
   if (rc) return rc;
   const KernelArgs& a = plan.a;
   int grid = p->max_ctas > 0 ? p->max_ctas : (a.two_per_sm ? 2 * sms : sms);
@@ -426,5 +456,22 @@ extern "C" int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream_) {
   cfg.numAttrs = (use_pdl && !(p->flags & DYNMM_CONV_VOLATILE_WEIGHTS)) ? 1 : 0;
   DYNMM_CUDA(cudaLaunchKernelEx(&cfg, table[flags + (a.two_per_sm ? 16 : 0)], plan.maps[0], plan.maps[1], plan.maps[2], plan.maps[3], plan.map_b,
                                 plan.map_res, plan.map_out, a));
+  return DYNMM_OK;
+}
+
+extern "C" int dynmm_conv_tile_grid(const dynmm_conv_params* p, dynmm_tile_flags* grid) {
+  DYNMM_CHECK_ARG(p && grid, "conv_tile_grid: null pointer");
+  ConvPlan plan;
+  static const bool allow_two = [] {
+    const char* e = getenv("DYNMM_CONV_2CTA");
+    return !(e && e[0] == '0');
+  }();
+  dynmm_conv_params q = *p;
+  q.out_flags.flags = nullptr;            // geometry only
+  int rc = plan_conv(&q, &plan, num_sms(), kSmemBudget, allow_two, /*allow_dual=*/true);
+  if (rc) return rc;
+  int32_t* keep = grid->flags;
+  *grid = plan.a.out_f;
+  grid->flags = keep;
   return DYNMM_OK;
 }

@@ -66,6 +66,9 @@ struct KernelArgs {
   unsigned long long* trace;        // debug: 16 cycle stamps per CTA, or NULL
   int flags;                        // kFlag* (program kernel: epilogue variant chosen at run time)
   int cost;                         // relative cost of one tile (program kernel: CTA split between jobs)
+  // tile-completion flags (dynmm_tile_flags in the header): layer-to-layer overlap without a kernel boundary
+  dynmm_tile_flags in_f, res_f, out_f;
+  int kh, kw, stride_h, stride_w, pad_h, pad_w, h_in, w_in;   // input window of an output tile (flag waits)
 };
 
 struct __align__(8) SmemCtl {
@@ -102,6 +105,59 @@ __device__ __forceinline__ TileCoord decode_tile(const KernelArgs& a, int tile) 
 }
 
 enum : int { kFlagRes = 1, kFlagGated = 2, kFlagRelu = 4, kFlagScale = 8 };
+
+// ---- tile-completion flags
+constexpr unsigned kFlagSpinLimit = 1u << 24;     // watchdog: a broken dependency traps instead of hanging the GPU
+
+__device__ __forceinline__ int ld_acquire_gpu_s32(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int32_t* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+
+// flag index of the output tile with origin (n0, h0, w0)
+__device__ __forceinline__ int flag_index(const dynmm_tile_flags& f, int n0, int h0, int w0) {
+  return ((n0 / f.box_n) * f.tiles_h + h0 / f.box_h) * f.tiles_w + w0 / f.box_w;
+}
+
+// Whole warp: have all producer tiles overlapping samples [n_lo, n_hi) x rows [h_lo, h_hi) x columns [w_lo, w_hi)
+// been published?  One flag per lane and pass.
+__device__ __forceinline__ bool region_ready(const dynmm_tile_flags& f, int n_lo, int n_hi, int h_lo, int h_hi, int w_lo,
+                                             int w_hi, int lane) {
+  const int g0 = n_lo / f.box_n, th0 = h_lo / f.box_h, tw0 = w_lo / f.box_w;
+  const int ng = (n_hi - 1) / f.box_n - g0 + 1, nh = (h_hi - 1) / f.box_h - th0 + 1, nw = (w_hi - 1) / f.box_w - tw0 + 1;
+  const int total = ng * nh * nw;
+  bool ok = true;
+  for (int i = lane; i < total; i += 32) {
+    const int tw = i % nw, r = i / nw;
+    const int th = r % nh, g = r / nh;
+    ok = ok && ld_acquire_gpu_s32(f.flags + ((g0 + g) * f.tiles_h + th0 + th) * f.tiles_w + tw0 + tw) >= f.need;
+  }
+  return __all_sync(0xffffffffu, ok);
+}
+
+// Whole warp: block until the input window (and the residual tile) of output tile `t` of this launch is complete.
+__device__ __forceinline__ void wait_tile_inputs(const KernelArgs& a, const TileCoord& t, int active, int lane) {
+  const int h0 = a.swap ? t.x1 : t.x2, w0 = a.swap ? t.x2 : t.x1;
+  const int bh = a.swap ? a.b1 : a.b2, bw = a.swap ? a.b2 : a.b1;
+  const int h1 = min(h0 + bh, a.h_out), w1 = min(w0 + bw, a.w_out);
+  const int n1 = min(t.n0 + a.bn, active);
+  if (h0 >= a.h_out || w0 >= a.w_out || t.n0 >= n1) return;
+  const int ih0 = max(h0 * a.stride_h - a.pad_h, 0), ih1 = min((h1 - 1) * a.stride_h - a.pad_h + a.kh, a.h_in);
+  const int iw0 = max(w0 * a.stride_w - a.pad_w, 0), iw1 = min((w1 - 1) * a.stride_w - a.pad_w + a.kw, a.w_in);
+  unsigned spins = 0;
+  while (!(region_ready(a.in_f, t.n0, n1, ih0, ih1, iw0, iw1, lane) &&
+           (a.res_f.flags == nullptr || region_ready(a.res_f, t.n0, n1, h0, h1, w0, w1, lane)))) {
+    if (++spins > kFlagSpinLimit) __trap();
+    __nanosleep(100);
+  }
+  __syncwarp();
+  fence_proxy_async_global();       // the TMA loads issued next (async proxy) must observe what the flags guard
+}
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
@@ -443,6 +499,32 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
   a.res_map = p->res_map;
   a.count = p->count;
   a.trace = static_cast<unsigned long long*>(p->trace);
+  a.kh = p->kh; a.kw = p->kw; a.stride_h = p->stride_h; a.stride_w = p->stride_w; a.pad_h = p->pad_h; a.pad_w = p->pad_w;
+  a.h_in = p->h_in; a.w_in = p->w_in;
+  a.in_f = p->in_flags;
+  a.res_f = p->res_flags;
+  if (a.in_f.flags == nullptr) a.res_f.flags = nullptr;        // ordinary stream order covers the residual too
+  DYNMM_CHECK_ARG(a.in_f.flags == nullptr || (p->in_map == nullptr && p->res_map == nullptr && p->gated == nullptr),
+                  "conv_igemm: in_flags cannot be combined with in_map / res_map / gated");
+  DYNMM_CHECK_ARG(a.in_f.flags == nullptr || p->residual == nullptr || a.res_f.flags != nullptr ||
+                      (p->flags & DYNMM_CONV_RESIDUAL_SETTLED),
+                  "conv_igemm: in_flags with a residual needs res_flags (or DYNMM_CONV_RESIDUAL_SETTLED)");
+  DYNMM_CHECK_ARG((a.in_f.flags == nullptr || (a.in_f.box_n >= 1 && a.in_f.box_h >= 1 && a.in_f.box_w >= 1 && a.in_f.need >= 1)) &&
+                      (a.res_f.flags == nullptr || (a.res_f.box_n >= 1 && a.res_f.box_h >= 1 && a.res_f.box_w >= 1 && a.res_f.need >= 1)),
+                  "conv_igemm: malformed tile flags");
+  // flags this launch publishes: one per pixel tile, complete at c_tiles
+  a.out_f.flags = p->out_flags.flags;
+  a.out_f.box_n = a.bn;
+  a.out_f.box_h = a.swap ? a.b1 : a.b2;
+  a.out_f.box_w = a.swap ? a.b2 : a.b1;
+  a.out_f.tiles_h = a.swap ? a.tiles1 : a.tiles2;
+  a.out_f.tiles_w = a.swap ? a.tiles2 : a.tiles1;
+  a.out_f.need = a.c_tiles;
+  DYNMM_CHECK_ARG(a.out_f.flags == nullptr ||
+                      (p->out_flags.box_n == a.out_f.box_n && p->out_flags.box_h == a.out_f.box_h &&
+                       p->out_flags.box_w == a.out_f.box_w && p->out_flags.tiles_h == a.out_f.tiles_h &&
+                       p->out_flags.tiles_w == a.out_f.tiles_w && p->out_flags.need == a.out_f.need),
+                  "conv_igemm: out_flags geometry does not match dynmm_conv_tile_grid() for this launch");
   auto magic = [](int d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)(((1ULL << 32) + d - 1) / d); };
   a.m_c = magic(a.c_tiles);
   a.m_1 = magic(a.tiles1);

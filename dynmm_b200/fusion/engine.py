@@ -235,6 +235,9 @@ class FusionEngine:
         # 64-channel NonBottleneck1D blocks: each 3x1 -> 1x3 pair as ONE fused kernel (dynmm_conv_pair_fwd, bit-identical
         # to the two launches); DYNMM_PAIR=0 keeps one launch per convolution
         self.use_pairs = os.environ.get("DYNMM_PAIR", "1") != "0"
+        # DYNMM_TILE_FLAGS=1: convolutions publish per-tile completion flags and their consumers wait on those instead
+        # of on the previous kernel as a whole (layer k+1 starts on the SMs layer k's early finishers free)
+        self.flag_pool = ops.TileFlagPool(device) if os.environ.get("DYNMM_TILE_FLAGS", "0") == "1" else None
 
     # ------------------------------------------------------------------ blocks
     @staticmethod
@@ -283,8 +286,10 @@ class FusionEngine:
         if before_last is not None:
             before_last()
         first = len(blk.convs) == 1
+        # residual_settled: a residual without flags is the block input, which the block's first convolution (an
+        # ordinary stream-ordered launch in that case) has already waited for
         out = blk.convs[-1](y, residual=idn, res_map=res_map, count=count, in_map=in_map if first else None,
-                            n_out=n_out, **(last_kw or {}))
+                            n_out=n_out, residual_settled=(blk.downsample is None and not first), **(last_kw or {}))
         keep.append(out)
         self.launches += 1
         return out
@@ -395,7 +400,14 @@ class FusionEngine:
         """See :meth:`_forward`; runs with the engine's device current (kernel attributes, streams and launches
         are per device)."""
         with torch.cuda.device(self.dev):
-            return self._forward(rgb, depth, **kw)
+            if self.flag_pool is None:
+                return self._forward(rgb, depth, **kw)
+            self.flag_pool.reset()                 # one memset per forward, ahead of both streams
+            ops.FLAG_POOL = self.flag_pool
+            try:
+                return self._forward(rgb, depth, **kw)
+            finally:
+                ops.FLAG_POOL = None
 
     def _forward(self, rgb: Tensor, depth: Tensor, *, temp: float = 1.0, hard_gate: bool = False,
                  baseline: bool = False, ini_stage: bool = False, weight: Optional[Tensor] = None,
@@ -532,6 +544,7 @@ class FusionEngine:
             for y in ys:
                 ops.nearest_resize_into(y, cat, off)
                 off += y.shape[3]
+            cat._dynmm_flags = None             # other kernels wrote into the buffer since the conv published its flags
             keep += pooled + ys
             self.launches += 6
         else:
@@ -542,6 +555,7 @@ class FusionEngine:
                 off += y.shape[3]
                 keep += [pooled, y]
                 self.launches += 3
+            cat._dynmm_flags = None             # other kernels wrote into the buffer since the conv published its flags
         keep += [cat] + skips
         if self.use_programs:
             x = cat

@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import ConvPairParams, ConvParams, WgradParams, check, ptr, stream_ptr
+from ._lib import ConvPairParams, ConvParams, TileFlags, WgradParams, check, ptr, stream_ptr
 
 Tensor = torch.Tensor
 
@@ -101,6 +101,31 @@ def permute3d(x: Tensor, perm: Sequence[int]) -> Tensor:
 
 # ------------------------------------------------------------------ conv
 
+class TileFlagPool:
+    """Device int32 flags for layer-to-layer overlap (``dynmm_tile_flags``): one pool per engine, zeroed at the start
+    of every forward (:meth:`reset`), carved up in launch order -- so the addresses are the same in every forward and a
+    captured CUDA graph stays valid.  While a pool is installed as ``ops.FLAG_POOL``, :func:`conv` publishes
+    completion flags for every output it can and consumes the flags its inputs carry (``tensor._dynmm_flags``)."""
+
+    def __init__(self, device, capacity: int = 1 << 18):
+        self.buf = torch.zeros(capacity, dtype=torch.int32, device=device)
+        self.off = 0
+
+    def reset(self):
+        self.buf.zero_()
+        self.off = 0
+
+    def alloc(self, n: int) -> Optional[int]:
+        if self.off + n > self.buf.numel():
+            return None                      # pool exhausted: this output simply carries no flags
+        p = self.buf.data_ptr() + 4 * self.off
+        self.off += n
+        return p
+
+
+FLAG_POOL: Optional[TileFlagPool] = None
+
+
 def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 1), pad=(0, 0),
          scale: Optional[Tensor] = None, shift: Optional[Tensor] = None, residual: Optional[Tensor] = None,
          relu: bool = False, gated: Optional[Tensor] = None, gate: Optional[Tensor] = None,
@@ -108,7 +133,8 @@ def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 
          count: Optional[Tensor] = None,
          out: Optional[Tensor] = None, n_out: Optional[int] = None, c_in: Optional[int] = None,
          out_c_off: int = 0, tile_n: int = 0, max_ctas: int = 0, direct: bool = False,
-         trace: Optional[Tensor] = None, volatile_weights: bool = False, dual: Optional[bool] = None) -> Tensor:
+         trace: Optional[Tensor] = None, volatile_weights: bool = False, dual: Optional[bool] = None,
+         residual_settled: bool = False) -> Tensor:
     """Fused conv + scale/shift + residual + ReLU + gated add (see dynmm_conv_igemm_fwd).
 
     x: NHWC bf16 [n_in, h, w, in_ld] (``c_in`` <= in_ld selects a channel prefix);
@@ -139,6 +165,31 @@ def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 
     p.flags = 1 if volatile_weights else 0       # DYNMM_CONV_VOLATILE_WEIGHTS: packed on this stream just before
     if dual is not None:                         # DYNMM_CONV_NO_DUAL / DYNMM_CONV_FORCE_DUAL (default: the planner decides)
         p.flags |= 4 if dual else 2
+    pool = FLAG_POOL
+    if pool is not None and not direct and CONV_RECORDER is None and trace is None:
+        # consume: the input's (and the residual's) completion flags replace the wait for the previous kernel.  Only
+        # when everything this launch reads from recent launches is covered: no sample indirection, no gated operand
+        # (that one comes from the other stream behind an event), residual flagged or known to be settled
+        fin = getattr(x, "_dynmm_flags", None)
+        fres = getattr(residual, "_dynmm_flags", None) if residual is not None else None
+        if fin is not None and in_map is None and res_map is None and gated is None and \
+                (residual is None or fres is not None or residual_settled):
+            p.in_flags = fin
+            if fres is not None:
+                p.res_flags = fres
+            elif residual is not None:
+                p.flags |= 8                     # DYNMM_CONV_RESIDUAL_SETTLED
+        # publish: flags for this output (geometry = the tiling the planner picks for exactly this launch)
+        grid = TileFlags()
+        if lib.dynmm_conv_tile_grid(ctypes.byref(p), ctypes.byref(grid)) == 0:
+            nflags = grid.tiles_h * grid.tiles_w * ((n + grid.box_n - 1) // grid.box_n)
+            addr = pool.alloc(nflags)
+            if addr is not None:
+                grid.flags = addr
+                p.out_flags = grid
+                keep = TileFlags()
+                ctypes.memmove(ctypes.byref(keep), ctypes.byref(grid), ctypes.sizeof(TileFlags))
+                out._dynmm_flags = keep
     p.trace = ptr(trace)
     if CONV_RECORDER is not None and not direct:
         # inside `with ConvProgram()`: the convolution becomes a job of the program's current phase

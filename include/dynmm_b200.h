@@ -160,6 +160,25 @@ int dynmm_se_gated_fuse(const void* rgb, const void* depth, const float* sig_r, 
  * int32, may be NULL = n) is the number of leading sample slots that are
  * computed at all; `in_map` (device int32[n], may be NULL) gives the input
  * sample read for output slot i. */
+
+/* Tile-completion flags of a convolution's OUTPUT tensor (layer-to-layer overlap without a kernel boundary).
+ * A launch with `out_flags` set adds 1 to flags[tile] (release, gpu scope) once every byte of output pixel tile
+ * `tile` x one channel tile is in memory; the tensor's pixel tiles form a grid of box_n x box_h x box_w pixels,
+ *   tile = ((n / box_n) * tiles_h + h / box_h) * tiles_w + w / box_w,
+ * and a tile is complete when its flag reaches `need` (the producer's number of channel tiles).  A consumer launch
+ * that gets this description as `in_flags` / `res_flags` does NOT wait for the previous kernel of the stream as a
+ * whole (no griddepcontrol.wait): its loader waits, per work unit, for exactly the producer tiles the unit's input
+ * window (and residual tile) overlaps -- so the CTAs of layer k+1 start on the SMs that layer k's early finishers
+ * free, run their prologue and every tile whose neighbourhood is complete while layer k's last tiles are still in
+ * flight.  flags must be zero before the producer starts (one memset per forward); dynmm_conv_tile_grid() fills the
+ * geometry for a given launch.  flags == NULL: not used. */
+typedef struct dynmm_tile_flags {
+  int32_t* flags;
+  int32_t box_n, box_h, box_w;
+  int32_t tiles_h, tiles_w;
+  int32_t need;
+} dynmm_tile_flags;
+
 typedef struct dynmm_conv_params {
   const void* in;         /* bf16 NHWC [n_in, h_in, w_in, in_ld] */
   const void* weight;     /* bf16 [kh*kw][c_out_pad][c_in], c_out_pad = c_out rounded up to 16 */
@@ -183,6 +202,10 @@ typedef struct dynmm_conv_params {
   int32_t max_ctas;       /* 0 = one per SM */
   int32_t flags;          /* DYNMM_CONV_* bits (fills the padding in front of `trace`: the layout is unchanged) */
   void* trace;            /* debug: device uint64[16 * ctas] in-kernel cycle stamps, or NULL */
+  dynmm_tile_flags in_flags;   /* completion flags of `in`'s producer (flags == NULL: ordinary stream order) */
+  dynmm_tile_flags res_flags;  /* completion flags of `residual`'s producer; required with in_flags when the
+                                  residual was written by a launch that may still be running */
+  dynmm_tile_flags out_flags;  /* flags this launch publishes (geometry from dynmm_conv_tile_grid), or NULL */
 } dynmm_conv_params;
 
 /* dynmm_conv_params.flags: `weight` / `scale` / `shift` were WRITTEN by earlier work on the same stream (training:
@@ -196,8 +219,14 @@ typedef struct dynmm_conv_params {
  * (tests, experiments).  Results are bit-identical either way. */
 #define DYNMM_CONV_NO_DUAL 2
 #define DYNMM_CONV_FORCE_DUAL 4
+/* with in_flags: `residual` was complete before the chain of flagged launches began (no res_flags needed) */
+#define DYNMM_CONV_RESIDUAL_SETTLED 8
 
 int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream);
+/* Geometry of the flags this launch would publish (host only; grid->flags is left untouched): the caller needs
+ * grid->tiles_h * grid->tiles_w * ceil(n / grid->box_n) zeroed int32 flags.  Returns DYNMM_EINVAL for launches that
+ * cannot publish flags. */
+int dynmm_conv_tile_grid(const dynmm_conv_params* p, dynmm_tile_flags* grid);
 /* ------------------------------------------------- convolution programs
  *
  * Many dependent convolutions in ONE persistent cooperative launch.  At batch 8 a layer of the gated

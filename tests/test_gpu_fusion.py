@@ -321,3 +321,39 @@ def test_edge_cases_batch_one_all_skipped_and_bad_sizes():
             eng.forward(torch.zeros(1, 3, 70, 96).cuda(), torch.zeros(1, 1, 70, 96).cuda())
         with pytest.raises(_lib.DynmmError):
             eng.forward(rgb, depth)                                           # CPU tensors
+
+
+def test_tile_flags_engine_is_bit_identical_at_full_size():
+    """DYNMM_TILE_FLAGS=1 (layers overlap through per-tile completion flags instead of kernel boundaries): the whole
+    480x640 batch-8 forward gives the bits of the stream-ordered engine, eager and under CUDA-graph replay (30 replays;
+    gate outcomes spread over all branches so that every depth stage runs with a partial sample list)."""
+    from dynmm_b200 import ops
+    from dynmm_b200.fusion.graph import GraphedForward
+    from oracle import fusion_oracle as fo
+    from oracle.make_golden import sample_inputs
+    cfg = fo.FusionConfig()
+    model, sd = _build(cfg, 0)
+    rgb, depth = sample_inputs(21, 8, 480, 640)
+    rgb_c, depth_c = rgb.cuda(), depth.cuda()
+    eng = model.engine()
+    wk = torch.eye(5)[torch.tensor([0, 1, 2, 3, 4, 0, 4, 2])].cuda()
+    with torch.no_grad():
+        assert eng.flag_pool is None or os.environ.get("DYNMM_TILE_FLAGS") == "1"
+        eng.flag_pool = None
+        ref, _ = eng.forward(rgb_c, depth_c, weight=wk)
+        ref = ref.clone()
+        model.hard_gate = True
+        ref_learned, w_ref = model(rgb_c, depth_c, True, True)
+        ref_learned = ref_learned.clone()
+        eng.flag_pool = ops.TileFlagPool(rgb_c.device)
+        got, _ = eng.forward(rgb_c, depth_c, weight=wk)
+        assert eng.flag_pool.off > 1000, "no flags were allocated"
+        assert torch.equal(got, ref), "eager forward with tile flags differs"
+        modes = dict(temp=1.0, hard_gate=True, baseline=False, ini_stage=False)
+        graphed = GraphedForward(eng, rgb_c, depth_c, modes, False)
+        for rep in range(30):
+            out, w = graphed(rgb_c, depth_c)
+            torch.cuda.synchronize()
+            assert torch.equal(w, w_ref)
+            assert torch.equal(out, ref_learned), f"graph replay {rep} with tile flags differs"
+        eng.flag_pool = None

@@ -491,3 +491,75 @@ def test_conv_dual_units_are_bit_identical(case):
         torch.cuda.synchronize()
         assert torch.equal(outs[0].view(torch.int16), outs[1].view(torch.int16)), (name, cnt)
         assert (outs[1][cnt:].float() == 7.0).all()
+
+
+def _flag_chain(x, layers, pool):
+    """A NonBottleneck1D-like chain through ops.conv; with a pool the launches publish / consume tile flags."""
+    from dynmm_b200 import ops
+    ops.FLAG_POOL = pool
+    try:
+        if pool is not None:
+            pool.reset()
+        outs = []
+        y, block_in = x, x
+        for i, (packed, shift, geom, use_res) in enumerate(layers):
+            cout, kh, kw, stride, pad = geom
+            res = block_in if (use_res and block_in.shape[3] == cout and stride == (1, 1) and
+                               block_in.shape[1:3] == y.shape[1:3]) else None
+            y = ops.conv(y, packed, c_out=cout, kh=kh, kw=kw, stride=stride, pad=pad, shift=shift, relu=True,
+                         residual=res, residual_settled=res is not None and not hasattr(res, "_dynmm_flags"))
+            outs.append(y)
+            if use_res:
+                block_in = y
+        return outs
+    finally:
+        ops.FLAG_POOL = None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(8, 60, 80, 128), (8, 30, 40, 256), (6, 15, 20, 512), (3, 24, 40, 64)],
+                         ids=["s2_c128", "s3_c256", "s4_c512", "c64"])
+def test_tile_flags_chain_is_bit_identical_under_graph_replay(shape):
+    """Layer-to-layer overlap through tile-completion flags (dynmm_tile_flags): a chain of 3x1 / 1x3 / strided
+    convolutions whose launches wait on their producers' flags instead of on the previous kernel gives exactly the
+    bits of the stream-ordered chain -- eager, and replayed 30 times from a CUDA graph (where consecutive launches
+    really overlap through programmatic dependent launch)."""
+    from dynmm_b200 import ops
+    n, h, w, c = shape
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(c + h)
+    x = torch.randn(n, h, w, c, device=dev, generator=g).to(torch.bfloat16)
+    geoms = [(c, 3, 1, (1, 1), (1, 0), False), (c, 1, 3, (1, 1), (0, 1), False),
+             (c, 3, 1, (1, 1), (1, 0), False), (c, 1, 3, (1, 1), (0, 1), True),
+             (c, 3, 1, (1, 1), (1, 0), False), (c, 1, 3, (1, 1), (0, 1), True),
+             (2 * c, 3, 1, (2, 1), (1, 0), False), (2 * c, 1, 3, (1, 2), (0, 1), False),
+             (2 * c, 3, 3, (1, 1), (1, 1), False), (2 * c, 1, 1, (1, 1), (0, 0), True)]
+    layers = []
+    cin = c
+    for cout, kh, kw, stride, pad, use_res in geoms:
+        wt = torch.randn(cout, cin, kh, kw, device=dev, generator=g) * (2.0 / (cin * kh * kw)) ** 0.5
+        layers.append((ops.pack_conv_weight(wt), torch.randn(cout, device=dev, generator=g) * 0.1,
+                       (cout, kh, kw, stride, pad), use_res))
+        cin = cout
+    ref = _flag_chain(x, layers, None)
+    pool = ops.TileFlagPool(dev)
+    got = _flag_chain(x, layers, pool)
+    torch.cuda.synchronize()
+    assert any(hasattr(t, "_dynmm_flags") for t in got), "no launch published flags"
+    for i, (a, b) in enumerate(zip(ref, got)):
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16)), f"eager, layer {i}"
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        _flag_chain(x, layers, pool)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        outs = _flag_chain(x, layers, pool)
+    for rep in range(30):
+        for t in outs:
+            t.fill_(3.0)
+        graph.replay()
+        torch.cuda.synchronize()
+        for i, (a, b) in enumerate(zip(ref, outs)):
+            assert torch.equal(a.view(torch.int16), b.view(torch.int16)), f"graph replay {rep}, layer {i}"

@@ -23,8 +23,9 @@ def main():
         sh = torch.randn(cout, device=dev)
         out = torch.empty(n, ho, wo, cout, dtype=torch.bfloat16, device=dev)
         trace = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+        dual = {"0": False, "1": True}.get(os.environ.get("DUAL", ""), None)
         kw_ = dict(c_out=cout, kh=kh, kw=kw, stride=stride, pad=(kh // 2, kw // 2), shift=sh, residual=r, relu=True,
-                   out=out)
+                   out=out, dual=dual)
         for _ in range(3):
             ops.conv(x, wt, **kw_)
         ops.conv(x, wt, trace=trace, **kw_)
@@ -34,7 +35,7 @@ def main():
         t = t[used]
         rel = (t[:, :16] - t[:, :1]).float()
         tiles = t[:, 10].float()
-        print(f"== {name}: {int(used.sum())} CTAs, tiles/CTA avg {tiles.mean():.1f} max {tiles.max():.0f}")
+        print(f"== {name} dual={dual}: {int(used.sum())} CTAs, tiles/CTA avg {tiles.mean():.1f} max {tiles.max():.0f}")
         order = [0, 1, 2, 3, 12, 11, 4, 5, 13, 14, 15, 6, 7, 8, 9]
         for i in order:
             nm = NAMES[i]
