@@ -102,12 +102,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     tmem_alloc(&ctl->tmem_base, kPerSm == 1 ? 512 : args.tmem_cols);
     tmem_relinquish();
   }
-  if (warp >= 2) {   // epilogue warps stage the shift vector once: no global loads inside the tile loop
-    for (int c = threadIdx.x - 64; c < args.c_out; c += 32 * kEpiWarps) smem_shift[c] = args.shift ? args.shift[c] : 0.f;
-  }
+  // `count` of a depth-encoder launch: when the gate plan that wrote it is known to be complete (every launch but the
+  // first after dynmm_gate_plan), the load is issued here and overlaps the programmatic-dependent-launch wait
+  int active_early = args.n;
+  if (args.count && args.count_settled) active_early = min(__ldg(args.count), args.n);
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();                 // barriers initialised, TMEM allocated -- nothing slower than that in front of it
   tc_fence_after();
+  if (warp >= 2) {
+    // epilogue warps stage the shift vector once (no global loads inside the tile loop); its global-load latency now
+    // overlaps the first TMA loads and UMMAs instead of delaying them: only the epilogue warps wait for it
+    for (int c = threadIdx.x - 64; c < args.c_out; c += 32 * kEpiWarps) smem_shift[c] = args.shift ? args.shift[c] : 0.f;
+    named_barrier(3, 32 * kEpiWarps);
+  }
   // One CTA per SM owns all 512 TMEM columns, so the allocation starts at column 0 / lane 0: using the CONSTANT
   // keeps every tcgen05.mma operand in uniform registers.  Two CTAs per SM allocate what they need (2 x 64 columns)
   // and carry the base in a register.
@@ -122,7 +129,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   // previous layer's early finishers freed -- already works while that layer's last tiles are in flight.
   if (args.in_f.flags == nullptr) asm volatile("griddepcontrol.wait;\n" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
-  const int active = args.count ? min(*args.count, args.n) : args.n;
+  const int active = (args.count && !args.count_settled) ? min(*args.count, args.n) : active_early;
   const int n_groups = (active + args.bn - 1) / args.bn;
   // A work unit = `mt` consecutive pixel tiles x one channel tile (mt = 2: both tiles share every streamed weight
   // tile).  unit -> channel tile ct = unit % c_tiles, pixel tiles m = (unit / c_tiles) * mt + w.

@@ -63,6 +63,7 @@ struct KernelArgs {
   const int32_t* in_map;
   const int32_t* res_map;
   const int32_t* count;
+  int count_settled;                // `count` was written before the previous kernel of the stream started
   unsigned long long* trace;        // debug: 16 cycle stamps per CTA, or NULL
   int flags;                        // kFlag* (program kernel: epilogue variant chosen at run time)
   int cost;                         // relative cost of one tile (program kernel: CTA split between jobs)
@@ -317,6 +318,15 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
   DYNMM_CHECK_ARG((reinterpret_cast<uintptr_t>(p->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->out) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(p->weight) & 15) == 0,
                   "conv_igemm: pointers must be 16-byte aligned");
+  // EXPERIMENT (DYNMM_CONV_SMALL=1): every convolution planned into <= 113 KiB of shared memory and <= 256 TMEM columns,
+  // so that two CTAs -- of consecutive launches (programmatic dependent launch then really overlaps the next
+  // prologue with this tail) or of the RGB and the depth stream -- share an SM.
+  static const bool small_mode = [] {
+    const char* e = getenv("DYNMM_CONV_SMALL");
+    return e && e[0] == '1';
+  }();
+  const bool small = small_mode && allow_two_per_sm && !p->trace;
+  if (small) smem_budget = 113 * 1024;
   KernelArgs& a = plan->a;
   a = KernelArgs{};
   CUtensorMap* maps = plan->maps;
@@ -385,7 +395,7 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
       const int c64 = (c_out_pad + 63) / 64 * 64;
       tile_n = 64;
       long long best = -1;
-      for (int cand = 64; cand <= 256 && cand <= c64 && c64 != 192; cand *= 2) {
+      for (int cand = 64; cand <= (small ? 128 : 256) && cand <= c64 && c64 != 192; cand *= 2) {
         const long long tiles = 1LL * m_tiles * ceil_div(c_out_pad, cand);
         const long long est = ceil_div_ll(tiles, sms) * (cand > 128 ? 2 : 1);
         // DYNMM_CONV_WIDE=1 (experiment, default off): ties go to the WIDER tile (one round of 256 instead of two of 128)
@@ -414,7 +424,7 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
     b_tile_bytes = tile_n * kBlockK * 2;
     b_total = num_taps * a.k_chunks * b_tile_bytes;
     a.tma_epi = (tile_n % 64 == 0) ? 1 : 0;
-    a.aux_slots = (a.tma_epi && p->residual) ? kAuxSlots : 0;
+    a.aux_slots = (a.tma_epi && p->residual && !small) ? kAuxSlots : 0;   // small: residual read from global
     a.b_resident = (a.c_tiles == 1 && b_total <= kResidentBudget) ? 1 : 0;
     if (a.b_resident && a.aux_slots) a.aux_slots = 2;
     shift_bytes = (p->c_out + 8) * 4 + 16;
@@ -423,7 +433,7 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
     a.stages = (smem_budget - 2048 - epi_bytes - shift_bytes - (a.b_resident ? b_total : 0)) / a.stage_bytes;
     if (a.stages < 2 && a.b_resident) {     // not enough room next to the resident weights: stream them instead
       a.b_resident = 0;
-      a.aux_slots = (a.tma_epi && p->residual) ? kAuxSlots : 0;
+      a.aux_slots = (a.tma_epi && p->residual && !small) ? kAuxSlots : 0;
       epi_bytes = (a.tma_epi ? 2 * kSubBytes : 0) + a.aux_slots * kSubBytes;
       a.stage_bytes = a.a_bytes + a.tpg * b_tile_bytes;
       a.stages = (smem_budget - 2048 - epi_bytes - shift_bytes) / a.stage_bytes;
@@ -460,7 +470,7 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
     return e ? atoi(e) : 1;
   }();
   const bool force_dual = (p->flags & DYNMM_CONV_FORCE_DUAL) || dual_mode > 1;
-  if (allow_dual && dual_mode > 0 && !(p->flags & DYNMM_CONV_NO_DUAL) && !a.b_resident && a.tma_epi && tile_n <= 128 &&
+  if (allow_dual && !small && dual_mode > 0 && !(p->flags & DYNMM_CONV_NO_DUAL) && !a.b_resident && a.tma_epi && tile_n <= 128 &&
       m_tiles >= 2 && !a.two_per_sm && (force_dual || 4LL * m_tiles * a.c_tiles > 3LL * sms)) {
     const int stage2 = 2 * a.a_bytes + a.tpg * b_tile_bytes;
     for (int aux2 = a.aux_slots > 2 ? 2 : a.aux_slots; aux2 >= 0; --aux2) {
@@ -481,6 +491,7 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
   a.acc_stride = (tile_n + 31) / 32 * 32;
   a.tmem_cols = 32;
   while (a.tmem_cols < 2 * a.mt * a.acc_stride) a.tmem_cols *= 2;
+  if (small && a.tmem_cols <= 256) a.two_per_sm = 1;
   a.n = p->n;
   a.h_out = p->h_out;
   a.w_out = p->w_out;
@@ -498,6 +509,7 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
   a.in_map = p->in_map;
   a.res_map = p->res_map;
   a.count = p->count;
+  a.count_settled = (p->flags & DYNMM_CONV_COUNT_SETTLED) ? 1 : 0;
   a.trace = static_cast<unsigned long long*>(p->trace);
   a.kh = p->kh; a.kw = p->kw; a.stride_h = p->stride_h; a.stride_w = p->stride_w; a.pad_h = p->pad_h; a.pad_w = p->pad_w;
   a.h_in = p->h_in; a.w_in = p->w_in;

@@ -250,8 +250,11 @@ class FusionEngine:
                    and c.relu for c, k in zip(blk.convs, shapes))
 
     def _block(self, x: Tensor, blk: Block, keep: list, *, count=None, in_map=None, before_last: Callable = None,
-               last_kw: Optional[dict] = None) -> Tensor:
+               last_kw: Optional[dict] = None, count_settled: bool = False) -> Tensor:
+        """``count_settled``: the gate plan that wrote ``count`` completed before the previous kernel of this stream
+        started (every depth block but the first) -- the conv kernels then read it ahead of their launch wait."""
         n_out = x.shape[0]
+        cs = dict(count_settled=True) if (count_settled and count is not None) else {}
         if self.use_pairs and self._pairable(blk):
             c0, c1, c2, c3 = blk.convs
             y = ops.conv_pair(x, c0.weight, c0.shift, c1.weight, c1.shift, relu2=True, count=count, in_map=in_map,
@@ -261,8 +264,8 @@ class FusionEngine:
             if before_last is not None:
                 before_last()
             if last_kw:                # gated add / redirected output: the second pair stays two launches
-                y = c2(y, count=count, n_out=n_out)
-                out = c3(y, residual=x, res_map=in_map, count=count, n_out=n_out, **last_kw)
+                y = c2(y, count=count, n_out=n_out, **cs)
+                out = c3(y, residual=x, res_map=in_map, count=count, n_out=n_out, **cs, **last_kw)
                 keep += [y, out]
                 self.launches += 2
             else:
@@ -273,11 +276,11 @@ class FusionEngine:
             return out
         y = x
         for i, cv in enumerate(blk.convs[:-1]):
-            y = cv(y, count=count, in_map=in_map if i == 0 else None, n_out=n_out)
+            y = cv(y, count=count, in_map=in_map if i == 0 else None, n_out=n_out, **cs)
             keep.append(y)
             self.launches += 1
         if blk.downsample is not None:
-            idn = blk.downsample(x, count=count, in_map=in_map, n_out=n_out)
+            idn = blk.downsample(x, count=count, in_map=in_map, n_out=n_out, **cs)
             keep.append(idn)
             self.launches += 1
             res_map = None
@@ -289,7 +292,8 @@ class FusionEngine:
         # residual_settled: a residual without flags is the block input, which the block's first convolution (an
         # ordinary stream-ordered launch in that case) has already waited for
         out = blk.convs[-1](y, residual=idn, res_map=res_map, count=count, in_map=in_map if first else None,
-                            n_out=n_out, residual_settled=(blk.downsample is None and not first), **(last_kw or {}))
+                            n_out=n_out, residual_settled=(blk.downsample is None and not first), **cs,
+                            **(last_kw or {}))
         keep.append(out)
         self.launches += 1
         return out
@@ -494,7 +498,8 @@ class FusionEngine:
                 for s in range(4):
                     cnt = plan.count[s:s + 1]
                     for bi, blk in enumerate(self.stages["encoder_depth"][s]):
-                        d = self._block(d, blk, keep, count=cnt, in_map=plan.perm if (s == 0 and bi == 0) else None)
+                        d = self._block(d, blk, keep, count=cnt, in_map=plan.perm if (s == 0 and bi == 0) else None,
+                                        count_settled=not (s == 0 and bi == 0))
                     depth_out.append(d)
                     done[s].record(side)
 

@@ -134,7 +134,7 @@ def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 
          out: Optional[Tensor] = None, n_out: Optional[int] = None, c_in: Optional[int] = None,
          out_c_off: int = 0, tile_n: int = 0, max_ctas: int = 0, direct: bool = False,
          trace: Optional[Tensor] = None, volatile_weights: bool = False, dual: Optional[bool] = None,
-         residual_settled: bool = False) -> Tensor:
+         residual_settled: bool = False, count_settled: bool = False) -> Tensor:
     """Fused conv + scale/shift + residual + ReLU + gated add (see dynmm_conv_igemm_fwd).
 
     x: NHWC bf16 [n_in, h, w, in_ld] (``c_in`` <= in_ld selects a channel prefix);
@@ -165,6 +165,8 @@ def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 
     p.flags = 1 if volatile_weights else 0       # DYNMM_CONV_VOLATILE_WEIGHTS: packed on this stream just before
     if dual is not None:                         # DYNMM_CONV_NO_DUAL / DYNMM_CONV_FORCE_DUAL (default: the planner decides)
         p.flags |= 4 if dual else 2
+    if count_settled and count is not None:
+        p.flags |= 16                            # DYNMM_CONV_COUNT_SETTLED
     pool = FLAG_POOL
     if pool is not None and not direct and CONV_RECORDER is None and trace is None:
         # consume: the input's (and the residual's) completion flags replace the wait for the previous kernel.  Only

@@ -221,6 +221,9 @@ typedef struct dynmm_conv_params {
 #define DYNMM_CONV_FORCE_DUAL 4
 /* with in_flags: `residual` was complete before the chain of flagged launches began (no res_flags needed) */
 #define DYNMM_CONV_RESIDUAL_SETTLED 8
+/* `count` was written by a kernel that completed before the PREVIOUS kernel of this stream started (every depth-encoder
+ * launch but the first after dynmm_gate_plan): the kernel reads it while it waits for the previous kernel */
+#define DYNMM_CONV_COUNT_SETTLED 16
 
 int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream);
 /* Geometry of the flags this launch would publish (host only; grid->flags is left untouched): the caller needs

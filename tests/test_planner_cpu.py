@@ -20,7 +20,7 @@ def plan_report(tmp_path_factory):
     if not os.path.exists(NVCC):
         pytest.skip("nvcc not available")
     exe = str(tmp_path_factory.mktemp("plan") / "plan_report")
-    subprocess.run([NVCC, "-std=c++17", "-DDYNMM_PLAN_DRYRUN", "-I", os.path.join(ROOT, "dynmm_b200", "csrc"), "-o", exe,
+    subprocess.run([NVCC, "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-DDYNMM_PLAN_DRYRUN", "-I", os.path.join(ROOT, "dynmm_b200", "csrc"), "-o", exe,
                     os.path.join(ROOT, "tools", "plan_report.cu")], check=True, capture_output=True)
     return exe
 
