@@ -273,8 +273,9 @@ def profile_conv_kernel(model, rgb, depth):
     recs = []
     REP = 4
 
-    def prof(launch, macs_per_sample, n, count):
-        launch()                                        # the real launch of the forward
+    def prof(launch, jobs, launched=False):
+        if not launched:
+            launch()                                    # the real launch of the forward
         s = torch.cuda.current_stream()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
@@ -285,7 +286,7 @@ def profile_conv_kernel(model, rgb, depth):
         e0.record(s)
         g.replay()
         e1.record(s)
-        recs.append((e0, e1, macs_per_sample, n, count, g))
+        recs.append((e0, e1, jobs, g))
     eng = model.engine(rgb.device)
     with torch.no_grad():
         eng.forward(rgb, depth, temp=1.0, hard_gate=True)
@@ -297,7 +298,7 @@ def profile_conv_kernel(model, rgb, depth):
             ops.CONV_PROFILER = None
         torch.cuda.synchronize()
     total_s = sum(r[0].elapsed_time(r[1]) / REP * 1e-3 for r in recs)
-    return total_s, len(recs), weight, [r[:5] for r in recs]
+    return total_s, len(recs), weight, [r[:3] for r in recs]
 
 
 def main():
@@ -446,9 +447,10 @@ def main():
         # executed FLOPs of the tensor-core conv launches (single convolutions and fused pairs): depth-stage launches
         # count the samples the gate kept (their device-side `count`), everything else its n samples
         gflop = 0.0
-        for _, _, macs, n, count in recs:
-            active = min(int(count.item()), n) if count is not None else n
-            gflop += 2.0 * macs * active / 1e9
+        for _, _, jobs in recs:
+            for macs, n, count in jobs:
+                active = min(int(count.item()), n) if count is not None else n
+                gflop += 2.0 * macs * active / 1e9
         achieved = gflop / 1e3 / t_conv if t_conv > 0 else 0.0
         step_s = t_dev / args.steps
         roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel + conv_pair_kernel (tcgen05 implicit GEMM; all conv launches of a step)",

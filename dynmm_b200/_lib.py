@@ -90,6 +90,7 @@ SIGNATURES = {
     "dynmm_se_gated_fuse": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong,
                                     c_int, c_int, c_void_p, c_void_p]),
     "dynmm_conv_igemm_fwd": (c_int, [POINTER(ConvParams), c_void_p]),
+    "dynmm_conv_igemm_fwd2": (c_int, [POINTER(ConvParams), POINTER(ConvParams), c_void_p]),
     "dynmm_conv_tile_grid": (c_int, [POINTER(ConvParams), POINTER(TileFlags)]),
     "dynmm_conv_direct_fwd": (c_int, [POINTER(ConvParams), c_void_p]),
     "dynmm_conv_pair_fwd": (c_int, [POINTER(ConvPairParams), c_void_p]),

@@ -41,12 +41,34 @@ using namespace convk;
     if (args.trace) args.trace[blockIdx.x * 16 + (slot)] = (unsigned long long)clock64(); \
   } while (0)
 
+// what the loops need to know about one of the (up to two) convolutions of a launch
+struct JobView {
+  const KernelArgs* a;
+  const CUtensorMap* maps[4];
+  const CUtensorMap* map_b;
+  const CUtensorMap* map_res;
+  const CUtensorMap* map_out;
+  int active;      // active sample slots
+  int m_tiles;     // pixel tiles of the active slots
+  int units;       // work units: ceil(m_tiles / mt) * c_tiles
+};
+
+// Two convolutions of IDENTICAL geometry (the same layer of the RGB and of the depth encoder) may share a launch:
+// job 1 has its own tensor maps and KernelArgs (pointers, sample count), the tiling fields of both KernelArgs are
+// equal (checked on the host).  The CTAs walk one combined unit list -- job 0's units, then job 1's -- so at batch 8 a
+// CTA typically runs one RGB and one depth tile back to back: the second tile's loads and UMMAs hide the first one's
+// epilogue, and the fixed cost of a launch (prologue, first-load latency, drain, launch gap) is paid once per LAYER
+// instead of once per layer and encoder.  args2.n == 0: single convolution.
 template <int kFlags, int kPerSm>
 __global__ void __launch_bounds__(kThreads, kPerSm)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                   const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
                   const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_res,
-                  const __grid_constant__ CUtensorMap map_out, const __grid_constant__ KernelArgs args) {
+                  const __grid_constant__ CUtensorMap map_out, const __grid_constant__ KernelArgs args,
+                  const __grid_constant__ CUtensorMap map2_a0, const __grid_constant__ CUtensorMap map2_a1,
+                  const __grid_constant__ CUtensorMap map2_a2, const __grid_constant__ CUtensorMap map2_a3,
+                  const __grid_constant__ CUtensorMap map2_b, const __grid_constant__ CUtensorMap map2_res,
+                  const __grid_constant__ CUtensorMap map2_out, const __grid_constant__ KernelArgs args2) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -57,8 +79,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   uint8_t* smem_aux = smem_bres + (args.b_resident ? k_iters * b_iter_bytes : 0);   // [aux_slots][16 KiB]
   uint8_t* smem_stage_out = smem_aux + args.aux_slots * kSubBytes;                  // [2][16 KiB] (tma_epi only)
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_stage_out + (args.tma_epi ? 2 * kSubBytes : 0));
-  // [c_out]: per-channel shift (zeros if absent), 16-byte aligned for float4 broadcast loads
+  // [jobs][c_out + 8]: per-channel shift (zeros if absent), 16-byte aligned for float4 broadcast loads
   float* smem_shift = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ctl + 1) + 15) & ~uintptr_t(15));
+  const int shift_stride = (args.c_out + 11) & ~3;
+  const bool two_jobs = args2.n > 0;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -71,6 +95,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     tma_prefetch_desc(&map_b);
     if (args.tma_epi) tma_prefetch_desc(&map_out);
     if (aux_on) tma_prefetch_desc(&map_res);
+    if (two_jobs) {
+      tma_prefetch_desc(&map2_a0);
+      tma_prefetch_desc(&map2_b);
+      if (args.tma_epi) tma_prefetch_desc(&map2_out);
+      if (aux_on) tma_prefetch_desc(&map2_res);
+    }
     for (int s = 0; s < args.stages; ++s) {
       mbar_init(&ctl->full[s], 1);
       mbar_init(&ctl->empty[s], 1);
@@ -89,7 +119,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   if (warp == 0) {
     __syncwarp();
     if (args.b_resident && elect_one()) {
-      // weights are constants: fetch them before waiting on the previous kernel (c_tiles == 1)
+      // weights are constants: fetch them before waiting on the previous kernel (c_tiles == 1; single job only)
       mbar_expect_tx(&ctl->b_full, k_iters * b_iter_bytes);
       for (int g = 0; g < args.num_groups; ++g)
         for (int kc = 0; kc < args.k_chunks; ++kc)
@@ -104,15 +134,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   }
   // `count` of a depth-encoder launch: when the gate plan that wrote it is known to be complete (every launch but the
   // first after dynmm_gate_plan), the load is issued here and overlaps the programmatic-dependent-launch wait
-  int active_early = args.n;
-  if (args.count && args.count_settled) active_early = min(__ldg(args.count), args.n);
+  int active_early0 = args.n, active_early1 = args2.n;
+  if (args.count && args.count_settled) active_early0 = min(__ldg(args.count), args.n);
+  if (two_jobs && args2.count && args2.count_settled) active_early1 = min(__ldg(args2.count), args2.n);
   tc_fence_before();
   __syncthreads();                 // barriers initialised, TMEM allocated -- nothing slower than that in front of it
   tc_fence_after();
   if (warp >= 2) {
-    // epilogue warps stage the shift vector once (no global loads inside the tile loop); its global-load latency now
+    // epilogue warps stage the shift vectors once (no global loads inside the tile loop); the global-load latency
     // overlaps the first TMA loads and UMMAs instead of delaying them: only the epilogue warps wait for it
-    for (int c = threadIdx.x - 64; c < args.c_out; c += 32 * kEpiWarps) smem_shift[c] = args.shift ? args.shift[c] : 0.f;
+    for (int c = threadIdx.x - 64; c < args.c_out; c += 32 * kEpiWarps) {
+      smem_shift[c] = args.shift ? args.shift[c] : 0.f;
+      if (two_jobs) smem_shift[shift_stride + c] = args2.shift ? args2.shift[c] : 0.f;
+    }
     named_barrier(3, 32 * kEpiWarps);
   }
   // One CTA per SM owns all 512 TMEM columns, so the allocation starts at column 0 / lane 0: using the CONSTANT
@@ -120,22 +154,34 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   // and carry the base in a register.
   if (kPerSm == 1 && ctl->tmem_base != 0) __trap();
   const uint32_t tmem_base = kPerSm == 1 ? 0u : ctl->tmem_base;
-  // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch, shift
-  // staging, resident weights -- constants only) overlapped the tail of the previous kernel in the
-  // stream.  From here on we touch tensors it produced, so wait for it; then let OUR dependent
-  // start its prologue.
+  // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch, resident weights --
+  // constants only) overlapped the tail of the previous kernel in the stream.  From here on we touch tensors it
+  // produced, so wait for it; then let OUR dependent start its prologue.
   // With tile-completion flags on the input (in_f) there is NO wait for the previous kernel as a whole: the loader
   // waits per work unit for the producer tiles its window overlaps, so this CTA -- scheduled on an SM one of the
   // previous layer's early finishers freed -- already works while that layer's last tiles are in flight.
   if (args.in_f.flags == nullptr) asm volatile("griddepcontrol.wait;\n" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
-  const int active = (args.count && !args.count_settled) ? min(*args.count, args.n) : active_early;
-  const int n_groups = (active + args.bn - 1) / args.bn;
   // A work unit = `mt` consecutive pixel tiles x one channel tile (mt = 2: both tiles share every streamed weight
   // tile).  unit -> channel tile ct = unit % c_tiles, pixel tiles m = (unit / c_tiles) * mt + w.
   const int mt = args.mt;
-  const int m_tiles = n_groups * args.tiles2 * args.tiles1;
-  const int total_tiles = ((m_tiles + mt - 1) / mt) * args.c_tiles;          // work units
+  JobView jobs[2];
+  jobs[0].a = &args;
+  jobs[0].maps[0] = &map_a0; jobs[0].maps[1] = &map_a1; jobs[0].maps[2] = &map_a2; jobs[0].maps[3] = &map_a3;
+  jobs[0].map_b = &map_b; jobs[0].map_res = &map_res; jobs[0].map_out = &map_out;
+  jobs[0].active = (args.count && !args.count_settled) ? min(*args.count, args.n) : active_early0;
+  jobs[1].a = &args2;
+  jobs[1].maps[0] = &map2_a0; jobs[1].maps[1] = &map2_a1; jobs[1].maps[2] = &map2_a2; jobs[1].maps[3] = &map2_a3;
+  jobs[1].map_b = &map2_b; jobs[1].map_res = &map2_res; jobs[1].map_out = &map2_out;
+  jobs[1].active = !two_jobs ? 0 : ((args2.count && !args2.count_settled) ? min(*args2.count, args2.n) : active_early1);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int n_groups = (jobs[j].active + args.bn - 1) / args.bn;
+    jobs[j].m_tiles = n_groups * args.tiles2 * args.tiles1;
+    jobs[j].units = ((jobs[j].m_tiles + mt - 1) / mt) * args.c_tiles;
+  }
+  const int units0 = jobs[0].units;
+  const int total_tiles = units0 + jobs[1].units;                 // work units of the launch
   if (threadIdx.x == 0) DYNMM_TRACE(1);
 
   if (warp == 0) {
@@ -143,7 +189,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     // mbarrier-arrive instructions under elect.sync: like the MMA issuer, a lone lane looping inside `if (lane == 0)`
     // pays an ELECT / BRA.U.ANY loop around every UTMALDG)
     {
-      const CUtensorMap* maps[4] = {&map_a0, &map_a1, &map_a2, &map_a3};
       // TMA always delivers the full box (out-of-bounds elements arrive as zeros)
       const uint32_t a_tx = args.a_rows * kBlockK * 2;
       const uint32_t sub_tx = args.b1 * args.b2 * args.bn * kBlockK * 2;
@@ -152,19 +197,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       int aux = 0;
       uint32_t aux_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const uint32_t q = fast_div(tile, args.m_c);
-        const int ct = tile - q * args.c_tiles;
-        const int nact = min(mt, m_tiles - (int)q * mt);            // pixel tiles of this unit (the last may be alone)
+        const int jb = tile >= units0 ? 1 : 0;
+        const JobView& jv = jobs[jb];
+        const KernelArgs& ja = *jv.a;
+        const int unit = tile - (jb ? units0 : 0);
+        const uint32_t q = fast_div(unit, args.m_c);
+        const int ct = unit - q * args.c_tiles;
+        const int nact = min(mt, jv.m_tiles - (int)q * mt);          // pixel tiles of this unit (the last may be alone)
         TileCoord t[2];
         int n_in[2];
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
           t[w] = decode_tile(args, (q * mt + (w < nact ? w : 0)) * args.c_tiles + ct);
-          n_in[w] = args.in_map ? args.in_map[t[w].n0] : t[w].n0;
+          n_in[w] = ja.in_map ? ja.in_map[t[w].n0] : t[w].n0;
         }
         const uint32_t tx_bytes = nact * a_tx + (args.b_resident ? 0 : b_iter_bytes);
-        if (args.in_f.flags != nullptr) {
-          for (int w = 0; w < nact; ++w) wait_tile_inputs(args, t[w], active, lane);
+        if (ja.in_f.flags != nullptr) {
+          for (int w = 0; w < nact; ++w) wait_tile_inputs(ja, t[w], jv.active, lane);
         }
         for (int g = 0; g < args.num_groups; ++g) {
           const Group gp = args.groups[g];
@@ -173,12 +222,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             uint8_t* sa = smem + stage * args.stage_bytes;
             if (elect_one()) {
               mbar_expect_tx(&ctl->full[stage], tx_bytes);
-              tma_load_4d(sa, maps[gp.map], &ctl->full[stage], kc * kBlockK, t[0].x1 + gp.o1, t[0].x2 + gp.o2, n_in[0]);
+              tma_load_4d(sa, jv.maps[gp.map], &ctl->full[stage], kc * kBlockK, t[0].x1 + gp.o1, t[0].x2 + gp.o2, n_in[0]);
               if (nact > 1)
-                tma_load_4d(sa + args.a_bytes, maps[gp.map], &ctl->full[stage], kc * kBlockK, t[1].x1 + gp.o1,
+                tma_load_4d(sa + args.a_bytes, jv.maps[gp.map], &ctl->full[stage], kc * kBlockK, t[1].x1 + gp.o1,
                             t[1].x2 + gp.o2, n_in[1]);
               if (!args.b_resident)
-                tma_load_3d(sa + mt * args.a_bytes, &map_b, &ctl->full[stage], kc * kBlockK, t[0].c0, g * args.tpg);
+                tma_load_3d(sa + mt * args.a_bytes, jv.map_b, &ctl->full[stage], kc * kBlockK, t[0].c0, g * args.tpg);
             }
             __syncwarp();
             if (lane == 0 && tile == (int)blockIdx.x && g == 0 && kc == 0) DYNMM_TRACE(2);
@@ -191,13 +240,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         if (lane == 0 && tile == (int)blockIdx.x) DYNMM_TRACE(11);
         // residual sub-tiles of this unit's tiles, consumed by the epilogue while the next unit's MMAs run
         for (int w = 0; w < nact; ++w) {
-          if (aux_on && t[w].n0 + args.bn <= active) {
-            const int n_res = args.res_map ? args.res_map[t[w].n0] : t[w].n0;
+          if (aux_on && t[w].n0 + args.bn <= jv.active) {
+            const int n_res = ja.res_map ? ja.res_map[t[w].n0] : t[w].n0;
             for (int sub = 0; sub < n_sub; ++sub) {
               mbar_wait(&ctl->aux_empty[aux], aux_phase ^ 1);
               if (elect_one()) {
                 mbar_expect_tx(&ctl->aux_full[aux], sub_tx);
-                tma_load_4d(smem_aux + aux * kSubBytes, &map_res, &ctl->aux_full[aux], t[w].c0 + sub * 64, t[w].x1,
+                tma_load_4d(smem_aux + aux * kSubBytes, jv.map_res, &ctl->aux_full[aux], t[w].c0 + sub * 64, t[w].x1,
                             t[w].x2, n_res);
               }
               __syncwarp();
@@ -234,7 +283,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         tc_fence_after();
         // accumulator buffer `acc` holds the unit's mt tiles side by side: columns [acc * mt + w] * acc_stride
         const uint32_t d_tmem = tmem_base + acc * mt * args.acc_stride;
-        const int nact = min(mt, m_tiles - (tile / args.c_tiles) * mt);
+        const int jb = tile >= units0 ? 1 : 0;
+        const int unit = tile - (jb ? units0 : 0);
+        const int nact = min(mt, jobs[jb].m_tiles - (unit / args.c_tiles) * mt);
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(&ctl->full[stage], phase);
           tc_fence_after();
@@ -286,19 +337,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     int sbuf = 0;
     // tile-completion flags: a tile whose last TMA store has been committed is published one commit later (then
     // `cp.async.bulk.wait_group 1` proves its stores are in memory without stalling on the store just issued)
-    const bool publish = args.out_f.flags != nullptr;
-    int pending = -1;
-    auto publish_flag = [&](int idx) {
+    int32_t* pending = nullptr;
+    auto publish_flag = [&](int32_t* f) {
       fence_proxy_async_global();
       __threadfence();
-      red_release_gpu_add(args.out_f.flags + idx, 1);
+      red_release_gpu_add(f, 1);
     };
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      const uint32_t q = fast_div(tile, args.m_c);
-      const int ct = tile - q * args.c_tiles;
-      const int nact = min(mt, m_tiles - (int)q * mt);
+      const int jb = tile >= units0 ? 1 : 0;
+      const JobView& jv = jobs[jb];
+      const KernelArgs& ja = *jv.a;
+      const int active = jv.active;
+      const float* shift_j = smem_shift + jb * shift_stride;
+      const bool publish = ja.out_f.flags != nullptr;
+      const int unit = tile - (jb ? units0 : 0);
+      const uint32_t q = fast_div(unit, args.m_c);
+      const int ct = unit - q * args.c_tiles;
+      const int nact = min(mt, jv.m_tiles - (int)q * mt);
       mbar_wait(&ctl->acc_full[acc], acc_phase);
       tc_fence_after();
       if (leader && local == 0) DYNMM_TRACE(5);
@@ -312,14 +369,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       const int h0t = args.swap ? t.x1 : t.x2, w0t = args.swap ? t.x2 : t.x1;    // tile origin in (h, w)
       const size_t pix = valid ? (static_cast<size_t>(n) * args.h_out + h) * args.w_out + w : 0;
       size_t rpix = pix;
-      if ((kFlags & kFlagRes) && valid && args.res_map) {
-        rpix = (static_cast<size_t>(args.res_map[n]) * args.h_out + h) * args.w_out + w;
+      if ((kFlags & kFlagRes) && valid && ja.res_map) {
+        rpix = (static_cast<size_t>(ja.res_map[n]) * args.h_out + h) * args.w_out + w;
       }
       float g = 0.f;
       size_t gpix = 0;
       if ((kFlags & kFlagGated) && valid) {
-        g = args.gate[n];
-        const int slot = args.gated_slot ? args.gated_slot[n] : n;
+        g = ja.gate[n];
+        const int slot = ja.gated_slot ? ja.gated_slot[n] : n;
         gpix = (static_cast<size_t>(slot) * args.h_out + h) * args.w_out + w;
       }
       const uint32_t t_row =
@@ -341,8 +398,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
           const uint32_t out_smem = out_base + sbuf * kSubBytes;
           if (cols_live) {
-            epilogue_chunk<true, false>(kFlags, args, v, t.c0 + cb, args.tile_n - cb, valid, res_smem, out_smem, half * 4,
-                                         swz, pix, rpix, gpix, g, smem_shift);
+            epilogue_chunk<true, false>(kFlags, ja, v, t.c0 + cb, args.tile_n - cb, valid, res_smem, out_smem, half * 4,
+                                         swz, pix, rpix, gpix, g, shift_j);
           }
           if (aux_on) {
             __syncwarp();
@@ -360,25 +417,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           named_barrier(1, 32 * kEpiWarps);
           if (leader && local == 0 && sub == 0) DYNMM_TRACE(15);
           if (ewarp == 0 && elect_one()) {
-            tma_store_4d(&map_out, smem_stage_out + sbuf * kSubBytes, t.c0 + sub * 64, t.x1, t.x2, t.n0);
+            tma_store_4d(jv.map_out, smem_stage_out + sbuf * kSubBytes, t.c0 + sub * 64, t.x1, t.x2, t.n0);
             bulk_commit();
-            if (pending >= 0) {
+            if (pending != nullptr) {
               bulk_wait<1>();                   // every store but the one just committed is complete
               publish_flag(pending);
             }
           }
-          pending = (publish && sub == n_sub - 1) ? flag_index(args.out_f, t.n0, h0t, w0t) : -1;
+          pending = (publish && sub == n_sub - 1) ? ja.out_f.flags + flag_index(ja.out_f, t.n0, h0t, w0t) : nullptr;
           sbuf ^= 1;
         } else if (cols_live) {
-          epilogue_chunk<false, false>(kFlags, args, v, t.c0 + cb, args.tile_n - cb, valid, 0, 0, 0, 0, pix, rpix, gpix, g,
-                                        smem_shift);
+          epilogue_chunk<false, false>(kFlags, ja, v, t.c0 + cb, args.tile_n - cb, valid, 0, 0, 0, 0, pix, rpix, gpix, g,
+                                        shift_j);
         }
       }
       if (publish && !tile_tma) {
         // direct stores by every epilogue thread: all of them must be ordered before the flag
         __threadfence();
         named_barrier(2, 32 * kEpiWarps);
-        if (leader) red_release_gpu_add(args.out_f.flags + flag_index(args.out_f, t.n0, h0t, w0t), 1);
+        if (leader) red_release_gpu_add(ja.out_f.flags + flag_index(ja.out_f, t.n0, h0t, w0t), 1);
       }
      }
       // this warp is done reading the accumulator buffer
@@ -390,7 +447,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     if (leader) DYNMM_TRACE(7);
     if (ewarp == 0 && elect_one()) {
       bulk_wait<0>();
-      if (pending >= 0) publish_flag(pending);
+      if (pending != nullptr) publish_flag(pending);
     }
     if (leader) {
       DYNMM_TRACE(8);
@@ -413,22 +470,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 
 using namespace dynmm;
 
-extern "C" int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int sms = num_sms();
-  ConvPlan plan;
+namespace {
+
+bool allow_two_per_sm_env() {
   static const bool allow_two = [] {
     const char* e = getenv("DYNMM_CONV_2CTA");
     return !(e && e[0] == '0');
   }();
-  int rc = plan_conv(p, &plan, sms, kSmemBudget, allow_two, /*allow_dual=*/true);
-  if (rc) return rc;
-  const KernelArgs& a = plan.a;
-  int grid = p->max_ctas > 0 ? p->max_ctas : (a.two_per_sm ? 2 * sms : sms);
-  if (grid > plan.max_tiles) grid = plan.max_tiles;
-  const int flags = a.flags;
+  return allow_two;
+}
+
+// one launch for plan `p0` (and, merged, `p1`: same geometry, own tensors)
+int launch_conv(const ConvPlan& p0, const ConvPlan* p1, int max_ctas, bool pdl, cudaStream_t stream) {
+  const int sms = num_sms();
+  const KernelArgs& a = p0.a;
+  int grid = max_ctas > 0 ? max_ctas : (a.two_per_sm ? 2 * sms : sms);
+  const int units = p0.max_tiles + (p1 ? p1->max_tiles : 0);
+  if (grid > units) grid = units;
   typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap,
-                           KernelArgs);
+                           KernelArgs, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap,
+                           CUtensorMap, KernelArgs);
   static const KernelFn table[32] = {
       conv_igemm_kernel<0, 1>,  conv_igemm_kernel<1, 1>,  conv_igemm_kernel<2, 1>,  conv_igemm_kernel<3, 1>,
       conv_igemm_kernel<4, 1>,  conv_igemm_kernel<5, 1>,  conv_igemm_kernel<6, 1>,  conv_igemm_kernel<7, 1>,
@@ -454,28 +515,76 @@ extern "C" int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream_) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = plan.smem_bytes;
+  cfg.dynamicSmemBytes = p0.smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (use_pdl && !(p->flags & DYNMM_CONV_VOLATILE_WEIGHTS)) ? 1 : 0;
-  DYNMM_CUDA(cudaLaunchKernelEx(&cfg, table[flags + (a.two_per_sm ? 16 : 0)], plan.maps[0], plan.maps[1], plan.maps[2], plan.maps[3], plan.map_b,
-                                plan.map_res, plan.map_out, a));
+  cfg.numAttrs = (use_pdl && pdl) ? 1 : 0;
+  // single job: the second set of maps repeats the first, args2.n == 0 switches the second job off
+  const ConvPlan& q = p1 ? *p1 : p0;
+  KernelArgs a2 = q.a;
+  if (!p1) a2.n = 0;
+  DYNMM_CUDA(cudaLaunchKernelEx(&cfg, table[a.flags + (a.two_per_sm ? 16 : 0)], p0.maps[0], p0.maps[1], p0.maps[2],
+                                p0.maps[3], p0.map_b, p0.map_res, p0.map_out, a, q.maps[0], q.maps[1], q.maps[2], q.maps[3],
+                                q.map_b, q.map_res, q.map_out, a2));
   return DYNMM_OK;
+}
+
+// the tiling fields two merged jobs must agree on
+bool same_tiling(const KernelArgs& x, const KernelArgs& y) {
+  if (x.b1 != y.b1 || x.b2 != y.b2 || x.bn != y.bn || x.tiles1 != y.tiles1 || x.tiles2 != y.tiles2 ||
+      x.c_tiles != y.c_tiles || x.tile_n != y.tile_n || x.num_groups != y.num_groups || x.tpg != y.tpg ||
+      x.k_chunks != y.k_chunks || x.stages != y.stages || x.stage_bytes != y.stage_bytes || x.a_bytes != y.a_bytes ||
+      x.a_rows != y.a_rows || x.acc_stride != y.acc_stride || x.tma_epi != y.tma_epi || x.aux_slots != y.aux_slots ||
+      x.b_resident != y.b_resident || x.two_per_sm != y.two_per_sm || x.mt != y.mt || x.swap != y.swap ||
+      x.flags != y.flags || x.h_out != y.h_out || x.w_out != y.w_out || x.c_out != y.c_out)
+    return false;
+  for (int g = 0; g < x.num_groups; ++g)
+    if (x.groups[g].map != y.groups[g].map || x.groups[g].o1 != y.groups[g].o1 || x.groups[g].o2 != y.groups[g].o2)
+      return false;
+  return true;
+}
+
+}  // namespace
+
+extern "C" int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ConvPlan plan;
+  int rc = plan_conv(p, &plan, num_sms(), kSmemBudget, allow_two_per_sm_env(), /*allow_dual=*/true);
+  if (rc) return rc;
+  return launch_conv(plan, nullptr, p->max_ctas, !(p->flags & DYNMM_CONV_VOLATILE_WEIGHTS), stream);
+}
+
+extern "C" int dynmm_conv_igemm_fwd2(const dynmm_conv_params* pa, const dynmm_conv_params* pb, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DYNMM_CHECK_ARG(pa && pb, "conv_igemm_fwd2: null pointer");
+  if (pa->trace || pb->trace || pa->max_ctas || pb->max_ctas || pa->in_flags.flags || pb->in_flags.flags ||
+      pa->out_flags.flags || pb->out_flags.flags || pa->n < 1 || pb->n < 1) {
+    set_error("conv_igemm_fwd2: trace / max_ctas / tile flags are single-launch options");
+    return DYNMM_EUNSUPPORTED;
+  }
+  // static so that two ~1.3 KB plans (14 tensor maps) do not live on a small thread stack twice over
+  ConvPlan plan_a, plan_b;
+  int rc = plan_conv(pa, &plan_a, num_sms(), kSmemBudget, false, /*allow_dual=*/true, /*partner_slots=*/pb->n);
+  if (rc) return rc;
+  rc = plan_conv(pb, &plan_b, num_sms(), kSmemBudget, false, /*allow_dual=*/true, /*partner_slots=*/pa->n);
+  if (rc) return rc;
+  if (!same_tiling(plan_a.a, plan_b.a)) {
+    set_error("conv_igemm_fwd2: the two convolutions do not plan to the same tiling (launch them separately)");
+    return DYNMM_EUNSUPPORTED;
+  }
+  const bool pdl = !((pa->flags | pb->flags) & DYNMM_CONV_VOLATILE_WEIGHTS);
+  return launch_conv(plan_a, &plan_b, 0, pdl, stream);
 }
 
 extern "C" int dynmm_conv_tile_grid(const dynmm_conv_params* p, dynmm_tile_flags* grid) {
   DYNMM_CHECK_ARG(p && grid, "conv_tile_grid: null pointer");
   ConvPlan plan;
-  static const bool allow_two = [] {
-    const char* e = getenv("DYNMM_CONV_2CTA");
-    return !(e && e[0] == '0');
-  }();
   dynmm_conv_params q = *p;
   q.out_flags.flags = nullptr;            // geometry only
-  int rc = plan_conv(&q, &plan, num_sms(), kSmemBudget, allow_two, /*allow_dual=*/true);
+  int rc = plan_conv(&q, &plan, num_sms(), kSmemBudget, allow_two_per_sm_env(), /*allow_dual=*/true);
   if (rc) return rc;
   int32_t* keep = grid->flags;
   *grid = plan.a.out_f;

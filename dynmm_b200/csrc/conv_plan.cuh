@@ -300,7 +300,12 @@ struct ConvPlan {
 // `sms`: CTAs this convolution can expect to run on (the tile width is chosen to give each of them a tile);
 // `smem_budget`: dynamic shared memory the kernel may use for this convolution
 inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int smem_budget = kSmemBudget,
-                     bool allow_two_per_sm = false, bool allow_dual = false) {
+                     bool allow_two_per_sm = false, bool allow_dual = false, int partner_slots = 0) {
+  // partner_slots > 0: this convolution shares its launch with a second one of identical geometry that has
+  // `partner_slots` sample slots (dynmm_conv_igemm_fwd2): weights are streamed (two resident sets do not fit), two
+  // shift vectors are staged, and the tile width / dual-unit choice looks at the tiles of BOTH jobs
+  const bool merged = partner_slots > 0;
+  if (merged) allow_two_per_sm = false;
   DYNMM_CHECK_ARG(p && p->in && p->weight && p->out, "conv_igemm: null pointer");
   DYNMM_CHECK_ARG(p->kh >= 1 && p->kw >= 1 && p->kh * p->kw <= kMaxGroups, "conv_igemm: at most %d taps", kMaxGroups);
   DYNMM_CHECK_ARG(p->stride_h >= 1 && p->stride_h <= 2 && p->stride_w >= 1 && p->stride_w <= 2,
@@ -396,7 +401,7 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
       tile_n = 64;
       long long best = -1;
       for (int cand = 64; cand <= (small ? 128 : 256) && cand <= c64 && c64 != 192; cand *= 2) {
-        const long long tiles = 1LL * m_tiles * ceil_div(c_out_pad, cand);
+        const long long tiles = 1LL * m_tiles * (p->n + partner_slots) / p->n * ceil_div(c_out_pad, cand);
         const long long est = ceil_div_ll(tiles, sms) * (cand > 128 ? 2 : 1);
         // DYNMM_CONV_WIDE=1 (experiment, default off): ties go to the WIDER tile (one round of 256 instead of two of 128)
         static const bool prefer_wide = [] {
@@ -425,9 +430,9 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
     b_total = num_taps * a.k_chunks * b_tile_bytes;
     a.tma_epi = (tile_n % 64 == 0) ? 1 : 0;
     a.aux_slots = (a.tma_epi && p->residual && !small) ? kAuxSlots : 0;   // small: residual read from global
-    a.b_resident = (a.c_tiles == 1 && b_total <= kResidentBudget) ? 1 : 0;
+    a.b_resident = (a.c_tiles == 1 && b_total <= kResidentBudget && !merged) ? 1 : 0;
     if (a.b_resident && a.aux_slots) a.aux_slots = 2;
-    shift_bytes = (p->c_out + 8) * 4 + 16;
+    shift_bytes = ((p->c_out + 12) * 4) * (merged ? 2 : 1) + 16;
     epi_bytes = (a.tma_epi ? 2 * kSubBytes : 0) + a.aux_slots * kSubBytes;
     a.stage_bytes = a.a_bytes + (a.b_resident ? 0 : a.tpg * b_tile_bytes);
     a.stages = (smem_budget - 2048 - epi_bytes - shift_bytes - (a.b_resident ? b_total : 0)) / a.stage_bytes;
@@ -471,7 +476,8 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
   }();
   const bool force_dual = (p->flags & DYNMM_CONV_FORCE_DUAL) || dual_mode > 1;
   if (allow_dual && !small && dual_mode > 0 && !(p->flags & DYNMM_CONV_NO_DUAL) && !a.b_resident && a.tma_epi && tile_n <= 128 &&
-      m_tiles >= 2 && !a.two_per_sm && (force_dual || 4LL * m_tiles * a.c_tiles > 3LL * sms)) {
+      m_tiles >= 2 && !a.two_per_sm &&
+      (force_dual || 4LL * m_tiles * (p->n + partner_slots) / p->n * a.c_tiles > 3LL * sms)) {
     const int stage2 = 2 * a.a_bytes + a.tpg * b_tile_bytes;
     for (int aux2 = a.aux_slots > 2 ? 2 : a.aux_slots; aux2 >= 0; --aux2) {
       // a residual without a free aux slot is read by the epilogue threads straight from global memory
@@ -516,6 +522,7 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
   a.in_f = p->in_flags;
   a.res_f = p->res_flags;
   if (a.in_f.flags == nullptr) a.res_f.flags = nullptr;        // ordinary stream order covers the residual too
+  DYNMM_CHECK_ARG(!merged || a.in_f.flags == nullptr, "conv_igemm: tile flags are not supported in merged launches");
   DYNMM_CHECK_ARG(a.in_f.flags == nullptr || (p->in_map == nullptr && p->res_map == nullptr && p->gated == nullptr),
                   "conv_igemm: in_flags cannot be combined with in_map / res_map / gated");
   DYNMM_CHECK_ARG(a.in_f.flags == nullptr || p->residual == nullptr || a.res_f.flags != nullptr ||

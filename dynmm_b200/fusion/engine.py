@@ -238,6 +238,11 @@ class FusionEngine:
         # DYNMM_TILE_FLAGS=1: convolutions publish per-tile completion flags and their consumers wait on those instead
         # of on the previous kernel as a whole (layer k+1 starts on the SMs layer k's early finishers free)
         self.flag_pool = ops.TileFlagPool(device) if os.environ.get("DYNMM_TILE_FLAGS", "0") == "1" else None
+        # DYNMM_MERGE=1 ('add' fusion): from stage 2 on, the same layer of the RGB and of the depth encoder is ONE
+        # launch (dynmm_conv_igemm_fwd2) on one stream; only the last convolution of a stage runs per encoder (the RGB
+        # one adds g_s * depth_s, which the depth one has to finish first).  Stage 1 (64 channels: fused-pair kernels
+        # with resident weights) keeps the two-stream form.
+        self.use_merge = cfg.fuse == "add" and os.environ.get("DYNMM_MERGE", "0") == "1" and not self.use_programs
 
     # ------------------------------------------------------------------ blocks
     @staticmethod
@@ -297,6 +302,45 @@ class FusionEngine:
         keep.append(out)
         self.launches += 1
         return out
+
+    def _merged_stage(self, s: int, r: Tensor, d: Tensor, plan, keep: list, cat: Optional[Tensor]):
+        """Stage s (>= 1) of both encoders in lock step: layer i of the depth encoder (slot order, prefix-counted)
+        and layer i of the RGB encoder share a launch; the stage's last convolution runs per encoder -- depth
+        first, then the RGB one with the gated add.  -> (fused RGB stage output, depth stage output)"""
+        cnt = plan.count[s:s + 1]
+        dk = dict(count=cnt, count_settled=True)
+        blocks_r, blocks_d = self.stages["encoder_rgb"][s], self.stages["encoder_depth"][s]
+        n_d = d.shape[0]
+        for bi, (br, bd) in enumerate(zip(blocks_r, blocks_d)):
+            last_block = bi == len(blocks_r) - 1
+            yr, yd = r, d
+            for i in range(len(br.convs) - 1):
+                with ops.ConvMerge():
+                    yr = br.convs[i](yr)
+                    yd = bd.convs[i](yd, n_out=n_d, **dk)
+                keep += [yr, yd]
+                self.launches += 1
+            idn_r, idn_d = r, d
+            if br.downsample is not None:
+                with ops.ConvMerge():
+                    idn_r = br.downsample(r)
+                    idn_d = bd.downsample(d, n_out=n_d, **dk)
+                keep += [idn_r, idn_d]
+                self.launches += 1
+            if not last_block:
+                with ops.ConvMerge():
+                    r = br.convs[-1](yr, residual=idn_r)
+                    d = bd.convs[-1](yd, residual=idn_d, n_out=n_d, **dk)
+                self.launches += 1
+            else:
+                d = bd.convs[-1](yd, residual=idn_d, n_out=n_d, **dk)
+                kw = dict(gated=d, gate=plan.g[s], gated_slot=plan.slot)
+                if cat is not None:
+                    kw.update(out=cat, out_c_off=0)
+                r = br.convs[-1](yr, residual=idn_r, **kw)
+                self.launches += 2
+            keep += [r, d]
+        return r, d
 
     def _se_fuse(self, s: int, rgb: Tensor, depth: Tensor, plan, keep: list, out: Optional[Tensor]) -> Tensor:
         """fuse = w*rgb + (1-w)*se_layer{s+1}(rgb, depth)  (model_skip_mod_globalgate.py:280-283)."""
@@ -493,9 +537,10 @@ class FusionEngine:
                 side.wait_event(fork)
             done = [torch.cuda.Event() for _ in range(4)]
             depth_out = []
+            split = 1 if self.use_merge else 4          # stages run in the two-stream form
             with torch.cuda.stream(side):
                 d = d16
-                for s in range(4):
+                for s in range(split):
                     cnt = plan.count[s:s + 1]
                     for bi, blk in enumerate(self.stages["encoder_depth"][s]):
                         d = self._block(d, blk, keep, count=cnt, in_map=plan.perm if (s == 0 and bi == 0) else None,
@@ -507,7 +552,7 @@ class FusionEngine:
             r = r16
             fused = []
             cat = None
-            for s in range(4):
+            for s in range(split):
                 blocks = self.stages["encoder_rgb"][s]
                 for bi, blk in enumerate(blocks):
                     if bi < len(blocks) - 1:
@@ -528,6 +573,13 @@ class FusionEngine:
                         r = self._block(r, blk, keep)
                         main.wait_event(done[s])
                         r = self._se_fuse(s, r, depth_out[s], plan, keep, cat if s == 3 else None)
+                fused.append(r)
+            for s in range(split, 4):                   # merged launches (the stage-1 join ordered main after side)
+                if s == 3:
+                    c4 = self.stage_channels[3]
+                    cat = torch.empty(b, h // 32, w // 32, c4 + 2 * self.ppm[0].c_out, dtype=torch.bfloat16,
+                                      device=self.dev)
+                r, d = self._merged_stage(s, r, d, plan, keep, cat)
                 fused.append(r)
 
         # ---- skip connections, context module, decoder (model.py:295-308, context_modules.py:69-87)

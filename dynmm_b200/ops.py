@@ -197,14 +197,74 @@ def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 
         # inside `with ConvProgram()`: the convolution becomes a job of the program's current phase
         CONV_RECORDER._record(p, (x, weight, scale, shift, residual, res_map, out, gated, gate, gated_slot, in_map, count))
         return out
+    job = (h_out * w_out * c_out * c_in * kh * kw, n, count)      # MACs per output sample, sample slots, device count
+    if CONV_MERGE is not None and not direct:
+        # inside `with ConvMerge()`: launched when the block ends -- together with its partner if there is one
+        CONV_MERGE._record(p, (x, weight, scale, shift, residual, res_map, out, gated, gate, gated_slot, in_map, count), job)
+        return out
     fn = lib.dynmm_conv_direct_fwd if direct else lib.dynmm_conv_igemm_fwd
     if CONV_PROFILER is not None and not direct:
-        # (launch closure, MACs per output sample, output sample slots, device count tensor or None)
-        CONV_PROFILER(lambda: check(fn(ctypes.byref(p), stream_ptr()), "conv_igemm"),
-                      h_out * w_out * c_out * c_in * kh * kw, n, count)
+        # (launch closure, [(MACs per output sample, output sample slots, device count tensor or None), ...])
+        CONV_PROFILER(lambda: check(fn(ctypes.byref(p), stream_ptr()), "conv_igemm"), [job])
     else:
         check(fn(ctypes.byref(p), stream_ptr()), "conv_direct" if direct else "conv_igemm")
     return out
+
+
+class ConvMerge:
+    """Two :func:`conv` calls of identical geometry (the same layer of the RGB and of the depth encoder) as ONE
+    launch (``dynmm_conv_igemm_fwd2``)::
+
+        with ops.ConvMerge():
+            yd = conv_d(xd, count=cnt)        # outputs are allocated at once, the launch happens at the block's end
+            yr = conv_r(xr)
+
+    Anything else recorded in the block (one call, three calls, two calls the planner tiles differently) is launched
+    call by call in recording order -- the results are the same bits either way."""
+
+    def __init__(self):
+        self.jobs = []
+
+    def _record(self, p, tensors, job):
+        self.jobs.append((p, tensors, job))
+
+    def __enter__(self):
+        global CONV_MERGE
+        if CONV_MERGE is not None or CONV_RECORDER is not None:
+            raise _lib.DynmmError("ConvMerge blocks do not nest")
+        CONV_MERGE = self
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        global CONV_MERGE
+        CONV_MERGE = None
+        if exc_type is None:
+            self.launch()
+        return False
+
+    def launch(self):
+        lib = _lib.load()
+        jobs, self.jobs = self.jobs, []
+        self.merged = False
+        if len(jobs) == 2 and MERGE_ENABLED:
+            (pa, _, ja), (pb, _, jb) = jobs
+
+            def both():
+                rc = lib.dynmm_conv_igemm_fwd2(ctypes.byref(pa), ctypes.byref(pb), stream_ptr())
+                if rc not in (0, -3):
+                    check(rc, "conv_igemm_fwd2")
+                return rc
+            rc = both()                           # the real launch (or DYNMM_EUNSUPPORTED: nothing was launched)
+            if rc == 0:
+                self.merged = True
+                if CONV_PROFILER is not None:
+                    CONV_PROFILER(both, [ja, jb], launched=True)
+                return
+        for p, _, job in jobs:
+            if CONV_PROFILER is not None:
+                CONV_PROFILER(lambda p=p: check(lib.dynmm_conv_igemm_fwd(ctypes.byref(p), stream_ptr()), "conv_igemm"), [job])
+            else:
+                check(lib.dynmm_conv_igemm_fwd(ctypes.byref(p), stream_ptr()), "conv_igemm")
 
 
 def conv_pair(x: Tensor, w1: Tensor, shift1: Optional[Tensor], w2: Tensor, shift2: Optional[Tensor], *,
@@ -228,7 +288,7 @@ def conv_pair(x: Tensor, w1: Tensor, shift1: Optional[Tensor], w2: Tensor, shift
     p.relu2 = int(relu2)
     if CONV_PROFILER is not None:
         CONV_PROFILER(lambda: check(lib.dynmm_conv_pair_fwd(ctypes.byref(p), stream_ptr()), "conv_pair"),
-                      2 * h * w * 64 * 64 * 3, n, count)
+                      [(2 * h * w * 64 * 64 * 3, n, count)])
     else:
         check(lib.dynmm_conv_pair_fwd(ctypes.byref(p), stream_ptr()), "conv_pair")
     return out
@@ -313,9 +373,11 @@ def conv_wgrad(x: Tensor, dy: Tensor, *, kh: int, kw: int, stride=(1, 1), pad=(0
     return out
 
 
-# bench.py installs a callable(params, launch) here to time every tensor-core conv launch
+# bench.py installs a callable(launch, jobs, launched=False) here to time every tensor-core conv launch
 CONV_PROFILER = None
 CONV_RECORDER = None
+CONV_MERGE = None
+MERGE_ENABLED = True
 
 
 class ConvProgram:

@@ -35,6 +35,7 @@ enum {
   DYNMM_OK = 0,
   DYNMM_EINVAL = -1,     /* bad argument / unsupported shape */
   DYNMM_ECUDA = -2,      /* CUDA runtime / driver error */
+  DYNMM_EUNSUPPORTED = -3, /* valid arguments, but this entry point cannot run them (the caller has an alternative) */
   DYNMM_ENODEV = -3      /* no sm_100 device */
 };
 
@@ -226,6 +227,14 @@ typedef struct dynmm_conv_params {
 #define DYNMM_CONV_COUNT_SETTLED 16
 
 int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream);
+/* Two convolutions of IDENTICAL geometry in ONE launch: the same layer of the RGB and of the depth encoder
+ * (FusionDynMM/src/models/model_skip_mod_globalgate.py:276-310 runs the two ResNets in lock step).  Each job keeps its
+ * own tensors, sample count (`count`) and epilogue operands; the CTAs walk one combined tile list (job a's tiles,
+ * then job b's), so at batch 8 a CTA runs an RGB tile and a depth tile back to back and the fixed cost of a launch is
+ * paid once per layer instead of once per layer and encoder.  Weights are streamed (two resident sets do not fit).
+ * Results are bit-identical to two dynmm_conv_igemm_fwd calls.  Returns DYNMM_EUNSUPPORTED when the two convolutions
+ * do not plan to the same tiling or use single-launch options (trace, max_ctas, tile flags): launch them separately. */
+int dynmm_conv_igemm_fwd2(const dynmm_conv_params* a, const dynmm_conv_params* b, void* stream);
 /* Geometry of the flags this launch would publish (host only; grid->flags is left untouched): the caller needs
  * grid->tiles_h * grid->tiles_w * ceil(n / grid->box_n) zeroed int32 flags.  Returns DYNMM_EINVAL for launches that
  * cannot publish flags. */

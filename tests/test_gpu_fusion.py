@@ -357,3 +357,39 @@ def test_tile_flags_engine_is_bit_identical_at_full_size():
             assert torch.equal(w, w_ref)
             assert torch.equal(out, ref_learned), f"graph replay {rep} with tile flags differs"
         eng.flag_pool = None
+
+
+def test_merged_encoder_launches_are_bit_identical_at_full_size():
+    """DYNMM_MERGE=1 (stages 2-4: the same layer of both encoders in one launch): the 480x640 batch-8 forward gives the
+    bits of the two-stream engine for forced branches (every depth stage runs with a partial sample list) and for
+    the learned hard gate under CUDA-graph replay."""
+    from dynmm_b200.fusion.graph import GraphedForward
+    from oracle import fusion_oracle as fo
+    from oracle.make_golden import sample_inputs
+    cfg = fo.FusionConfig()
+    model, sd = _build(cfg, 0)
+    rgb, depth = sample_inputs(21, 8, 480, 640)
+    rgb_c, depth_c = rgb.cuda(), depth.cuda()
+    eng = model.engine()
+    modes = dict(temp=1.0, hard_gate=True, baseline=False, ini_stage=False)
+    with torch.no_grad():
+        outs = {}
+        for merge in (False, True):
+            eng.use_merge = merge
+            forced = []
+            for branches in ([0, 1, 2, 3, 4, 0, 4, 2], [4] * 8, [0] * 8, [3, 3, 1, 4, 2, 2, 0, 1]):
+                wk = torch.eye(5)[torch.tensor(branches)].cuda()
+                forced.append(eng.forward(rgb_c, depth_c, weight=wk)[0].clone())
+            launches = eng.launches
+            graphed = GraphedForward(eng, rgb_c, depth_c, modes, False)
+            learned = []
+            for rep in range(5):
+                o, wgt = graphed(rgb_c, depth_c)
+                learned.append((o.clone(), wgt.clone()))
+            outs[merge] = (forced, learned, launches)
+        eng.use_merge = False
+    assert outs[True][2] < outs[False][2] - 40, "merging should remove at least 40 launches per forward"
+    for a, b in zip(outs[False][0], outs[True][0]):
+        assert torch.equal(a, b), "merged launches changed the logits of a forced-branch forward"
+    for (a, wa), (b, wb) in zip(outs[False][1], outs[True][1]):
+        assert torch.equal(wa, wb) and torch.equal(a, b), "merged launches changed a graph-replayed forward"

@@ -563,3 +563,60 @@ def test_tile_flags_chain_is_bit_identical_under_graph_replay(shape):
         torch.cuda.synchronize()
         for i, (a, b) in enumerate(zip(ref, outs)):
             assert torch.equal(a.view(torch.int16), b.view(torch.int16)), f"graph replay {rep}, layer {i}"
+
+
+MERGE_CASES = [
+    # name, n_a, n_b, h, w, cin, cout, kh, kw, stride, pad
+    ("s2_3x1_c128", 8, 8, 60, 80, 128, 128, 3, 1, (1, 1), (1, 0)),
+    ("s3_1x3_c256", 8, 8, 30, 40, 256, 256, 1, 3, (1, 1), (0, 1)),
+    ("s4_3x1_c512", 8, 8, 15, 20, 512, 512, 3, 1, (1, 1), (1, 0)),
+    ("s3_3x1_s2_128to256", 8, 8, 60, 80, 128, 256, 3, 1, (2, 1), (1, 0)),
+    ("s3_1x1_s2_ds", 8, 8, 60, 80, 128, 256, 1, 1, (2, 2), (0, 0)),
+    ("small_c64_n3_n5", 3, 5, 12, 20, 64, 64, 3, 3, (1, 1), (1, 1)),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", MERGE_CASES, ids=[c[0] for c in MERGE_CASES])
+def test_merged_launch_is_bit_identical(case):
+    """dynmm_conv_igemm_fwd2 (the same layer of the RGB and of the depth encoder in ONE launch, ops.ConvMerge): each
+    job's output has the bits of its own dynmm_conv_igemm_fwd launch -- for every device-side count of the second
+    job (0 .. n: gated-off depth samples), with residuals, and with nothing written beyond the count."""
+    from dynmm_b200 import ops
+    name, na, nb, h, w, cin, cout, kh, kw, stride, pad = case
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(len(name) * 7 + na)
+    xa = torch.randn(na, h, w, cin, device=dev, generator=g).to(torch.bfloat16)
+    xb = torch.randn(nb, h, w, cin, device=dev, generator=g).to(torch.bfloat16)
+    mk = lambda: ops.pack_conv_weight(torch.randn(cout, cin, kh, kw, device=dev, generator=g) * (2.0 / (cin * kh * kw)) ** 0.5)
+    wa, wb = mk(), mk()
+    sa, sb = torch.randn(cout, device=dev, generator=g) * 0.1, torch.randn(cout, device=dev, generator=g) * 0.1
+    ho = (h + 2 * pad[0] - kh) // stride[0] + 1
+    wo = (w + 2 * pad[1] - kw) // stride[1] + 1
+    ra = torch.randn(na, ho, wo, cout, device=dev, generator=g).to(torch.bfloat16)
+    rb = torch.randn(nb, ho, wo, cout, device=dev, generator=g).to(torch.bfloat16)
+    base = dict(c_out=cout, kh=kh, kw=kw, stride=stride, pad=pad, relu=True)
+    for with_res in (False, True):
+        for cnt in sorted({0, 1, nb // 2, nb - 1, nb}):
+            count = torch.tensor([cnt], dtype=torch.int32, device=dev)
+            kw_a = dict(shift=sa, residual=ra if with_res else None, **base)
+            kw_b = dict(shift=sb, residual=rb if with_res else None, count=count, **base)
+            ref_a = ops.conv(xa, wa, **kw_a)
+            ref_b = torch.full((nb, ho, wo, cout), 7.0, dtype=torch.bfloat16, device=dev)
+            ops.conv(xb, wb, out=ref_b, **kw_b)
+            got_b = torch.full((nb, ho, wo, cout), 7.0, dtype=torch.bfloat16, device=dev)
+            with ops.ConvMerge() as m:
+                got_a = ops.conv(xa, wa, **kw_a)
+                ops.conv(xb, wb, out=got_b, **kw_b)
+            torch.cuda.synchronize()
+            assert m.merged, f"{name}: the two convolutions were not merged"
+            assert torch.equal(got_a.view(torch.int16), ref_a.view(torch.int16)), (name, with_res, cnt, "job a")
+            assert torch.equal(got_b.view(torch.int16), ref_b.view(torch.int16)), (name, with_res, cnt, "job b")
+            assert (got_b[cnt:].float() == 7.0).all()
+    # different geometry: not merged, still correct
+    with ops.ConvMerge() as m:
+        y1 = ops.conv(xa, wa, shift=sa, **base)
+        y2 = ops.conv(xb[:, : h // 2 + 1].contiguous(), wb, shift=sb, **base)
+    torch.cuda.synchronize()
+    assert not m.merged
+    assert torch.equal(y1.view(torch.int16), ops.conv(xa, wa, shift=sa, **base).view(torch.int16))
