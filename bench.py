@@ -311,6 +311,10 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-train", action="store_true", help="skip the data-parallel training-step leg (configs[2])")
     ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager-on-this-GPU baseline")
+    ap.add_argument("--in-flight", type=int, default=2,
+                    help="forwards in flight per GPU: each on its own stream and captured-graph instance (1 = one "
+                         "stream, strictly one batch after the other)")
+    ap.add_argument("--dump-launches", default="", help="write the per-launch conv timings of the roofline pass here")
     ap.add_argument("--min-seconds", type=float, default=1.0,
                     help="the timed region repeats the K-step block until it lasts at least this long")
     ap.add_argument("--batch", type=int, default=BATCH,
@@ -350,16 +354,39 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    in_flight = max(1, args.in_flight) if not args.no_graph else 1
+    streams = [torch.cuda.Stream(device=dev) for _ in range(in_flight)]
+
+    def run_steps(nsteps, nflight):
+        """nsteps forwards; with nflight > 1 step i runs on stream i % nflight with captured-graph instance
+        i % nflight (own activation buffers), so consecutive batches overlap on the GPU.  Everything is ordered
+        after / before the current stream, where the timing events are recorded."""
+        cur = torch.cuda.current_stream()
+        if nflight == 1:
+            model.graph_instance = 0
+            for i in range(nsteps):
+                model(*batches[i % 3], True, True)
+            return
+        for st in streams[:nflight]:
+            st.wait_stream(cur)
+        for i in range(nsteps):
+            j = i % nflight
+            with torch.cuda.stream(streams[j]):
+                model.graph_instance = j
+                model(*batches[i % 3], True, True)
+        for st in streams[:nflight]:
+            cur.wait_stream(st)
+        model.graph_instance = 0
+
     with torch.no_grad():
         # ---------------- device-resident throughput ("value"): K steps between two events, the block repeated
         # until the timed region lasts >= --min-seconds (K = 20 alone would be a 30 ms measurement)
-        for i in range(args.warmup):
-            model(*batches[i % 3], True)
+        run_steps(max(args.warmup, 2 * in_flight), in_flight)
+        run_steps(args.warmup, 1)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(args.steps):
-            model(*batches[i % 3], True, True)
+        run_steps(args.steps, in_flight)
         e1.record()
         torch.cuda.synchronize()
         est = max(e0.elapsed_time(e1) * 1e-3, 1e-6)
@@ -373,12 +400,24 @@ def main():
         sampler.start()
         e0.record()
         for _ in range(repeats):
-            for i in range(args.steps):
-                out, wgt = model(*batches[i % 3], True, True)
+            run_steps(args.steps, in_flight)
         e1.record()
         barrier()
         clocks = sampler.stop()
         t_dev = e0.elapsed_time(e1) * 1e-3 / repeats         # seconds per K steps
+        # the same steps strictly one after the other on one stream (latency of a batch; no inter-batch overlap)
+        single = None
+        if in_flight > 1:
+            barrier()
+            e0.record()
+            for _ in range(max(1, repeats // 2)):
+                run_steps(args.steps, 1)
+            e1.record()
+            barrier()
+            t_single = e0.elapsed_time(e1) * 1e-3 / max(1, repeats // 2)
+            single = {"value": batch * args.steps / t_single, "unit": "images/s (this rank)",
+                      "ms_per_step": t_single / args.steps * 1e3,
+                      "note": "one forward at a time on one stream: the latency of a batch of 8"}
         for i in range(3):                        # gate statistics of the workload (outside the timed region)
             _, wgt = model(*batches[i], True, True)
             hist += torch.bincount(wgt.argmax(1), minlength=5)
@@ -388,7 +427,7 @@ def main():
         # EvalPipeline overlaps batch i+1's upload / batch i-1's read-back with batch i's forward.
         from dynmm_b200.fusion import EvalPipeline
         host = [tuple(t.pin_memory() for t in synthetic_batch(1000 * rank + i, batch)) for i in range(3)]
-        pipe = EvalPipeline(model, batch, H, W, dev)
+        pipe = EvalPipeline(model, batch, H, W, dev, in_flight=in_flight)
         for _ in pipe.run(host[i % 3] for i in range(args.warmup)):
             pass
         e2e_steps = args.steps * max(1, min(repeats, 10))
@@ -451,6 +490,14 @@ def main():
             for macs, n, count in jobs:
                 active = min(int(count.item()), n) if count is not None else n
                 gflop += 2.0 * macs * active / 1e9
+        if args.dump_launches:
+            with open(args.dump_launches, "w") as fh:
+                fh.write("# launch  us  GFLOP  TFLOP/s  jobs(macs_per_sample x active)\n")
+                for i, (a0, a1, jobs) in enumerate(recs):
+                    us = a0.elapsed_time(a1) / 4 * 1e3
+                    gf = sum(2.0 * m * (min(int(c.item()), n) if c is not None else n) for m, n, c in jobs) / 1e9
+                    desc = " + ".join(f"{m / 1e6:.1f}M x {min(int(c.item()), n) if c is not None else n}" for m, n, c in jobs)
+                    fh.write(f"{i:4d} {us:8.2f} {gf:8.3f} {gf / us * 1e3 if us > 0 else 0:8.1f}  {desc}\n")
         achieved = gflop / 1e3 / t_conv if t_conv > 0 else 0.0
         step_s = t_dev / args.steps
         roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel + conv_pair_kernel (tcgen05 implicit GEMM; all conv launches of a step)",
@@ -519,11 +566,14 @@ def main():
             "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload,
-                       "per_gpu_batch": batch, "global_batch": batch * world, "parallelism": f"dp{world} (replicas, no data-path collective in eval)",
+                       "per_gpu_batch": batch, "global_batch": batch * world,
+                       "parallelism": f"dp{world} (replicas, no data-path collective in eval); {in_flight} batch(es) of "
+                                      f"{batch} in flight per GPU (one stream + captured-graph instance each)",
                        "gate_path_dtype": "f32", "cuda_graph": not args.no_graph,
                        "timed_region": f"{repeats} x {args.steps} steps between one pair of CUDA events (>= {args.min_seconds} s)",
                        "l2": "3 rotating resident batches; per-step working set > 126 MB L2, no explicit flush",
                        "gate_branch_histogram": h, "gate_skip_flop_savings_pct": 100.0 * saved},
+            "single_stream": single,
             "rank_ms_per_step": rank_ms,
             "rank_time_max_over_mean": max(rank_ms) / (sum(rank_ms) / len(rank_ms)),
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": batch * 4 * H * W * 4,

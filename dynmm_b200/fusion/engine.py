@@ -225,6 +225,7 @@ class FusionEngine:
                                      w2.reshape(w2.shape[0], -1).contiguous(), p.t(k + ".2.bias").contiguous())
                 self.se.append(layer)
         self.side = torch.cuda.Stream(device=device)
+        self.side2 = torch.cuda.Stream(device=device)      # skip-connection 1x1 convs, off the encoders' critical path
         self.launches = 0          # kernels launched by the last forward (for bench accounting)
         # DYNMM_PROGRAM=1 ('add' fusion only): the encoders, the skip convs and each decoder module run as persistent
         # convolution PROGRAMS (one cooperative launch per chain of dependent convs, dynmm_conv_program_*) instead of
@@ -238,11 +239,11 @@ class FusionEngine:
         # DYNMM_TILE_FLAGS=1: convolutions publish per-tile completion flags and their consumers wait on those instead
         # of on the previous kernel as a whole (layer k+1 starts on the SMs layer k's early finishers free)
         self.flag_pool = ops.TileFlagPool(device) if os.environ.get("DYNMM_TILE_FLAGS", "0") == "1" else None
-        # DYNMM_MERGE=1 ('add' fusion): from stage 2 on, the same layer of the RGB and of the depth encoder is ONE
+        # DYNMM_MERGE (default on; 'add' fusion): from stage 2 on, the same layer of the RGB and of the depth encoder is ONE
         # launch (dynmm_conv_igemm_fwd2) on one stream; only the last convolution of a stage runs per encoder (the RGB
         # one adds g_s * depth_s, which the depth one has to finish first).  Stage 1 (64 channels: fused-pair kernels
         # with resident weights) keeps the two-stream form.
-        self.use_merge = cfg.fuse == "add" and os.environ.get("DYNMM_MERGE", "0") == "1" and not self.use_programs
+        self.use_merge = cfg.fuse == "add" and os.environ.get("DYNMM_MERGE", "1") == "1" and not self.use_programs
 
     # ------------------------------------------------------------------ blocks
     @staticmethod
@@ -548,6 +549,29 @@ class FusionEngine:
                     depth_out.append(d)
                     done[s].record(side)
 
+            # the skip-connection convolutions (model.py:295-297) only feed the decoder: each one is launched on a
+            # third stream the moment its stage output exists, and the decoder waits for it where it adds the skip
+            skips = []
+            skip_done = []
+
+            def emit_skip(s, x):
+                if s >= 3:
+                    return
+                if self.skips[s] is None:
+                    skips.append(x)
+                    skip_done.append(None)
+                    return
+                ready = torch.cuda.Event()
+                ready.record(main)
+                self.side2.wait_event(ready)
+                with torch.cuda.stream(self.side2):
+                    y = self.skips[s](x)
+                    ev = torch.cuda.Event()
+                    ev.record(self.side2)
+                skips.append(y)
+                skip_done.append(ev)
+                self.launches += 1
+
             # ---- RGB encoder on the main stream; the last conv of each stage adds g_s * depth_s
             r = r16
             fused = []
@@ -574,6 +598,7 @@ class FusionEngine:
                         main.wait_event(done[s])
                         r = self._se_fuse(s, r, depth_out[s], plan, keep, cat if s == 3 else None)
                 fused.append(r)
+                emit_skip(s, r)
             for s in range(split, 4):                   # merged launches (the stage-1 join ordered main after side)
                 if s == 3:
                     c4 = self.stage_channels[3]
@@ -581,16 +606,11 @@ class FusionEngine:
                                       device=self.dev)
                 r, d = self._merged_stage(s, r, d, plan, keep, cat)
                 fused.append(r)
+                emit_skip(s, r)
 
-        # ---- skip connections, context module, decoder (model.py:295-308, context_modules.py:69-87)
-        if skips is None:
-            skips = []
-            for s in range(3):
-                if self.skips[s] is not None:
-                    skips.append(self.skips[s](fused[s]))
-                    self.launches += 1
-                else:
-                    skips.append(fused[s])
+        # ---- context module, decoder (model.py:295-308, context_modules.py:69-87)
+        if self.use_programs:
+            skip_done = [None, None, None]
         c4 = self.stage_channels[3]
         off = c4
         if self.use_programs:
@@ -634,6 +654,8 @@ class FusionEngine:
                 keep.append(x)
                 for blk in m["blocks"]:
                     x = self._block(x, blk, keep)
+                if skip_done[2 - i] is not None:
+                    main.wait_event(skip_done[2 - i])
                 x = ops.upsample2x_dw3x3(x, m["up_w"], m["up_b"], skip)
                 self.launches += 1
                 keep.append(x)

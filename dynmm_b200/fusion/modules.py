@@ -484,6 +484,10 @@ class SkipGateESANet(nn.Module):
         self._engine_key = None
         self._pending_weights: List[Tensor] = []
         self.use_cuda_graph = False          # opt-in: replay one captured graph per input shape
+        # which captured-graph instance a forward replays: instances own their activation buffers, so forwards of
+        # DIFFERENT instances launched on different streams overlap on the GPU (two batches in flight: the stem of
+        # batch i+1 fills the SMs the latency-bound decoder tail of batch i leaves idle) -- see EvalPipeline
+        self.graph_instance = 0
         # training arithmetic on CUDA: "fp32" = the reference's (library convs, our gate ops);
         # "bf16" = encoder/decoder convolutions forward + backward on the tcgen05 kernels (train_ops.py)
         self.train_precision = "fp32"
@@ -576,13 +580,14 @@ class SkipGateESANet(nn.Module):
             self._graphs = {}
         return self._engine
 
-    def _forward_engine(self, rgb, depth, labels_only=False):
+    def _forward_engine(self, rgb, depth, labels_only=False, instance=None):
         eng = self.engine(rgb.device)
+        instance = self.graph_instance if instance is None else instance
         modes = dict(temp=float(self.temp), hard_gate=bool(self.hard_gate), baseline=bool(self.baseline),
                      ini_stage=bool(self.ini_stage))
         if self.use_cuda_graph and not self.ini_stage:
             from .graph import GraphedForward
-            key = (tuple(rgb.shape), tuple(sorted(modes.items())), labels_only)
+            key = (tuple(rgb.shape), tuple(sorted(modes.items())), labels_only, instance)
             g = self._graphs.get(key)
             if g is None:
                 g = self._graphs[key] = GraphedForward(eng, rgb, depth, modes, labels_only)
@@ -595,14 +600,14 @@ class SkipGateESANet(nn.Module):
         return eng.forward(rgb, depth, **modes)
 
     @torch.no_grad()
-    def predict_labels(self, rgb, depth, out=None, return_weight=False):
+    def predict_labels(self, rgb, depth, out=None, return_weight=False, instance=None):
         """argmax_c(self(rgb, depth, True)) as uint8 [B,H,W] -- what eval.py:109-120 computes per batch --
         produced by the final upsampling kernel itself, so the 40-channel full-resolution logits are
         never written to memory.  Eval mode, CUDA tensors.  ``return_weight``: also the gate weights [B,5]
         (like ``forward(..., test=True, return_weight=True)``)."""
         if self.training or not rgb.is_cuda:
             raise RuntimeError("predict_labels runs the CUDA engine: call model.eval() and pass CUDA tensors")
-        labels, weight = self._forward_engine(rgb, depth, labels_only=True)
+        labels, weight = self._forward_engine(rgb, depth, labels_only=True, instance=instance)
         if self.save_weight_info:
             self._pending_weights.append(weight.detach().clone())
         if out is not None:

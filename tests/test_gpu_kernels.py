@@ -572,7 +572,8 @@ MERGE_CASES = [
     ("s4_3x1_c512", 8, 8, 15, 20, 512, 512, 3, 1, (1, 1), (1, 0)),
     ("s3_3x1_s2_128to256", 8, 8, 60, 80, 128, 256, 3, 1, (2, 1), (1, 0)),
     ("s3_1x1_s2_ds", 8, 8, 60, 80, 128, 256, 1, 1, (2, 2), (0, 0)),
-    ("small_c64_n3_n5", 3, 5, 12, 20, 64, 64, 3, 3, (1, 1), (1, 1)),
+    ("small_c64_3x3", 5, 5, 12, 20, 64, 64, 3, 3, (1, 1), (1, 1)),
+    ("s3_1x3_c256_n8_n6", 8, 6, 30, 40, 256, 256, 1, 3, (1, 1), (0, 1)),
 ]
 
 

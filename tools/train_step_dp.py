@@ -91,6 +91,12 @@ def main():
               f"grad buckets={len(buckets.buckets)}")
     assert ok
     if world > 1:
+        # captured graphs hold NCCL work: release them before tearing the communicator down (otherwise the
+        # destroy can hang until the launcher kills the ranks)
+        if use_graph:
+            del gstep
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 if __name__ == "__main__":
