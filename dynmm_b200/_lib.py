@@ -54,6 +54,24 @@ class ConvPairParams(Structure):
     ]
 
 
+class ChainLayer(Structure):
+    """Mirror of ``dynmm_chain_layer`` (include/dynmm_b200.h)."""
+    _fields_ = [("weight", c_void_p), ("shift", c_void_p), ("taps_h", c_int32), ("relu", c_int32),
+                ("residual", c_int32), ("store", c_int32)]
+
+
+class ChainJob(Structure):
+    """Mirror of ``dynmm_chain_job`` (include/dynmm_b200.h)."""
+    _fields_ = [("image", c_void_p), ("in_", c_void_p), ("out", c_void_p), ("out_last", c_void_p), ("count", c_void_p),
+                ("n", c_int32), ("n_layers", c_int32), ("count_settled", c_int32), ("reserved", c_int32)]
+
+
+class ChainParams(Structure):
+    """Mirror of ``dynmm_chain_params`` (include/dynmm_b200.h)."""
+    _fields_ = [("jobs", ChainJob * 2), ("n_jobs", c_int32), ("h", c_int32), ("w", c_int32), ("c", c_int32),
+                ("flags", c_void_p), ("scratch", c_void_p), ("scratch_bytes", c_longlong), ("trace", c_void_p)]
+
+
 class WgradParams(Structure):
     """Mirror of ``dynmm_wgrad_params`` (include/dynmm_b200.h)."""
     _fields_ = [
@@ -94,6 +112,10 @@ SIGNATURES = {
     "dynmm_conv_tile_grid": (c_int, [POINTER(ConvParams), POINTER(TileFlags)]),
     "dynmm_conv_direct_fwd": (c_int, [POINTER(ConvParams), c_void_p]),
     "dynmm_conv_pair_fwd": (c_int, [POINTER(ConvPairParams), c_void_p]),
+    "dynmm_conv_chain_image_bytes": (c_longlong, [c_int]),
+    "dynmm_conv_chain_build": (c_int, [POINTER(ChainLayer), c_int, c_int, c_void_p]),
+    "dynmm_conv_chain_plan": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int32), POINTER(c_longlong)]),
+    "dynmm_conv_chain_fwd": (c_int, [POINTER(ChainParams), c_void_p]),
     "dynmm_conv_program_bytes": (c_longlong, [c_int]),
     "dynmm_conv_program_build": (c_int, [POINTER(ConvParams), POINTER(c_int32), c_int, c_void_p, c_longlong,
                                          POINTER(c_int32)]),

@@ -28,10 +28,10 @@ inline EncodeTiledFn get_encode_fn() {
 }
 
 inline int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box) {
+               const uint32_t* box, bool swizzle128 = true) {
 #ifdef DYNMM_PLAN_DRYRUN
   // host-only planner report (tools/plan_report.cu): no driver, no descriptors -- only the tiling decisions matter
-  (void)m; (void)base; (void)rank; (void)dims; (void)strides_bytes; (void)box;
+  (void)m; (void)base; (void)rank; (void)dims; (void)strides_bytes; (void)box; (void)swizzle128;
   return DYNMM_OK;
 #endif
   EncodeTiledFn fn = get_encode_fn();
@@ -69,7 +69,7 @@ inline int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t
     }
   }();
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with %d (rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u)", (int)r, rank,
               (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],

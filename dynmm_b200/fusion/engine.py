@@ -148,6 +148,7 @@ class EngineConfig:
     upsampling: str = "learned-3x3-zeropad"
     context_module: str = "ppm"
     activation: str = "relu"
+    gate: str = "global"            # "global": GlobalGate (SkipGateESANet); "local": one two-way gate per fusion site
 
 
 class FusionEngine:
@@ -172,7 +173,19 @@ class FusionEngine:
             raise NotImplementedError("the CUDA engine implements context_module='ppm' (bins 1,5)")
         self.cfg, self.dev = cfg, device
         p = _Packer(sd, device)
-        self.gate = {k: v.to(device) for k, v in pack_gate(sd).items()}
+        if cfg.gate == "local":
+            if cfg.fuse != "add":
+                raise NotImplementedError("the local-gate engine blends by addition (model_skip_mod.py:241-311)")
+            # SqueezeAndExciteReweigh of site i (rgb_depth_fusion.py:29-65): the SE 1x1 convs as fp32 matrices
+            self.gate = None
+            self.local_gates = []
+            for i in range(4):
+                k = f"gate_layer{i}.se.fc"
+                w1, w2 = p.t(k + ".0.weight"), p.t(k + ".2.weight")
+                self.local_gates.append((w1.reshape(w1.shape[0], -1).contiguous(), p.t(k + ".0.bias").contiguous(),
+                                         w2.reshape(w2.shape[0], -1).contiguous(), p.t(k + ".2.bias").contiguous()))
+        else:
+            self.gate = {k: v.to(device) for k, v in pack_gate(sd).items()}
         # stem: [7][7][cin][64] fp32 + folded BN
         self.stem = {}
         for enc in ("encoder_rgb", "encoder_depth"):
@@ -244,6 +257,17 @@ class FusionEngine:
         # one adds g_s * depth_s, which the depth one has to finish first).  Stage 1 (64 channels: fused-pair kernels
         # with resident weights) keeps the two-stream form.
         self.use_merge = cfg.fuse == "add" and os.environ.get("DYNMM_MERGE", "1") == "1" and not self.use_programs
+        # DYNMM_CHAIN (default on, merged stages only): blocks 2.. of an encoder stage (stride 1, 128 or 256 channels) run
+        # as ONE chain kernel per stage for both encoders (dynmm_conv_chain_fwd: activations stay in shared memory from
+        # layer to layer); the stage's first block (stride 2, down-sampling) and the RGB encoder's last convolution (gated
+        # add) stay per-layer launches.  DYNMM_CHAIN_STAGES: comma-separated stage indices (0-based), default "2".
+        self.chain_imgs = {}
+        if self.use_merge and os.environ.get("DYNMM_CHAIN", "1") == "1":
+            for s in {int(v) for v in os.environ.get("DYNMM_CHAIN_STAGES", "2").split(",") if v.strip()}:
+                if 1 <= s <= 3:
+                    imgs = self._chain_images(s)
+                    if imgs is not None:
+                        self.chain_imgs[s] = imgs
 
     # ------------------------------------------------------------------ blocks
     @staticmethod
@@ -304,6 +328,35 @@ class FusionEngine:
         self.launches += 1
         return out
 
+    def _chain_images(self, s: int):
+        """ChainImages (RGB without its last convolution, depth complete) for blocks 1.. of stage s, or None when the
+        blocks are not plain 128- / 256-channel NonBottleneck1D blocks."""
+        out = []
+        for enc, drop in (("encoder_rgb", True), ("encoder_depth", False)):
+            blocks = self.stages[enc][s][1:]
+            if not blocks:
+                return None
+            c = blocks[0].convs[0].c_in
+            shapes = [(3, 1), (1, 3), (3, 1), (1, 3)]
+            for blk in blocks:
+                if blk.downsample is not None or len(blk.convs) != 4 or c not in (128, 256):
+                    return None
+                if not all(cv.c_in == c and cv.c_out == c and (cv.kh, cv.kw) == k and cv.stride == (1, 1) and
+                           cv.scale is None and cv.pad == (k[0] // 2, k[1] // 2) for cv, k in zip(blk.convs, shapes)):
+                    return None
+            layers = ops.nbt1d_chain_layers([[(cv.weight, cv.shift, cv.relu) for cv in blk.convs] for blk in blocks],
+                                            drop_last=drop)
+            out.append(ops.ChainImage(layers, c, self.dev))
+        return tuple(out)
+
+    def _chain_flags(self, n: int) -> Tensor:
+        """n zeroed int32 flags for one chain launch, carved from the pool this forward zeroed at its start."""
+        if self._flag_off + n > self._flag_pool.numel():
+            return torch.zeros(n, dtype=torch.int32, device=self.dev)
+        f = self._flag_pool[self._flag_off:self._flag_off + n]
+        self._flag_off += (n + 3) // 4 * 4
+        return f
+
     def _merged_stage(self, s: int, r: Tensor, d: Tensor, plan, keep: list, cat: Optional[Tensor]):
         """Stage s (>= 1) of both encoders in lock step: layer i of the depth encoder (slot order, prefix-counted)
         and layer i of the RGB encoder share a launch; the stage's last convolution runs per encoder -- depth
@@ -312,7 +365,26 @@ class FusionEngine:
         dk = dict(count=cnt, count_settled=True)
         blocks_r, blocks_d = self.stages["encoder_rgb"][s], self.stages["encoder_depth"][s]
         n_d = d.shape[0]
+        chain = self.chain_imgs.get(s)
+        if chain is not None:
+            # geometry of blocks 1..: the stage's first block halves the map
+            ho, wo = (r.shape[1] + 1) // 2, (r.shape[2] + 1) // 2
+            cplan = ops.chain_plan(ho, wo, chain[0].c, r.shape[0] + n_d)
+            if cplan is None:
+                chain = None
         for bi, (br, bd) in enumerate(zip(blocks_r, blocks_d)):
+            if chain is not None and bi == 1:
+                (out_r, last_r), (d, _) = ops.conv_chain(
+                    [dict(x=r, image=chain[0]), dict(x=d, image=chain[1], **dk)],
+                    flags=self._chain_flags(cplan[0] + r.shape[0] + n_d))
+                kw = dict(gated=d, gate=plan.g[s], gated_slot=plan.slot)
+                if cat is not None:
+                    kw.update(out=cat, out_c_off=0)
+                keep += [r, out_r, last_r, d]
+                r = blocks_r[-1].convs[-1](last_r, residual=out_r if out_r is not None else r, **kw)
+                keep.append(r)
+                self.launches += 2
+                break
             last_block = bi == len(blocks_r) - 1
             yr, yd = r, d
             for i in range(len(br.convs) - 1):
@@ -477,6 +549,10 @@ class FusionEngine:
         keep: list = []
         main = torch.cuda.current_stream()
         side = self.side
+        if self.chain_imgs:
+            self._flag_pool = torch.zeros(4096, dtype=torch.int32, device=self.dev)   # one memset per forward
+            self._flag_off = 0
+            keep.append(self._flag_pool)
         wr, sr, br = self.stem["encoder_rgb"]
         wd, sdp, bd = self.stem["encoder_depth"]
         learned = weight is None and not baseline and not ini_stage
@@ -611,6 +687,195 @@ class FusionEngine:
         # ---- context module, decoder (model.py:295-308, context_modules.py:69-87)
         if self.use_programs:
             skip_done = [None, None, None]
+        out = self._decode(cat, skips, skip_done, keep, main, out, labels, want_logits)
+        # all side-stream work was joined by the stage-4 wait; temporaries may now be released
+        del keep
+        return out, weight
+
+    # ------------------------------------------------------------------ local gates (SkipESANet)
+    def _local_gate_weight(self, i: int, gap_r: Tensor, gap_d: Tensor, alive: Optional[Tensor], prev: Optional[Tensor],
+                           *, temp: float, hard: bool, random_policy: bool) -> Tensor:
+        """SqueezeAndExciteReweigh.forward (rgb_depth_fusion.py:35-65) on the global average pools of the two
+        streams: score = sigmoid(mean(x * SE(x))) only needs gap(x); Gumbel-softmax with the noise drawn like
+        F.gumbel_softmax draws it; chained with the previous site's weight.  -> [B, 2] fp32."""
+        from .local_gate import gumbel_softmax
+        b = gap_r.shape[0]
+        if random_policy:
+            b0 = torch.randint(0, 2, (b,))                       # global CPU generator, like the reference (:38)
+            w = torch.stack([b0, 1 - b0], dim=1).to(self.dev, torch.float32)
+        else:
+            if alive is not None:                                # closed samples have no depth features: any finite
+                gap_d = torch.where(alive.view(-1, 1), gap_d, torch.zeros_like(gap_d))   # value (the chain zeroes w)
+            w1, b1, w2, b2 = self.local_gates[i]
+            gap = torch.cat([gap_r, gap_d], dim=1)               # gap(cat(rgb, depth)), never materialised
+            se = torch.sigmoid(torch.relu(gap @ w1.t() + b1) @ w2.t() + b2)
+            score = torch.sigmoid((gap * se).mean(dim=1))
+            w = gumbel_softmax(torch.stack([score, 1 - score], dim=1) / temp, hard)
+        if prev is not None:
+            b1_ = w[:, 1] * prev
+            w = torch.stack([1 - b1_, b1_], dim=1)
+        return w
+
+    @torch.no_grad()
+    def forward_local(self, rgb: Tensor, depth: Tensor, *, block_rule: Sequence[int], temp: float = 1.0,
+                      hard: bool = True, random_policy: bool = False, ini_stage: bool = False,
+                      out: Optional[Tensor] = None):
+        """``SkipESANet.forward`` in eval mode (model_skip_mod.py:246-322) on the CUDA kernels, with REAL skipping:
+        site s decides before stage s + 1 runs, so the depth encoder's stage s + 1 only processes the samples that
+        can still use depth features -- the blend of this site (rule 1, or rule 2 with a non-zero weight) or, through
+        the chain w_t[1] *= w_{t-1}[1], a later one.  Those samples are compacted to the front of the stage's
+        tensors (slot order; ``count`` / ``in_map`` / ``gated_slot`` of the conv kernels), recomputed per stage from
+        the gate weights on the device: no host synchronisation, CUDA-graph capturable.
+        -> (logits [B,classes,H,W] fp32, [w_0 .. w_3] gate weights [B,2] fp32, [count_1 .. count_4] device int32)"""
+        with torch.cuda.device(self.dev):
+            return self._forward_local(rgb, depth, block_rule=list(block_rule), temp=temp, hard=hard,
+                                       random_policy=random_policy, ini_stage=ini_stage, out=out)
+
+    def _forward_local(self, rgb, depth, *, block_rule, temp, hard, random_policy, ini_stage, out):
+        if self.cfg.gate != "local":
+            raise _lib.DynmmError("forward_local needs an engine built with gate='local'")
+        rgb = rgb.float().contiguous()
+        depth = depth.float().contiguous()
+        b, _, h, w = rgb.shape
+        if h % 32 or w % 32:
+            raise _lib.DynmmError(f"input size {h}x{w} must be a multiple of 32 (five stride-2 stages)")
+        self.launches = 0
+        keep: list = []
+        main = torch.cuda.current_stream()
+        side = self.side
+        dev = self.dev
+        wr, sr, br = self.stem["encoder_rgb"]
+        wd, sdp, bd = self.stem["encoder_depth"]
+        dynamic = [r == 2 for r in block_rule]
+        gate_kw = dict(temp=temp, hard=hard, random_policy=random_policy)
+        # ---- stem; gate 0 looks at the UNPOOLED, unfused stem maps (model_skip_mod.py:253): squeeze pass
+        weights: List[Tensor] = []
+        if dynamic[0] and not random_policy:
+            part, inv_area = ops.stem_squeeze(rgb, depth, wr, sr, br, wd, sdp, bd)
+            gap = part.sum(dim=1) * inv_area                          # [B, 128] = [rgb 64 | depth 64]
+            weights.append(self._local_gate_weight(0, gap[:, :64], gap[:, 64:], None, None, **gate_kw))
+            keep.append(part)
+            self.launches += 1
+        else:
+            # the reference evaluates every gate (its Gumbel / randint draws advance the generator) even where the
+            # rule ignores the result: keep the draw order
+            z = torch.zeros(b, 64, device=dev)
+            weights.append(self._local_gate_weight(0, z, z, None, None, **gate_kw))
+        if self.stem_packed is not None:
+            _, _, r16, d16 = ops.stem_s2d(rgb, depth, self.stem_packed, sr, br, sdp, bd, want_f32=False)
+            self.launches += 2
+        else:
+            _, _, r16, d16 = ops.stem(rgb, depth, wr, sr, br, wd, sdp, bd, want_f32=False)
+            self.launches += 1
+        keep += [r16, d16]
+
+        ones = torch.ones(b, dtype=torch.bool, device=dev)
+        alive = ones                     # chain still open: every dynamic site so far kept a non-zero depth weight
+        prev_w: Optional[Tensor] = None  # w_{s-1}[:, 1] of the last dynamic site (None with ini_stage)
+        prev_slot: Optional[Tensor] = None   # sample -> slot in the previous depth tensor
+        r, d = r16, d16
+        fused, counts = [], []
+        skips, skip_done = [], []
+        cat = None
+        arange = torch.arange(b, device=dev, dtype=torch.int32)
+        for s in range(4):
+            rule = block_rule[s]
+            wgt = weights[s]
+            if rule == 2:
+                g = wgt[:, 1].contiguous()
+                alive = alive & (g != 0) if not ini_stage else alive
+            elif rule == 1:
+                g = torch.ones(b, device=dev)
+            else:
+                g = torch.zeros(b, device=dev)
+            # who needs depth stage s + 1: this site's blend, a later static add, or a later dynamic site whose chain
+            # is still open (without chaining -- ini_stage -- every later dynamic site may still open)
+            later_add = any(rr == 1 for rr in block_rule[s + 1:])
+            later_dyn = any(rr == 2 for rr in block_rule[s + 1:])
+            need = (g != 0)
+            if later_add:
+                need = ones
+            elif later_dyn:
+                need = need | alive
+            if s > 0:
+                need = need & (prev_slot >= 0)                        # features of a closed chain no longer exist
+            # slot order of this stage: needed samples first (stable), the rest behind `count`
+            order = torch.argsort((~need).to(torch.int8), stable=True).to(torch.int32)
+            count = need.sum().to(torch.int32).reshape(1)
+            slot = torch.empty(b, dtype=torch.int32, device=dev)
+            slot[order.long()] = arange
+            slot = torch.where(need, slot, torch.full_like(slot, -1))
+            in_map = (order if prev_slot is None else prev_slot[order.long()].clamp_min(0)).to(torch.int32).contiguous()
+            gated_slot = slot.clamp_min(0).contiguous()
+            counts.append(count)
+            keep += [order, count, slot, in_map, gated_slot, g, need]
+            # ---- depth stage on the side stream
+            fork = torch.cuda.Event()
+            fork.record(main)
+            side.wait_event(fork)
+            done = torch.cuda.Event()
+            with torch.cuda.stream(side):
+                for bi, blk in enumerate(self.stages["encoder_depth"][s]):
+                    d = self._block(d, blk, keep, count=count, in_map=in_map if bi == 0 else None)
+                done.record(side)
+            # ---- RGB stage on the main stream; rule != 0: the last conv adds g * depth
+            blocks = self.stages["encoder_rgb"][s]
+            for bi, blk in enumerate(blocks):
+                if bi < len(blocks) - 1:
+                    r = self._block(r, blk, keep)
+                    continue
+                last_kw = {}
+                if s == 3:
+                    c4 = self.stage_channels[3]
+                    cat = torch.empty(b, h // 32, w // 32, c4 + 2 * self.ppm[0].c_out, dtype=torch.bfloat16, device=dev)
+                    last_kw.update(out=cat, out_c_off=0)
+                if rule != 0:
+                    last_kw.update(gated=d, gate=g, gated_slot=gated_slot)
+                    r = self._block(r, blk, keep, before_last=lambda: main.wait_event(done), last_kw=last_kw)
+                else:
+                    r = self._block(r, blk, keep, last_kw=last_kw or None)
+                    main.wait_event(done)                              # join the side stream (gate features below)
+            fused.append(r)
+            if s < 3:
+                # skip connection conv of this stage (decoder input)
+                if self.skips[s] is not None:
+                    skips.append(self.skips[s](r))
+                    self.launches += 1
+                else:
+                    skips.append(r)
+                skip_done.append(None)
+                # gate s + 1 looks at the stage outputs BEFORE the blend (:260, :278, :296):
+                # gap(rgb) = gap(fuse) - g * gap(depth) (the blend is linear)
+                if dynamic[s + 1] and not random_policy:
+                    c = r.shape[3]
+                    inv_area = 1.0 / (r.shape[1] * r.shape[2])
+                    pf = ops.gap_partial(r, c=c)
+                    pd = ops.gap_partial(d, c=c, count=count)
+                    gap_f = pf.sum(dim=1) * inv_area
+                    gap_d_slots = pd.sum(dim=1) * inv_area
+                    has = slot >= 0
+                    gap_d = torch.where(has.view(-1, 1), gap_d_slots[gated_slot.long()], torch.zeros_like(gap_f))
+                    gap_r = gap_f - g.view(-1, 1) * gap_d
+                    keep += [pf, pd]
+                    self.launches += 2
+                    nxt = self._local_gate_weight(s + 1, gap_r, gap_d, has, None, **gate_kw)
+                else:
+                    z = torch.zeros(b, r.shape[3], device=dev)
+                    nxt = self._local_gate_weight(s + 1, z, z, None, None, **gate_kw)
+                if rule == 2 and not ini_stage:
+                    prev_w = weights[s][:, 1]
+                if prev_w is not None:                                  # chain (rgb_depth_fusion.py:60-63)
+                    b1_ = nxt[:, 1] * prev_w
+                    nxt = torch.stack([1 - b1_, b1_], dim=1)
+                weights.append(nxt)
+            prev_slot = slot
+        out = self._decode(cat, skips, skip_done, keep, main, out, None, True)
+        del keep
+        return out, weights, counts
+
+    def _decode(self, cat: Tensor, skips: list, skip_done: list, keep: list, main, out, labels, want_logits):
+        """Pyramid pooling, the three decoder modules and the learned final up-samplings (model.py:295-308,
+        context_modules.py:69-87) on the stage-4 output in ``cat[..., :c4]`` and the three skip tensors."""
         c4 = self.stage_channels[3]
         off = c4
         if self.use_programs:
@@ -666,6 +931,4 @@ class FusionEngine:
         out = ops.upsample2x_dw3x3(x, self.up[1][0], self.up[1][1], to_nchw_f32=True, out=out, labels=labels,
                                    want_logits=want_logits)
         self.launches += 3
-        # all side-stream work was joined by the stage-4 wait; temporaries may now be released
-        del keep
-        return out, weight
+        return out

@@ -27,13 +27,17 @@ Notes that matter for a re-implementation:
     reference's forward never calls them (model_skip_mod.py:241-311 always adds) -- kept that way;
   * ``SqueezeAndExcitationWeight.linear`` is a parameter the reference never uses (model_utils.py:64); kept for the keys.
 
-Scope: module surface + parity with reference-generated vectors (tests/golden/local_gate_*.npz) on the differentiable
-graph.  Convolutions run on the tcgen05 kernels with ``train_precision='bf16'`` exactly like ``SkipGateESANet``'s
-training graph (modules.Conv2d); the sample-skipping CUDA ENGINE is specific to the global gate (its 5-way decision is
-known before stage 1, the local gates' are not) and raising for this class would be wrong -- every local gate needs the
-depth features of its stage for all samples whose chain is still open, so the reference's variant has no stage-0
-decision to plan from.  Chained hard gates (w_{s-1}[1] == 0 closes all later sites) would allow prefix-style skipping
-per stage; that is the next step for this row.
+Two execution paths, same surface:
+  * the differentiable PyTorch graph (training mode, CPU tensors, ``use_engine = False``): parity with the
+    reference-generated vectors (tests/golden/local_gate_*.npz); convolutions optionally on the tcgen05 kernels with
+    ``train_precision='bf16'`` exactly like ``SkipGateESANet``'s training graph (modules.Conv2d);
+  * eval mode on CUDA tensors: ``FusionEngine.forward_local`` (bf16 NHWC kernels of the global-gate engine) with REAL
+    per-stage skipping.  The local gates' decisions are not known before stage 1 (unlike the global gate's), but site s
+    decides before stage s + 1 runs and chained hard gates (w_{s-1}[1] == 0 closes all later sites,
+    rgb_depth_fusion.py:60-63) make the set of samples that can still use depth features shrink monotonically: every
+    stage re-plans its slot order on the device from the gate weights, the depth encoder's convolutions run on the
+    ``count`` prefix only.  Configurations the engine does not implement (bilinear up-sampling, swish, ...) run the
+    PyTorch graph, with one warning.
 """
 from __future__ import annotations
 
@@ -112,6 +116,10 @@ class SkipESANet(nn.Module):
         super().__init__()
         channels_decoder = [128, 128, 128] if channels_decoder is None else list(channels_decoder)
         nr_decoder_blocks = [1, 1, 1] if nr_decoder_blocks is None else list(nr_decoder_blocks)
+        self._cfg = dict(encoder=encoder_rgb, encoder_depth=encoder_depth, encoder_block=encoder_block,
+                         nr_decoder_blocks=tuple(nr_decoder_blocks), num_classes=num_classes, upsampling=upsampling,
+                         context_module=context_module, activation=activation,
+                         encoder_decoder_fusion=encoder_decoder_fusion)
         self.fuse_depth_in_rgb_encoder = fuse_depth_in_rgb_encoder
         # 0: rgb only, 1: rgb + depth, 2: dynamic (:38, :49)
         self.block_rule = block_rule if block_rule else [1, 1, 1, 1]
@@ -157,6 +165,9 @@ class SkipESANet(nn.Module):
         self.weight_list = [torch.Tensor() for _ in range(4)]
         self._pending: List[List[Tensor]] = [[] for _ in range(4)]
         self.train_precision = "fp32"        # "bf16": stage convolutions on the tcgen05 kernels (modules.Conv2d)
+        self.use_engine = True               # eval mode + CUDA tensors: FusionEngine.forward_local (bf16, real skipping)
+        self._engine = None
+        self.last_counts = None              # device int32 [1] x 4: depth samples each stage processed (engine path)
 
     # ------------------------------------------------------------------ reference API
     def freeze(self):                                             # :215-218
@@ -210,9 +221,64 @@ class SkipESANet(nn.Module):
         w = weight.to(rgb.dtype)
         return w[:, 0:1] * rgb + w[:, 1:2] * (rgb + depth)       # the reference's statement (:258, :276, :294, :309)
 
+    def engine(self, device=None):
+        """The packed CUDA engine for the current weights (rebuilt when a parameter or buffer changes)."""
+        from .engine import EngineConfig, FusionEngine
+        device = device or next(self.parameters()).device
+        if self._engine is None:
+            self._version_probe = list(self.parameters()) + list(self.buffers())
+        key = (str(device), tuple(p._version for p in self._version_probe))
+        if self._engine is None or self._engine_key != key:
+            c = self._cfg
+            if c["encoder_depth"] != c["encoder"]:
+                raise NotImplementedError("the CUDA engine needs encoder_rgb == encoder_depth")
+            if c["encoder_decoder_fusion"] != "add":
+                raise NotImplementedError("the CUDA engine implements encoder_decoder_fusion='add'")
+            # the reference's forward always blends by addition, whatever fuse_depth_in_rgb_encoder built (:241-311)
+            cfg = EngineConfig(encoder=c["encoder"], encoder_block=c["encoder_block"], fuse="add",
+                               nr_decoder_blocks=c["nr_decoder_blocks"], num_classes=c["num_classes"],
+                               upsampling=c["upsampling"], context_module=c["context_module"],
+                               activation=c["activation"], gate="local")
+            self._engine = FusionEngine(self.state_dict(), cfg, device)
+            self._engine_key = key
+        return self._engine
+
+    def invalidate_engine(self):
+        self._engine = None
+
+    def train(self, mode: bool = True):
+        if mode:
+            self._engine = None            # an optimizer is about to change the weights
+        return super().train(mode)
+
+    def load_state_dict(self, *args, **kw):
+        self._engine = None
+        return super().load_state_dict(*args, **kw)
+
+    def _forward_engine(self, rgb, depth, test):
+        eng = self.engine(rgb.device)
+        out, weights, counts = eng.forward_local(rgb, depth, block_rule=self.block_rule, temp=float(self.gate_layer0.temp),
+                                                 hard=True if test else bool(self.hard_gate),
+                                                 random_policy=bool(self.random_policy), ini_stage=bool(self.ini_stage))
+        self.last_counts = counts
+        if self.save_weight_info:
+            for i in range(4):
+                self._pending[i].append(weights[i].detach())
+        return out
+
     def forward(self, rgb, depth, test=False):                   # :246-322
         if self.train_precision not in ("fp32", "bf16"):
             raise ValueError("train_precision must be 'fp32' or 'bf16'")
+        if self.use_engine and not self.training and rgb.is_cuda and not torch.is_grad_enabled() and \
+                getattr(self, "_engine_unsupported", None) is None and rgb.shape[2] % 32 == 0 and rgb.shape[3] % 32 == 0:
+            # A configuration the engine does not implement is a NotImplementedError: such a model runs the PyTorch
+            # graph below (one warning).  A missing library / wrong device is a DynmmError and propagates.
+            try:
+                return self._forward_engine(rgb, depth, test)
+            except NotImplementedError as e:
+                self._engine_unsupported = str(e) or "unsupported configuration"
+                warnings.warn("dynmm_b200: the CUDA engine does not implement this configuration (" +
+                              self._engine_unsupported + "); eval forwards run the PyTorch graph instead")
         low = rgb.is_cuda and self.train_precision == "bf16"
         gate_args = dict(hard=self.hard_gate, random=self.random_policy, test=test)
         rgb = self.encoder_rgb.forward_first_conv(rgb)

@@ -13,7 +13,8 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import ConvPairParams, ConvParams, TileFlags, WgradParams, check, ptr, stream_ptr
+from ._lib import (ChainJob, ChainLayer, ChainParams, ConvPairParams, ConvParams, TileFlags, WgradParams, check, ptr,
+                   stream_ptr)
 
 Tensor = torch.Tensor
 
@@ -265,6 +266,110 @@ class ConvMerge:
                 CONV_PROFILER(lambda p=p: check(lib.dynmm_conv_igemm_fwd(ctypes.byref(p), stream_ptr()), "conv_igemm"), [job])
             else:
                 check(lib.dynmm_conv_igemm_fwd(ctypes.byref(p), stream_ptr()), "conv_igemm")
+
+
+class ChainImage:
+    """Device-resident description of a run of 3-tap convolutions for :func:`conv_chain` (dynmm_conv_chain_build):
+    ``layers`` = [(packed weight bf16 [3][c][c], shift fp32 [c] or None, taps_h, relu, residual, store), ...] with
+    residual 0 none / 1 chain input / 2 the ``out`` tensor as stored earlier, store 0 none / 1 ``out`` / 2 ``out_last``.
+    Built once per weight set; keeps the weight tensors alive."""
+
+    def __init__(self, layers: Sequence[tuple], c: int, device):
+        lib = _lib.load()
+        n = len(layers)
+        arr = (ChainLayer * n)()
+        self.keep = []
+        for i, (w, shift, taps_h, relu, residual, store) in enumerate(layers):
+            _cuda(w, shift)
+            if tuple(w.shape) != (3, c, c) or w.dtype != torch.bfloat16:
+                raise _lib.DynmmError(f"ChainImage: layer {i} weight must be packed bf16 [3][{c}][{c}]")
+            arr[i].weight, arr[i].shift = ptr(w), ptr(shift)
+            arr[i].taps_h, arr[i].relu, arr[i].residual, arr[i].store = int(taps_h), int(relu), int(residual), int(store)
+            self.keep += [w, shift]
+        nbytes = lib.dynmm_conv_chain_image_bytes(n)
+        if nbytes < 0:
+            raise _lib.DynmmError(f"ChainImage: unsupported number of layers {n}")
+        host = torch.zeros(nbytes, dtype=torch.uint8)
+        check(lib.dynmm_conv_chain_build(arr, n, c, host.data_ptr()), "conv_chain_build")
+        self.dev = host.to(device)
+        self.n_layers, self.c = n, c
+        self.stores_out = any(l[5] == 1 for l in layers)
+        self.stores_last = any(l[5] == 2 for l in layers)
+
+
+def nbt1d_chain_layers(blocks: Sequence[Sequence[tuple]], drop_last: bool = False):
+    """Layer list for :class:`ChainImage` from NonBottleneck1D blocks, each ``[(weight, shift, relu) x 4]`` in the order
+    3x1, 1x3, 3x1, 1x3 (resnet.py:124-147): the fourth convolution of a block adds the block input (the chain input for
+    the first block, the previous block's stored output afterwards) and stores the block output.  ``drop_last``: the very
+    last convolution is left to the caller (a gated epilogue); the layer before it is stored to ``out_last``."""
+    layers = []
+    for bi, blk in enumerate(blocks):
+        for i, (w, shift, relu) in enumerate(blk):
+            last = i == 3
+            layers.append((w, shift, i % 2 == 0, relu, (1 if bi == 0 else 2) if last else 0, 1 if last else 0))
+    if drop_last:
+        layers.pop()
+        w, shift, taps_h, relu, res, _ = layers[-1]
+        layers[-1] = (w, shift, taps_h, relu, res, 2)
+    return layers
+
+
+def chain_plan(h: int, w: int, c: int, total_slots: int):
+    """-> (units, scratch bytes) of a :func:`conv_chain` launch, or None when the geometry is not supported."""
+    lib = _lib.load()
+    units, nbytes = ctypes.c_int32(0), ctypes.c_longlong(0)
+    rc = lib.dynmm_conv_chain_plan(h, w, c, total_slots, ctypes.byref(units), ctypes.byref(nbytes))
+    if rc == -3:
+        return None
+    check(rc, "conv_chain_plan")
+    return units.value, nbytes.value
+
+
+def conv_chain(jobs: Sequence[dict], *, flags: Optional[Tensor] = None, trace: Optional[Tensor] = None):
+    """One launch for a run of NonBottleneck1D convolutions per job (dynmm_conv_chain_fwd); bit-identical to the
+    per-layer :func:`conv` calls.  ``jobs``: 1 or 2 dicts ``x`` (NHWC bf16 [n,h,w,c]), ``image`` (:class:`ChainImage`),
+    optional ``count`` / ``count_settled``.  ``flags``: zeroed int32 [units + sample slots] (allocated when None).
+    -> [(out, out_last), ...] per job (None where the image stores nothing there)."""
+    lib = _lib.load()
+    x0 = jobs[0]["x"]
+    _, h, w, c = x0.shape
+    total = sum(j["x"].shape[0] for j in jobs)
+    plan = chain_plan(h, w, c, total)
+    if plan is None:
+        raise _lib.DynmmError("conv_chain: unsupported geometry: " + lib.dynmm_last_error().decode())
+    units, scratch_bytes = plan
+    if flags is None:
+        flags = torch.zeros(units + total, dtype=torch.int32, device=x0.device)
+    elif flags.numel() < units + total or flags.dtype != torch.int32:
+        raise _lib.DynmmError("conv_chain: flags too small")
+    scratch = torch.empty(max(scratch_bytes, 16), dtype=torch.uint8, device=x0.device)
+    p = ChainParams()
+    p.n_jobs, p.h, p.w, p.c = len(jobs), h, w, c
+    p.flags, p.scratch, p.scratch_bytes, p.trace = ptr(flags), ptr(scratch), scratch.numel(), ptr(trace)
+    outs, prof_jobs, keep = [], [], [flags, scratch]
+    for i, j in enumerate(jobs):
+        x, img = j["x"], j["image"]
+        _cuda(x, j.get("count"))
+        if tuple(x.shape[1:]) != (h, w, c) or x.dtype != torch.bfloat16 or img.c != c:
+            raise _lib.DynmmError("conv_chain: jobs must share one geometry (NHWC bf16 [n,h,w,c])")
+        out = torch.empty_like(x) if img.stores_out else None
+        last = torch.empty_like(x) if img.stores_last else None
+        pj = p.jobs[i]
+        pj.image, pj.in_, pj.out, pj.out_last = img.dev.data_ptr(), ptr(x), ptr(out), ptr(last)
+        pj.count, pj.n, pj.n_layers = ptr(j.get("count")), x.shape[0], img.n_layers
+        pj.count_settled = int(bool(j.get("count_settled", False)) and j.get("count") is not None)
+        outs.append((out, last))
+        prof_jobs.append((h * w * c * c * 3 * img.n_layers, x.shape[0], j.get("count")))
+        keep += [x, out, last]
+    if CONV_PROFILER is not None:
+        CONV_PROFILER(lambda: check(lib.dynmm_conv_chain_fwd(ctypes.byref(p), stream_ptr()), "conv_chain"), prof_jobs)
+    else:
+        check(lib.dynmm_conv_chain_fwd(ctypes.byref(p), stream_ptr()), "conv_chain")
+    for o in outs:                      # the scratch buffer must outlive the launch: tie it to the results
+        for t in o:
+            if t is not None:
+                t._dynmm_keep = keep
+    return outs
 
 
 def conv_pair(x: Tensor, w1: Tensor, shift1: Optional[Tensor], w2: Tensor, shift2: Optional[Tensor], *,

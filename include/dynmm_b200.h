@@ -286,6 +286,66 @@ typedef struct dynmm_conv_pair_params {
 } dynmm_conv_pair_params;
 int dynmm_conv_pair_fwd(const dynmm_conv_pair_params* p, void* stream);
 
+/* ------------------------------------------------- convolution chains
+ *
+ * A run of NonBottleneck1D convolutions (resnet.py:124-147: conv3x1 -> ReLU -> conv1x3 -> BN -> ReLU -> conv3x1 ->
+ * ReLU -> conv1x3 -> BN -> +identity -> ReLU, block after block) of ONE encoder stage or decoder module as ONE kernel:
+ * c -> c channels (c = 128 or 256), stride 1, 3 taps along H or along W per layer.  A CTA owns a strip of rows of one
+ * sample and keeps its activations in shared memory from the first layer to the last; the only per-layer traffic is
+ * the streamed weights, the rows a 3x1 layer needs from the strips above and below (exchanged through a global
+ * scratch buffer behind per-strip flags -- no grid-wide barrier), and the layer outputs the caller asked for.
+ * Arithmetic, accumulation order and rounding are those of dynmm_conv_igemm_fwd layer by layer: the results are
+ * bit-identical to the per-layer launches.
+ *
+ * Up to two jobs of identical geometry (the same stage of the RGB and of the depth encoder,
+ * model_skip_mod_globalgate.py:276-310) share a launch; each has its own layers, tensors and sample count.
+ *
+ *   per layer list (once):   bytes = dynmm_conv_chain_image_bytes(n_layers)
+ *                            dynmm_conv_chain_build(layers, n_layers, c, host_image)      host only
+ *                            copy host_image -> device (128-byte aligned)
+ *   per geometry:            dynmm_conv_chain_plan(h, w, c, total sample slots, &units, &scratch_bytes)
+ *   per forward:             dynmm_conv_chain_fwd(&params, stream)
+ *
+ * `flags`: units + total sample slots int32, ZERO before the first launch that uses them (the kernel leaves them
+ * zero again); `scratch`: scratch_bytes of device memory owned by the launch. */
+typedef struct dynmm_chain_layer {
+  const void* weight;     /* packed bf16 [3][c][c] as for dynmm_conv_igemm_fwd */
+  const float* shift;     /* [c] or NULL */
+  int32_t taps_h;         /* 1: 3x1 (taps along H), 0: 1x3 (taps along W) */
+  int32_t relu;
+  int32_t residual;       /* 0: none, 1: += in[n,h,w,:] (the chain input), 2: += out[n,h,w,:] as stored earlier */
+  int32_t store;          /* 0: stays in shared memory, 1: also written to `out`, 2: also written to `out_last` */
+} dynmm_chain_layer;
+
+typedef struct dynmm_chain_job {
+  const void* image;      /* device image of this job's layers (dynmm_conv_chain_build) */
+  const void* in;         /* bf16 NHWC [n, h, w, c] */
+  void* out;              /* bf16 NHWC [n, h, w, c] (store == 1 layers) or NULL */
+  void* out_last;         /* bf16 NHWC [n, h, w, c] (store == 2 layers) or NULL */
+  const int32_t* count;   /* device int32 (leading sample slots that are computed) or NULL = n */
+  int32_t n;
+  int32_t n_layers;
+  int32_t count_settled;  /* see DYNMM_CONV_COUNT_SETTLED */
+  int32_t reserved;
+} dynmm_chain_job;
+
+typedef struct dynmm_chain_params {
+  dynmm_chain_job jobs[2];
+  int32_t n_jobs;         /* 1 or 2 */
+  int32_t h, w, c;
+  int32_t* flags;
+  void* scratch;
+  long long scratch_bytes;
+  void* trace;            /* debug: device uint64[16 * units] cycle stamps, or NULL */
+} dynmm_chain_params;
+
+long long dynmm_conv_chain_image_bytes(int n_layers);
+int dynmm_conv_chain_build(const dynmm_chain_layer* layers, int n_layers, int c, void* host_image);
+/* DYNMM_EUNSUPPORTED when the geometry does not fit (channels, shared memory, more units than the GPU holds at once):
+ * launch the layers one by one instead. */
+int dynmm_conv_chain_plan(int h, int w, int c, int total_slots, int32_t* units, long long* scratch_bytes);
+int dynmm_conv_chain_fwd(const dynmm_chain_params* p, void* stream);
+
 /* Same contract, one thread per output element, CUDA cores.  Test comparator
  * for the tensor-core kernel at sizes the CPU oracle cannot reach; never used
  * by the product path. */

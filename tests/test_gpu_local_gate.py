@@ -59,6 +59,7 @@ def test_random_policy_matches_reference_vectors(name, golden_dir):
     model = SkipESANet(pretrained_on_imagenet=False, **kw)
     model.load_state_dict(seeded_state(model.state_dict(), seed), strict=True)
     model = model.cuda().eval()
+    model.use_engine = False                  # this test is about the differentiable graph
     rgb, depth = (t.cuda() for t in sample_inputs(seed + 100, b, kw["height"], kw["width"]))
     tag, rule, attrs, test, fseed = next(m for m in MODES if m[0] == "random")
     ref = torch.from_numpy(gold[f"{tag}_out"])
@@ -96,6 +97,7 @@ def test_hard_chain_is_monotone_on_device():
     model = SkipESANet(pretrained_on_imagenet=False, **kw)
     model.load_state_dict(seeded_state(model.state_dict(), seed), strict=True)
     model = model.cuda().eval()
+    model.use_engine = False
     rgb, depth = (t.cuda() for t in sample_inputs(seed + 100, 8, kw["height"], kw["width"]))
     apply_mode(model, [2, 2, 2, 2], dict(hard_gate=True))
     model.start_weight()
@@ -111,3 +113,92 @@ def test_hard_chain_is_monotone_on_device():
     assert (w[1:] <= w[:-1]).all()
     assert 0 < w.sum() < w.numel()
     model.end_weight()
+
+
+def _r34_model():
+    from dynmm_b200.fusion import SkipESANet
+    from oracle.make_golden_local import CASES, seeded_state
+    kw, seed, b = CASES["local_gate_r34_nbt1d_64x96"]
+    model = SkipESANet(pretrained_on_imagenet=False, **kw)
+    model.load_state_dict(seeded_state(model.state_dict(), seed), strict=True)
+    return model.cuda().eval(), kw, seed, b
+
+
+@pytest.mark.parametrize("tag", ["random", "static1111"])
+def test_engine_matches_reference_vectors(tag, golden_dir):
+    """Eval mode on CUDA runs FusionEngine.forward_local (bf16 kernels, per-stage skipping).  Modes whose decisions do
+    not depend on the device generator have reference vectors: random policy (CPU randint) and the static rule."""
+    from oracle.make_golden_local import MODES, apply_mode, sample_inputs
+    model, kw, seed, b = _r34_model()
+    gold = np.load(os.path.join(golden_dir, "local_gate_r34_nbt1d_64x96.npz"))
+    rgb, depth = (t.cuda() for t in sample_inputs(seed + 100, b, kw["height"], kw["width"]))
+    _, rule, attrs, test, fseed = next(m for m in MODES if m[0] == tag)
+    apply_mode(model, rule, attrs)
+    assert model.use_engine
+    model.start_weight()
+    torch.manual_seed(fseed)
+    with torch.no_grad():
+        out = model(rgb, depth, test)
+    assert model._engine is not None and getattr(model, "_engine_unsupported", None) is None
+    model._flush_weights()
+    if tag == "random":
+        for i in range(4):
+            np.testing.assert_array_equal(model.weight_list[i].numpy(), gold[f"{tag}_weight{i}"])
+        # chained one-hot decisions: stage s + 1 of the depth encoder only ran for samples still open after site s
+        w1 = np.stack([gold[f"{tag}_weight{i}"][:, 1] for i in range(4)])
+        counts = [int(c.item()) for c in model.last_counts]
+        assert counts[0] == int((w1[0] != 0).sum())
+        assert all(counts[s] <= counts[s - 1] for s in range(1, 4))
+    model.end_weight()
+    ref = torch.from_numpy(gold[f"{tag}_out"])
+    got = out[:, :, ::4, ::4].float().cpu()
+    err = ((got.double() - ref.double()).norm() / ref.double().norm()).item()
+    assert err <= 2e-2, f"{tag}: relative L2 error {err:.5f}"
+
+
+@pytest.mark.parametrize("rule,attrs,test", [
+    ([2, 2, 2, 2], dict(), True),                      # hard Gumbel gates, chained
+    ([2, 2, 2, 2], dict(hard_gate=True, ini_stage=True), False),
+    ([1, 1, 2, 2], dict(hard_gate=True), True),
+    ([0, 1, 2, 0], dict(), True),
+    ([2, 2, 2, 2], dict(), False),                     # soft gates: nothing can be skipped
+])
+def test_engine_matches_module_graph_on_device(rule, attrs, test):
+    """Same seed, same device generator: the engine draws the Gumbel noise in the order the module graph does, so the
+    decisions agree and the logits differ by the bf16 tolerance only; skipped depth work shows in the stage counts."""
+    from oracle.make_golden_local import apply_mode, sample_inputs
+    model, kw, seed, _ = _r34_model()
+    rgb, depth = (t.cuda() for t in sample_inputs(seed + 7, 6, kw["height"], kw["width"]))
+    apply_mode(model, rule, attrs)
+    res = {}
+    for use_engine in (False, True):
+        model.use_engine = use_engine
+        model.start_weight()
+        torch.manual_seed(77)
+        with torch.no_grad():
+            out = model(rgb, depth, test)
+        model._flush_weights()
+        res[use_engine] = (out.float().cpu(), [w.clone() for w in model.weight_list])
+        model.end_weight()
+    hard = test or attrs.get("hard_gate", False)
+    for i in range(4):
+        a, b = res[False][1][i], res[True][1][i]
+        if hard:
+            assert torch.equal(a.round(), b.round()), f"site {i}: decisions differ"
+        else:
+            torch.testing.assert_close(a, b, rtol=0, atol=2e-2)
+    ref, got = res[False][0], res[True][0]
+    err = ((got.double() - ref.double()).norm() / ref.double().norm()).item()
+    assert err <= 2e-2, f"relative L2 error {err:.5f}"
+    if hard and not attrs.get("ini_stage", False):
+        counts = [int(c.item()) for c in model.last_counts]
+        need = torch.ones(6, dtype=torch.bool)
+        for s in range(4):
+            # a sample needs depth stage s + 1 for this site's blend or, with an open chain, for a later one
+            w = res[True][1][s][:, 1]
+            later_add = any(r == 1 for r in rule[s + 1:])
+            later_dyn = any(r == 2 for r in rule[s + 1:])
+            g = {0: torch.zeros(6), 1: torch.ones(6), 2: w.round()}[rule[s]]
+            assert counts[s] <= 6
+            if not later_add and not later_dyn:
+                assert counts[s] <= int((g != 0).sum())

@@ -130,6 +130,9 @@ def test_engine_programs_match_per_launch_path(monkeypatch):
     cfg = fo.FusionConfig(height=96, width=128)
     sd = fo.make_state_dict(cfg, 0, 40.0)
     outs = []
+    # at 96x128 the deep stages are smaller than one pixel tile: the chain kernel and the per-layer kernel then sum the
+    # same products in different orders (see tests/test_gpu_chain.py), so compare the per-layer forms
+    monkeypatch.setenv("DYNMM_CHAIN", "0")
     for flag in ("1", "0"):
         monkeypatch.setenv("DYNMM_PROGRAM", flag)
         model = SkipGateESANet(height=96, width=128)
