@@ -182,6 +182,8 @@ def test_engine_matches_module_graph_on_device(rule, attrs, test):
         model.end_weight()
     hard = test or attrs.get("hard_gate", False)
     for i in range(4):
+        if rule[i] != 2:
+            continue      # the rule ignores this site's gate: the engine draws its noise (generator order) on dummy features
         a, b = res[False][1][i], res[True][1][i]
         if hard:
             assert torch.equal(a.round(), b.round()), f"site {i}: decisions differ"
