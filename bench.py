@@ -301,6 +301,47 @@ def profile_conv_kernel(model, rgb, depth):
     return total_s, len(recs), weight, [r[:3] for r in recs]
 
 
+def conv_roofline(model, batch_tensors, step_s, precision, use_graph, dump_path=""):
+    """Instrumented pass (rank 0): device time and executed tensor-core FLOPs of every conv launch of one step."""
+    hbm, tf_sust, tf_burst, src = measured_peaks()
+    model.use_cuda_graph = False
+    t_conv, n_conv, wgt, recs = profile_conv_kernel(model, *batch_tensors)
+    model.use_cuda_graph = use_graph
+    # executed FLOPs of the tensor-core conv launches (single convolutions, fused pairs, chains): depth-stage launches
+    # count the samples the gate kept (their device-side `count`), everything else its n samples.  In f32x3 mode a MAC
+    # of the reference is three bf16 tensor-core products (x_hi*w_hi + x_hi*w_lo + x_lo*w_hi): `gflop_per_step` counts
+    # the executed products, `gflop_per_step_fp32_equiv` the reference's MACs.
+    ppm = 3 if precision == "f32x3" else 1
+    gflop = 0.0
+    for _, _, jobs in recs:
+        for macs, n, count in jobs:
+            active = min(int(count.item()), n) if count is not None else n
+            gflop += 2.0 * macs * active / 1e9
+    if dump_path:
+        with open(dump_path, "w") as fh:
+            fh.write("# launch  us  GFLOP  TFLOP/s  jobs(macs_per_sample x active)\n")
+            for i, (a0, a1, jobs) in enumerate(recs):
+                us = a0.elapsed_time(a1) / 4 * 1e3
+                gf = sum(2.0 * m * (min(int(c.item()), n) if c is not None else n) for m, n, c in jobs) / 1e9
+                desc = " + ".join(f"{m / 1e6:.1f}M x {min(int(c.item()), n) if c is not None else n}" for m, n, c in jobs)
+                fh.write(f"{i:4d} {us:8.2f} {gf:8.3f} {gf / us * 1e3 if us > 0 else 0:8.1f}  {desc}\n")
+    achieved = gflop / 1e3 / t_conv if t_conv > 0 else 0.0
+    return {"bound": "tensor",
+            "kernel": "conv_igemm_kernel + conv_pair_kernel + conv_chain_kernel (tcgen05 implicit GEMM; all conv launches "
+                      "of a step)",
+            "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s", "frac": achieved / tf_sust,
+            "peak_source": f"{src} (bf16 sustained; burst {tf_burst})", "traffic": conv_traffic(),
+            "launches_per_step": n_conv, "gflop_per_step": gflop, "gflop_per_step_fp32_equiv": gflop / ppm,
+            "tensor_products_per_mac": ppm, "kernel_s_per_step": t_conv,
+            "note": "achieved = executed bf16 tensor-core FLOPs / summed conv kernel time (f32x3: three products per MAC "
+                    "of the reference, see tensor_products_per_mac; the fp32-equivalent rate is achieved / 3).  "
+                    "kernel_s_per_step = sum over the step's conv launches of their device time (each launch "
+                    "replayed 4x from a CUDA graph between events on its own stream); the RGB and depth "
+                    "encoder streams overlap in the timed step, so this sum is not a share of ms_per_step. "
+                    "Kernel shares of the step: profiles/ (ncu launch list).",
+            "step_s": step_s}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -314,6 +355,11 @@ def main():
     ap.add_argument("--in-flight", type=int, default=2,
                     help="forwards in flight per GPU: each on its own stream and captured-graph instance (1 = one "
                          "stream, strictly one batch after the other)")
+    ap.add_argument("--precision", default="f32x3", choices=["bf16", "f32x3"],
+                    help="engine arithmetic of the HEADLINE numbers: f32x3 (fp32-grade: bf16 hi + lo operands, three "
+                         "tensor-core products per MAC; logits within 1e-3 of the reference's fp32 path -- the precision "
+                         "configs[1] is quoted at) or bf16 (stated tolerance 2e-2).  The other mode is measured too and "
+                         "reported under its own key in the same line")
     ap.add_argument("--dump-launches", default="", help="write the per-launch conv timings of the roofline pass here")
     ap.add_argument("--min-seconds", type=float, default=1.0,
                     help="the timed region repeats the K-step block until it lasts at least this long")
@@ -343,6 +389,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     model = build_model().to(dev)
+    model.engine_precision = args.precision
     model.use_cuda_graph = not args.no_graph
     # three resident batches rotate so no step re-reads the previous step's inputs; the per-step
     # working set (~0.6 GB of activations + 0.4 GB of logits) exceeds the 126 MB L2 by itself.
@@ -479,40 +526,64 @@ def main():
     # ---------------- roofline of the dominant kernel (rank 0, N=1 style instrumented pass)
     roofline, cpu_base, eager = None, None, None
     if rank == 0:
-        hbm, tf_sust, tf_burst, src = measured_peaks()
-        model.use_cuda_graph = False
-        t_conv, n_conv, wgt, recs = profile_conv_kernel(model, *batches[0])
-        model.use_cuda_graph = not args.no_graph
-        # executed FLOPs of the tensor-core conv launches (single convolutions and fused pairs): depth-stage launches
-        # count the samples the gate kept (their device-side `count`), everything else its n samples
-        gflop = 0.0
-        for _, _, jobs in recs:
-            for macs, n, count in jobs:
-                active = min(int(count.item()), n) if count is not None else n
-                gflop += 2.0 * macs * active / 1e9
-        if args.dump_launches:
-            with open(args.dump_launches, "w") as fh:
-                fh.write("# launch  us  GFLOP  TFLOP/s  jobs(macs_per_sample x active)\n")
-                for i, (a0, a1, jobs) in enumerate(recs):
-                    us = a0.elapsed_time(a1) / 4 * 1e3
-                    gf = sum(2.0 * m * (min(int(c.item()), n) if c is not None else n) for m, n, c in jobs) / 1e9
-                    desc = " + ".join(f"{m / 1e6:.1f}M x {min(int(c.item()), n) if c is not None else n}" for m, n, c in jobs)
-                    fh.write(f"{i:4d} {us:8.2f} {gf:8.3f} {gf / us * 1e3 if us > 0 else 0:8.1f}  {desc}\n")
-        achieved = gflop / 1e3 / t_conv if t_conv > 0 else 0.0
-        step_s = t_dev / args.steps
-        roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel + conv_pair_kernel (tcgen05 implicit GEMM; all conv launches of a step)",
-                    "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s", "frac": achieved / tf_sust,
-                    "peak_source": f"{src} (bf16 sustained; burst {tf_burst})", "traffic": conv_traffic(),
-                    "launches_per_step": n_conv, "gflop_per_step": gflop, "kernel_s_per_step": t_conv,
-                    "note": "kernel_s_per_step = sum over the step's conv launches of their device time (each launch "
-                            "replayed 4x from a CUDA graph between events on its own stream); the RGB and depth "
-                            "encoder streams overlap in the timed step, so this sum is not a share of ms_per_step. "
-                            "Kernel shares of the step: profiles/ (ncu launch list).",
-                    "step_s": step_s}
+        roofline = conv_roofline(model, batches[0], t_dev / args.steps, args.precision, not args.no_graph,
+                                 args.dump_launches)
         if world == 1 and not args.no_eager:
             eager = gpu_eager_baselines(model, *batches[0])
             eager["ours_over_bf16_eager"] = value / eager["bf16"]["images_per_s"]
             eager["ours_over_fp32_eager"] = value / eager["fp32"]["images_per_s"]
+
+    # ---------------- the other arithmetic mode, same workload, reduced protocol (>= 0.5 s timed region, e2e, roofline)
+    other = None
+    other_prec = "bf16" if args.precision == "f32x3" else "f32x3"
+    if not args.no_graph:
+        model.engine_precision = other_prec
+        with torch.no_grad():
+            run_steps(max(args.warmup, 2 * in_flight), in_flight)
+            torch.cuda.synchronize()
+            e0.record()
+            run_steps(args.steps, in_flight)
+            e1.record()
+            torch.cuda.synchronize()
+            reps2 = max(1, min(int(0.5 / max(e0.elapsed_time(e1) * 1e-3, 1e-6) + 0.999), 100))
+            if world > 1:
+                r = torch.tensor([reps2], device=dev)
+                dist.all_reduce(r, op=dist.ReduceOp.MAX)
+                reps2 = int(r.item())
+            barrier()
+            e0.record()
+            for _ in range(reps2):
+                run_steps(args.steps, in_flight)
+            e1.record()
+            barrier()
+            t2 = e0.elapsed_time(e1) * 1e-3 / reps2
+            pipe2 = EvalPipeline(model, batch, H, W, dev, in_flight=in_flight)
+            for _ in pipe2.run(host[i % 3] for i in range(args.warmup)):
+                pass
+            steps2 = args.steps * max(1, min(reps2, 5))
+            barrier()
+            t0 = time.perf_counter()
+            for labels in pipe2.run(host[i % 3] for i in range(steps2)):
+                pass
+            barrier()
+            t2e = (time.perf_counter() - t0) * args.steps / steps2
+            del pipe2
+        tt = torch.tensor([t2, t2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t2, t2e = tt.tolist()
+        other = {"dtype": other_prec, "value": images / t2, "unit": "images/s", "ms_per_step": t2 / args.steps * 1e3,
+                 "e2e": {"value": images / t2e, "unit": "images/s", "ms_per_step": t2e / args.steps * 1e3},
+                 "gpu_launches_per_step": model.engine(dev).launches,
+                 "timed_region": f"{reps2} x {args.steps} steps (>= 0.5 s)",
+                 "tolerance": ("logits relative L2 <= 2e-2, arg-max agreement >= 99 % (tests/test_gpu_fusion.py)"
+                               if other_prec == "bf16" else "logits relative L2 <= 1e-3 (tests/test_gpu_f32x3.py)")}
+        if rank == 0:
+            other["roofline"] = conv_roofline(model, batches[0], t2 / args.steps, other_prec, True)
+            if eager is not None:
+                key = "bf16" if other_prec == "bf16" else "fp32"
+                eager[f"{other_prec}_over_{key}_eager"] = other["value"] / eager[key]["images_per_s"]
+        model.engine_precision = args.precision
 
     # ---------------- configs[2]: data-parallel TRAINING step, global batch 32 (strong: 32/N per GPU) and 32 per GPU
     # (weak), gradient all-reduce overlapped with backward; the eval model is released first
@@ -564,7 +635,14 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "precision_note": ("f32x3: fp32-grade arithmetic on the bf16 tensor cores (activations and weights as bf16 hi + "
+                               "lo halves, three products per MAC, fp32 accumulation and element-wise math); logits within "
+                               "1e-3 relative of the reference's fp32 path (measured 6e-5, tests/test_gpu_f32x3.py), hard gate "
+                               "decisions bit-exact.  The bf16 engine (stated tolerance 2e-2) is reported under \"bf16\"."
+                               if args.precision == "f32x3" else
+                               "bf16 activations and weights, fp32 accumulation: stated tolerance 2e-2 on the logits; the "
+                               "fp32-grade engine is reported under \"f32x3\"."),
             "config": {"workload": workload,
                        "per_gpu_batch": batch, "global_batch": batch * world,
                        "parallelism": f"dp{world} (replicas, no data-path collective in eval); {in_flight} batch(es) of "
@@ -587,6 +665,7 @@ def main():
             "gpu_launches_per_step": launches,
             "clocks": clocks,
             "roofline": roofline,
+            ("bf16" if args.precision == "f32x3" else "f32x3"): other,
             "gpu_eager_baseline": eager,
             "train": train,
             "cpu_baseline": cpu_base,

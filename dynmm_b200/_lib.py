@@ -126,6 +126,14 @@ SIGNATURES = {
     "dynmm_pack_conv_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dynmm_fold_pack_conv": (c_int, [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 5 + [c_float, c_void_p, c_void_p,
                                                                                            c_void_p]),
+    "dynmm_fold_pack_conv_split": (c_int, [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 5 + [c_float, c_void_p, c_void_p,
+                                                                                                 c_void_p]),
+    "dynmm_split_from_f32": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
+    "dynmm_upsample2x_dw3x3_split": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_void_p, c_void_p, c_void_p]),
+    "dynmm_adaptive_avgpool_split": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dynmm_nearest_resize_into_split": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                                c_void_p]),
     "dynmm_fold_bn": (c_int, [c_int] + [c_void_p] * 5 + [c_float, c_void_p, c_void_p, c_void_p]),
     "dynmm_permute3d_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dynmm_channel_sum_workspace": (c_longlong, [c_longlong, c_int]),

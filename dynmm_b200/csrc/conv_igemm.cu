@@ -52,8 +52,9 @@ using namespace convk;
 // CTA typically runs one RGB and one depth tile back to back: the second tile's loads and UMMAs hide the first one's
 // epilogue, and the fixed cost of a launch (prologue, first-load latency, drain, launch gap) is paid once per LAYER
 // instead of once per layer and encoder.  args2.n == 0: single convolution.
-template <int kFlags, int kPerSm>
-__global__ void __launch_bounds__(kThreads, kPerSm)
+// kMode: 0 = one CTA per SM, 1 = two CTAs per SM (large C = 64 layers), 2 = split operands (DYNMM_CONV_SPLIT; one per SM)
+template <int kFlags, int kMode>
+__global__ void __launch_bounds__(kThreads, kMode == 1 ? 2 : 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                   const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
                   const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_res,
@@ -62,6 +63,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                   const __grid_constant__ CUtensorMap map2_a2, const __grid_constant__ CUtensorMap map2_a3,
                   const __grid_constant__ CUtensorMap map2_b, const __grid_constant__ CUtensorMap map2_res,
                   const __grid_constant__ CUtensorMap map2_out, const __grid_constant__ KernelArgs args2) {
+  constexpr int kPerSm = kMode == 1 ? 2 : 1;
+  constexpr bool kSplit = kMode == 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -71,7 +74,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   uint8_t* smem_bres = smem + args.stages * args.stage_bytes;      // resident weights [k_iters][tpg][tile_n][128 B]
   uint8_t* smem_aux = smem_bres + (args.b_resident ? k_iters * b_iter_bytes : 0);   // [aux_slots][16 KiB]
   uint8_t* smem_stage_out = smem_aux + args.aux_slots * kSubBytes;                  // [2][16 KiB] (tma_epi only)
-  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_stage_out + (args.tma_epi ? 2 * kSubBytes : 0));
+  // split: a staging buffer holds the hi and the lo sub-tile
+  constexpr int stage_out_bytes = kSplit ? 2 * kSubBytes : kSubBytes;
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_stage_out + (args.tma_epi ? 2 * stage_out_bytes : 0));
   // [jobs][c_out + 8]: per-channel shift (zeros if absent), 16-byte aligned for float4 broadcast loads
   float* smem_shift = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ctl + 1) + 15) & ~uintptr_t(15));
   const int shift_stride = (args.c_out + 11) & ~3;
@@ -87,7 +92,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     tma_prefetch_desc(&map_a0);
     tma_prefetch_desc(&map_b);
     if (args.tma_epi) tma_prefetch_desc(&map_out);
-    if (aux_on) tma_prefetch_desc(&map_res);
+    if (aux_on || kSplit) tma_prefetch_desc(&map_res);
     if (two_jobs) {
       tma_prefetch_desc(&map2_a0);
       tma_prefetch_desc(&map2_b);
@@ -202,11 +207,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           for (int kc = 0; kc < args.k_chunks; ++kc) {
             mbar_wait(&ctl->empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * args.stage_bytes;
+            // split activations: chunks [0, kc_c) and [kc_c, 2 kc_c) both read the hi half, [2 kc_c, 3 kc_c) the lo
+            // half, which starts at channel in_ld / 2
+            int ka = kc * kBlockK;
+            if (args.kc_c && kc >= args.kc_c)
+              ka = kc < 2 * args.kc_c ? (kc - args.kc_c) * kBlockK : ja.in_lo_off + (kc - 2 * args.kc_c) * kBlockK;
             if (elect_one()) {
               mbar_expect_tx(&ctl->full[stage], tx_bytes);
-              tma_load_4d(sa, maps_j[gp.map], &ctl->full[stage], kc * kBlockK, t[0].x1 + gp.o1, t[0].x2 + gp.o2, n_in[0]);
+              tma_load_4d(sa, maps_j[gp.map], &ctl->full[stage], ka, t[0].x1 + gp.o1, t[0].x2 + gp.o2, n_in[0]);
               if (nact > 1)
-                tma_load_4d(sa + args.a_bytes, maps_j[gp.map], &ctl->full[stage], kc * kBlockK, t[1].x1 + gp.o1,
+                tma_load_4d(sa + args.a_bytes, maps_j[gp.map], &ctl->full[stage], ka, t[1].x1 + gp.o1,
                             t[1].x2 + gp.o2, n_in[1]);
               if (!args.b_resident)
                 tma_load_3d(sa + mt * args.a_bytes, &mb, &ctl->full[stage], kc * kBlockK, t[0].c0, g * args.tpg);
@@ -332,8 +342,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       __threadfence();
       red_release_gpu_add(f, 1);
     };
-    auto epilogue_unit = [&](const KernelArgs& ja, const CUtensorMap& mout, const float* shift_j, int active,
-                             int m_tiles_j, int unit) {
+    auto epilogue_unit = [&](const KernelArgs& ja, const CUtensorMap& mout, const CUtensorMap& mlo, const float* shift_j,
+                             int active, int m_tiles_j, int unit) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const bool publish = ja.out_f.flags != nullptr;
@@ -380,9 +390,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             mbar_wait(&ctl->aux_full[aux], aux_phase);
             res_smem = aux_base + aux * kSubBytes;
           }
-          const uint32_t out_smem = out_base + sbuf * kSubBytes;
+          const uint32_t out_smem = out_base + sbuf * stage_out_bytes;
           if (cols_live) {
-            epilogue_chunk<true, false>(kFlags, ja, v, t.c0 + cb, args.tile_n - cb, valid, res_smem, out_smem, half * 4,
+            epilogue_chunk<true, false, kSplit>(kFlags, ja, v, t.c0 + cb, args.tile_n - cb, valid, res_smem, out_smem, half * 4,
                                          swz, pix, rpix, gpix, g, shift_j);
           }
           if (aux_on) {
@@ -401,7 +411,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           named_barrier(1, 32 * kEpiWarps);
           if (leader && local == 0 && sub == 0) DYNMM_TRACE(15);
           if (ewarp == 0 && elect_one()) {
-            tma_store_4d(&mout, smem_stage_out + sbuf * kSubBytes, t.c0 + sub * 64, t.x1, t.x2, t.n0);
+            tma_store_4d(&mout, smem_stage_out + sbuf * stage_out_bytes, t.c0 + sub * 64, t.x1, t.x2, t.n0);
+            if (kSplit)          // lo half through its own map (the residual map slot: split launches have no residual ring)
+              tma_store_4d(&mlo, smem_stage_out + sbuf * stage_out_bytes + kSubBytes, t.c0 + sub * 64, t.x1, t.x2, t.n0);
             bulk_commit();
             if (pending != nullptr) {
               bulk_wait<1>();                   // every store but the one just committed is complete
@@ -411,7 +423,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           pending = (publish && sub == n_sub - 1) ? ja.out_f.flags + flag_index(ja.out_f, t.n0, h0t, w0t) : nullptr;
           sbuf ^= 1;
         } else if (cols_live) {
-          epilogue_chunk<false, false>(kFlags, ja, v, t.c0 + cb, args.tile_n - cb, valid, 0, 0, 0, 0, pix, rpix, gpix, g,
+          epilogue_chunk<false, false, kSplit>(kFlags, ja, v, t.c0 + cb, args.tile_n - cb, valid, 0, 0, 0, 0, pix, rpix, gpix, g,
                                         shift_j);
         }
       }
@@ -430,9 +442,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     };
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       if (kPerSm == 2 || tile < units0) {
-        epilogue_unit(args, map_out, smem_shift, active0, m_tiles0, tile);
+        epilogue_unit(args, map_out, map_res, smem_shift, active0, m_tiles0, tile);
       } else {
-        epilogue_unit(args2, map2_out, smem_shift + shift_stride, active1, m_tiles1, tile - units0);
+        epilogue_unit(args2, map2_out, map2_res, smem_shift + shift_stride, active1, m_tiles1, tile - units0);
       }
     }
     if (leader) DYNMM_TRACE(7);
@@ -481,7 +493,11 @@ int launch_conv(const ConvPlan& p0, const ConvPlan* p1, int max_ctas, bool pdl, 
   typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap,
                            KernelArgs, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap,
                            CUtensorMap, KernelArgs);
-  static const KernelFn table[32] = {
+  static const KernelFn table[48] = {
+      conv_igemm_kernel<0, 0>,  conv_igemm_kernel<1, 0>,  conv_igemm_kernel<2, 0>,  conv_igemm_kernel<3, 0>,
+      conv_igemm_kernel<4, 0>,  conv_igemm_kernel<5, 0>,  conv_igemm_kernel<6, 0>,  conv_igemm_kernel<7, 0>,
+      conv_igemm_kernel<8, 0>,  conv_igemm_kernel<9, 0>,  conv_igemm_kernel<10, 0>, conv_igemm_kernel<11, 0>,
+      conv_igemm_kernel<12, 0>, conv_igemm_kernel<13, 0>, conv_igemm_kernel<14, 0>, conv_igemm_kernel<15, 0>,
       conv_igemm_kernel<0, 1>,  conv_igemm_kernel<1, 1>,  conv_igemm_kernel<2, 1>,  conv_igemm_kernel<3, 1>,
       conv_igemm_kernel<4, 1>,  conv_igemm_kernel<5, 1>,  conv_igemm_kernel<6, 1>,  conv_igemm_kernel<7, 1>,
       conv_igemm_kernel<8, 1>,  conv_igemm_kernel<9, 1>,  conv_igemm_kernel<10, 1>, conv_igemm_kernel<11, 1>,
@@ -493,9 +509,10 @@ int launch_conv(const ConvPlan& p0, const ConvPlan* p1, int max_ctas, bool pdl, 
   static PerDeviceOnce attr_once;
   DYNMM_CUDA(attr_once.run([] {
     cudaError_t e = cudaSuccess;
-    for (int i = 0; i < 32 && e == cudaSuccess; ++i) {
-      e = cudaFuncSetAttribute(table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, i < 16 ? kSmemBudget : 113 * 1024);
-      if (e == cudaSuccess && i >= 16) e = cudaFuncSetAttribute(table[i], cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    for (int i = 0; i < 48 && e == cudaSuccess; ++i) {
+      const bool two = i >= 16 && i < 32;
+      e = cudaFuncSetAttribute(table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, two ? 113 * 1024 : kSmemBudget);
+      if (e == cudaSuccess && two) e = cudaFuncSetAttribute(table[i], cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     }
     return e;
   }));
@@ -517,7 +534,7 @@ int launch_conv(const ConvPlan& p0, const ConvPlan* p1, int max_ctas, bool pdl, 
   const ConvPlan& q = p1 ? *p1 : p0;
   KernelArgs a2 = q.a;
   if (!p1) a2.n = 0;
-  DYNMM_CUDA(cudaLaunchKernelEx(&cfg, table[a.flags + (a.two_per_sm ? 16 : 0)], p0.maps[0], p0.maps[1], p0.maps[2],
+  DYNMM_CUDA(cudaLaunchKernelEx(&cfg, table[a.flags + (a.split ? 32 : (a.two_per_sm ? 16 : 0))], p0.maps[0], p0.maps[1], p0.maps[2],
                                 p0.maps[3], p0.map_b, p0.map_res, p0.map_out, a, q.maps[0], q.maps[1], q.maps[2], q.maps[3],
                                 q.map_b, q.map_res, q.map_out, a2));
   return DYNMM_OK;
@@ -530,7 +547,8 @@ bool same_tiling(const KernelArgs& x, const KernelArgs& y) {
       x.k_chunks != y.k_chunks || x.stages != y.stages || x.stage_bytes != y.stage_bytes || x.a_bytes != y.a_bytes ||
       x.a_rows != y.a_rows || x.acc_stride != y.acc_stride || x.tma_epi != y.tma_epi || x.aux_slots != y.aux_slots ||
       x.b_resident != y.b_resident || x.two_per_sm != y.two_per_sm || x.mt != y.mt || x.swap != y.swap ||
-      x.flags != y.flags || x.h_out != y.h_out || x.w_out != y.w_out || x.c_out != y.c_out)
+      x.flags != y.flags || x.h_out != y.h_out || x.w_out != y.w_out || x.c_out != y.c_out || x.split != y.split ||
+      x.kc_c != y.kc_c || x.in_lo_off != y.in_lo_off || x.out_lo_off != y.out_lo_off)
     return false;
   for (int g = 0; g < x.num_groups; ++g)
     if (x.groups[g].map != y.groups[g].map || x.groups[g].o1 != y.groups[g].o1 || x.groups[g].o2 != y.groups[g].o2)

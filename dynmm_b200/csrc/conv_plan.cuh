@@ -70,6 +70,10 @@ struct KernelArgs {
   // tile-completion flags (dynmm_tile_flags in the header): layer-to-layer overlap without a kernel boundary
   dynmm_tile_flags in_f, res_f, out_f;
   int kh, kw, stride_h, stride_w, pad_h, pad_w, h_in, w_in;   // input window of an output tile (flag waits)
+  int split;                        // DYNMM_CONV_SPLIT: [hi | lo] activation halves, 3-product contraction
+  int kc_c;                         // split: K chunks of one half (c_in / 64), 0 otherwise
+  int in_lo_off;                    // split: first channel of the input's lo half (in_ld / 2)
+  int out_lo_off;                   // split: first channel of the output's lo half (out_ld / 2)
 };
 
 struct __align__(8) SmemCtl {
@@ -181,7 +185,7 @@ __device__ __forceinline__ uint4 ld_feat(const __nv_bfloat16* p) {
 //   else: direct global loads / stores (narrow channel tiles, partially active sample boxes).
 //   kCg : residual / gated features were written earlier in the SAME kernel by other CTAs (program kernel):
 //         read them through L2 (ld.global.cg), never through the non-coherent path.
-template <bool kTma, bool kCg>
+template <bool kTma, bool kCg, bool kSplit = false>
 __device__ __forceinline__ void epilogue_chunk(const int kFlags, const KernelArgs& args, const uint32_t (&v)[32], int c_first,
                                                int cols_left, bool valid, uint32_t res_smem, uint32_t out_smem,
                                                uint32_t chunk0, uint32_t swz, size_t pix, size_t rpix, size_t gpix,
@@ -213,8 +217,18 @@ __device__ __forceinline__ void epilogue_chunk(const int kFlags, const KernelArg
         } else {
           r = valid ? ld_feat<kCg>(args.residual + rpix * args.res_ld + c) : make_uint4(0, 0, 0, 0);
         }
-        f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x); f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
-        f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z); f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
+        if (kSplit) {
+          // fp32-grade residual = hi + lo, reconstructed before it is added (read from global in both epilogue flavours)
+          const uint4 q = valid ? ld_feat<kCg>(args.residual + rpix * args.res_ld + (args.res_ld >> 1) + c)
+                                : make_uint4(0, 0, 0, 0);
+          f[0] += bf16_lo(r.x) + bf16_lo(q.x); f[1] += bf16_hi(r.x) + bf16_hi(q.x);
+          f[2] += bf16_lo(r.y) + bf16_lo(q.y); f[3] += bf16_hi(r.y) + bf16_hi(q.y);
+          f[4] += bf16_lo(r.z) + bf16_lo(q.z); f[5] += bf16_hi(r.z) + bf16_hi(q.z);
+          f[6] += bf16_lo(r.w) + bf16_lo(q.w); f[7] += bf16_hi(r.w) + bf16_hi(q.w);
+        } else {
+          f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x); f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
+          f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z); f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
+        }
       }
       if (kFlags & kFlagRelu) {
 #pragma unroll
@@ -223,8 +237,16 @@ __device__ __forceinline__ void epilogue_chunk(const int kFlags, const KernelArg
       if (kFlags & kFlagGated) {
         if (g != 0.f) {      // gated-off samples never touch the depth features
           const uint4 r = ld_feat<kCg>(args.gated + gpix * args.gated_ld + c);
-          f[0] += g * bf16_lo(r.x); f[1] += g * bf16_hi(r.x); f[2] += g * bf16_lo(r.y); f[3] += g * bf16_hi(r.y);
-          f[4] += g * bf16_lo(r.z); f[5] += g * bf16_hi(r.z); f[6] += g * bf16_lo(r.w); f[7] += g * bf16_hi(r.w);
+          if (kSplit) {
+            const uint4 q = ld_feat<kCg>(args.gated + gpix * args.gated_ld + (args.gated_ld >> 1) + c);
+            f[0] += g * (bf16_lo(r.x) + bf16_lo(q.x)); f[1] += g * (bf16_hi(r.x) + bf16_hi(q.x));
+            f[2] += g * (bf16_lo(r.y) + bf16_lo(q.y)); f[3] += g * (bf16_hi(r.y) + bf16_hi(q.y));
+            f[4] += g * (bf16_lo(r.z) + bf16_lo(q.z)); f[5] += g * (bf16_hi(r.z) + bf16_hi(q.z));
+            f[6] += g * (bf16_lo(r.w) + bf16_lo(q.w)); f[7] += g * (bf16_hi(r.w) + bf16_hi(q.w));
+          } else {
+            f[0] += g * bf16_lo(r.x); f[1] += g * bf16_hi(r.x); f[2] += g * bf16_lo(r.y); f[3] += g * bf16_hi(r.y);
+            f[4] += g * bf16_lo(r.z); f[5] += g * bf16_hi(r.z); f[6] += g * bf16_lo(r.w); f[7] += g * bf16_hi(r.w);
+          }
         }
       }
       uint4 o;
@@ -232,10 +254,22 @@ __device__ __forceinline__ void epilogue_chunk(const int kFlags, const KernelArg
       o.y = pack_bf16(f[2], f[3]);
       o.z = pack_bf16(f[4], f[5]);
       o.w = pack_bf16(f[6], f[7]);
+      uint4 l = make_uint4(0, 0, 0, 0);
+      if (kSplit) {
+        // lo half: what the bf16 rounding of the hi half dropped
+        l.x = pack_bf16(f[0] - bf16_lo(o.x), f[1] - bf16_hi(o.x));
+        l.y = pack_bf16(f[2] - bf16_lo(o.y), f[3] - bf16_hi(o.y));
+        l.z = pack_bf16(f[4] - bf16_lo(o.z), f[5] - bf16_hi(o.z));
+        l.w = pack_bf16(f[6] - bf16_lo(o.w), f[7] - bf16_hi(o.w));
+      }
       if (kTma) {
         sts128(out_smem + chunk, o);
+        if (kSplit) sts128(out_smem + kSubBytes + chunk, l);      // staging buffer = [hi sub-tile][lo sub-tile]
       } else if (valid) {
         *reinterpret_cast<uint4*>(args.out + pix * args.out_ld + c) = o;
+        if (kSplit) {
+          *reinterpret_cast<uint4*>(args.out + pix * args.out_ld + (args.out_ld >> 1) + c) = l;
+        }
       }
     }
   }
@@ -306,6 +340,7 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
   // shift vectors are staged, and the tile width / dual-unit choice looks at the tiles of BOTH jobs
   const bool merged = partner_slots > 0;
   if (merged) allow_two_per_sm = false;
+  const bool split = (p->flags & DYNMM_CONV_SPLIT) != 0;
   DYNMM_CHECK_ARG(p && p->in && p->weight && p->out, "conv_igemm: null pointer");
   DYNMM_CHECK_ARG(p->kh >= 1 && p->kw >= 1 && p->kh * p->kw <= kMaxGroups, "conv_igemm: at most %d taps", kMaxGroups);
   DYNMM_CHECK_ARG(p->stride_h >= 1 && p->stride_h <= 2 && p->stride_w >= 1 && p->stride_w <= 2,
@@ -316,6 +351,10 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
   DYNMM_CHECK_ARG(!p->residual || p->res_ld % 8 == 0, "conv_igemm: res_ld %% 8");
   DYNMM_CHECK_ARG(!p->gated || (p->gated_ld % 8 == 0 && p->gate), "conv_igemm: gated needs gate[] and gated_ld %% 8");
   DYNMM_CHECK_ARG(p->n >= 1 && p->n_in >= 1, "conv_igemm: empty batch");
+  DYNMM_CHECK_ARG(!split || (p->c_in % kBlockK == 0 && p->in_ld % 16 == 0 && p->in_ld >= 2 * p->c_in && p->out_ld % 16 == 0 &&
+                             p->out_ld >= 2 * p->c_out && p->res_ld % 16 == 0 && p->gated_ld % 16 == 0 && !p->trace &&
+                             !p->in_flags.flags && !p->out_flags.flags),
+                  "conv_igemm: DYNMM_CONV_SPLIT needs c_in %% 64 == 0 and [hi | lo] tensors (ld >= 2 * c, ld %% 16 == 0)");
   const int h_exp = (p->h_in + 2 * p->pad_h - p->kh) / p->stride_h + 1;
   const int w_exp = (p->w_in + 2 * p->pad_w - p->kw) / p->stride_w + 1;
   DYNMM_CHECK_ARG(h_exp == p->h_out && w_exp == p->w_out, "conv_igemm: output size %dx%d does not match %dx%d",
@@ -417,7 +456,7 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
     DYNMM_CHECK_ARG(tile_n >= 16 && tile_n <= 256 && tile_n % 16 == 0, "conv_igemm: tile_n %d", tile_n);
     a.tile_n = tile_n;
     a.c_tiles = ceil_div(c_out_pad, tile_n);
-    a.k_chunks = ceil_div(p->c_in, kBlockK);
+    a.k_chunks = ceil_div(p->c_in, kBlockK) * (split ? 3 : 1);
     a.a_rows = a.b1 * (a.b2 + a.tpg - 1) * a.bn;
     a.a_bytes = (a.a_rows * kBlockK * 2 + 1023) / 1024 * 1024;
     if (a.a_bytes < kBlockM * kBlockK * 2) a.a_bytes = kBlockM * kBlockK * 2;   // UMMA reads 128 rows
@@ -429,17 +468,18 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
     b_tile_bytes = tile_n * kBlockK * 2;
     b_total = num_taps * a.k_chunks * b_tile_bytes;
     a.tma_epi = (tile_n % 64 == 0) ? 1 : 0;
-    a.aux_slots = (a.tma_epi && p->residual && !small) ? kAuxSlots : 0;   // small: residual read from global
+    // small / split: residual read from global by the epilogue threads (split: both halves, no room for 2 x 16 KiB slots)
+    a.aux_slots = (a.tma_epi && p->residual && !small && !split) ? kAuxSlots : 0;
     a.b_resident = (a.c_tiles == 1 && b_total <= kResidentBudget && !merged) ? 1 : 0;
     if (a.b_resident && a.aux_slots) a.aux_slots = 2;
     shift_bytes = ((p->c_out + 12) * 4) * (merged ? 2 : 1) + 16;
-    epi_bytes = (a.tma_epi ? 2 * kSubBytes : 0) + a.aux_slots * kSubBytes;
+    epi_bytes = (a.tma_epi ? (split ? 4 : 2) * kSubBytes : 0) + a.aux_slots * kSubBytes;
     a.stage_bytes = a.a_bytes + (a.b_resident ? 0 : a.tpg * b_tile_bytes);
     a.stages = (smem_budget - 2048 - epi_bytes - shift_bytes - (a.b_resident ? b_total : 0)) / a.stage_bytes;
     if (a.stages < 2 && a.b_resident) {     // not enough room next to the resident weights: stream them instead
       a.b_resident = 0;
-      a.aux_slots = (a.tma_epi && p->residual && !small) ? kAuxSlots : 0;
-      epi_bytes = (a.tma_epi ? 2 * kSubBytes : 0) + a.aux_slots * kSubBytes;
+      a.aux_slots = (a.tma_epi && p->residual && !small && !split) ? kAuxSlots : 0;
+      epi_bytes = (a.tma_epi ? (split ? 4 : 2) * kSubBytes : 0) + a.aux_slots * kSubBytes;
       a.stage_bytes = a.a_bytes + a.tpg * b_tile_bytes;
       a.stages = (smem_budget - 2048 - epi_bytes - shift_bytes) / a.stage_bytes;
     }
@@ -448,7 +488,7 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
     // TMA engine and the epilogue warps idle in turn; with <= 113 KiB per CTA two CTAs share the SM and fill each
     // other's bubbles.  One residual slot and at most 4 stages per CTA.
     a.two_per_sm = 0;
-    if (allow_two_per_sm && halo && a.b_resident && tile_n == 64 && a.c_tiles == 1 && a.tma_epi && !p->trace &&
+    if (allow_two_per_sm && !split && halo && a.b_resident && tile_n == 64 && a.c_tiles == 1 && a.tma_epi && !p->trace &&
         m_tiles >= 4 * sms) {
       const int aux2 = a.aux_slots ? 1 : 0;
       const int epi2 = 2 * kSubBytes + aux2 * kSubBytes;
@@ -475,7 +515,7 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
     return e ? atoi(e) : 1;
   }();
   const bool force_dual = (p->flags & DYNMM_CONV_FORCE_DUAL) || dual_mode > 1;
-  if (allow_dual && !small && dual_mode > 0 && !(p->flags & DYNMM_CONV_NO_DUAL) && !a.b_resident && a.tma_epi && tile_n <= 128 &&
+  if (allow_dual && !small && !split && dual_mode > 0 && !(p->flags & DYNMM_CONV_NO_DUAL) && !a.b_resident && a.tma_epi && tile_n <= 128 &&
       m_tiles >= 2 && !a.two_per_sm &&
       (force_dual || 4LL * m_tiles * (p->n + partner_slots) / p->n * a.c_tiles > 3LL * sms)) {
     const int stage2 = 2 * a.a_bytes + a.tpg * b_tile_bytes;
@@ -519,6 +559,10 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
   a.trace = static_cast<unsigned long long*>(p->trace);
   a.kh = p->kh; a.kw = p->kw; a.stride_h = p->stride_h; a.stride_w = p->stride_w; a.pad_h = p->pad_h; a.pad_w = p->pad_w;
   a.h_in = p->h_in; a.w_in = p->w_in;
+  a.split = split ? 1 : 0;
+  a.kc_c = split ? p->c_in / kBlockK : 0;
+  a.in_lo_off = split ? p->in_ld / 2 : 0;
+  a.out_lo_off = split ? p->out_ld / 2 : 0;
   a.in_f = p->in_flags;
   a.res_f = p->res_flags;
   if (a.in_f.flags == nullptr) a.res_f.flags = nullptr;        // ordinary stream order covers the residual too
@@ -562,7 +606,7 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
   bool used[4] = {false, false, false, false};
   if (halo) {
     used[0] = true;
-    int rc = pixel_map(&maps[0], p->in, p->c_in, p->w_in, p->h_in, p->n_in, (uint64_t)p->in_ld * es,
+    int rc = pixel_map(&maps[0], p->in, split ? p->in_ld : p->c_in, p->w_in, p->h_in, p->n_in, (uint64_t)p->in_ld * es,
                        (uint64_t)p->in_ld * p->w_in * es, (uint64_t)p->in_ld * p->w_in * p->h_in * es,
                        a.b2 + a.tpg - 1);
     if (rc) return rc;
@@ -588,7 +632,7 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
       DYNMM_CHECK_ARG(sub_w >= 1 && sub_h >= 1, "conv_igemm: input too small for stride");
       const __nv_bfloat16* base =
           static_cast<const __nv_bfloat16*>(p->in) + (static_cast<size_t>(py) * p->w_in + px) * p->in_ld;
-      int rc = pixel_map(&maps[m], base, p->c_in, sub_w, sub_h, p->n_in, (uint64_t)p->in_ld * p->stride_w * es,
+      int rc = pixel_map(&maps[m], base, split ? p->in_ld : p->c_in, sub_w, sub_h, p->n_in, (uint64_t)p->in_ld * p->stride_w * es,
                          (uint64_t)p->in_ld * p->w_in * p->stride_h * es,
                          (uint64_t)p->in_ld * p->w_in * p->h_in * es, a.b2);
       if (rc) return rc;
@@ -599,8 +643,9 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
   for (int m = 0; m < 4; ++m)
     if (!used[m]) maps[m] = maps[first_used];
   {
-    const uint64_t dims[3] = {(uint64_t)p->c_in, (uint64_t)c_out_pad, (uint64_t)num_taps};
-    const uint64_t strides[2] = {(uint64_t)p->c_in * es, (uint64_t)p->c_in * c_out_pad * es};
+    const uint64_t c_in_w = (uint64_t)p->c_in * (split ? 3 : 1);          // split: [W_hi | W_lo | W_hi] along K
+    const uint64_t dims[3] = {c_in_w, (uint64_t)c_out_pad, (uint64_t)num_taps};
+    const uint64_t strides[2] = {c_in_w * es, c_in_w * c_out_pad * es};
     const uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)tile_n, (uint32_t)a.tpg};
     int rc = encode_map(&map_b, p->weight, 3, dims, strides, box);
     if (rc) return rc;
@@ -614,6 +659,13 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
     int rc = pixel_map(&map_out, p->out, p->c_out, p->w_out, p->h_out, p->n, (uint64_t)p->out_ld * es,
                        (uint64_t)p->out_ld * p->w_out * es, (uint64_t)p->out_ld * p->w_out * p->h_out * es, a.b2);
     if (rc) return rc;
+    if (split) {
+      // no residual ring in split mode: the second epilogue map is the store map of the output's lo half
+      rc = pixel_map(&map_res, static_cast<const __nv_bfloat16*>(p->out) + p->out_ld / 2, p->c_out, p->w_out, p->h_out, p->n,
+                     (uint64_t)p->out_ld * es, (uint64_t)p->out_ld * p->w_out * es,
+                     (uint64_t)p->out_ld * p->w_out * p->h_out * es, a.b2);
+      if (rc) return rc;
+    }
     if (a.aux_slots) {
       DYNMM_CHECK_ARG((reinterpret_cast<uintptr_t>(p->residual) & 15) == 0,
                       "conv_igemm: residual must be 16-byte aligned");

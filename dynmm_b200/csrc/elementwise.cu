@@ -350,6 +350,7 @@ upsample2x_dw_nhwc_strip_kernel(const __nv_bfloat16* __restrict__ in, int h, int
 // produces 64 consecutive output columns: lane l owns columns 2l, 2l+1 (one 8-byte store, 256 B per
 // warp, fully coalesced), reading 2x3 staged inputs without bank conflicts.
 constexpr int kUpTy = 8, kUpTx = 32;
+template <bool kSplit>      // kSplit: `in` is [n,h,w,2c] = [hi | lo] halves of fp32-grade values (DYNMM_CONV_SPLIT layout)
 __global__ void __launch_bounds__(256)
 upsample2x_dw_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int h, int w, int c,
                              const float* __restrict__ wgt, const float* __restrict__ bias,
@@ -383,13 +384,17 @@ upsample2x_dw_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int h, int w,
     const int p = i / cv;
     const int lx = p % (kUpTx + 2), ly = p / (kUpTx + 2);
     const int y = y0 + ly - 1, x = x0 + lx - 1;
-    uint4 v = make_uint4(0, 0, 0, 0);
+    uint4 v = make_uint4(0, 0, 0, 0), q = make_uint4(0, 0, 0, 0);
     if (y >= 0 && y < h && x >= 0 && x < w) {
-      v = __ldg(reinterpret_cast<const uint4*>(in + ((1LL * s * h + y) * w + x) * c + ch8));
+      const __nv_bfloat16* px = in + ((1LL * s * h + y) * w + x) * (kSplit ? 2 * c : c) + ch8;
+      v = __ldg(reinterpret_cast<const uint4*>(px));
+      if (kSplit) q = __ldg(reinterpret_cast<const uint4*>(px + c));
     }
     float* d = s_in + ch8 * CS + ly * RS + lx;
-    d[0 * CS] = bf16_lo(v.x); d[1 * CS] = bf16_hi(v.x); d[2 * CS] = bf16_lo(v.y); d[3 * CS] = bf16_hi(v.y);
-    d[4 * CS] = bf16_lo(v.z); d[5 * CS] = bf16_hi(v.z); d[6 * CS] = bf16_lo(v.w); d[7 * CS] = bf16_hi(v.w);
+    d[0 * CS] = bf16_lo(v.x) + bf16_lo(q.x); d[1 * CS] = bf16_hi(v.x) + bf16_hi(q.x);
+    d[2 * CS] = bf16_lo(v.y) + bf16_lo(q.y); d[3 * CS] = bf16_hi(v.y) + bf16_hi(q.y);
+    d[4 * CS] = bf16_lo(v.z) + bf16_lo(q.z); d[5 * CS] = bf16_hi(v.z) + bf16_hi(q.z);
+    d[6 * CS] = bf16_lo(v.w) + bf16_lo(q.w); d[7 * CS] = bf16_hi(v.w) + bf16_hi(q.w);
   }
   __syncthreads();
   // A lane owns input column x = x0 + lane and produces the 2x2 output block (2y..2y+1, 2x..2x+1).
@@ -516,6 +521,153 @@ __global__ void nearest_resize_into_kernel(const __nv_bfloat16* __restrict__ src
   }
 }
 
+
+// ---------------------------------------------------------------- fp32-grade ("f32x3") variants: [hi | lo] bf16 halves
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): ~16 mantissa bits in two bf16 tensors (DYNMM_CONV_SPLIT layout:
+// the hi halves in channels [0, ld/2), the lo halves in [ld/2, ld)).  The kernels below read both halves, work in fp32
+// and write both halves.
+__device__ __forceinline__ void split8(const float (&f)[8], uint4& hi, uint4& lo) {
+  hi.x = pack_bf16(f[0], f[1]); hi.y = pack_bf16(f[2], f[3]); hi.z = pack_bf16(f[4], f[5]); hi.w = pack_bf16(f[6], f[7]);
+  lo.x = pack_bf16(f[0] - bf16_lo(hi.x), f[1] - bf16_hi(hi.x));
+  lo.y = pack_bf16(f[2] - bf16_lo(hi.y), f[3] - bf16_hi(hi.y));
+  lo.z = pack_bf16(f[4] - bf16_lo(hi.z), f[5] - bf16_hi(hi.z));
+  lo.w = pack_bf16(f[6] - bf16_lo(hi.w), f[7] - bf16_hi(hi.w));
+}
+__device__ __forceinline__ void join8(const uint4& hi, const uint4& lo, float (&f)[8]) {
+  f[0] = bf16_lo(hi.x) + bf16_lo(lo.x); f[1] = bf16_hi(hi.x) + bf16_hi(lo.x);
+  f[2] = bf16_lo(hi.y) + bf16_lo(lo.y); f[3] = bf16_hi(hi.y) + bf16_hi(lo.y);
+  f[4] = bf16_lo(hi.z) + bf16_lo(lo.z); f[5] = bf16_hi(hi.z) + bf16_hi(lo.z);
+  f[6] = bf16_lo(hi.w) + bf16_lo(lo.w); f[7] = bf16_hi(hi.w) + bf16_hi(lo.w);
+}
+
+// fp32 [rows][c] -> [rows][2c]
+__global__ void split_from_f32_kernel(const float* __restrict__ x, long long rows, int c, __nv_bfloat16* __restrict__ out) {
+  const int cv = c >> 3;
+  const long long total = rows * cv;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv) * 8;
+    const long long r = i / cv;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x + r * c + c8));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(x + r * c + c8 + 4));
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint4 hi, lo;
+    split8(f, hi, lo);
+    *reinterpret_cast<uint4*>(out + r * 2 * c + c8) = hi;
+    *reinterpret_cast<uint4*>(out + r * 2 * c + c + c8) = lo;
+  }
+}
+
+// nearest x2 + depthwise 3x3 + bias (+ skip), NHWC split in / out: a thread owns 8 channels of one output pixel
+__global__ void upsample2x_dw_nhwc_split_kernel(const __nv_bfloat16* __restrict__ in, int n, int h, int w, int c,
+                                                const float* __restrict__ wgt, const float* __restrict__ bias,
+                                                const __nv_bfloat16* __restrict__ skip, __nv_bfloat16* __restrict__ out) {
+  const int cv = c >> 3;
+  const long long total = 1LL * n * 4 * h * w * cv;
+  const int H = 2 * h, W = 2 * w;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv) * 8;
+    long long r = i / cv;
+    const int X = (int)(r % W);
+    r /= W;
+    const int Y = (int)(r % H);
+    const int s = (int)(r / H);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = bias ? bias[c8 + e] : 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yy = Y + dy;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int xx = X + dx;
+        if (xx < 0 || xx >= W) continue;
+        const __nv_bfloat16* px = in + ((1LL * s * h + (yy >> 1)) * w + (xx >> 1)) * 2 * c + c8;
+        float f[8];
+        join8(__ldg(reinterpret_cast<const uint4*>(px)), __ldg(reinterpret_cast<const uint4*>(px + c)), f);
+        const int k = (dy + 1) * 3 + dx + 1;
+        const float4 wa = __ldg(reinterpret_cast<const float4*>(wgt + k * c + c8));
+        const float4 wb = __ldg(reinterpret_cast<const float4*>(wgt + k * c + c8 + 4));
+        acc[0] = fmaf(f[0], wa.x, acc[0]); acc[1] = fmaf(f[1], wa.y, acc[1]);
+        acc[2] = fmaf(f[2], wa.z, acc[2]); acc[3] = fmaf(f[3], wa.w, acc[3]);
+        acc[4] = fmaf(f[4], wb.x, acc[4]); acc[5] = fmaf(f[5], wb.y, acc[5]);
+        acc[6] = fmaf(f[6], wb.z, acc[6]); acc[7] = fmaf(f[7], wb.w, acc[7]);
+      }
+    }
+    const long long o = ((1LL * s * H + Y) * W + X) * 2 * c + c8;
+    if (skip) {
+      float f[8];
+      join8(__ldg(reinterpret_cast<const uint4*>(skip + o)), __ldg(reinterpret_cast<const uint4*>(skip + o + c)), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    }
+    uint4 hi, lo;
+    split8(acc, hi, lo);
+    *reinterpret_cast<uint4*>(out + o) = hi;
+    *reinterpret_cast<uint4*>(out + o + c) = lo;
+  }
+}
+
+// adaptive average pooling of the first c channels of a split tensor with pitch ld -> [n, bins, bins, 2c]
+__global__ void __launch_bounds__(256)
+adaptive_avgpool_split_kernel(const __nv_bfloat16* __restrict__ in, int h, int w, int c, int ld, int bins,
+                              __nv_bfloat16* __restrict__ out) {
+  __shared__ float s_part[32][64 + 4];
+  const int by = blockIdx.x / bins, bx = blockIdx.x % bins, s = blockIdx.y;
+  const int y0 = (by * h) / bins, y1 = ((by + 1) * h + bins - 1) / bins;
+  const int x0 = (bx * w) / bins, x1 = ((bx + 1) * w + bins - 1) / bins;
+  const int ww = x1 - x0, npix = (y1 - y0) * ww;
+  const int oct = threadIdx.x & 7, lane_p = threadIdx.x >> 3;
+  const int ch0 = blockIdx.z * 64 + oct * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (ch0 < c) {
+    for (int p = lane_p; p < npix; p += 32) {
+      const int y = y0 + p / ww, x = x0 + p % ww;
+      const __nv_bfloat16* px = in + ((1LL * s * h + y) * w + x) * ld + ch0;
+      float f[8];
+      join8(__ldg(reinterpret_cast<const uint4*>(px)), __ldg(reinterpret_cast<const uint4*>(px + (ld >> 1))), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s_part[lane_p][oct * 8 + e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int ch = blockIdx.z * 64 + threadIdx.x;
+    if (ch < c) {
+      float t = 0.f;
+#pragma unroll
+      for (int l = 0; l < 32; ++l) t += s_part[l][threadIdx.x];
+      t = t / (float)npix;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(t);
+      __nv_bfloat16* o = out + ((1LL * s * bins + by) * bins + bx) * 2 * c;
+      o[ch] = hi;
+      o[c + ch] = __float2bfloat16_rn(t - __bfloat162float(hi));
+    }
+  }
+}
+
+// nearest resize of a split tensor [n,hs,ws,2c] into channels [c_off, c_off + c) of both halves of dst (pitch ld)
+__global__ void nearest_resize_into_split_kernel(const __nv_bfloat16* __restrict__ src, int n, int hs, int ws, int c,
+                                                 __nv_bfloat16* __restrict__ dst, int h, int w, int ld, int c_off) {
+  const int cv = c >> 3;
+  const long long total = 1LL * n * h * w * cv * 2;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const int half = (int)(i & 1);
+    long long r = i >> 1;
+    const int c8 = (int)(r % cv) * 8;
+    r /= cv;
+    const int x = (int)(r % w);
+    r /= w;
+    const int y = (int)(r % h);
+    const int s = (int)(r / h);
+    const int sy = min((int)((long long)y * hs / h), hs - 1), sx = min((int)((long long)x * ws / w), ws - 1);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + ((1LL * s * hs + sy) * ws + sx) * 2 * c + half * c + c8));
+    *reinterpret_cast<uint4*>(dst + ((1LL * s * h + y) * w + x) * ld + half * (ld >> 1) + c_off + c8) = v;
+  }
+}
+
 }  // namespace
 }  // namespace dynmm
 
@@ -623,15 +775,20 @@ extern "C" int dynmm_nhwc_bf16_to_nchw_f32(const void* in, int n, int c, int h, 
   return DYNMM_OK;
 }
 
-extern "C" int dynmm_upsample2x_dw3x3(const void* in, int n, int h, int w, int c, const float* weight,
-                                      const float* bias, const void* skip, void* out_nhwc_bf16, float* out_nchw_f32,
-                                      uint8_t* labels, void* stream_) {
+namespace {
+int upsample2x_impl(const void* in, int n, int h, int w, int c, const float* weight, const float* bias, const void* skip,
+                    void* out_nhwc_bf16, float* out_nchw_f32, uint8_t* labels, bool split, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DYNMM_CHECK_ARG(in && weight && n >= 1 && h >= 1 && w >= 1 && c >= 8 && c % 8 == 0, "upsample2x: c %% 8");
   DYNMM_CHECK_ARG(!(out_nhwc_bf16 && (out_nchw_f32 || labels)) && (out_nhwc_bf16 || out_nchw_f32 || labels),
                   "upsample2x: either the NHWC output, or the NCHW logits and/or the arg-max labels");
   DYNMM_CHECK_ARG(!labels || c <= 256, "upsample2x: labels are uint8");
-  if (out_nhwc_bf16) {
+  if (out_nhwc_bf16 && split) {
+    const long long total = 1LL * n * 4 * h * w * (c / 8);
+    upsample2x_dw_nhwc_split_kernel<<<grid_for(total, 256, 16), 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(in), n, h, w, c, weight, bias, static_cast<const __nv_bfloat16*>(skip),
+        static_cast<__nv_bfloat16*>(out_nhwc_bf16));
+  } else if (out_nhwc_bf16) {
     static const bool use_strip = [] {
       const char* e = getenv("DYNMM_UPSAMPLE");
       return !(e && e[0] == 'p');           // DYNMM_UPSAMPLE=pixel: the one-thread-per-output-pixel kernel
@@ -661,12 +818,59 @@ extern "C" int dynmm_upsample2x_dw3x3(const void* in, int n, int h, int w, int c
     DYNMM_CHECK_ARG(smem <= 200 * 1024, "upsample2x: too many channels for the NCHW output");
     static PerDeviceOnce attr_once;      // the limit checked above, so one setting serves every channel count
     DYNMM_CUDA(attr_once.run([] {
-      return cudaFuncSetAttribute(upsample2x_dw_to_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaError_t e = cudaFuncSetAttribute(upsample2x_dw_to_nchw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           200 * 1024);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(upsample2x_dw_to_nchw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      return e;
     }));
     dim3 grid(ceil_div(w, kUpTx), ceil_div(h, kUpTy), n);
-    upsample2x_dw_to_nchw_kernel<<<grid, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(in), h, w, c, weight,
-                                                              bias, out_nchw_f32, labels);
+    if (split)
+      upsample2x_dw_to_nchw_kernel<true><<<grid, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(in), h, w, c, weight,
+                                                                      bias, out_nchw_f32, labels);
+    else
+      upsample2x_dw_to_nchw_kernel<false><<<grid, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(in), h, w, c,
+                                                                       weight, bias, out_nchw_f32, labels);
   }
+  DYNMM_LAUNCH_CHECK();
+  return DYNMM_OK;
+}
+}  // namespace
+
+extern "C" int dynmm_upsample2x_dw3x3(const void* in, int n, int h, int w, int c, const float* weight,
+                                      const float* bias, const void* skip, void* out_nhwc_bf16, float* out_nchw_f32,
+                                      uint8_t* labels, void* stream) {
+  return upsample2x_impl(in, n, h, w, c, weight, bias, skip, out_nhwc_bf16, out_nchw_f32, labels, false, stream);
+}
+extern "C" int dynmm_upsample2x_dw3x3_split(const void* in, int n, int h, int w, int c, const float* weight,
+                                            const float* bias, const void* skip, void* out_nhwc_bf16, float* out_nchw_f32,
+                                            uint8_t* labels, void* stream) {
+  return upsample2x_impl(in, n, h, w, c, weight, bias, skip, out_nhwc_bf16, out_nchw_f32, labels, true, stream);
+}
+extern "C" int dynmm_split_from_f32(const float* x, long long rows, int c, void* out, void* stream) {
+  DYNMM_CHECK_ARG(x && out && rows >= 1 && c >= 8 && c % 8 == 0, "split_from_f32: c %% 8");
+  split_from_f32_kernel<<<grid_for(rows * (c / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, rows, c, static_cast<__nv_bfloat16*>(out));
+  DYNMM_LAUNCH_CHECK();
+  return DYNMM_OK;
+}
+extern "C" int dynmm_adaptive_avgpool_split(const void* in, int n, int h, int w, int c, int ld, int bins, void* out,
+                                            void* stream) {
+  DYNMM_CHECK_ARG(in && out && n >= 1 && h >= 1 && w >= 1 && c >= 8 && c % 8 == 0 && ld % 16 == 0 && ld >= 2 * c &&
+                      bins >= 1 && bins <= 64,
+                  "avgpool_split: bad args");
+  adaptive_avgpool_split_kernel<<<dim3(bins * bins, n, ceil_div(c, 64)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(in), h, w, c, ld, bins, static_cast<__nv_bfloat16*>(out));
+  DYNMM_LAUNCH_CHECK();
+  return DYNMM_OK;
+}
+extern "C" int dynmm_nearest_resize_into_split(const void* src, int n, int hs, int ws, int c, void* dst, int h, int w,
+                                               int ld, int c_off, void* stream) {
+  DYNMM_CHECK_ARG(src && dst && c % 8 == 0 && ld % 16 == 0 && c_off % 8 == 0 && c_off + c <= ld / 2,
+                  "resize_split: c/ld/c_off");
+  const long long total = 1LL * n * h * w * (c / 8) * 2;
+  nearest_resize_into_split_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), n, hs, ws, c, static_cast<__nv_bfloat16*>(dst), h, w, ld, c_off);
   DYNMM_LAUNCH_CHECK();
   return DYNMM_OK;
 }

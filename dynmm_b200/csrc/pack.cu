@@ -51,6 +51,39 @@ __global__ void fold_pack_conv_kernel(const float* __restrict__ w, int co, int c
   }
 }
 
+// the same folding with the fp32 result split into bf16 halves: packed[tap][o][3 * ci] = [hi | lo | hi]
+__global__ void fold_pack_conv_split_kernel(const float* __restrict__ w, int co, int ci, int taps, int co_pad,
+                                            const float* __restrict__ bias, const float* __restrict__ bn_w,
+                                            const float* __restrict__ bn_b, const float* __restrict__ bn_mean,
+                                            const float* __restrict__ bn_var, float eps, __nv_bfloat16* __restrict__ packed,
+                                            float* __restrict__ shift) {
+  const size_t total = static_cast<size_t>(taps) * co_pad * ci;
+  const size_t tid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  for (size_t i = tid; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % ci);
+    const size_t r = i / ci;
+    const int o = static_cast<int>(r % co_pad);
+    const int t = static_cast<int>(r / co_pad);
+    float v = 0.f;
+    if (o < co) {
+      v = w[(static_cast<size_t>(o) * ci + c) * taps + t];
+      if (bn_w) v = __fmul_rn(v, bn_scale(bn_w, bn_var, eps, o));
+    }
+    const __nv_bfloat16 hi = __float2bfloat16(v);
+    const __nv_bfloat16 lo = __float2bfloat16(__fsub_rn(v, __bfloat162float(hi)));
+    __nv_bfloat16* row = packed + r * (3 * static_cast<size_t>(ci));
+    row[c] = hi;
+    row[ci + c] = lo;
+    row[2 * ci + c] = hi;
+  }
+  if (shift) {
+    for (size_t o = tid; o < static_cast<size_t>(co); o += static_cast<size_t>(gridDim.x) * blockDim.x) {
+      const int oi = static_cast<int>(o);
+      shift[o] = bn_w ? bn_shift(bn_b, bn_mean, bias, bn_scale(bn_w, bn_var, eps, oi), oi) : (bias ? bias[o] : 0.f);
+    }
+  }
+}
+
 __global__ void fold_bn_kernel(int c, const float* __restrict__ bias, const float* __restrict__ bn_w,
                                const float* __restrict__ bn_b, const float* __restrict__ bn_mean,
                                const float* __restrict__ bn_var, float eps, float* __restrict__ scale,
@@ -104,6 +137,26 @@ extern "C" int dynmm_fold_pack_conv(const float* w, int c_out, int c_in, int kh,
   fold_pack_conv_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(w, c_out, c_in, kh * kw, co_pad, bias, bn_weight, bn_bias,
                                                                     bn_mean, bn_var, eps,
                                                                     static_cast<__nv_bfloat16*>(packed), shift);
+  DYNMM_LAUNCH_CHECK();
+  return DYNMM_OK;
+}
+
+extern "C" int dynmm_fold_pack_conv_split(const float* w, int c_out, int c_in, int kh, int kw, const float* bias,
+                                          const float* bn_weight, const float* bn_bias, const float* bn_mean,
+                                          const float* bn_var, float eps, void* packed, float* shift, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DYNMM_CHECK_ARG(w && packed, "fold_pack_conv_split: null pointer");
+  DYNMM_CHECK_ARG(c_out >= 1 && c_in >= 1 && kh >= 1 && kw >= 1, "fold_pack_conv_split: bad shape");
+  const bool bn = bn_weight != nullptr;
+  DYNMM_CHECK_ARG(!bn || (bn_bias && bn_mean && bn_var), "fold_pack_conv_split: BatchNorm needs weight, bias, mean and var");
+  DYNMM_CHECK_ARG(shift || !(bn || bias), "fold_pack_conv_split: a bias / BatchNorm needs the shift output");
+  const int co_pad = (c_out + 15) / 16 * 16;
+  const long long total = 1LL * kh * kw * co_pad * c_in;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+  fold_pack_conv_split_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(w, c_out, c_in, kh * kw, co_pad, bias, bn_weight,
+                                                                          bn_bias, bn_mean, bn_var, eps,
+                                                                          static_cast<__nv_bfloat16*>(packed), shift);
   DYNMM_LAUNCH_CHECK();
   return DYNMM_OK;
 }

@@ -68,10 +68,11 @@ class ConvLayer:
     stride: tuple
     pad: tuple
     relu: bool
+    split: bool = False            # fp32-grade mode: [hi | lo] activations, weight packed [W_hi | W_lo | W_hi]
 
     def __call__(self, x: Tensor, **kw) -> Tensor:
         return ops.conv(x, self.weight, c_out=self.c_out, kh=self.kh, kw=self.kw, stride=self.stride, pad=self.pad,
-                        scale=self.scale, shift=self.shift, relu=self.relu, c_in=self.c_in, **kw)
+                        scale=self.scale, shift=self.shift, relu=self.relu, c_in=self.c_in, split=self.split, **kw)
 
 
 @dataclasses.dataclass
@@ -81,8 +82,8 @@ class Block:
 
 
 class _Packer:
-    def __init__(self, sd: Dict[str, Tensor], device):
-        self.sd, self.dev = sd, device
+    def __init__(self, sd: Dict[str, Tensor], device, split: bool = False):
+        self.sd, self.dev, self.split = sd, device, split
 
     def t(self, key):
         return self.sd[key].detach().float().to(self.dev)
@@ -98,9 +99,9 @@ class _Packer:
         w = self.t(key + ".weight")
         bias = self.t(key + ".bias") if key + ".bias" in self.sd else None
         bn_t = [self.t(bn + s) for s in (".weight", ".bias", ".running_mean", ".running_var")] if bn is not None else None
-        packed, shift = ops.fold_pack_conv(w, bias, bn_t, bn_eps)
+        packed, shift = ops.fold_pack_conv(w, bias, bn_t, bn_eps, split=self.split)
         c_out, c_in, kh, kw = w.shape
-        return ConvLayer(packed, None, shift, c_in, c_out, kh, kw, tuple(stride), tuple(pad), relu)
+        return ConvLayer(packed, None, shift, c_in, c_out, kh, kw, tuple(stride), tuple(pad), relu, self.split)
 
     def nbt1d(self, key, stride=1) -> Block:
         """resnet.py:124-147: 3x1 -> ReLU -> 1x3 -> BN(1e-3) -> ReLU -> 3x1 -> ReLU -> 1x3 -> BN -> +id -> ReLU."""
@@ -149,6 +150,10 @@ class EngineConfig:
     context_module: str = "ppm"
     activation: str = "relu"
     gate: str = "global"            # "global": GlobalGate (SkipGateESANet); "local": one two-way gate per fusion site
+    # "bf16": bf16 activations and weights, fp32 accumulation (stated tolerance 2e-2 on the logits);
+    # "f32x3": fp32-grade arithmetic on the same tensor cores -- activations and weights as bf16 hi + lo halves, three
+    # products per MAC (DYNMM_CONV_SPLIT), element-wise kernels in fp32: logits within 1e-3 of the fp32 reference
+    precision: str = "bf16"
 
 
 class FusionEngine:
@@ -171,8 +176,13 @@ class FusionEngine:
             raise NotImplementedError("the CUDA engine implements upsampling='learned-3x3-zeropad'")
         if "ppm" not in cfg.context_module or cfg.context_module == "ppm-1-2-4-8" or "appm" in cfg.context_module:
             raise NotImplementedError("the CUDA engine implements context_module='ppm' (bins 1,5)")
+        if cfg.precision not in ("bf16", "f32x3"):
+            raise ValueError("EngineConfig.precision must be 'bf16' or 'f32x3'")
+        self.split = cfg.precision == "f32x3"
+        if self.split and (cfg.fuse != "add" or cfg.gate != "global"):
+            raise NotImplementedError("precision='f32x3' is implemented for the global gate with fuse='add'")
         self.cfg, self.dev = cfg, device
-        p = _Packer(sd, device)
+        p = _Packer(sd, device, self.split)
         if cfg.gate == "local":
             if cfg.fuse != "add":
                 raise NotImplementedError("the local-gate engine blends by addition (model_skip_mod.py:241-311)")
@@ -244,14 +254,15 @@ class FusionEngine:
         # convolution PROGRAMS (one cooperative launch per chain of dependent convs, dynmm_conv_program_*) instead of
         # one launch per convolution on two streams.  Same arithmetic, bit-identical results; measured slower at
         # batch 8 in round 1 (profiles/r1_program_*), so the per-launch path stays the default.
-        self.use_programs = cfg.fuse == "add" and os.environ.get("DYNMM_PROGRAM", "0") == "1"
+        self.use_programs = cfg.fuse == "add" and os.environ.get("DYNMM_PROGRAM", "0") == "1" and not self.split
         self.programs: list = []   # ConvPrograms of the last forward (a captured graph must keep them alive)
         # 64-channel NonBottleneck1D blocks: each 3x1 -> 1x3 pair as ONE fused kernel (dynmm_conv_pair_fwd, bit-identical
         # to the two launches); DYNMM_PAIR=0 keeps one launch per convolution
-        self.use_pairs = os.environ.get("DYNMM_PAIR", "1") != "0"
+        self.use_pairs = os.environ.get("DYNMM_PAIR", "1") != "0" and not self.split
         # DYNMM_TILE_FLAGS=1: convolutions publish per-tile completion flags and their consumers wait on those instead
         # of on the previous kernel as a whole (layer k+1 starts on the SMs layer k's early finishers free)
-        self.flag_pool = ops.TileFlagPool(device) if os.environ.get("DYNMM_TILE_FLAGS", "0") == "1" else None
+        self.flag_pool = ops.TileFlagPool(device) if (os.environ.get("DYNMM_TILE_FLAGS", "0") == "1" and
+                                                      not self.split) else None
         # DYNMM_MERGE (default on; 'add' fusion): from stage 2 on, the same layer of the RGB and of the depth encoder is ONE
         # launch (dynmm_conv_igemm_fwd2) on one stream; only the last convolution of a stage runs per encoder (the RGB
         # one adds g_s * depth_s, which the depth one has to finish first).  Stage 1 (64 channels: fused-pair kernels
@@ -262,7 +273,7 @@ class FusionEngine:
         # layer to layer); the stage's first block (stride 2, down-sampling) and the RGB encoder's last convolution (gated
         # add) stay per-layer launches.  DYNMM_CHAIN_STAGES: comma-separated stage indices (0-based), default "2".
         self.chain_imgs = {}
-        if self.use_merge and os.environ.get("DYNMM_CHAIN", "1") == "1":
+        if self.use_merge and os.environ.get("DYNMM_CHAIN", "1") == "1" and not self.split:
             for s in {int(v) for v in os.environ.get("DYNMM_CHAIN_STAGES", "2").split(",") if v.strip()}:
                 if 1 <= s <= 3:
                     imgs = self._chain_images(s)
@@ -556,7 +567,15 @@ class FusionEngine:
         wr, sr, br = self.stem["encoder_rgb"]
         wd, sdp, bd = self.stem["encoder_depth"]
         learned = weight is None and not baseline and not ini_stage
-        if self.stem_packed is not None:
+        if self.split:
+            # fp32-grade mode: the stem (three split products already) hands its fp32 maps on as [hi | lo] halves
+            if self.stem_packed is not None:
+                r32, d32, _, _ = ops.stem_s2d(rgb, depth, self.stem_packed, sr, br, sdp, bd, want_f32=True)
+            else:
+                r32, d32, _, _ = ops.stem(rgb, depth, wr, sr, br, wd, sdp, bd, want_f32=True)
+            r16, d16 = ops.split_from_f32(r32), ops.split_from_f32(d32)
+            self.launches += 4
+        elif self.stem_packed is not None:
             r32, d32, r16, d16 = ops.stem_s2d(rgb, depth, self.stem_packed, sr, br, sdp, bd, want_f32=learned)
             self.launches += 2
         elif self.se is None:
@@ -661,8 +680,8 @@ class FusionEngine:
                     if s == 3:
                         # stage-4 output lands directly in the pyramid-pooling concat buffer
                         c4 = self.stage_channels[3]
-                        cat = torch.empty(b, h // 32, w // 32, c4 + 2 * self.ppm[0].c_out, dtype=torch.bfloat16,
-                                          device=self.dev)
+                        cat = torch.empty(b, h // 32, w // 32, (c4 + 2 * self.ppm[0].c_out) * (2 if self.split else 1),
+                                          dtype=torch.bfloat16, device=self.dev)
                     if self.se is None:
                         last_kw = dict(gated=depth_out[s], gate=plan.g[s], gated_slot=plan.slot)
                         if s == 3:
@@ -678,8 +697,8 @@ class FusionEngine:
             for s in range(split, 4):                   # merged launches (the stage-1 join ordered main after side)
                 if s == 3:
                     c4 = self.stage_channels[3]
-                    cat = torch.empty(b, h // 32, w // 32, c4 + 2 * self.ppm[0].c_out, dtype=torch.bfloat16,
-                                      device=self.dev)
+                    cat = torch.empty(b, h // 32, w // 32, (c4 + 2 * self.ppm[0].c_out) * (2 if self.split else 1),
+                                      dtype=torch.bfloat16, device=self.dev)
                 r, d = self._merged_stage(s, r, d, plan, keep, cat)
                 fused.append(r)
                 emit_skip(s, r)
@@ -890,11 +909,12 @@ class FusionEngine:
             keep += pooled + ys
             self.launches += 6
         else:
+            sp = self.split
             for i, bins in enumerate((1, 5)):
-                pooled = ops.adaptive_avgpool(cat, bins, c=c4)
+                pooled = ops.adaptive_avgpool(cat, bins, c=c4, split=sp)
                 y = self.ppm[i](pooled)
-                ops.nearest_resize_into(y, cat, off)
-                off += y.shape[3]
+                ops.nearest_resize_into(y, cat, off, split=sp)
+                off += y.shape[3] // (2 if sp else 1)
                 keep += [pooled, y]
                 self.launches += 3
             cat._dynmm_flags = None             # other kernels wrote into the buffer since the conv published its flags
@@ -921,14 +941,14 @@ class FusionEngine:
                     x = self._block(x, blk, keep)
                 if skip_done[2 - i] is not None:
                     main.wait_event(skip_done[2 - i])
-                x = ops.upsample2x_dw3x3(x, m["up_w"], m["up_b"], skip)
+                x = ops.upsample2x_dw3x3(x, m["up_w"], m["up_b"], skip, split=self.split)
                 self.launches += 1
                 keep.append(x)
         x = self.conv_out(x)
         keep.append(x)
-        x = ops.upsample2x_dw3x3(x, self.up[0][0], self.up[0][1])
+        x = ops.upsample2x_dw3x3(x, self.up[0][0], self.up[0][1], split=self.split)
         keep.append(x)
         out = ops.upsample2x_dw3x3(x, self.up[1][0], self.up[1][1], to_nchw_f32=True, out=out, labels=labels,
-                                   want_logits=want_logits)
+                                   want_logits=want_logits, split=self.split)
         self.launches += 3
         return out

@@ -59,20 +59,23 @@ def _f32(t: Optional[Tensor]) -> Optional[Tensor]:
     return None if t is None else t.detach().float().contiguous()
 
 
-def fold_pack_conv(w: Tensor, bias: Optional[Tensor] = None, bn: Optional[Sequence[Tensor]] = None, eps: float = 1e-5):
+def fold_pack_conv(w: Tensor, bias: Optional[Tensor] = None, bn: Optional[Sequence[Tensor]] = None, eps: float = 1e-5,
+                   split: bool = False):
     """One launch (dynmm_fold_pack_conv): eval-mode BatchNorm ``bn = (weight, bias, running_mean, running_var)`` and
     the conv bias folded, weights packed like :func:`pack_conv_weight`.  -> (packed bf16, shift fp32 [c_out] or None);
-    bit-identical to ``pack_conv_weight(w * scale.view(-1,1,1,1))`` with :func:`fold_bn`'s scale / shift."""
+    bit-identical to ``pack_conv_weight(w * scale.view(-1,1,1,1))`` with :func:`fold_bn`'s scale / shift.
+    ``split``: the folded fp32 weights as bf16 halves [taps, c_out_pad, 3 * c_in] = [hi | lo | hi] for ``conv(split=True)``."""
     lib = _lib.load()
     w = _f32(w)
     bias = _f32(bias)
     bn = [_f32(t) for t in bn] if bn is not None else [None] * 4
     _cuda(w, bias, *bn)
     c_out, c_in, kh, kw = w.shape
-    packed = torch.empty(kh * kw, (c_out + 15) // 16 * 16, c_in, dtype=torch.bfloat16, device=w.device)
+    packed = torch.empty(kh * kw, (c_out + 15) // 16 * 16, c_in * (3 if split else 1), dtype=torch.bfloat16, device=w.device)
     shift = torch.empty(c_out, dtype=torch.float32, device=w.device) if (bias is not None or bn[0] is not None) else None
-    check(lib.dynmm_fold_pack_conv(ptr(w), c_out, c_in, kh, kw, ptr(bias), ptr(bn[0]), ptr(bn[1]), ptr(bn[2]), ptr(bn[3]),
-                                   float(eps), ptr(packed), ptr(shift), stream_ptr()), "fold_pack_conv")
+    fn = lib.dynmm_fold_pack_conv_split if split else lib.dynmm_fold_pack_conv
+    check(fn(ptr(w), c_out, c_in, kh, kw, ptr(bias), ptr(bn[0]), ptr(bn[1]), ptr(bn[2]), ptr(bn[3]),
+             float(eps), ptr(packed), ptr(shift), stream_ptr()), "fold_pack_conv")
     return packed, shift
 
 
@@ -135,8 +138,12 @@ def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 
          out: Optional[Tensor] = None, n_out: Optional[int] = None, c_in: Optional[int] = None,
          out_c_off: int = 0, tile_n: int = 0, max_ctas: int = 0, direct: bool = False,
          trace: Optional[Tensor] = None, volatile_weights: bool = False, dual: Optional[bool] = None,
-         residual_settled: bool = False, count_settled: bool = False) -> Tensor:
+         residual_settled: bool = False, count_settled: bool = False, split: bool = False) -> Tensor:
     """Fused conv + scale/shift + residual + ReLU + gated add (see dynmm_conv_igemm_fwd).
+
+    ``split`` (DYNMM_CONV_SPLIT, fp32-grade arithmetic): x / out / residual / gated are [hi | lo] bf16 halves with
+    pitch 2 * channels (hi in [0, ld/2), lo in [ld/2, ld)), ``weight`` comes from ``fold_pack_conv(split=True)``;
+    ``c_in`` / ``c_out`` stay the logical channel counts.
 
     x: NHWC bf16 [n_in, h, w, in_ld] (``c_in`` <= in_ld selects a channel prefix);
     weight: packed by :func:`pack_conv_weight`.  ``out`` may be a wider NHWC buffer, written
@@ -144,12 +151,12 @@ def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 
     lib = _lib.load()
     _cuda(x, weight, scale, shift, residual, gated, gate, gated_slot, in_map, count, out)
     n_in, h_in, w_in, in_ld = x.shape
-    c_in = in_ld if c_in is None else c_in
+    c_in = (in_ld // 2 if split else in_ld) if c_in is None else c_in
     n = n_in if n_out is None else n_out
     h_out = (h_in + 2 * pad[0] - kh) // stride[0] + 1
     w_out = (w_in + 2 * pad[1] - kw) // stride[1] + 1
     if out is None:
-        out = torch.empty(n, h_out, w_out, c_out, dtype=torch.bfloat16, device=x.device)
+        out = torch.empty(n, h_out, w_out, c_out * (2 if split else 1), dtype=torch.bfloat16, device=x.device)
     p = ConvParams()
     p.in_, p.weight, p.scale, p.shift = ptr(x), ptr(weight), ptr(scale), ptr(shift)
     p.residual, p.res_map = ptr(residual), ptr(res_map)
@@ -168,7 +175,9 @@ def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 
         p.flags |= 4 if dual else 2
     if count_settled and count is not None:
         p.flags |= 16                            # DYNMM_CONV_COUNT_SETTLED
-    pool = FLAG_POOL
+    if split:
+        p.flags |= 32                            # DYNMM_CONV_SPLIT
+    pool = FLAG_POOL if not split else None
     if pool is not None and not direct and CONV_RECORDER is None and trace is None:
         # consume: the input's (and the residual's) completion flags replace the wait for the previous kernel.  Only
         # when everything this launch reads from recent launches is covered: no sample indirection, no gated operand
@@ -198,7 +207,8 @@ def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 
         # inside `with ConvProgram()`: the convolution becomes a job of the program's current phase
         CONV_RECORDER._record(p, (x, weight, scale, shift, residual, res_map, out, gated, gate, gated_slot, in_map, count))
         return out
-    job = (h_out * w_out * c_out * c_in * kh * kw, n, count)      # MACs per output sample, sample slots, device count
+    # MACs per output sample (three bf16 products per MAC with split operands), sample slots, device count
+    job = (h_out * w_out * c_out * c_in * kh * kw * (3 if split else 1), n, count)
     if CONV_MERGE is not None and not direct:
         # inside `with ConvMerge()`: launched when the block ends -- together with its partner if there is one
         CONV_MERGE._record(p, (x, weight, scale, shift, residual, res_map, out, gated, gate, gated_slot, in_map, count), job)
@@ -841,44 +851,63 @@ def nhwc_bf16_to_nchw_f32(x: Tensor, c: Optional[int] = None) -> Tensor:
     return out
 
 
+def split_from_f32(x: Tensor) -> Tensor:
+    """fp32 [..., c] -> bf16 [..., 2c] = [hi | lo] halves (hi = bf16(x), lo = bf16(x - hi)): the activation format of
+    the fp32-grade ("f32x3") engine mode."""
+    lib = _lib.load()
+    x = x.contiguous()
+    _cuda(x)
+    c = x.shape[-1]
+    out = torch.empty(*x.shape[:-1], 2 * c, dtype=torch.bfloat16, device=x.device)
+    check(lib.dynmm_split_from_f32(ptr(x), x.numel() // c, c, ptr(out), stream_ptr()), "split_from_f32")
+    return out
+
+
 def upsample2x_dw3x3(x: Tensor, weight: Tensor, bias: Optional[Tensor], skip: Optional[Tensor] = None,
                      to_nchw_f32: bool = False, out: Optional[Tensor] = None, labels: Optional[Tensor] = None,
-                     want_logits: bool = True):
+                     want_logits: bool = True, split: bool = False):
     """x NHWC bf16; weight fp32 tap-major [9, c] (``conv.weight.reshape(c, 9).t().contiguous()``).
     Final upsampling (``to_nchw_f32``): returns the NCHW fp32 logits; with ``labels`` (uint8 [n,2h,2w]) the
     arg-max over channels is produced in the same pass, and ``want_logits=False`` skips the logits."""
     lib = _lib.load()
     _cuda(x, weight, bias, skip, out, labels)
-    n, h, w, c = x.shape
+    n, h, w, ld = x.shape
+    c = ld // 2 if split else ld                 # split: x / skip / NHWC out are [hi | lo] halves
+    fn = lib.dynmm_upsample2x_dw3x3_split if split else lib.dynmm_upsample2x_dw3x3
     if to_nchw_f32 or labels is not None:
         if want_logits:
             out = torch.empty(n, c, 2 * h, 2 * w, dtype=torch.float32, device=x.device) if out is None else out
         else:
             out = None
-        check(lib.dynmm_upsample2x_dw3x3(ptr(x), n, h, w, c, ptr(weight), ptr(bias), None, None, ptr(out),
-                                         ptr(labels), stream_ptr()), "upsample2x_dw3x3")
+        check(fn(ptr(x), n, h, w, c, ptr(weight), ptr(bias), None, None, ptr(out), ptr(labels), stream_ptr()),
+              "upsample2x_dw3x3")
     else:
-        out = torch.empty(n, 2 * h, 2 * w, c, dtype=torch.bfloat16, device=x.device) if out is None else out
-        check(lib.dynmm_upsample2x_dw3x3(ptr(x), n, h, w, c, ptr(weight), ptr(bias), ptr(skip), ptr(out), None, None,
-                                         stream_ptr()), "upsample2x_dw3x3")
+        out = torch.empty(n, 2 * h, 2 * w, ld, dtype=torch.bfloat16, device=x.device) if out is None else out
+        check(fn(ptr(x), n, h, w, c, ptr(weight), ptr(bias), ptr(skip), ptr(out), None, None, stream_ptr()),
+              "upsample2x_dw3x3")
     return out
 
 
-def adaptive_avgpool(x: Tensor, bins: int, c: Optional[int] = None) -> Tensor:
+def adaptive_avgpool(x: Tensor, bins: int, c: Optional[int] = None, split: bool = False) -> Tensor:
     lib = _lib.load()
     _cuda(x)
     n, h, w, ld = x.shape
-    c = ld if c is None else c
-    out = torch.empty(n, bins, bins, c, dtype=torch.bfloat16, device=x.device)
-    check(lib.dynmm_adaptive_avgpool(ptr(x), n, h, w, c, ld, bins, ptr(out), stream_ptr()), "adaptive_avgpool")
+    c = (ld // 2 if split else ld) if c is None else c
+    out = torch.empty(n, bins, bins, c * (2 if split else 1), dtype=torch.bfloat16, device=x.device)
+    fn = lib.dynmm_adaptive_avgpool_split if split else lib.dynmm_adaptive_avgpool
+    check(fn(ptr(x), n, h, w, c, ld, bins, ptr(out), stream_ptr()), "adaptive_avgpool")
     return out
 
 
-def nearest_resize_into(src: Tensor, dst: Tensor, c_off: int) -> None:
+def nearest_resize_into(src: Tensor, dst: Tensor, c_off: int, split: bool = False) -> None:
     lib = _lib.load()
     _cuda(src, dst)
     n, hs, ws, c = src.shape
     _, h, w, ld = dst.shape
+    if split:
+        check(lib.dynmm_nearest_resize_into_split(ptr(src), n, hs, ws, c // 2, ptr(dst), h, w, ld, c_off, stream_ptr()),
+              "nearest_resize_into_split")
+        return
     check(lib.dynmm_nearest_resize_into(ptr(src), n, hs, ws, c, ptr(dst), h, w, ld, c_off, stream_ptr()),
           "nearest_resize_into")
 

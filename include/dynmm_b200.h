@@ -225,8 +225,20 @@ typedef struct dynmm_conv_params {
 /* `count` was written by a kernel that completed before the PREVIOUS kernel of this stream started (every depth-encoder
  * launch but the first after dynmm_gate_plan): the kernel reads it while it waits for the previous kernel */
 #define DYNMM_CONV_COUNT_SETTLED 16
+/* fp32-grade arithmetic on the bf16 tensor cores ("f32x3"): every activation tensor of the launch (in, out, residual,
+ * gated) holds fp32-grade values as TWO bf16 halves, hi = bf16(x) in channels [0, ld/2) and lo = bf16(x - hi) in
+ * [ld/2, ld) of its channel pitch ld; `weight` is packed [taps][c_out_pad][3 * c_in] = [W_hi | W_lo | W_hi]
+ * (dynmm_fold_pack_conv_split) and the contraction runs over the three products x_hi*W_hi + x_hi*W_lo + x_lo*W_hi with
+ * fp32 accumulation (the dropped x_lo*W_lo term is 2^-16 relative).  c_in / c_out stay the logical channel counts
+ * (c_in a multiple of 64); the epilogue works on the reconstructed fp32 values and writes hi / lo again. */
+#define DYNMM_CONV_SPLIT 32
 
 int dynmm_conv_igemm_fwd(const dynmm_conv_params* p, void* stream);
+/* dynmm_fold_pack_conv with the folded fp32 weights split into bf16 halves for DYNMM_CONV_SPLIT launches:
+ * packed [kh*kw][c_out_pad16][3 * c_in] = [hi | lo | hi] along the last axis. */
+int dynmm_fold_pack_conv_split(const float* w, int c_out, int c_in, int kh, int kw, const float* bias,
+                               const float* bn_weight, const float* bn_bias, const float* bn_mean, const float* bn_var,
+                               float eps, void* packed, float* shift, void* stream);
 /* Two convolutions of IDENTICAL geometry in ONE launch: the same layer of the RGB and of the depth encoder
  * (FusionDynMM/src/models/model_skip_mod_globalgate.py:276-310 runs the two ResNets in lock step).  Each job keeps its
  * own tensors, sample count (`count`) and epilogue operands; the CTAs walk one combined tile list (job a's tiles,
@@ -482,6 +494,16 @@ int dynmm_upsample2x_dw3x3(const void* in, int n, int h, int w, int c, const flo
                            const float* bias, const void* skip, void* out_nhwc_bf16,
                            float* out_nchw_f32, uint8_t* labels, void* stream);
 
+/* fp32-grade ("f32x3") variants of the decoder / context helpers for DYNMM_CONV_SPLIT tensors ([hi | lo] bf16 halves,
+ * hi in channels [0, ld/2), lo in [ld/2, ld)): both halves are read, the arithmetic is fp32, both halves are written.
+ * `c` is the logical channel count.  dynmm_split_from_f32 turns an fp32 NHWC map (the stem's gate-path copies) into
+ * the split form. */
+int dynmm_split_from_f32(const float* x, long long rows, int c, void* out /* bf16 [rows][2c] */, void* stream);
+int dynmm_upsample2x_dw3x3_split(const void* in, int n, int h, int w, int c, const float* weight, const float* bias,
+                                 const void* skip, void* out_nhwc_bf16, float* out_nchw_f32, uint8_t* labels, void* stream);
+int dynmm_adaptive_avgpool_split(const void* in, int n, int h, int w, int c, int ld, int bins, void* out, void* stream);
+int dynmm_nearest_resize_into_split(const void* src, int n, int hs, int ws, int c, void* dst, int h, int w, int ld,
+                                    int c_off, void* stream);
 /* PyramidPoolingModule pooling + broadcast (context_modules.py:69-84) for NHWC bf16 input
  * [n,h,w,ld] (first c channels): adaptive average pool to bins x bins (fp32 accumulate) -> out [n,bins,bins,c] bf16. */
 int dynmm_adaptive_avgpool(const void* in, int n, int h, int w, int c, int ld, int bins, void* out, void* stream);

@@ -1,0 +1,175 @@
+"""fp32-grade engine mode ("f32x3"): activations and weights as bf16 hi + lo halves, three tensor-core products per
+MAC (DYNMM_CONV_SPLIT), element-wise kernels in fp32.  north_star's fp32 bar: logits within 1e-3 relative of the
+reference's fp32 path (tests/golden: produced by the reference's SkipGateESANet), hard decisions bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+F32_TOL = 1e-3          # north_star: "logits ... within 1e-3 relative for fp32"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _setup():
+    from dynmm_b200 import _lib
+    _lib.require_device()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm()).item()
+
+
+def _join(t):
+    c = t.shape[-1] // 2
+    return t[..., :c].float() + t[..., c:].float()
+
+
+def test_split_roundtrip_keeps_16_bits():
+    from dynmm_b200 import ops
+    x = torch.randn(3, 5, 7, 64, device="cuda") * 3
+    s = ops.split_from_f32(x)
+    assert s.shape == (3, 5, 7, 128) and s.dtype == torch.bfloat16
+    assert torch.equal(s[..., :64], x.to(torch.bfloat16))
+    assert (_join(s) - x).abs().max().item() <= 2.0 ** -16 * x.abs().max().item()
+
+
+@pytest.mark.parametrize("c_in,c_out,k,stride,h,w,res,gated", [
+    (128, 128, (3, 1), (1, 1), 30, 40, True, False),      # halo mode, residual
+    (64, 128, (3, 3), (2, 2), 32, 48, False, False),      # strided, per-tap loads
+    (256, 256, (1, 3), (1, 1), 15, 20, True, True),       # gated depth add
+    (128, 40, (3, 3), (1, 1), 24, 32, False, False),      # conv_out: 40 classes
+    (512, 128, (1, 1), (1, 1), 5, 5, False, False),       # pyramid-pooling branch
+])
+def test_split_conv_matches_fp32(c_in, c_out, k, stride, h, w, res, gated):
+    from dynmm_b200 import ops
+    dev = "cuda"
+    torch.manual_seed(c_in + c_out)
+    n = 3
+    kh, kw = k
+    x = torch.randn(n, c_in, h, w, device=dev)
+    wt = torch.randn(c_out, c_in, kh, kw, device=dev) / (c_in * kh * kw) ** 0.5
+    bias = torch.randn(c_out, device=dev) * 0.1
+    pad = (kh // 2, kw // 2)
+    ref = F.conv2d(x, wt, bias, stride=stride, padding=pad)
+    packed, shift = ops.fold_pack_conv(wt, bias, None, split=True)
+    xs = ops.split_from_f32(x.permute(0, 2, 3, 1).contiguous())
+    kw_ = {}
+    if res:
+        r = torch.randn_like(ref)
+        ref = ref + r
+        kw_["residual"] = ops.split_from_f32(r.permute(0, 2, 3, 1).contiguous())
+    ref = torch.relu(ref)
+    if gated:
+        g = torch.tensor([0.0, 1.0, 0.37], device=dev)
+        dpt = torch.randn_like(ref)
+        ref = ref + g.view(-1, 1, 1, 1) * dpt
+        kw_.update(gated=ops.split_from_f32(dpt.permute(0, 2, 3, 1).contiguous()), gate=g)
+    out = ops.conv(xs, packed, c_out=c_out, kh=kh, kw=kw, stride=stride, pad=pad, shift=shift, relu=True, split=True, **kw_)
+    got = _join(out).permute(0, 3, 1, 2)
+    err = _rel_l2(got, ref)
+    assert err < 2e-5, f"relative L2 {err:.2e}"
+    assert (got - ref).abs().max().item() < 1e-3 * ref.abs().max().item()
+
+
+def test_split_elementwise_kernels_match_fp32():
+    from dynmm_b200 import ops
+    dev = "cuda"
+    torch.manual_seed(5)
+    n, h, w, c = 2, 9, 12, 40
+    x = torch.randn(n, c, h, w, device=dev)
+    wt = torch.randn(c, 1, 3, 3, device=dev) * 0.3
+    b = torch.randn(c, device=dev) * 0.1
+    skip = torch.randn(n, c, 2 * h, 2 * w, device=dev)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), wt, b, padding=1, groups=c)
+    taps = wt.reshape(c, 9).t().contiguous()
+    xs = ops.split_from_f32(x.permute(0, 2, 3, 1).contiguous())
+    ss = ops.split_from_f32(skip.permute(0, 2, 3, 1).contiguous())
+    got = _join(ops.upsample2x_dw3x3(xs, taps, b, ss, split=True)).permute(0, 3, 1, 2)
+    assert _rel_l2(got, ref + skip) < 1e-5
+    labels = torch.empty(n, 2 * h, 2 * w, dtype=torch.uint8, device=dev)
+    out = ops.upsample2x_dw3x3(xs, taps, b, to_nchw_f32=True, labels=labels, split=True)
+    assert _rel_l2(out, ref) < 1e-5
+    assert torch.equal(labels.long(), out.argmax(1))
+    # pyramid pooling helpers on a concat buffer [hi(96) | lo(96)]: the first 64 channels hold the features
+    cat = torch.zeros(n, h, w, 192, dtype=torch.bfloat16, device=dev)
+    feat = torch.randn(n, h, w, 64, device=dev)
+    fs = ops.split_from_f32(feat)
+    cat[..., :64], cat[..., 96:160] = fs[..., :64], fs[..., 64:]
+    for bins in (1, 5):
+        pooled = _join(ops.adaptive_avgpool(cat, bins, c=64, split=True)).permute(0, 3, 1, 2)
+        ref_p = F.adaptive_avg_pool2d(_join(fs).permute(0, 3, 1, 2), bins)
+        assert _rel_l2(pooled, ref_p) < 1e-5
+    y = torch.randn(n, 5, 5, 32, device=dev)
+    ys = ops.split_from_f32(y)
+    ops.nearest_resize_into(ys, cat, 64, split=True)
+    ref_y = F.interpolate(_join(ys).permute(0, 3, 1, 2), size=(h, w), mode="nearest").permute(0, 2, 3, 1)
+    got_y = cat[..., 64:96].float() + cat[..., 160:192].float()
+    assert torch.equal(got_y, ref_y)
+
+
+def _build(cfg, seed, gate_scale=40.0):
+    from dynmm_b200.fusion import SkipGateESANet
+    from oracle import fusion_oracle as fo
+    sd = fo.make_state_dict(cfg, seed, gate_scale)
+    model = SkipGateESANet(height=cfg.height, width=cfg.width, encoder_rgb=cfg.encoder, encoder_depth=cfg.encoder,
+                           encoder_block=cfg.encoder_block, channels_decoder=list(cfg.channels_decoder),
+                           nr_decoder_blocks=list(cfg.nr_decoder_blocks),
+                           fuse_depth_in_rgb_encoder=cfg.fuse_depth_in_rgb_encoder)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    model.engine_precision = "f32x3"
+    return model, sd
+
+
+def test_f32x3_engine_matches_reference_golden_vectors(golden_dir):
+    """The reference's own fp32 outputs (tests/golden) to 1e-3 relative, hard decisions bit-exact."""
+    from oracle import fusion_oracle as fo
+    from oracle.make_golden import sample_inputs
+    cfg = fo.FusionConfig(height=64, width=96)
+    gold = np.load(os.path.join(golden_dir, "fusion_r34_nbt1d_add_64x96.npz"))
+    model, sd = _build(cfg, 0, float(gold["gate_scale"]))
+    rgb, depth = sample_inputs(1, 4, 64, 96)
+    rgb, depth = rgb.cuda(), depth.cuda()
+    errs = {}
+    with torch.no_grad():
+        for tag, temp, hard in (("soft_t1", 1.0, False), ("hard_t1", 1.0, True), ("soft_t01", 0.1, False)):
+            model.temp, model.hard_gate = temp, hard
+            out, w = model(rgb, depth, True, True)
+            assert model.engine().split
+            if hard:
+                np.testing.assert_array_equal(w.cpu().numpy(), gold[tag + "_weight"])
+            ref = torch.from_numpy(gold[tag + "_out_sample"])
+            errs[tag] = _rel_l2(out[:, :, ::4, ::4].cpu(), ref)
+        eng = model.engine()
+        for k in range(5):
+            wk = torch.eye(5)[torch.full((4,), k)].cuda()
+            out, _ = eng.forward(rgb, depth, weight=wk)
+            errs[f"branch{k}"] = _rel_l2(out[:, :, ::4, ::4].cpu(), torch.from_numpy(gold[f"branch{k}_out_sample"]))
+    assert max(errs.values()) <= F32_TOL, errs
+    print("f32x3 vs reference fp32:", {k: f"{v:.1e}" for k, v in errs.items()})
+
+
+def test_f32x3_engine_full_size_matches_oracle_and_labels():
+    """480x640: two images against the fp32 CPU oracle, logits 1e-3 relative and (almost) every arg-max label."""
+    from oracle import fusion_oracle as fo
+    from oracle.make_golden import sample_inputs
+    cfg = fo.FusionConfig()
+    model, sd = _build(cfg, 0)
+    model.hard_gate = True
+    rgb, depth = sample_inputs(11, 2, 480, 640)
+    with torch.no_grad():
+        out, w = model(rgb.cuda(), depth.cuda(), True, True)
+        ref = fo.forward(sd, cfg, rgb, depth, hard_gate=True)
+    assert torch.equal(w.cpu(), ref["weight"])
+    err = _rel_l2(out.cpu(), ref["out"])
+    assert err <= F32_TOL, f"relative L2 {err:.2e}"
+    agree = (out.cpu().argmax(1) == ref["out"].argmax(1)).float().mean().item()
+    assert agree >= 0.9999, agree
