@@ -123,9 +123,9 @@ def measured_peaks():
     return 6650.0, 1400.0, 1590.0, "fallback"
 
 
-def conv_traffic():
-    """DRAM bytes per conv launch from the committed ncu capture (profiles/r1b_conv_traffic.json)."""
-    for name in ("r1b_conv_traffic.json", "r1_conv_traffic.json"):
+def conv_traffic(precision="bf16"):
+    """DRAM bytes per conv launch from the committed ncu capture (profiles/r2_<precision>_conv_traffic.json)."""
+    for name in (f"r2_{precision}_conv_traffic.json", "r1b_conv_traffic.json", "r1_conv_traffic.json"):
         try:
             return json.load(open(os.path.join(ROOT, "profiles", name)))["dram_bytes_per_launch"]
         except Exception:
@@ -330,7 +330,7 @@ def conv_roofline(model, batch_tensors, step_s, precision, use_graph, dump_path=
             "kernel": "conv_igemm_kernel + conv_pair_kernel + conv_chain_kernel (tcgen05 implicit GEMM; all conv launches "
                       "of a step)",
             "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s", "frac": achieved / tf_sust,
-            "peak_source": f"{src} (bf16 sustained; burst {tf_burst})", "traffic": conv_traffic(),
+            "peak_source": f"{src} (bf16 sustained; burst {tf_burst})", "traffic": conv_traffic(precision),
             "launches_per_step": n_conv, "gflop_per_step": gflop, "gflop_per_step_fp32_equiv": gflop / ppm,
             "tensor_products_per_mac": ppm, "kernel_s_per_step": t_conv,
             "note": "achieved = executed bf16 tensor-core FLOPs / summed conv kernel time (f32x3: three products per MAC "

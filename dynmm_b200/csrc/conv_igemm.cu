@@ -350,6 +350,30 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       const uint32_t q = fast_div(unit, args.m_c);
       const int ct = unit - q * args.c_tiles;
       const int nact = min(mt, m_tiles_j - (int)q * mt);
+      // split operands: the residual halves are read from global memory (no room for a TMA ring next to the hi + lo
+      // staging tiles).  The loads of a sub-tile are issued one step ahead -- sub-tile 0 before the wait for the
+      // accumulator, sub-tile s + 1 right after sub-tile s is converted -- so their latency hides behind the UMMAs /
+      // the TMEM load instead of sitting in the middle of the conversion (measured: 5000 -> 750 cycles per tile).
+      uint4 pre_hi[4], pre_lo[4];
+      auto prefetch_res = [&](const TileCoord& t, int sub) {
+        const int n = t.n0 + nl;
+        const int p1 = t.x1 + i1, p2 = t.x2 + i2;
+        const int h = args.swap ? p1 : p2, w = args.swap ? p2 : p1;
+        const bool valid = nl < args.bn && n < active && h < args.h_out && w < args.w_out;
+        const size_t rn = (valid && ja.res_map) ? ja.res_map[n] : n;
+        const size_t rpix = (rn * args.h_out + h) * args.w_out + w;
+        const int c = t.c0 + sub * 64 + half * 32;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool ok = valid && sub * 64 + half * 32 + j * 8 < args.tile_n && c + j * 8 < args.c_out;
+          pre_hi[j] = ok ? __ldg(reinterpret_cast<const uint4*>(ja.residual + rpix * args.res_ld + c + j * 8))
+                         : make_uint4(0, 0, 0, 0);
+          pre_lo[j] = ok ? __ldg(reinterpret_cast<const uint4*>(ja.residual + rpix * args.res_ld + (args.res_ld >> 1) + c + j * 8))
+                         : make_uint4(0, 0, 0, 0);
+        }
+      };
+      constexpr bool kPreRes = kSplit && (kFlags & kFlagRes) != 0;
+      if (kPreRes) prefetch_res(decode_tile(args, (q * mt) * args.c_tiles + ct), 0);
       mbar_wait(&ctl->acc_full[acc], acc_phase);
       tc_fence_after();
       if (leader && local == 0) DYNMM_TRACE(5);
@@ -393,8 +417,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           const uint32_t out_smem = out_base + sbuf * stage_out_bytes;
           if (cols_live) {
             epilogue_chunk<true, false, kSplit>(kFlags, ja, v, t.c0 + cb, args.tile_n - cb, valid, res_smem, out_smem, half * 4,
-                                         swz, pix, rpix, gpix, g, shift_j);
+                                         swz, pix, rpix, gpix, g, shift_j, kPreRes ? pre_hi : nullptr, pre_lo);
           }
+          if (kPreRes && sub + 1 < n_sub) prefetch_res(t, sub + 1);
           if (aux_on) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&ctl->aux_empty[aux]);
@@ -424,7 +449,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           sbuf ^= 1;
         } else if (cols_live) {
           epilogue_chunk<false, false, kSplit>(kFlags, ja, v, t.c0 + cb, args.tile_n - cb, valid, 0, 0, 0, 0, pix, rpix, gpix, g,
-                                        shift_j);
+                                        shift_j, kPreRes ? pre_hi : nullptr, pre_lo);
+          if (kPreRes && sub + 1 < n_sub) prefetch_res(t, sub + 1);
         }
       }
       if (publish && !tile_tma) {

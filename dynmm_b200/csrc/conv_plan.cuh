@@ -189,7 +189,8 @@ template <bool kTma, bool kCg, bool kSplit = false>
 __device__ __forceinline__ void epilogue_chunk(const int kFlags, const KernelArgs& args, const uint32_t (&v)[32], int c_first,
                                                int cols_left, bool valid, uint32_t res_smem, uint32_t out_smem,
                                                uint32_t chunk0, uint32_t swz, size_t pix, size_t rpix, size_t gpix,
-                                               float g, const float* shift_smem) {
+                                               float g, const float* shift_smem, const uint4* pre_hi = nullptr,
+                                               const uint4* pre_lo = nullptr) {
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     const int c = c_first + j;
@@ -218,9 +219,15 @@ __device__ __forceinline__ void epilogue_chunk(const int kFlags, const KernelArg
           r = valid ? ld_feat<kCg>(args.residual + rpix * args.res_ld + c) : make_uint4(0, 0, 0, 0);
         }
         if (kSplit) {
-          // fp32-grade residual = hi + lo, reconstructed before it is added (read from global in both epilogue flavours)
-          const uint4 q = valid ? ld_feat<kCg>(args.residual + rpix * args.res_ld + (args.res_ld >> 1) + c)
-                                : make_uint4(0, 0, 0, 0);
+          // fp32-grade residual = hi + lo, reconstructed before it is added; both halves come from global memory --
+          // prefetched into registers by the caller (pre_hi / pre_lo: this thread's four 8-channel groups) or loaded here
+          uint4 q;
+          if (pre_hi != nullptr) {
+            r = pre_hi[j >> 3];
+            q = pre_lo[j >> 3];
+          } else {
+            q = valid ? ld_feat<kCg>(args.residual + rpix * args.res_ld + (args.res_ld >> 1) + c) : make_uint4(0, 0, 0, 0);
+          }
           f[0] += bf16_lo(r.x) + bf16_lo(q.x); f[1] += bf16_hi(r.x) + bf16_hi(q.x);
           f[2] += bf16_lo(r.y) + bf16_lo(q.y); f[3] += bf16_hi(r.y) + bf16_hi(q.y);
           f[4] += bf16_lo(r.z) + bf16_lo(q.z); f[5] += bf16_hi(r.z) + bf16_hi(q.z);
@@ -352,7 +359,7 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
   DYNMM_CHECK_ARG(!p->gated || (p->gated_ld % 8 == 0 && p->gate), "conv_igemm: gated needs gate[] and gated_ld %% 8");
   DYNMM_CHECK_ARG(p->n >= 1 && p->n_in >= 1, "conv_igemm: empty batch");
   DYNMM_CHECK_ARG(!split || (p->c_in % kBlockK == 0 && p->in_ld % 16 == 0 && p->in_ld >= 2 * p->c_in && p->out_ld % 16 == 0 &&
-                             p->out_ld >= 2 * p->c_out && p->res_ld % 16 == 0 && p->gated_ld % 16 == 0 && !p->trace &&
+                             p->out_ld >= 2 * p->c_out && p->res_ld % 16 == 0 && p->gated_ld % 16 == 0 &&
                              !p->in_flags.flags && !p->out_flags.flags),
                   "conv_igemm: DYNMM_CONV_SPLIT needs c_in %% 64 == 0 and [hi | lo] tensors (ld >= 2 * c, ld %% 16 == 0)");
   const int h_exp = (p->h_in + 2 * p->pad_h - p->kh) / p->stride_h + 1;

@@ -273,7 +273,7 @@ __global__ void upsample2x_dw_nhwc_kernel(const __nv_bfloat16* __restrict__ in, 
 // thread (16 FMAs per channel instead of 36) and stores 4 x 8 bytes; the per-pixel kernel above re-loads 9 inputs
 // and 18 weight vectors for every 16-byte store.
 constexpr int kUpStripRows = 8;      // longest strip; short maps use shorter strips so that the grid still fills the GPU
-template <bool kSkip>
+template <bool kSkip, bool kSplit = false>       // kSplit: in / skip / out are [hi | lo] halves with pitch 2c (f32x3 mode)
 __global__ void __launch_bounds__(256)
 upsample2x_dw_nhwc_strip_kernel(const __nv_bfloat16* __restrict__ in, int h, int w, int c,
                                 const float* __restrict__ wgt, const float* __restrict__ bias,
@@ -298,14 +298,19 @@ upsample2x_dw_nhwc_strip_kernel(const __nv_bfloat16* __restrict__ in, int h, int
     st[2][0][ch] = k[0] + k[3];        st[2][1][ch] = (k[1] + k[2]) + (k[4] + k[5]); st[2][2][ch] = k[6];    st[2][3][ch] = k[7] + k[8];
     st[3][0][ch] = (k[0] + k[1]) + (k[3] + k[4]); st[3][1][ch] = k[2] + k[5]; st[3][2][ch] = k[6] + k[7];    st[3][3][ch] = k[8];
   }
-  const __nv_bfloat16* base = in + static_cast<size_t>(s) * h * w * c + c4;
+  const int ld = kSplit ? 2 * c : c;
+  const __nv_bfloat16* base = in + static_cast<size_t>(s) * h * w * ld + c4;
   auto load_row = [&](int y, float (&r)[3][4]) {        // columns x-1, x, x+1 of input row y (zeros outside)
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const int xx = x + j - 1;
-      uint2 v = make_uint2(0u, 0u);
-      if (y >= 0 && y < h && xx >= 0 && xx < w) v = __ldg(reinterpret_cast<const uint2*>(base + (static_cast<size_t>(y) * w + xx) * c));
-      r[j][0] = bf16_lo(v.x); r[j][1] = bf16_hi(v.x); r[j][2] = bf16_lo(v.y); r[j][3] = bf16_hi(v.y);
+      uint2 v = make_uint2(0u, 0u), q = make_uint2(0u, 0u);
+      if (y >= 0 && y < h && xx >= 0 && xx < w) {
+        v = __ldg(reinterpret_cast<const uint2*>(base + (static_cast<size_t>(y) * w + xx) * ld));
+        if (kSplit) q = __ldg(reinterpret_cast<const uint2*>(base + (static_cast<size_t>(y) * w + xx) * ld + c));
+      }
+      r[j][0] = bf16_lo(v.x) + bf16_lo(q.x); r[j][1] = bf16_hi(v.x) + bf16_hi(q.x);
+      r[j][2] = bf16_lo(v.y) + bf16_lo(q.y); r[j][3] = bf16_hi(v.y) + bf16_hi(q.y);
     }
   };
   float up[3][4], mid[3][4], dn[3][4];
@@ -325,15 +330,25 @@ upsample2x_dw_nhwc_strip_kernel(const __nv_bfloat16* __restrict__ in, int h, int
     }
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-      const size_t oo = ((static_cast<size_t>(s) * H + 2 * y + (p >> 1)) * W + 2 * x + (p & 1)) * c + c4;
+      const size_t oo = ((static_cast<size_t>(s) * H + 2 * y + (p >> 1)) * W + 2 * x + (p & 1)) * ld + c4;
       if (kSkip) {
         const uint2 v = __ldg(reinterpret_cast<const uint2*>(skip + oo));
         o[p][0] += bf16_lo(v.x); o[p][1] += bf16_hi(v.x); o[p][2] += bf16_lo(v.y); o[p][3] += bf16_hi(v.y);
+        if (kSplit) {
+          const uint2 q = __ldg(reinterpret_cast<const uint2*>(skip + oo + c));
+          o[p][0] += bf16_lo(q.x); o[p][1] += bf16_hi(q.x); o[p][2] += bf16_lo(q.y); o[p][3] += bf16_hi(q.y);
+        }
       }
       uint2 ov;
       ov.x = pack_bf16(o[p][0], o[p][1]);
       ov.y = pack_bf16(o[p][2], o[p][3]);
       *reinterpret_cast<uint2*>(out + oo) = ov;
+      if (kSplit) {
+        uint2 lv;
+        lv.x = pack_bf16(o[p][0] - bf16_lo(ov.x), o[p][1] - bf16_hi(ov.x));
+        lv.y = pack_bf16(o[p][2] - bf16_lo(ov.y), o[p][3] - bf16_hi(ov.y));
+        *reinterpret_cast<uint2*>(out + oo + c) = lv;
+      }
     }
 #pragma unroll
     for (int j = 0; j < 3; ++j)
@@ -783,7 +798,20 @@ int upsample2x_impl(const void* in, int n, int h, int w, int c, const float* wei
   DYNMM_CHECK_ARG(!(out_nhwc_bf16 && (out_nchw_f32 || labels)) && (out_nhwc_bf16 || out_nchw_f32 || labels),
                   "upsample2x: either the NHWC output, or the NCHW logits and/or the arg-max labels");
   DYNMM_CHECK_ARG(!labels || c <= 256, "upsample2x: labels are uint8");
-  if (out_nhwc_bf16 && split) {
+  if (out_nhwc_bf16 && split && n <= 65535 && getenv("DYNMM_UPSAMPLE") == nullptr) {
+    int rows = kUpStripRows;
+    while (rows > 1 && 1LL * ceil_div(w * (c / 4), 256) * ceil_div(h, rows) * n < 4LL * num_sms()) rows >>= 1;
+    dim3 grid(ceil_div(w * (c / 4), 256), ceil_div(h, rows), n);
+    if (skip) {
+      upsample2x_dw_nhwc_strip_kernel<true, true><<<grid, 256, 0, stream>>>(
+          static_cast<const __nv_bfloat16*>(in), h, w, c, weight, bias, static_cast<const __nv_bfloat16*>(skip),
+          static_cast<__nv_bfloat16*>(out_nhwc_bf16), rows);
+    } else {
+      upsample2x_dw_nhwc_strip_kernel<false, true><<<grid, 256, 0, stream>>>(
+          static_cast<const __nv_bfloat16*>(in), h, w, c, weight, bias, nullptr, static_cast<__nv_bfloat16*>(out_nhwc_bf16),
+          rows);
+    }
+  } else if (out_nhwc_bf16 && split) {
     const long long total = 1LL * n * 4 * h * w * (c / 8);
     upsample2x_dw_nhwc_split_kernel<<<grid_for(total, 256, 16), 256, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(in), n, h, w, c, weight, bias, static_cast<const __nv_bfloat16*>(skip),

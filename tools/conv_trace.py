@@ -15,17 +15,24 @@ def main():
     for name, n, h, w, cin, cout, kh, kw, stride, res in SHAPES:
         if only and only not in name:
             continue
-        x = torch.randn(n, h, w, cin, device=dev).to(torch.bfloat16)
-        wt = ops.pack_conv_weight(torch.randn(cout, cin, kh, kw, device=dev) * 0.05)
+        split = os.environ.get("SPLIT") == "1"          # fp32-grade operands ([hi | lo] halves, K = 3 * c_in)
+        if split:
+            x = ops.split_from_f32(torch.randn(n, h, w, cin, device=dev))
+            wt, _ = ops.fold_pack_conv(torch.randn(cout, cin, kh, kw, device=dev) * 0.05, None, None, split=True)
+        else:
+            x = torch.randn(n, h, w, cin, device=dev).to(torch.bfloat16)
+            wt = ops.pack_conv_weight(torch.randn(cout, cin, kh, kw, device=dev) * 0.05)
         ho = (h + 2 * (kh // 2) - kh) // stride[0] + 1
         wo = (w + 2 * (kw // 2) - kw) // stride[1] + 1
         r = torch.randn(n, ho, wo, cout, device=dev).to(torch.bfloat16) if res else None
+        if split and res:
+            r = ops.split_from_f32(torch.randn(n, ho, wo, cout, device=dev))
         sh = torch.randn(cout, device=dev)
-        out = torch.empty(n, ho, wo, cout, dtype=torch.bfloat16, device=dev)
+        out = torch.empty(n, ho, wo, cout * (2 if split else 1), dtype=torch.bfloat16, device=dev)
         trace = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
         dual = {"0": False, "1": True}.get(os.environ.get("DUAL", ""), None)
         kw_ = dict(c_out=cout, kh=kh, kw=kw, stride=stride, pad=(kh // 2, kw // 2), shift=sh, residual=r, relu=True,
-                   out=out, dual=dual)
+                   out=out, dual=dual, split=split, c_in=cin)
         for _ in range(3):
             ops.conv(x, wt, **kw_)
         ops.conv(x, wt, trace=trace, **kw_)

@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--noises", default="0,0.3,0.6,1.0")
     ap.add_argument("--labels", action="store_true", help="predict_labels (arg-max fused, no logits written)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--precision", default="f32x3", choices=["bf16", "f32x3"], help="engine arithmetic (see bench.py)")
     args = ap.parse_args()
 
     import torch.distributed as dist
@@ -49,6 +50,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     model = bench.build_model().to(dev)
+    model.engine_precision = args.precision
     model.use_cuda_graph = not args.no_graph
     total = args.batches * world
     # the same resident batch list on every rank (a rank only forwards its own share)
@@ -71,10 +73,12 @@ def main():
         if rank == 0:
             d = pt.as_dict()
             d.update({"n_gpus": world, "per_gpu_batch": args.batch, "height": bench.H, "width": bench.W,
+                      "dtype": args.precision,
                       "api": "predict_labels" if args.labels else "forward(test=True, return_weight=True)"})
             print(json.dumps(d))
     if rank == 0:
         print(json.dumps({"workload": "FusionDynMM robustness sweep (configs[4])", "mode": args.mode, "n_gpus": world,
+                          "dtype": args.precision,
                           "noises": noises, "images_per_s": [p.images_per_s for p in points],
                           "gate_branch_histograms": [p.histogram for p in points],
                           "flop_saved_pct": [p.saved_pct for p in points]}))

@@ -7,6 +7,7 @@ import torch
 import bench
 
 model = bench.build_model().cuda()
+model.engine_precision = os.environ.get("PRECISION", "f32x3")
 rgb, depth = (t.cuda() for t in bench.synthetic_batch(0, bench.BATCH))
 with torch.no_grad():
     for _ in range(3):
@@ -16,4 +17,4 @@ with torch.no_grad():
     out, w = model(rgb, depth, True, True)
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
-print("branches", w.argmax(1).tolist(), "launches", model.engine().launches)
+print("precision", model.engine_precision, "branches", w.argmax(1).tolist(), "launches", model.engine().launches)

@@ -29,16 +29,16 @@ conv = {"n": 0, "t": 0, "rd": 0, "wr": 0, "l2": 0, "tw": 0}
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["t"]):
     out.append(f"{k:50s} {a['n']:4d} {a['t']*1e6:8.1f} {100*a['t']/tot:5.1f}% {a['rd']/1e6:10.1f} {a['wr']/1e6:10.1f} "
                f"{a['l2']/1e6:9.1f} {(a['rd']+a['wr'])/a['t']/1e9:9.0f} {a['tw']/a['t'] if a['t'] else 0:7.1f}")
-    if "conv_igemm" in k:
+    if "conv_igemm" in k or "conv_chain" in k or "conv_pair" in k:
         for f in conv:
             conv[f] += a[f]
 out.append(f"{'TOTAL (serialised, cold L2 per launch)':50s} {sum(a['n'] for a in agg.values()):4d} {tot*1e6:8.1f}")
 out.append("")
-out.append(f"conv_igemm_kernel (all variants): {conv['n']} launches, {conv['t']*1e6:.1f} us ({100*conv['t']/tot:.1f}% of GPU time), "
+out.append(f"tensor-core conv kernels (conv_igemm / conv_pair / conv_chain, all variants): {conv['n']} launches, {conv['t']*1e6:.1f} us ({100*conv['t']/tot:.1f}% of GPU time), "
            f"DRAM {conv['rd']/1e6:.1f} MB read + {conv['wr']/1e6:.1f} MB written = {(conv['rd']+conv['wr'])/conv['n']/1e6:.2f} MB per launch, "
            f"L2 traffic {conv['l2']/1e6:.0f} MB, time-weighted tensor pipe active {conv['tw']/conv['t']:.1f}%")
 open(src.replace(".csv", "_summary.txt"), "w").write("\n".join(out) + "\n")
-json.dump({"kernel": "conv_igemm_kernel", "launches_per_step": conv["n"], "dram_bytes_per_launch": (conv["rd"] + conv["wr"]) / conv["n"],
+json.dump({"kernel": "conv_igemm_kernel + conv_pair_kernel + conv_chain_kernel", "launches_per_step": conv["n"], "dram_bytes_per_launch": (conv["rd"] + conv["wr"]) / conv["n"],
            "dram_read_bytes_per_step": conv["rd"], "dram_write_bytes_per_step": conv["wr"], "l2_bytes_per_step": conv["l2"],
            "tensor_pipe_active_pct_time_weighted": conv["tw"] / conv["t"], "kernel_time_s_per_step_serialized": conv["t"],
            "share_of_gpu_time": conv["t"] / tot,
