@@ -342,6 +342,36 @@ def conv_roofline(model, batch_tensors, step_s, precision, use_graph, dump_path=
             "step_s": step_s}
 
 
+def branch_sweep(model, rgb, depth, batch, reps: int = 40):
+    """the untrained gate's branch mix is synthetic, so also report the forced extremes -- every sample on
+    branch 0 (all four depth stages skipped: 40.6 % of the FLOPs), on branch 4 (nothing skipped) and a uniform mix --
+    one forward at a time (single stream, CUDA-graph replay), device-resident inputs."""
+    from dynmm_b200.fusion.graph import GraphedForward
+    eng = model.engine(rgb.device)
+    out = {}
+    cases = (("all_branch0", [0] * batch), ("uniform_0to4", [i % 5 for i in range(batch)]), ("all_branch4", [4] * batch))
+    for name, br in cases:
+        wk = torch.eye(5, device=rgb.device)[torch.tensor(br, device=rgb.device)].contiguous()
+        g = GraphedForward(eng, rgb, depth, dict(weight=wk))
+        for _ in range(3):
+            g(rgb, depth)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        gf = sum(GFLOP_BY_BRANCH[k] for k in br) / batch
+        out[name] = {"images_per_s": batch / ms * 1e3, "ms_per_step": ms, "gflop_per_image": gf,
+                     "flop_saved_pct": 100.0 * (1.0 - gf / GFLOP_BY_BRANCH[4])}
+        del g
+    out["note"] = ("forced gate decisions (weight one-hot per sample), single stream, graph replay; GFLOP per image from "
+                   "the conv-only table of SURVEY 8(d)")
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -352,6 +382,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-train", action="store_true", help="skip the data-parallel training-step leg (configs[2])")
     ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager-on-this-GPU baseline")
+    ap.add_argument("--no-modality", action="store_true",
+                    help="skip the ModalityDynMM forwards (configs[0] / configs[3], tools/modality_bench.py)")
     ap.add_argument("--in-flight", type=int, default=2,
                     help="forwards in flight per GPU: each on its own stream and captured-graph instance (1 = one "
                          "stream, strictly one batch after the other)")
@@ -524,10 +556,13 @@ def main():
     launches = model.engine(dev).launches
 
     # ---------------- roofline of the dominant kernel (rank 0, N=1 style instrumented pass)
-    roofline, cpu_base, eager = None, None, None
+    roofline, cpu_base, eager, sweep = None, None, None, None
     if rank == 0:
         roofline = conv_roofline(model, batches[0], t_dev / args.steps, args.precision, not args.no_graph,
                                  args.dump_launches)
+        if world == 1 and not args.no_graph:
+            with torch.no_grad():
+                sweep = branch_sweep(model, batches[0][0], batches[0][1], batch)
         if world == 1 and not args.no_eager:
             eager = gpu_eager_baselines(model, *batches[0])
             eager["ours_over_bf16_eager"] = value / eager["bf16"]["images_per_s"]
@@ -628,6 +663,17 @@ def main():
         cpu_base = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
                     "sample": "8 forwards of 8 images (480x640, eval, hard gate, fp32) after 1 warm-up"}
 
+    # ---------------- configs[0] / configs[3]: modality-level DynMM forwards next to their CPU restatement (own process)
+    modality = None
+    if rank == 0 and world == 1 and not args.no_modality and not args.no_cpu_baseline:
+        import subprocess
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "modality_bench.py")], capture_output=True,
+                               text=True, timeout=240)
+            modality = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")] or None
+        except Exception as e:          # a secondary figure: never fail the headline line over it
+            modality = {"error": str(e)[:200]}
+
     if rank == 0:
         h = hist.tolist()
         tot = max(sum(h), 1)
@@ -665,9 +711,11 @@ def main():
             "gpu_launches_per_step": launches,
             "clocks": clocks,
             "roofline": roofline,
+            "branch_sweep": sweep,
             ("bf16" if args.precision == "f32x3" else "f32x3"): other,
             "gpu_eager_baseline": eager,
             "train": train,
+            "modality": modality,
             "cpu_baseline": cpu_base,
         }
         print(json.dumps(line))
