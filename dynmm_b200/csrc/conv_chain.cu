@@ -106,13 +106,6 @@ __device__ __forceinline__ void st_release_gpu(int32_t* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
 
-// global -> shared bulk copy (16-byte multiples) completing on an mbarrier
-__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst),
-               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
 // mbarrier wait with a watchdog: a broken dependency traps (the launch fails) instead of hanging the GPU
 __device__ __forceinline__ void chain_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
