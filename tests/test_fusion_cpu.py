@@ -139,3 +139,21 @@ def test_conv_program_recorder_phases():
     with pytest.raises(_lib.DynmmError):
         prog._record(_lib.ConvParams(), (None,) * 12)
     assert prog.phases == [0, 0, 0, 1, 1, 1, 1]
+
+
+def test_chain_layer_lists_follow_the_block_structure():
+    """ops.nbt1d_chain_layers (host logic of dynmm_conv_chain_*): taps alternate 3x1 / 1x3, the fourth convolution of
+    a block adds the block input (chain input for the first block, the stored block output afterwards) and stores its
+    output; with drop_last the gated last convolution is left out and the layer before it is stored separately."""
+    from dynmm_b200 import ops
+    blocks = [[(f"w{b}{i}", f"s{b}{i}", True) for i in range(4)] for b in range(3)]
+    full = ops.nbt1d_chain_layers(blocks)
+    assert len(full) == 12
+    assert [l[2] for l in full] == [True, False] * 6                       # taps_h
+    assert [l[4] for l in full] == [0, 0, 0, 1, 0, 0, 0, 2, 0, 0, 0, 2]    # residual source
+    assert [l[5] for l in full] == [0, 0, 0, 1] * 3                        # stored to `out`
+    cut = ops.nbt1d_chain_layers(blocks, drop_last=True)
+    assert len(cut) == 11 and cut[-1][0] == "w22" and cut[-1][5] == 2 and cut[-1][4] == 0
+    assert [l[5] for l in cut[:-1]] == [0, 0, 0, 1, 0, 0, 0, 1, 0, 0]
+    one = ops.nbt1d_chain_layers(blocks[:1], drop_last=True)               # a two-block stage: nothing stored to `out`
+    assert [l[5] for l in one] == [0, 0, 2]
