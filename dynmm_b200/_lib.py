@@ -94,6 +94,8 @@ SIGNATURES = {
     "dynmm_global_gate_workspace": (c_longlong, [c_int, c_int, c_int]),
     "dynmm_global_gate_logits": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [c_void_p] * 7
                                  + [c_void_p, c_void_p, c_void_p]),
+    "dynmm_global_gate_decide": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [c_void_p] * 7
+                                 + [c_void_p, c_float, c_int] + [c_void_p] * 8),
     "dynmm_stem_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int] + [c_void_p] * 6 + [c_void_p] * 4
                        + [c_void_p] * 3 + [c_void_p]),
     "dynmm_stem_gap_tiles": (c_longlong, [c_int, c_int, c_int]),

@@ -234,7 +234,20 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int split
     float s[kTaps];
 #pragma unroll
     for (int t = 0; t < kTaps; ++t) s[t] = 0.f;
-    for (int k = 0; k < splits; ++k) {
+    // four splits' loads in flight per step (the adds stay in split order: same rounding as the plain loop)
+    int k = 0;
+    for (; k + 4 <= splits; k += 4) {
+      float v[4][kTaps];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int t = 0; t < kTaps; ++t) v[u][t] = (t < taps) ? __ldg(partial + (k + u) * per + t * plane + i) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int t = 0; t < kTaps; ++t) s[t] += v[u][t];
+    }
+    for (; k < splits; ++k) {
 #pragma unroll
       for (int t = 0; t < kTaps; ++t) {
         if (t < taps) s[t] += __ldg(partial + k * per + t * plane + i);

@@ -253,6 +253,93 @@ __global__ void gate_plan_kernel(const float* __restrict__ weight, int b, float*
   }
 }
 
+// ---------------------------------------------------------------- GAP finish + fc + DiffSoftmax + plan in one launch
+// The tail of the gate (gate_head_kernel -> diffsoftmax_fwd_kernel -> gate_plan_kernel, three launches of a few
+// microseconds each on the critical path in front of the depth encoder) as ONE single-block kernel: thread n does the
+// arithmetic of sample n with exactly the operations and the order of the three kernels, then thread 0 sorts.
+__global__ void gate_decide_kernel(const float* __restrict__ partial, int blocks, float area, const float* __restrict__ wfc,
+                                   int b, float tau, int hard, float* __restrict__ logits, float* __restrict__ weight,
+                                   float* __restrict__ g, int32_t* __restrict__ perm, int32_t* __restrict__ slot,
+                                   int32_t* __restrict__ count, long long* __restrict__ hist) {
+  extern __shared__ int s_need[];   // [b]
+  for (int n = threadIdx.x; n < b; n += blockDim.x) {
+    float mean[kGateC];
+    for (int c = 0; c < kGateC; ++c) {
+      float s = 0.f;
+      for (int i = 0; i < blocks; ++i) s += partial[(1LL * n * blocks + i) * kGateC + c];
+      mean[c] = s / area;
+    }
+    float z[5];
+    float m = -INFINITY;
+    for (int k = 0; k < 5; ++k) {
+      float s = 0.f;
+#pragma unroll
+      for (int ci = 0; ci < kGateC; ++ci) s = fmaf(mean[ci], wfc[k * kGateC + ci], s);
+      logits[n * 5 + k] = s;
+      z[k] = s / tau;
+      m = fmaxf(m, z[k]);
+    }
+    float sum = 0.f;
+    for (int k = 0; k < 5; ++k) {
+      z[k] = expf(z[k] - m);
+      sum += z[k];
+    }
+    int best = 0;
+    float bestv = -1.f;
+    for (int k = 0; k < 5; ++k) {
+      z[k] = z[k] / sum;
+      if (z[k] > bestv) {
+        bestv = z[k];
+        best = k;
+      }
+    }
+    float w[5];
+    for (int k = 0; k < 5; ++k) {
+      w[k] = hard ? (k == best ? 1.f : 0.f) : z[k];
+      weight[n * 5 + k] = w[k];
+    }
+    const float g1 = 1.f - w[0];
+    const float g2 = 1.f - (w[0] + w[1]);
+    const float g3 = 1.f - ((w[0] + w[1]) + w[2]);
+    const float g4 = w[4];
+    g[0 * b + n] = g1;
+    g[1 * b + n] = g2;
+    g[2 * b + n] = g3;
+    g[3 * b + n] = g4;
+    int need = 0;
+    if (g1 != 0.f) need = 1;
+    if (g2 != 0.f) need = 2;
+    if (g3 != 0.f) need = 3;
+    if (g4 != 0.f) need = 4;
+    s_need[n] = need;
+    if (hist) {
+      int hb = 0;
+      float bv = w[0];
+      if (w[1] > bv) { bv = w[1]; hb = 1; }
+      if (w[2] > bv) { bv = w[2]; hb = 2; }
+      if (w[3] > bv) { bv = w[3]; hb = 3; }
+      if (w[4] > bv) { bv = w[4]; hb = 4; }
+      atomicAdd(reinterpret_cast<unsigned long long*>(hist + hb), 1ULL);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int pos = 0;
+    int cnt[4] = {0, 0, 0, 0};
+    for (int need = 4; need >= 0; --need) {
+      for (int i = 0; i < b; ++i) {
+        if (s_need[i] == need) {
+          perm[pos] = i;
+          slot[i] = pos;
+          ++pos;
+        }
+      }
+      if (need >= 1) cnt[need - 1] = pos;
+    }
+    for (int s = 0; s < 4; ++s) count[s] = cnt[s];
+  }
+}
+
 }  // namespace
 }  // namespace dynmm
 
@@ -302,6 +389,57 @@ extern "C" long long dynmm_global_gate_workspace(int b, int h, int w) {
   const long long conv1 = 1LL * b * h1 * w1 * kGateC * sizeof(float);
   const long long partial = 1LL * b * ceil_div(h2 * w2, 128) * kGateC * sizeof(float);
   return conv1 + partial + 256;
+}
+
+namespace {
+// conv1 + conv2/GAP launches shared by the two entry points; *partial_out / *blocks_out: the GAP partial sums
+int gate_convs(const float* rgb, const float* depth, int b, int h, int w, const float* w1p, const float* scale1,
+               const float* shift1, const float* w2p, const float* scale2, const float* shift2, void* work,
+               float** partial_out, int* blocks_out, float* area_out, cudaStream_t stream) {
+  int h1, w1, h2, w2;
+  gate_dims(h, w, &h1, &w1, &h2, &w2);
+  DYNMM_CHECK_ARG(b >= 1 && h1 >= 5 && w1 >= 5, "global_gate: feature map %dx%d too small", h, w);
+  float* conv1 = static_cast<float*>(work);
+  const long long conv1_bytes = (1LL * b * h1 * w1 * kGateC * sizeof(float) + 255) / 256 * 256;
+  float* partial = reinterpret_cast<float*>(static_cast<char*>(work) + conv1_bytes);
+  const int smem1 = kGateC * kTaps * 128 * sizeof(float);
+  static PerDeviceOnce attr_once;
+  DYNMM_CUDA(attr_once.run([] {
+    return cudaFuncSetAttribute(gate_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGateC * kTaps * 128 * 4);
+  }));
+  const long long items = 1LL * b * h1 * ceil_div(w1, kPx);
+  int grid1 = 2 * num_sms();
+  if (grid1 > ceil_div_ll(items, 8)) grid1 = (int)ceil_div_ll(items, 8);
+  gate_conv1_kernel<<<grid1, 256, smem1, stream>>>(rgb, depth, b, h, w, h1, w1, w1p, scale1, shift1, conv1);
+  DYNMM_LAUNCH_CHECK();
+  const int blocks2 = ceil_div(h2 * w2, 128);
+  gate_conv2_gap_kernel<<<dim3(blocks2, b), 128, 0, stream>>>(conv1, h1, w1, h2, w2, w2p, scale2, shift2, partial);
+  DYNMM_LAUNCH_CHECK();
+  *partial_out = partial;
+  *blocks_out = blocks2;
+  *area_out = (float)(h2 * w2);
+  return DYNMM_OK;
+}
+}  // namespace
+
+extern "C" int dynmm_global_gate_decide(const float* rgb, const float* depth, int b, int h, int w, const float* w1p,
+                                        const float* scale1, const float* shift1, const float* w2p,
+                                        const float* scale2, const float* shift2, const float* wfc, void* work,
+                                        float tau, int hard, float* logits, float* weight, float* g, int32_t* perm,
+                                        int32_t* slot, int32_t* count, long long* hist, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DYNMM_CHECK_ARG(rgb && depth && w1p && w2p && wfc && work && logits && weight && g && perm && slot && count,
+                  "global_gate_decide: null pointer");
+  DYNMM_CHECK_ARG(b <= 8192, "global_gate_decide: batch too large");
+  float* partial = nullptr;
+  int blocks2 = 0;
+  float area = 0.f;
+  int rc = gate_convs(rgb, depth, b, h, w, w1p, scale1, shift1, w2p, scale2, shift2, work, &partial, &blocks2, &area, stream);
+  if (rc) return rc;
+  gate_decide_kernel<<<1, 128, b * sizeof(int), stream>>>(partial, blocks2, area, wfc, b, tau, hard, logits, weight, g, perm,
+                                                         slot, count, hist);
+  DYNMM_LAUNCH_CHECK();
+  return DYNMM_OK;
 }
 
 extern "C" int dynmm_global_gate_logits(const float* rgb, const float* depth, int b, int h, int w, const float* w1p,

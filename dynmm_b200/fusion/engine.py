@@ -619,13 +619,14 @@ class FusionEngine:
         side.wait_event(fork)
         with torch.cuda.stream(side if gate_on_side else main):
             if learned:
+                # GlobalGate + DiffSoftmax + plan: two convolutions and one decision kernel
                 gw = self.gate
-                logits = ops.global_gate_logits(r32, d32, gw["w1"], gw["s1"], gw["b1"], gw["w2"], gw["s2"], gw["b2"],
-                                                gw["wfc"])
-                weight, _, _ = ops.diffsoftmax_fwd(logits, temp, hard_gate)
-                self.launches += 4
-            plan = ops.gate_plan(weight, hist=hist)
-        self.launches += 1
+                weight, plan, _ = ops.global_gate_decide(r32, d32, gw["w1"], gw["s1"], gw["b1"], gw["w2"], gw["s2"],
+                                                         gw["b2"], gw["wfc"], temp, hard_gate, hist=hist)
+                self.launches += 3
+            else:
+                plan = ops.gate_plan(weight, hist=hist)
+                self.launches += 1
         keep += [r32, d32, r16, d16, weight, plan]
 
         self.programs = []

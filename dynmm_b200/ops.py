@@ -708,6 +708,28 @@ def global_gate_logits(rgb32: Tensor, depth32: Tensor, w1, scale1, shift1, w2, s
     return logits
 
 
+def global_gate_decide(rgb32: Tensor, depth32: Tensor, w1, scale1, shift1, w2, scale2, shift2, wfc, tau: float, hard: bool,
+                       hist: Optional[Tensor] = None):
+    """GlobalGate.forward + DiffSoftmax + the skip plan in three launches (dynmm_global_gate_decide)
+    -> (weight [b,5], GatePlan, logits [b,5])."""
+    lib = _lib.load()
+    _cuda(rgb32, depth32, hist)
+    b, h, w, _ = rgb32.shape
+    need = lib.dynmm_global_gate_workspace(b, h, w)
+    if need < 0:
+        raise _lib.DynmmError(f"global gate: feature map {h}x{w} too small for two 5x5/s2 convolutions")
+    work = torch.empty(need, dtype=torch.uint8, device=rgb32.device)
+    logits = torch.empty(b, 5, dtype=torch.float32, device=rgb32.device)
+    weight = torch.empty(b, 5, dtype=torch.float32, device=rgb32.device)
+    plan = GatePlan(b, rgb32.device)
+    check(lib.dynmm_global_gate_decide(ptr(rgb32), ptr(depth32), b, h, w, ptr(w1), ptr(scale1), ptr(shift1), ptr(w2),
+                                       ptr(scale2), ptr(shift2), ptr(wfc), ptr(work), float(tau), int(hard), ptr(logits),
+                                       ptr(weight), ptr(plan.g), ptr(plan.perm), ptr(plan.slot), ptr(plan.count), ptr(hist),
+                                       stream_ptr()), "global_gate_decide")
+    plan._work = work
+    return weight, plan, logits
+
+
 def diffsoftmax_fwd(logits: Tensor, tau: float, hard: bool):
     """-> (y, y_soft, index) ; logits [rows, n] fp32."""
     lib = _lib.load()

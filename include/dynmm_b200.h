@@ -83,6 +83,16 @@ int dynmm_global_gate_logits(const float* rgb, const float* depth, int b, int h,
                              const float* w2, const float* scale2, const float* shift2,
                              const float* wfc, void* work, float* logits, void* stream);
 
+/* The whole gate of an eval forward in three launches: the two convolutions of dynmm_global_gate_logits, then ONE
+ * kernel for GAP finish + fc + DiffSoftmax (tau, hard) + the plan of dynmm_gate_plan -- the arithmetic and its order
+ * are those of the separate calls (same logits, same decisions), two launches fewer on the path in front of the depth
+ * encoder.  logits / weight [b,5]; g, perm, slot, count, hist as in dynmm_gate_plan. */
+int dynmm_global_gate_decide(const float* rgb, const float* depth, int b, int h, int w,
+                             const float* w1, const float* scale1, const float* shift1,
+                             const float* w2, const float* scale2, const float* shift2,
+                             const float* wfc, void* work, float tau, int hard, float* logits, float* weight,
+                             float* g, int32_t* perm, int32_t* slot, int32_t* count, long long* hist, void* stream);
+
 /* ------------------------------------------------------------------ stem */
 
 /* ResNet.forward_first_conv x2 + add + max_pool2d x2
