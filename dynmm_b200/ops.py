@@ -370,12 +370,12 @@ def conv_chain(jobs: Sequence[dict], *, flags: Optional[Tensor] = None, trace: O
         pj.count_settled = int(bool(j.get("count_settled", False)) and j.get("count") is not None)
         outs.append((out, last))
         prof_jobs.append((h * w * c * c * 3 * img.n_layers, x.shape[0], j.get("count")))
-        keep += [x, out, last]
+        keep.append(x)
     if CONV_PROFILER is not None:
         CONV_PROFILER(lambda: check(lib.dynmm_conv_chain_fwd(ctypes.byref(p), stream_ptr()), "conv_chain"), prof_jobs)
     else:
         check(lib.dynmm_conv_chain_fwd(ctypes.byref(p), stream_ptr()), "conv_chain")
-    for o in outs:                      # the scratch buffer must outlive the launch: tie it to the results
+    for o in outs:                      # scratch / flags must outlive the launch: tie them (not the results: no cycle) to it
         for t in o:
             if t is not None:
                 t._dynmm_keep = keep
