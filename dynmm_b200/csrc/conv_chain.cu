@@ -10,7 +10,9 @@
 //     contiguous bytes, SBO = 128, LBO = plane_bytes), so the A operand of a tap is the same buffer with the start
 //     address moved by one slot (1x3) or one padded row (3x1): no im2col, no halo copies, any strip shape.  Column W
 //     of every row is a permanent zero slot (it is both the right padding of its row and the left padding of the
-//     next), the rows above / below the image are zero-filled by the TMA load and never written;
+//     next), the rows above / below the image are written as zeros by the input load and never touched again;
+//     the input load itself is plain coalesced ld.global (lanes along the channels of a pixel) + st.shared, conflict
+//     free because plane_bytes = 16 (mod 128) -- a TMA box with a 16-byte inner extent was 3x slower;
 //   * the M tile is 128 consecutive slots (a strip is `tiles` of them), N = all c output channels in one UMMA
 //     (128 x c x 16), accumulators in TMEM (tiles * c <= 512 columns);
 //   * weights stream through a TMA pipeline ([c][64] SWIZZLE_128B tiles, one per (k chunk, tap)), prefetched across
@@ -19,8 +21,10 @@
 //     the layer has retired), plus global copies where the caller wants them (block outputs: the residual of the
 //     next block, the result);
 //   * a 3x1 layer needs the last row of the strip above and the first row of the strip below: the producer layer
-//     writes its edge rows to a global scratch buffer, publishes a per-strip counter (release), the neighbours poll
-//     it (acquire) and copy the rows into their halo slots.  Strips of other samples never wait for each other.
+//     writes its edge rows to a global scratch buffer and every epilogue warp adds 1 to the strip's counter (release,
+//     gpu scope); the neighbours poll it (acquire) until it reaches 8 or 16 per exchange, copy the rows into their halo
+//     slots and arrive on an mbarrier only the MMA issuer waits on.  Strips of other samples never wait for each other;
+//     the last strip of a sample to finish clears the counters (the launch is idempotent, CUDA-graph replayable).
 //
 // Accumulation order per output element is (k chunk, tap, k16) and the epilogue arithmetic is that of
 // conv_igemm.cu: results are bit-identical to the per-layer launches (tests/test_gpu_chain.py).

@@ -174,8 +174,8 @@ class FusionEngine:
             raise NotImplementedError("fuse_depth_in_rgb_encoder must be 'add' or 'SE-add', got " + str(cfg.fuse))
         if cfg.upsampling != "learned-3x3-zeropad":
             raise NotImplementedError("the CUDA engine implements upsampling='learned-3x3-zeropad'")
-        if "ppm" not in cfg.context_module or cfg.context_module == "ppm-1-2-4-8" or "appm" in cfg.context_module:
-            raise NotImplementedError("the CUDA engine implements context_module='ppm' (bins 1,5)")
+        if "ppm" not in cfg.context_module or "appm" in cfg.context_module:
+            raise NotImplementedError("the CUDA engine implements context_module='ppm' (bins 1,5) and 'ppm-1-2-4-8'")
         if cfg.precision not in ("bf16", "f32x3"):
             raise ValueError("EngineConfig.precision must be 'bf16' or 'f32x3'")
         self.split = cfg.precision == "f32x3"
@@ -220,7 +220,10 @@ class FusionEngine:
         self.stage_channels = [st[-1].convs[-1].c_out for st in self.stages["encoder_rgb"]]
         self.skips = [p.conv_bn_act(f"skip_layer{i}.0", 1) if f"skip_layer{i}.0.conv.weight" in sd else None
                       for i in (1, 2, 3)]
-        self.ppm = [p.conv_bn_act(f"context_module.features.{i}.1", 1) for i in range(2)]
+        # pyramid pooling bins (context_modules.py:28-38): 'ppm' = (1, 5), 'ppm-1-2-4-8' = (1, 2, 4, 8)
+        self.ppm_bins = (1, 2, 4, 8) if cfg.context_module == "ppm-1-2-4-8" else (1, 5)
+        self.ppm = [p.conv_bn_act(f"context_module.features.{i}.1", 1) for i in range(len(self.ppm_bins))]
+        self.ppm_c = sum(cv.c_out for cv in self.ppm)          # channels the branches add to the concat buffer
         self.ppm_final = p.conv_bn_act("context_module.final_conv", 1)
         self.dec = []
         for i in range(3):
@@ -633,7 +636,7 @@ class FusionEngine:
         skips = None
         if self.use_programs:
             c4 = self.stage_channels[3]
-            cat = torch.empty(b, h // 32, w // 32, c4 + 2 * self.ppm[0].c_out, dtype=torch.bfloat16, device=self.dev)
+            cat = torch.empty(b, h // 32, w // 32, c4 + self.ppm_c, dtype=torch.bfloat16, device=self.dev)
             fused, skips = self._encoder_program(r16, d16, plan, cat, keep)
         else:
             # ---- depth encoder on the side stream, in slot order, prefix-counted
@@ -690,7 +693,7 @@ class FusionEngine:
                     if s == 3:
                         # stage-4 output lands directly in the pyramid-pooling concat buffer
                         c4 = self.stage_channels[3]
-                        cat = torch.empty(b, h // 32, w // 32, (c4 + 2 * self.ppm[0].c_out) * (2 if self.split else 1),
+                        cat = torch.empty(b, h // 32, w // 32, (c4 + self.ppm_c) * (2 if self.split else 1),
                                           dtype=torch.bfloat16, device=self.dev)
                     if self.se is None:
                         last_kw = dict(gated=depth_out[s], gate=plan.g[s], gated_slot=plan.slot)
@@ -707,7 +710,7 @@ class FusionEngine:
             for s in range(split, 4):                   # merged launches (the stage-1 join ordered main after side)
                 if s == 3:
                     c4 = self.stage_channels[3]
-                    cat = torch.empty(b, h // 32, w // 32, (c4 + 2 * self.ppm[0].c_out) * (2 if self.split else 1),
+                    cat = torch.empty(b, h // 32, w // 32, (c4 + self.ppm_c) * (2 if self.split else 1),
                                       dtype=torch.bfloat16, device=self.dev)
                 r, d = self._merged_stage(s, r, d, plan, keep, cat)
                 fused.append(r)
@@ -856,7 +859,7 @@ class FusionEngine:
                 last_kw = {}
                 if s == 3:
                     c4 = self.stage_channels[3]
-                    cat = torch.empty(b, h // 32, w // 32, c4 + 2 * self.ppm[0].c_out, dtype=torch.bfloat16, device=dev)
+                    cat = torch.empty(b, h // 32, w // 32, c4 + self.ppm_c, dtype=torch.bfloat16, device=dev)
                     last_kw.update(out=cat, out_c_off=0)
                 if rule != 0:
                     last_kw.update(gated=d, gate=g, gated_slot=gated_slot)
@@ -908,19 +911,19 @@ class FusionEngine:
         c4 = self.stage_channels[3]
         off = c4
         if self.use_programs:
-            pooled = [ops.adaptive_avgpool(cat, bins, c=c4) for bins in (1, 5)]
-            with ops.ConvProgram() as prog:          # the two pyramid branches are independent: one phase
-                ys = [self.ppm[i](pooled[i]) for i in range(2)]
+            pooled = [ops.adaptive_avgpool(cat, bins, c=c4) for bins in self.ppm_bins]
+            with ops.ConvProgram() as prog:          # the pyramid branches are independent: one phase
+                ys = [self.ppm[i](pooled[i]) for i in range(len(self.ppm_bins))]
             self.programs.append(prog)
             for y in ys:
                 ops.nearest_resize_into(y, cat, off)
                 off += y.shape[3]
             cat._dynmm_flags = None             # other kernels wrote into the buffer since the conv published its flags
             keep += pooled + ys
-            self.launches += 6
+            self.launches += 3 * len(self.ppm_bins)
         else:
             sp = self.split
-            for i, bins in enumerate((1, 5)):
+            for i, bins in enumerate(self.ppm_bins):
                 pooled = ops.adaptive_avgpool(cat, bins, c=c4, split=sp)
                 y = self.ppm[i](pooled)
                 ops.nearest_resize_into(y, cat, off, split=sp)

@@ -620,7 +620,7 @@ class SkipGateESANet(nn.Module):
 
     # ------------------------------------------------------------------ forward
     def _forward_eval_cuda(self, rgb, depth):
-        """Eval forward on CUDA tensors: the engine.  A CONFIGURATION the engine does not implement (swish, ppm-1-2-4-8,
+        """Eval forward on CUDA tensors: the engine.  A CONFIGURATION the engine does not implement (swish, appm,
         bilinear upsampling, mixed encoders, input not a multiple of 32, ...) is a NotImplementedError from the engine:
         such a model trained on the differentiable graph, so validation uses that graph too (one warning).  A missing
         library / wrong device is a DynmmError and always propagates -- there is no silent CPU or library fallback."""

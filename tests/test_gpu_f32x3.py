@@ -183,3 +183,30 @@ def test_full_size_batch_8_both_precisions_match_oracle():
         err16 = _rel_l2(out16.cpu(), ref["out"])
         assert err16 <= 2e-2, f"bf16: relative L2 {err16:.2e}"
     print(f"480x640 x 8 vs oracle: f32x3 {err:.1e} (arg-max agreement {agree:.5f}), bf16 {err16:.1e}")
+
+
+def test_ppm_1_2_4_8_context_module_on_the_engine():
+    """context_module='ppm-1-2-4-8' (context_modules.py:28-38: four pooling branches) runs on the engine in both
+    precisions; the comparison is the module's own fp32 PyTorch graph on the same weights (the oracle restates 'ppm')."""
+    from dynmm_b200.fusion import SkipGateESANet
+    from oracle.make_golden import sample_inputs
+    torch.manual_seed(3)
+    model = SkipGateESANet(height=96, width=128, num_classes=40, context_module="ppm-1-2-4-8").cuda().eval()
+    g = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+                m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+        model.gate_layer.fc.weight.mul_(40.0)
+    model.hard_gate = True
+    rgb, depth = (t.cuda() for t in sample_inputs(5, 4, 96, 128))
+    with torch.no_grad():
+        ref, w_ref = model._forward_torch(rgb, depth)          # eval mode: (logits, gate weight)
+        for precision, tol in (("f32x3", F32_TOL), ("bf16", 2e-2)):
+            model.engine_precision = precision
+            out, w = model(rgb, depth, True, True)
+            assert getattr(model, "_engine_unsupported", None) is None and model.engine().ppm_bins == (1, 2, 4, 8)
+            assert torch.equal(w, w_ref)
+            err = _rel_l2(out, ref)
+            assert err <= tol, f"{precision}: relative L2 {err:.2e}"
