@@ -133,6 +133,10 @@ SIGNATURES = {
     "dynmm_split_from_f32": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
     "dynmm_upsample2x_dw3x3_split": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p, c_void_p]),
+    "dynmm_upsample2x_dw3x3_ex": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_int, c_void_p]),
+    "dynmm_bilinear_resize_into": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                           c_void_p]),
     "dynmm_adaptive_avgpool_split": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dynmm_nearest_resize_into_split": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                                 c_void_p]),

@@ -216,9 +216,12 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ i
 // Each output pixel (Y,X) reads the 3x3 neighbourhood of the nearest-upsampled map, i.e. input
 // pixels ((Y+dy)>>1, (X+dx)>>1); the 4x larger intermediate of the reference never exists.
 // NHWC variant: a thread owns 8 channels of one output pixel (16-byte loads/stores).
+// `clamp`: replication padding of the up-sampled map (Upsample 'learned-3x3' / the fixed bilinear stencil, model.py:
+// 372-399) instead of zero padding -- out-of-range taps read the border pixel.
 __global__ void upsample2x_dw_nhwc_kernel(const __nv_bfloat16* __restrict__ in, int n, int h, int w, int c,
                                           const float* __restrict__ wgt, const float* __restrict__ bias,
-                                          const __nv_bfloat16* __restrict__ skip, __nv_bfloat16* __restrict__ out) {
+                                          const __nv_bfloat16* __restrict__ skip, __nv_bfloat16* __restrict__ out,
+                                          int clamp) {
   const int cv = c >> 3;
   const long long total = 1LL * n * 4 * h * w * cv;
   const int H = 2 * h, W = 2 * w;
@@ -234,11 +237,13 @@ __global__ void upsample2x_dw_nhwc_kernel(const __nv_bfloat16* __restrict__ in, 
     for (int e = 0; e < 8; ++e) acc[e] = bias ? bias[c8 + e] : 0.f;
 #pragma unroll
     for (int dy = -1; dy <= 1; ++dy) {
-      const int yy = Y + dy;
+      int yy = Y + dy;
+      if (clamp) yy = min(max(yy, 0), H - 1);
       if (yy < 0 || yy >= H) continue;
 #pragma unroll
       for (int dx = -1; dx <= 1; ++dx) {
-        const int xx = X + dx;
+        int xx = X + dx;
+        if (clamp) xx = min(max(xx, 0), W - 1);
         if (xx < 0 || xx >= W) continue;
         const uint4 v =
             __ldg(reinterpret_cast<const uint4*>(in + ((1LL * s * h + (yy >> 1)) * w + (xx >> 1)) * c + c8));
@@ -277,7 +282,8 @@ template <bool kSkip, bool kSplit = false>       // kSplit: in / skip / out are 
 __global__ void __launch_bounds__(256)
 upsample2x_dw_nhwc_strip_kernel(const __nv_bfloat16* __restrict__ in, int h, int w, int c,
                                 const float* __restrict__ wgt, const float* __restrict__ bias,
-                                const __nv_bfloat16* __restrict__ skip, __nv_bfloat16* __restrict__ out, int strip_rows) {
+                                const __nv_bfloat16* __restrict__ skip, __nv_bfloat16* __restrict__ out, int strip_rows,
+                                int clamp) {
   const int cg = c >> 2;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= w * cg) return;
@@ -300,10 +306,12 @@ upsample2x_dw_nhwc_strip_kernel(const __nv_bfloat16* __restrict__ in, int h, int
   }
   const int ld = kSplit ? 2 * c : c;
   const __nv_bfloat16* base = in + static_cast<size_t>(s) * h * w * ld + c4;
-  auto load_row = [&](int y, float (&r)[3][4]) {        // columns x-1, x, x+1 of input row y (zeros outside)
+  auto load_row = [&](int y, float (&r)[3][4]) {        // columns x-1, x, x+1 of input row y (zeros / border outside)
+    if (clamp) y = min(max(y, 0), h - 1);
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      const int xx = x + j - 1;
+      int xx = x + j - 1;
+      if (clamp) xx = min(max(xx, 0), w - 1);
       uint2 v = make_uint2(0u, 0u), q = make_uint2(0u, 0u);
       if (y >= 0 && y < h && xx >= 0 && xx < w) {
         v = __ldg(reinterpret_cast<const uint2*>(base + (static_cast<size_t>(y) * w + xx) * ld));
@@ -369,7 +377,7 @@ template <bool kSplit>      // kSplit: `in` is [n,h,w,2c] = [hi | lo] halves of 
 __global__ void __launch_bounds__(256)
 upsample2x_dw_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int h, int w, int c,
                              const float* __restrict__ wgt, const float* __restrict__ bias,
-                             float* __restrict__ out, uint8_t* __restrict__ labels) {
+                             float* __restrict__ out, uint8_t* __restrict__ labels, int clamp) {
   extern __shared__ float s_in[];                 // [c][kUpTy + 2][kUpTx + 2 (+1 pad)], then [c][16] stencil weights
   constexpr int RS = kUpTx + 3;                   // row stride (35): odd -> conflict-free transposed fill
   constexpr int CS = (kUpTy + 2) * RS;            // channel stride
@@ -398,7 +406,11 @@ upsample2x_dw_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int h, int w,
     const int ch8 = (i % cv) * 8;
     const int p = i / cv;
     const int lx = p % (kUpTx + 2), ly = p / (kUpTx + 2);
-    const int y = y0 + ly - 1, x = x0 + lx - 1;
+    int y = y0 + ly - 1, x = x0 + lx - 1;
+    if (clamp) {
+      y = min(max(y, 0), h - 1);
+      x = min(max(x, 0), w - 1);
+    }
     uint4 v = make_uint4(0, 0, 0, 0), q = make_uint4(0, 0, 0, 0);
     if (y >= 0 && y < h && x >= 0 && x < w) {
       const __nv_bfloat16* px = in + ((1LL * s * h + y) * w + x) * (kSplit ? 2 * c : c) + ch8;
@@ -575,7 +587,8 @@ __global__ void split_from_f32_kernel(const float* __restrict__ x, long long row
 // nearest x2 + depthwise 3x3 + bias (+ skip), NHWC split in / out: a thread owns 8 channels of one output pixel
 __global__ void upsample2x_dw_nhwc_split_kernel(const __nv_bfloat16* __restrict__ in, int n, int h, int w, int c,
                                                 const float* __restrict__ wgt, const float* __restrict__ bias,
-                                                const __nv_bfloat16* __restrict__ skip, __nv_bfloat16* __restrict__ out) {
+                                                const __nv_bfloat16* __restrict__ skip, __nv_bfloat16* __restrict__ out,
+                                                int clamp) {
   const int cv = c >> 3;
   const long long total = 1LL * n * 4 * h * w * cv;
   const int H = 2 * h, W = 2 * w;
@@ -591,11 +604,13 @@ __global__ void upsample2x_dw_nhwc_split_kernel(const __nv_bfloat16* __restrict_
     for (int e = 0; e < 8; ++e) acc[e] = bias ? bias[c8 + e] : 0.f;
 #pragma unroll
     for (int dy = -1; dy <= 1; ++dy) {
-      const int yy = Y + dy;
+      int yy = Y + dy;
+      if (clamp) yy = min(max(yy, 0), H - 1);
       if (yy < 0 || yy >= H) continue;
 #pragma unroll
       for (int dx = -1; dx <= 1; ++dx) {
-        const int xx = X + dx;
+        int xx = X + dx;
+        if (clamp) xx = min(max(xx, 0), W - 1);
         if (xx < 0 || xx >= W) continue;
         const __nv_bfloat16* px = in + ((1LL * s * h + (yy >> 1)) * w + (xx >> 1)) * 2 * c + c8;
         float f[8];
@@ -680,6 +695,50 @@ __global__ void nearest_resize_into_split_kernel(const __nv_bfloat16* __restrict
     const int sy = min((int)((long long)y * hs / h), hs - 1), sx = min((int)((long long)x * ws / w), ws - 1);
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + ((1LL * s * hs + sy) * ws + sx) * 2 * c + half * c + c8));
     *reinterpret_cast<uint4*>(dst + ((1LL * s * h + y) * w + x) * ld + half * (ld >> 1) + c_off + c8) = v;
+  }
+}
+
+// F.interpolate(mode='bilinear', align_corners=False) of src [n,hs,ws,(2)c] into channels [c_off, c_off + c) of dst
+// (pitch ld); split: both tensors are [hi | lo] halves, the interpolation runs on the reconstructed fp32 values
+template <bool kSplit>
+__global__ void bilinear_resize_into_kernel(const __nv_bfloat16* __restrict__ src, int n, int hs, int ws, int c,
+                                            __nv_bfloat16* __restrict__ dst, int h, int w, int ld, int c_off) {
+  const int cv = c >> 3;
+  const int sld = kSplit ? 2 * c : c;
+  const long long total = 1LL * n * h * w * cv;
+  const float ry = (float)hs / (float)h, rx = (float)ws / (float)w;
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv) * 8;
+    long long r = i / cv;
+    const int x = (int)(r % w);
+    r /= w;
+    const int y = (int)(r % h);
+    const int s = (int)(r / h);
+    // area_pixel_compute_source_index(scale, dst, align_corners=false): max(0, (dst + 0.5) * scale - 0.5)
+    const float fy = fmaxf((y + 0.5f) * ry - 0.5f, 0.f), fx = fmaxf((x + 0.5f) * rx - 0.5f, 0.f);
+    const int y0 = min((int)fy, hs - 1), x0 = min((int)fx, ws - 1);
+    const int y1 = min(y0 + 1, hs - 1), x1 = min(x0 + 1, ws - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    float v[4][8];
+    const int ys[2] = {y0, y1}, xs[2] = {x0, x1};
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const __nv_bfloat16* px = src + ((1LL * s * hs + ys[a]) * ws + xs[b]) * sld + c8;
+        const uint4 hi = __ldg(reinterpret_cast<const uint4*>(px));
+        const uint4 lo = kSplit ? __ldg(reinterpret_cast<const uint4*>(px + c)) : make_uint4(0, 0, 0, 0);
+        join8(hi, lo, v[a * 2 + b]);
+      }
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = hy * (hx * v[0][e] + lx * v[1][e]) + ly * (hx * v[2][e] + lx * v[3][e]);
+    uint4 hi, lo;
+    split8(o, hi, lo);
+    __nv_bfloat16* d = dst + ((1LL * s * h + y) * w + x) * ld + c_off + c8;
+    *reinterpret_cast<uint4*>(d) = hi;
+    if (kSplit) *reinterpret_cast<uint4*>(d + (ld >> 1)) = lo;
   }
 }
 
@@ -792,7 +851,7 @@ extern "C" int dynmm_nhwc_bf16_to_nchw_f32(const void* in, int n, int c, int h, 
 
 namespace {
 int upsample2x_impl(const void* in, int n, int h, int w, int c, const float* weight, const float* bias, const void* skip,
-                    void* out_nhwc_bf16, float* out_nchw_f32, uint8_t* labels, bool split, void* stream_) {
+                    void* out_nhwc_bf16, float* out_nchw_f32, uint8_t* labels, bool split, int clamp, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DYNMM_CHECK_ARG(in && weight && n >= 1 && h >= 1 && w >= 1 && c >= 8 && c % 8 == 0, "upsample2x: c %% 8");
   DYNMM_CHECK_ARG(!(out_nhwc_bf16 && (out_nchw_f32 || labels)) && (out_nhwc_bf16 || out_nchw_f32 || labels),
@@ -805,17 +864,17 @@ int upsample2x_impl(const void* in, int n, int h, int w, int c, const float* wei
     if (skip) {
       upsample2x_dw_nhwc_strip_kernel<true, true><<<grid, 256, 0, stream>>>(
           static_cast<const __nv_bfloat16*>(in), h, w, c, weight, bias, static_cast<const __nv_bfloat16*>(skip),
-          static_cast<__nv_bfloat16*>(out_nhwc_bf16), rows);
+          static_cast<__nv_bfloat16*>(out_nhwc_bf16), rows, clamp);
     } else {
       upsample2x_dw_nhwc_strip_kernel<false, true><<<grid, 256, 0, stream>>>(
           static_cast<const __nv_bfloat16*>(in), h, w, c, weight, bias, nullptr, static_cast<__nv_bfloat16*>(out_nhwc_bf16),
-          rows);
+          rows, clamp);
     }
   } else if (out_nhwc_bf16 && split) {
     const long long total = 1LL * n * 4 * h * w * (c / 8);
     upsample2x_dw_nhwc_split_kernel<<<grid_for(total, 256, 16), 256, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(in), n, h, w, c, weight, bias, static_cast<const __nv_bfloat16*>(skip),
-        static_cast<__nv_bfloat16*>(out_nhwc_bf16));
+        static_cast<__nv_bfloat16*>(out_nhwc_bf16), clamp);
   } else if (out_nhwc_bf16) {
     static const bool use_strip = [] {
       const char* e = getenv("DYNMM_UPSAMPLE");
@@ -828,17 +887,17 @@ int upsample2x_impl(const void* in, int n, int h, int w, int c, const float* wei
       if (skip) {
         upsample2x_dw_nhwc_strip_kernel<true><<<grid, 256, 0, stream>>>(
             static_cast<const __nv_bfloat16*>(in), h, w, c, weight, bias, static_cast<const __nv_bfloat16*>(skip),
-            static_cast<__nv_bfloat16*>(out_nhwc_bf16), rows);
+            static_cast<__nv_bfloat16*>(out_nhwc_bf16), rows, clamp);
       } else {
         upsample2x_dw_nhwc_strip_kernel<false><<<grid, 256, 0, stream>>>(
             static_cast<const __nv_bfloat16*>(in), h, w, c, weight, bias, nullptr, static_cast<__nv_bfloat16*>(out_nhwc_bf16),
-            rows);
+            rows, clamp);
       }
     } else {
       const long long total = 1LL * n * 4 * h * w * (c / 8);
       upsample2x_dw_nhwc_kernel<<<grid_for(total, 256, 16), 256, 0, stream>>>(
           static_cast<const __nv_bfloat16*>(in), n, h, w, c, weight, bias, static_cast<const __nv_bfloat16*>(skip),
-          static_cast<__nv_bfloat16*>(out_nhwc_bf16));
+          static_cast<__nv_bfloat16*>(out_nhwc_bf16), clamp);
     }
   } else {
     DYNMM_CHECK_ARG(!skip, "upsample2x: skip is only supported for the NHWC output");
@@ -855,10 +914,10 @@ int upsample2x_impl(const void* in, int n, int h, int w, int c, const float* wei
     dim3 grid(ceil_div(w, kUpTx), ceil_div(h, kUpTy), n);
     if (split)
       upsample2x_dw_to_nchw_kernel<true><<<grid, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(in), h, w, c, weight,
-                                                                      bias, out_nchw_f32, labels);
+                                                                      bias, out_nchw_f32, labels, clamp);
     else
       upsample2x_dw_to_nchw_kernel<false><<<grid, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(in), h, w, c,
-                                                                       weight, bias, out_nchw_f32, labels);
+                                                                       weight, bias, out_nchw_f32, labels, clamp);
   }
   DYNMM_LAUNCH_CHECK();
   return DYNMM_OK;
@@ -868,12 +927,33 @@ int upsample2x_impl(const void* in, int n, int h, int w, int c, const float* wei
 extern "C" int dynmm_upsample2x_dw3x3(const void* in, int n, int h, int w, int c, const float* weight,
                                       const float* bias, const void* skip, void* out_nhwc_bf16, float* out_nchw_f32,
                                       uint8_t* labels, void* stream) {
-  return upsample2x_impl(in, n, h, w, c, weight, bias, skip, out_nhwc_bf16, out_nchw_f32, labels, false, stream);
+  return upsample2x_impl(in, n, h, w, c, weight, bias, skip, out_nhwc_bf16, out_nchw_f32, labels, false, 0, stream);
 }
 extern "C" int dynmm_upsample2x_dw3x3_split(const void* in, int n, int h, int w, int c, const float* weight,
                                             const float* bias, const void* skip, void* out_nhwc_bf16, float* out_nchw_f32,
                                             uint8_t* labels, void* stream) {
-  return upsample2x_impl(in, n, h, w, c, weight, bias, skip, out_nhwc_bf16, out_nchw_f32, labels, true, stream);
+  return upsample2x_impl(in, n, h, w, c, weight, bias, skip, out_nhwc_bf16, out_nchw_f32, labels, true, 0, stream);
+}
+extern "C" int dynmm_upsample2x_dw3x3_ex(const void* in, int n, int h, int w, int c, const float* weight,
+                                         const float* bias, const void* skip, void* out_nhwc_bf16, float* out_nchw_f32,
+                                         uint8_t* labels, int flags, void* stream) {
+  return upsample2x_impl(in, n, h, w, c, weight, bias, skip, out_nhwc_bf16, out_nchw_f32, labels,
+                         (flags & DYNMM_UPSAMPLE_SPLIT) != 0, (flags & DYNMM_UPSAMPLE_REPLICATE) ? 1 : 0, stream);
+}
+extern "C" int dynmm_bilinear_resize_into(const void* src, int n, int hs, int ws, int c, void* dst, int h, int w, int ld,
+                                          int c_off, int split, void* stream) {
+  DYNMM_CHECK_ARG(src && dst && c >= 8 && c % 8 == 0 && ld % (split ? 16 : 8) == 0 && c_off % 8 == 0 &&
+                      c_off + c <= (split ? ld / 2 : ld),
+                  "bilinear_resize: c/ld/c_off");
+  const long long total = 1LL * n * h * w * (c / 8);
+  if (split)
+    bilinear_resize_into_kernel<true><<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(src), n, hs, ws, c, static_cast<__nv_bfloat16*>(dst), h, w, ld, c_off);
+  else
+    bilinear_resize_into_kernel<false><<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(src), n, hs, ws, c, static_cast<__nv_bfloat16*>(dst), h, w, ld, c_off);
+  DYNMM_LAUNCH_CHECK();
+  return DYNMM_OK;
 }
 extern "C" int dynmm_split_from_f32(const float* x, long long rows, int c, void* out, void* stream) {
   DYNMM_CHECK_ARG(x && out && rows >= 1 && c >= 8 && c % 8 == 0, "split_from_f32: c %% 8");

@@ -172,8 +172,11 @@ class FusionEngine:
             raise NotImplementedError("the CUDA engine fuses ReLU epilogues only; got activation=" + cfg.activation)
         if cfg.fuse not in ("add", "SE-add"):
             raise NotImplementedError("fuse_depth_in_rgb_encoder must be 'add' or 'SE-add', got " + str(cfg.fuse))
-        if cfg.upsampling != "learned-3x3-zeropad":
-            raise NotImplementedError("the CUDA engine implements upsampling='learned-3x3-zeropad'")
+        if cfg.upsampling not in ("learned-3x3-zeropad", "learned-3x3", "bilinear", "nearest"):
+            raise NotImplementedError("unknown upsampling mode " + str(cfg.upsampling))
+        if cfg.num_classes % 8:
+            # NHWC kernels move 16-byte channel groups: the 37-class data sets (SUN RGB-D) run the PyTorch graph
+            raise NotImplementedError(f"the CUDA engine needs num_classes % 8 == 0 (got {cfg.num_classes})")
         if "ppm" not in cfg.context_module or "appm" in cfg.context_module:
             raise NotImplementedError("the CUDA engine implements context_module='ppm' (bins 1,5) and 'ppm-1-2-4-8'")
         if cfg.precision not in ("bf16", "f32x3"):
@@ -231,12 +234,16 @@ class FusionEngine:
             self.dec.append({
                 "conv3x3": p.conv_bn_act(dk + ".conv3x3", 3),
                 "blocks": [p.nbt1d(f"{dk}.decoder_blocks.{b}") for b in range(cfg.nr_decoder_blocks[i])],
-                "up_w": p.taps_major(dk + ".upsample.conv.weight"),                          # [9][C]
-                "up_b": p.t(dk + ".upsample.conv.bias").contiguous(),
+                "up_w": None, "up_b": None,
             })
+            self.dec[-1]["up_w"], self.dec[-1]["up_b"] = self._up_params(p, dk + ".upsample", self.dec[-1]["conv3x3"].c_out)
         self.conv_out = p.conv("decoder.conv_out", pad=(1, 1))
-        self.up = [(p.taps_major(f"decoder.{u}.conv.weight"), p.t(f"decoder.{u}.conv.bias").contiguous())
-                   for u in ("upsample1", "upsample2")]
+        self.up = [self._up_params(p, f"decoder.{u}", self.conv_out.c_out) for u in ("upsample1", "upsample2")]
+        # model.py:360-410: 'learned-3x3' pads the up-sampled map by replication, 'bilinear' is that form with the
+        # fixed [1 2 1]^T [1 2 1] / 16 stencil, 'nearest' the identity stencil; the context module interpolates its
+        # pooled branches bilinearly only for 'bilinear' (model_skip_mod_globalgate.py:145-160: learned -> nearest)
+        self.up_replicate = cfg.upsampling in ("learned-3x3", "bilinear")
+        self.ctx_bilinear = cfg.upsampling == "bilinear"
         # SE-add fusion: the 1x1 convs of SqueezeAndExcitation as fp32 matrices (model_utils.py:40-45)
         self.se = None
         if cfg.fuse == "SE-add":
@@ -284,6 +291,15 @@ class FusionEngine:
                     imgs = self._chain_images(s)
                     if imgs is not None:
                         self.chain_imgs[s] = imgs
+
+    def _up_params(self, p: "_Packer", key: str, c: int):
+        """(tap-major [9][c] stencil, bias or None) of one Upsample module for dynmm_upsample2x_dw3x3."""
+        mode = self.cfg.upsampling
+        if "learned-3x3" in mode:
+            return p.taps_major(key + ".conv.weight"), p.t(key + ".conv.bias").contiguous()
+        if mode == "bilinear":
+            return ops.bilinear_stencil(c, self.dev), None
+        return ops.nearest_stencil(c, self.dev), None
 
     # ------------------------------------------------------------------ blocks
     @staticmethod
@@ -916,7 +932,7 @@ class FusionEngine:
                 ys = [self.ppm[i](pooled[i]) for i in range(len(self.ppm_bins))]
             self.programs.append(prog)
             for y in ys:
-                ops.nearest_resize_into(y, cat, off)
+                (ops.bilinear_resize_into if self.ctx_bilinear else ops.nearest_resize_into)(y, cat, off)
                 off += y.shape[3]
             cat._dynmm_flags = None             # other kernels wrote into the buffer since the conv published its flags
             keep += pooled + ys
@@ -926,7 +942,7 @@ class FusionEngine:
             for i, bins in enumerate(self.ppm_bins):
                 pooled = ops.adaptive_avgpool(cat, bins, c=c4, split=sp)
                 y = self.ppm[i](pooled)
-                ops.nearest_resize_into(y, cat, off, split=sp)
+                (ops.bilinear_resize_into if self.ctx_bilinear else ops.nearest_resize_into)(y, cat, off, split=sp)
                 off += y.shape[3] // (2 if sp else 1)
                 keep += [pooled, y]
                 self.launches += 3
@@ -938,7 +954,7 @@ class FusionEngine:
                 m = self.dec[i]
                 items = ([self.ppm_final] if i == 0 else []) + [m["conv3x3"]] + list(m["blocks"])
                 x = self._sequence_program(x, items, keep)
-                x = ops.upsample2x_dw3x3(x, m["up_w"], m["up_b"], skip)
+                x = ops.upsample2x_dw3x3(x, m["up_w"], m["up_b"], skip, replicate=self.up_replicate)
                 self.launches += 1
                 keep.append(x)
         else:
@@ -954,14 +970,14 @@ class FusionEngine:
                     x = self._block(x, blk, keep)
                 if skip_done[2 - i] is not None:
                     main.wait_event(skip_done[2 - i])
-                x = ops.upsample2x_dw3x3(x, m["up_w"], m["up_b"], skip, split=self.split)
+                x = ops.upsample2x_dw3x3(x, m["up_w"], m["up_b"], skip, split=self.split, replicate=self.up_replicate)
                 self.launches += 1
                 keep.append(x)
         x = self.conv_out(x)
         keep.append(x)
-        x = ops.upsample2x_dw3x3(x, self.up[0][0], self.up[0][1], split=self.split)
+        x = ops.upsample2x_dw3x3(x, self.up[0][0], self.up[0][1], split=self.split, replicate=self.up_replicate)
         keep.append(x)
         out = ops.upsample2x_dw3x3(x, self.up[1][0], self.up[1][1], to_nchw_f32=True, out=out, labels=labels,
-                                   want_logits=want_logits, split=self.split)
+                                   want_logits=want_logits, split=self.split, replicate=self.up_replicate)
         self.launches += 3
         return out

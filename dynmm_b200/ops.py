@@ -887,27 +887,55 @@ def split_from_f32(x: Tensor) -> Tensor:
 
 def upsample2x_dw3x3(x: Tensor, weight: Tensor, bias: Optional[Tensor], skip: Optional[Tensor] = None,
                      to_nchw_f32: bool = False, out: Optional[Tensor] = None, labels: Optional[Tensor] = None,
-                     want_logits: bool = True, split: bool = False):
+                     want_logits: bool = True, split: bool = False, replicate: bool = False):
     """x NHWC bf16; weight fp32 tap-major [9, c] (``conv.weight.reshape(c, 9).t().contiguous()``).
     Final upsampling (``to_nchw_f32``): returns the NCHW fp32 logits; with ``labels`` (uint8 [n,2h,2w]) the
-    arg-max over channels is produced in the same pass, and ``want_logits=False`` skips the logits."""
+    arg-max over channels is produced in the same pass, and ``want_logits=False`` skips the logits.
+    ``replicate``: replication instead of zero padding of the up-sampled map ('learned-3x3'; with the stencil of
+    :func:`bilinear_stencil` and no bias this is bilinear x2 up-sampling, align_corners=False)."""
     lib = _lib.load()
     _cuda(x, weight, bias, skip, out, labels)
     n, h, w, ld = x.shape
     c = ld // 2 if split else ld                 # split: x / skip / NHWC out are [hi | lo] halves
-    fn = lib.dynmm_upsample2x_dw3x3_split if split else lib.dynmm_upsample2x_dw3x3
+    flags = (1 if split else 0) | (2 if replicate else 0)       # DYNMM_UPSAMPLE_SPLIT | DYNMM_UPSAMPLE_REPLICATE
+    fn = lib.dynmm_upsample2x_dw3x3_ex
     if to_nchw_f32 or labels is not None:
         if want_logits:
             out = torch.empty(n, c, 2 * h, 2 * w, dtype=torch.float32, device=x.device) if out is None else out
         else:
             out = None
-        check(fn(ptr(x), n, h, w, c, ptr(weight), ptr(bias), None, None, ptr(out), ptr(labels), stream_ptr()),
+        check(fn(ptr(x), n, h, w, c, ptr(weight), ptr(bias), None, None, ptr(out), ptr(labels), flags, stream_ptr()),
               "upsample2x_dw3x3")
     else:
         out = torch.empty(n, 2 * h, 2 * w, ld, dtype=torch.bfloat16, device=x.device) if out is None else out
-        check(fn(ptr(x), n, h, w, c, ptr(weight), ptr(bias), ptr(skip), ptr(out), None, None, stream_ptr()),
+        check(fn(ptr(x), n, h, w, c, ptr(weight), ptr(bias), ptr(skip), ptr(out), None, None, flags, stream_ptr()),
               "upsample2x_dw3x3")
     return out
+
+
+def bilinear_stencil(c: int, device) -> Tensor:
+    """Tap-major [9, c] stencil [1 2 1]^T [1 2 1] / 16: nearest x2 + this depthwise conv with replication padding =
+    ``F.interpolate(scale_factor=2, mode='bilinear', align_corners=False)`` (the reference initialises its learned
+    up-sampling with it, model.py:385-395)."""
+    k = torch.tensor([0.0625, 0.125, 0.0625, 0.125, 0.25, 0.125, 0.0625, 0.125, 0.0625], device=device)
+    return k.view(9, 1).expand(9, c).contiguous()
+
+
+def nearest_stencil(c: int, device) -> Tensor:
+    """Tap-major [9, c] identity stencil: plain nearest x2 up-sampling through the same kernel."""
+    k = torch.zeros(9, c, device=device)
+    k[4] = 1.0
+    return k
+
+
+def bilinear_resize_into(src: Tensor, dst: Tensor, c_off: int, split: bool = False) -> None:
+    """``F.interpolate(mode='bilinear', align_corners=False)`` of src [n,hs,ws,c] into dst[..., c_off:c_off+c]."""
+    lib = _lib.load()
+    _cuda(src, dst)
+    n, hs, ws, c = src.shape
+    _, h, w, ld = dst.shape
+    check(lib.dynmm_bilinear_resize_into(ptr(src), n, hs, ws, c // 2 if split else c, ptr(dst), h, w, ld, c_off, int(split),
+                                         stream_ptr()), "bilinear_resize_into")
 
 
 def adaptive_avgpool(x: Tensor, bins: int, c: Optional[int] = None, split: bool = False) -> Tensor:

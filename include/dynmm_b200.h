@@ -511,6 +511,19 @@ int dynmm_upsample2x_dw3x3(const void* in, int n, int h, int w, int c, const flo
 int dynmm_split_from_f32(const float* x, long long rows, int c, void* out /* bf16 [rows][2c] */, void* stream);
 int dynmm_upsample2x_dw3x3_split(const void* in, int n, int h, int w, int c, const float* weight, const float* bias,
                                  const void* skip, void* out_nhwc_bf16, float* out_nchw_f32, uint8_t* labels, void* stream);
+/* The same up-sampling with options: DYNMM_UPSAMPLE_SPLIT = the _split variant; DYNMM_UPSAMPLE_REPLICATE = replication
+ * padding of the up-sampled map instead of zero padding (Upsample 'learned-3x3', model.py:372-384; with the fixed
+ * stencil [1 2 1]^T [1 2 1] / 16 and no bias it IS F.interpolate(mode='bilinear', align_corners=False) at scale 2,
+ * 'bilinear' of model.py:364-366). */
+#define DYNMM_UPSAMPLE_SPLIT 1
+#define DYNMM_UPSAMPLE_REPLICATE 2
+int dynmm_upsample2x_dw3x3_ex(const void* in, int n, int h, int w, int c, const float* weight, const float* bias,
+                              const void* skip, void* out_nhwc_bf16, float* out_nchw_f32, uint8_t* labels, int flags,
+                              void* stream);
+/* PyramidPoolingModule with upsampling_mode='bilinear' (context_modules.py:79-81): F.interpolate(mode='bilinear',
+ * align_corners=False) of src [n,hs,ws,c] into channels [c_off, c_off + c) of dst [n,h,w,ld]; split: [hi | lo] tensors. */
+int dynmm_bilinear_resize_into(const void* src, int n, int hs, int ws, int c, void* dst, int h, int w, int ld, int c_off,
+                               int split, void* stream);
 int dynmm_adaptive_avgpool_split(const void* in, int n, int h, int w, int c, int ld, int bins, void* out, void* stream);
 int dynmm_nearest_resize_into_split(const void* src, int n, int hs, int ws, int c, void* dst, int h, int w, int ld,
                                     int c_off, void* stream);

@@ -210,3 +210,51 @@ def test_ppm_1_2_4_8_context_module_on_the_engine():
             assert torch.equal(w, w_ref)
             err = _rel_l2(out, ref)
             assert err <= tol, f"{precision}: relative L2 {err:.2e}"
+
+
+@pytest.mark.parametrize("mode", ["bilinear", "nearest", "learned-3x3"])
+def test_other_upsampling_modes_on_the_engine(mode):
+    """Upsample modes of model.py:360-410 other than the default 'learned-3x3-zeropad': 'learned-3x3' pads the
+    up-sampled map by replication, 'bilinear' is that form with the fixed [1 2 1]^T [1 2 1] / 16 stencil (and bilinear
+    interpolation of the pyramid-pooling branches), 'nearest' the identity stencil -- all through the same kernels, in
+    both precisions, against the module's own fp32 PyTorch graph."""
+    from dynmm_b200.fusion import SkipGateESANet
+    from oracle.make_golden import sample_inputs
+    torch.manual_seed(7)
+    model = SkipGateESANet(height=96, width=128, num_classes=40, upsampling=mode).cuda().eval()
+    g = torch.Generator().manual_seed(8)
+    with torch.no_grad():
+        for name, m in model.named_modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+                m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+            if mode == "learned-3x3" and name.endswith("upsample.conv") or name.endswith(("upsample1.conv", "upsample2.conv")):
+                if hasattr(m, "weight") and m.weight is not None:
+                    m.weight.add_(torch.randn(m.weight.shape, generator=g).to(m.weight.device) * 0.05)
+                    m.bias.add_(torch.randn(m.bias.shape, generator=g).to(m.bias.device) * 0.05)
+        model.gate_layer.fc.weight.mul_(40.0)
+    model.hard_gate = True
+    rgb, depth = (t.cuda() for t in sample_inputs(9, 3, 96, 128))
+    with torch.no_grad():
+        ref, w_ref = model._forward_torch(rgb, depth)
+        for precision, tol in (("f32x3", F32_TOL), ("bf16", 2e-2)):
+            model.engine_precision = precision
+            out, w = model(rgb, depth, True, True)
+            assert getattr(model, "_engine_unsupported", None) is None, model._engine_unsupported
+            assert torch.equal(w, w_ref)
+            err = _rel_l2(out, ref)
+            assert err <= tol, f"{mode}/{precision}: relative L2 {err:.2e}"
+
+
+def test_37_classes_fall_back_to_the_module_graph():
+    """num_classes % 8 != 0 (SUN RGB-D: 37): the engine declines, the eval forward runs the PyTorch graph (one warning)."""
+    import warnings
+    from dynmm_b200.fusion import SkipGateESANet
+    from oracle.make_golden import sample_inputs
+    model = SkipGateESANet(height=64, width=64, num_classes=37).cuda().eval()
+    rgb, depth = (t.cuda() for t in sample_inputs(2, 2, 64, 64))
+    with warnings.catch_warnings(record=True) as rec, torch.no_grad():
+        warnings.simplefilter("always")
+        out = model(rgb, depth, True)
+    assert out.shape == (2, 37, 64, 64) and torch.isfinite(out).all()
+    assert any("CUDA engine does not implement" in str(r.message) for r in rec)
