@@ -134,7 +134,7 @@ SIGNATURES = {
     "dynmm_upsample2x_dw3x3_split": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p, c_void_p]),
     "dynmm_upsample2x_dw3x3_ex": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                          c_void_p, c_void_p, c_int, c_void_p]),
+                                          c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "dynmm_bilinear_resize_into": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                            c_void_p]),
     "dynmm_adaptive_avgpool_split": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -377,7 +377,9 @@ template <bool kSplit>      // kSplit: `in` is [n,h,w,2c] = [hi | lo] halves of 
 __global__ void __launch_bounds__(256)
 upsample2x_dw_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int h, int w, int c,
                              const float* __restrict__ wgt, const float* __restrict__ bias,
-                             float* __restrict__ out, uint8_t* __restrict__ labels, int clamp) {
+                             float* __restrict__ out, uint8_t* __restrict__ labels, int clamp, int c_valid) {
+  // c_valid <= c: channels that exist in the NCHW output / take part in the arg-max (the NHWC input may be padded to a
+  // multiple of 8 channels, e.g. 37 classes carried as 40)
   extern __shared__ float s_in[];                 // [c][kUpTy + 2][kUpTx + 2 (+1 pad)], then [c][16] stencil weights
   constexpr int RS = kUpTx + 3;                   // row stride (35): odd -> conflict-free transposed fill
   constexpr int CS = (kUpTy + 2) * RS;            // channel stride
@@ -439,7 +441,7 @@ upsample2x_dw_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int h, int w,
     float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     int arg[4] = {0, 0, 0, 0};
 #pragma unroll 2
-    for (int ch = 0; ch < c; ++ch) {
+    for (int ch = 0; ch < c_valid; ++ch) {
       const float b0 = bias ? __ldg(bias + ch) : 0.f;
       const float* base = s_in + ch * CS + ly * RS + lane;          // staged rows ly, ly+1, ly+2 = y-1, y, y+1
       const float al = base[0], am = base[1], ar = base[2];
@@ -454,7 +456,7 @@ upsample2x_dw_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, int h, int w,
       const float o10 = b0 + w2.x * bl + w2.y * bm + w2.z * dl + w2.w * dm;
       const float o11 = b0 + w3.x * bm + w3.y * br + w3.z * dm + w3.w * dr;
       if (out && x_ok) {
-        float* o = out + ((1LL * s * c + ch) * H + 2LL * y) * W + 2 * (x0 + lane);
+        float* o = out + ((1LL * s * c_valid + ch) * H + 2LL * y) * W + 2 * (x0 + lane);
         *reinterpret_cast<float2*>(o) = make_float2(o00, o01);
         *reinterpret_cast<float2*>(o + W) = make_float2(o10, o11);
       }
@@ -851,12 +853,15 @@ extern "C" int dynmm_nhwc_bf16_to_nchw_f32(const void* in, int n, int c, int h, 
 
 namespace {
 int upsample2x_impl(const void* in, int n, int h, int w, int c, const float* weight, const float* bias, const void* skip,
-                    void* out_nhwc_bf16, float* out_nchw_f32, uint8_t* labels, bool split, int clamp, void* stream_) {
+                    void* out_nhwc_bf16, float* out_nchw_f32, uint8_t* labels, bool split, int clamp, int c_valid,
+                    void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DYNMM_CHECK_ARG(in && weight && n >= 1 && h >= 1 && w >= 1 && c >= 8 && c % 8 == 0, "upsample2x: c %% 8");
   DYNMM_CHECK_ARG(!(out_nhwc_bf16 && (out_nchw_f32 || labels)) && (out_nhwc_bf16 || out_nchw_f32 || labels),
                   "upsample2x: either the NHWC output, or the NCHW logits and/or the arg-max labels");
   DYNMM_CHECK_ARG(!labels || c <= 256, "upsample2x: labels are uint8");
+  if (c_valid <= 0) c_valid = c;
+  DYNMM_CHECK_ARG(c_valid <= c && (c_valid == c || !out_nhwc_bf16), "upsample2x: c_valid applies to the NCHW / label outputs");
   if (out_nhwc_bf16 && split && n <= 65535 && getenv("DYNMM_UPSAMPLE") == nullptr) {
     int rows = kUpStripRows;
     while (rows > 1 && 1LL * ceil_div(w * (c / 4), 256) * ceil_div(h, rows) * n < 4LL * num_sms()) rows >>= 1;
@@ -914,10 +919,10 @@ int upsample2x_impl(const void* in, int n, int h, int w, int c, const float* wei
     dim3 grid(ceil_div(w, kUpTx), ceil_div(h, kUpTy), n);
     if (split)
       upsample2x_dw_to_nchw_kernel<true><<<grid, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(in), h, w, c, weight,
-                                                                      bias, out_nchw_f32, labels, clamp);
+                                                                      bias, out_nchw_f32, labels, clamp, c_valid);
     else
       upsample2x_dw_to_nchw_kernel<false><<<grid, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(in), h, w, c,
-                                                                       weight, bias, out_nchw_f32, labels, clamp);
+                                                                       weight, bias, out_nchw_f32, labels, clamp, c_valid);
   }
   DYNMM_LAUNCH_CHECK();
   return DYNMM_OK;
@@ -927,18 +932,18 @@ int upsample2x_impl(const void* in, int n, int h, int w, int c, const float* wei
 extern "C" int dynmm_upsample2x_dw3x3(const void* in, int n, int h, int w, int c, const float* weight,
                                       const float* bias, const void* skip, void* out_nhwc_bf16, float* out_nchw_f32,
                                       uint8_t* labels, void* stream) {
-  return upsample2x_impl(in, n, h, w, c, weight, bias, skip, out_nhwc_bf16, out_nchw_f32, labels, false, 0, stream);
+  return upsample2x_impl(in, n, h, w, c, weight, bias, skip, out_nhwc_bf16, out_nchw_f32, labels, false, 0, 0, stream);
 }
 extern "C" int dynmm_upsample2x_dw3x3_split(const void* in, int n, int h, int w, int c, const float* weight,
                                             const float* bias, const void* skip, void* out_nhwc_bf16, float* out_nchw_f32,
                                             uint8_t* labels, void* stream) {
-  return upsample2x_impl(in, n, h, w, c, weight, bias, skip, out_nhwc_bf16, out_nchw_f32, labels, true, 0, stream);
+  return upsample2x_impl(in, n, h, w, c, weight, bias, skip, out_nhwc_bf16, out_nchw_f32, labels, true, 0, 0, stream);
 }
 extern "C" int dynmm_upsample2x_dw3x3_ex(const void* in, int n, int h, int w, int c, const float* weight,
                                          const float* bias, const void* skip, void* out_nhwc_bf16, float* out_nchw_f32,
-                                         uint8_t* labels, int flags, void* stream) {
+                                         uint8_t* labels, int flags, int c_valid, void* stream) {
   return upsample2x_impl(in, n, h, w, c, weight, bias, skip, out_nhwc_bf16, out_nchw_f32, labels,
-                         (flags & DYNMM_UPSAMPLE_SPLIT) != 0, (flags & DYNMM_UPSAMPLE_REPLICATE) ? 1 : 0, stream);
+                         (flags & DYNMM_UPSAMPLE_SPLIT) != 0, (flags & DYNMM_UPSAMPLE_REPLICATE) ? 1 : 0, c_valid, stream);
 }
 extern "C" int dynmm_bilinear_resize_into(const void* src, int n, int hs, int ws, int c, void* dst, int h, int w, int ld,
                                           int c_off, int split, void* stream) {

@@ -93,7 +93,8 @@ class _Packer:
         w = self.t(key)
         return ops.permute3d(w.reshape(w.shape[0], 1, 9), (2, 1, 0)).view(9, w.shape[0])
 
-    def conv(self, key, *, stride=(1, 1), pad=(0, 0), bn: Optional[str] = None, bn_eps=1e-5, relu=False) -> ConvLayer:
+    def conv(self, key, *, stride=(1, 1), pad=(0, 0), bn: Optional[str] = None, bn_eps=1e-5, relu=False,
+             pad_out: int = 1) -> ConvLayer:
         """BN scale folded into the fp32 weights before bf16 packing, the epilogue only adds `shift`: one launch of
         dynmm_fold_pack_conv per convolution (no library element-wise kernels in the engine build)."""
         w = self.t(key + ".weight")
@@ -101,6 +102,12 @@ class _Packer:
         bn_t = [self.t(bn + s) for s in (".weight", ".bias", ".running_mean", ".running_var")] if bn is not None else None
         packed, shift = ops.fold_pack_conv(w, bias, bn_t, bn_eps, split=self.split)
         c_out, c_in, kh, kw = w.shape
+        if c_out % pad_out:
+            # extra output channels: the packed weight already has zero rows up to a multiple of 16; zero shifts
+            c_pad = (c_out + pad_out - 1) // pad_out * pad_out
+            if shift is not None:
+                shift = torch.cat([shift, torch.zeros(c_pad - c_out, device=shift.device)]).contiguous()
+            c_out = c_pad
         return ConvLayer(packed, None, shift, c_in, c_out, kh, kw, tuple(stride), tuple(pad), relu, self.split)
 
     def nbt1d(self, key, stride=1) -> Block:
@@ -154,6 +161,7 @@ class EngineConfig:
     # "f32x3": fp32-grade arithmetic on the same tensor cores -- activations and weights as bf16 hi + lo halves, three
     # products per MAC (DYNMM_CONV_SPLIT), element-wise kernels in fp32: logits within 1e-3 of the fp32 reference
     precision: str = "bf16"
+    encoder_decoder_fusion: str = "add"     # "None": the decoder modules do not add the encoder skip tensors (model.py:353-355)
 
 
 class FusionEngine:
@@ -174,9 +182,6 @@ class FusionEngine:
             raise NotImplementedError("fuse_depth_in_rgb_encoder must be 'add' or 'SE-add', got " + str(cfg.fuse))
         if cfg.upsampling not in ("learned-3x3-zeropad", "learned-3x3", "bilinear", "nearest"):
             raise NotImplementedError("unknown upsampling mode " + str(cfg.upsampling))
-        if cfg.num_classes % 8:
-            # NHWC kernels move 16-byte channel groups: the 37-class data sets (SUN RGB-D) run the PyTorch graph
-            raise NotImplementedError(f"the CUDA engine needs num_classes % 8 == 0 (got {cfg.num_classes})")
         if "ppm" not in cfg.context_module or "appm" in cfg.context_module:
             raise NotImplementedError("the CUDA engine implements context_module='ppm' (bins 1,5) and 'ppm-1-2-4-8'")
         if cfg.precision not in ("bf16", "f32x3"):
@@ -184,6 +189,9 @@ class FusionEngine:
         self.split = cfg.precision == "f32x3"
         if self.split and (cfg.fuse != "add" or cfg.gate != "global"):
             raise NotImplementedError("precision='f32x3' is implemented for the global gate with fuse='add'")
+        if cfg.encoder_decoder_fusion not in ("add", "None"):
+            raise NotImplementedError("encoder_decoder_fusion must be 'add' or 'None'")
+        self.dec_fusion = cfg.encoder_decoder_fusion == "add"
         self.cfg, self.dev = cfg, device
         p = _Packer(sd, device, self.split)
         if cfg.gate == "local":
@@ -237,7 +245,10 @@ class FusionEngine:
                 "up_w": None, "up_b": None,
             })
             self.dec[-1]["up_w"], self.dec[-1]["up_b"] = self._up_params(p, dk + ".upsample", self.dec[-1]["conv3x3"].c_out)
-        self.conv_out = p.conv("decoder.conv_out", pad=(1, 1))
+        # NHWC kernels move 16-byte channel groups: a class count that is not a multiple of 8 (SUN RGB-D: 37) is carried
+        # as the next multiple (zero weight rows / stencils / biases); the final kernel emits the real classes only
+        self.n_classes = cfg.num_classes
+        self.conv_out = p.conv("decoder.conv_out", pad=(1, 1), pad_out=8)
         self.up = [self._up_params(p, f"decoder.{u}", self.conv_out.c_out) for u in ("upsample1", "upsample2")]
         # model.py:360-410: 'learned-3x3' pads the up-sampled map by replication, 'bilinear' is that form with the
         # fixed [1 2 1]^T [1 2 1] / 16 stencil, 'nearest' the identity stencil; the context module interpolates its
@@ -264,7 +275,8 @@ class FusionEngine:
         # convolution PROGRAMS (one cooperative launch per chain of dependent convs, dynmm_conv_program_*) instead of
         # one launch per convolution on two streams.  Same arithmetic, bit-identical results; measured slower at
         # batch 8 in round 1 (profiles/r1_program_*), so the per-launch path stays the default.
-        self.use_programs = cfg.fuse == "add" and os.environ.get("DYNMM_PROGRAM", "0") == "1" and not self.split
+        self.use_programs = (cfg.fuse == "add" and os.environ.get("DYNMM_PROGRAM", "0") == "1" and not self.split and
+                             self.dec_fusion)
         self.programs: list = []   # ConvPrograms of the last forward (a captured graph must keep them alive)
         # 64-channel NonBottleneck1D blocks: each 3x1 -> 1x3 pair as ONE fused kernel (dynmm_conv_pair_fwd, bit-identical
         # to the two launches); DYNMM_PAIR=0 keeps one launch per convolution
@@ -296,7 +308,11 @@ class FusionEngine:
         """(tap-major [9][c] stencil, bias or None) of one Upsample module for dynmm_upsample2x_dw3x3."""
         mode = self.cfg.upsampling
         if "learned-3x3" in mode:
-            return p.taps_major(key + ".conv.weight"), p.t(key + ".conv.bias").contiguous()
+            w, b = p.taps_major(key + ".conv.weight"), p.t(key + ".conv.bias").contiguous()
+            if w.shape[1] < c:                       # padded class channels: zero stencil, zero bias
+                w = torch.cat([w, torch.zeros(9, c - w.shape[1], device=w.device)], dim=1).contiguous()
+                b = torch.cat([b, torch.zeros(c - b.shape[0], device=b.device)]).contiguous()
+            return w, b
         if mode == "bilinear":
             return ops.bilinear_stencil(c, self.dev), None
         return ops.nearest_stencil(c, self.dev), None
@@ -681,6 +697,10 @@ class FusionEngine:
             def emit_skip(s, x):
                 if s >= 3:
                     return
+                if not self.dec_fusion:               # no skip connections into the decoder
+                    skips.append(None)
+                    skip_done.append(None)
+                    return
                 if self.skips[s] is None:
                     skips.append(x)
                     skip_done.append(None)
@@ -886,7 +906,9 @@ class FusionEngine:
             fused.append(r)
             if s < 3:
                 # skip connection conv of this stage (decoder input)
-                if self.skips[s] is not None:
+                if not self.dec_fusion:
+                    skips.append(None)
+                elif self.skips[s] is not None:
                     skips.append(self.skips[s](r))
                     self.launches += 1
                 else:
@@ -947,7 +969,7 @@ class FusionEngine:
                 keep += [pooled, y]
                 self.launches += 3
             cat._dynmm_flags = None             # other kernels wrote into the buffer since the conv published its flags
-        keep += [cat] + skips
+        keep += [cat] + [t for t in skips if t is not None]
         if self.use_programs:
             x = cat
             for i, skip in enumerate((skips[2], skips[1], skips[0])):
@@ -978,6 +1000,7 @@ class FusionEngine:
         x = ops.upsample2x_dw3x3(x, self.up[0][0], self.up[0][1], split=self.split, replicate=self.up_replicate)
         keep.append(x)
         out = ops.upsample2x_dw3x3(x, self.up[1][0], self.up[1][1], to_nchw_f32=True, out=out, labels=labels,
-                                   want_logits=want_logits, split=self.split, replicate=self.up_replicate)
+                                   want_logits=want_logits, split=self.split, replicate=self.up_replicate,
+                                   c_valid=self.n_classes)
         self.launches += 3
         return out

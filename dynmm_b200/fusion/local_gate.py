@@ -232,13 +232,12 @@ class SkipESANet(nn.Module):
             c = self._cfg
             if c["encoder_depth"] != c["encoder"]:
                 raise NotImplementedError("the CUDA engine needs encoder_rgb == encoder_depth")
-            if c["encoder_decoder_fusion"] != "add":
-                raise NotImplementedError("the CUDA engine implements encoder_decoder_fusion='add'")
             # the reference's forward always blends by addition, whatever fuse_depth_in_rgb_encoder built (:241-311)
             cfg = EngineConfig(encoder=c["encoder"], encoder_block=c["encoder_block"], fuse="add",
                                nr_decoder_blocks=c["nr_decoder_blocks"], num_classes=c["num_classes"],
                                upsampling=c["upsampling"], context_module=c["context_module"],
-                               activation=c["activation"], gate="local")
+                               activation=c["activation"], gate="local",
+                               encoder_decoder_fusion=c["encoder_decoder_fusion"])
             self._engine = FusionEngine(self.state_dict(), cfg, device)
             self._engine_key = key
         return self._engine

@@ -572,12 +572,11 @@ class SkipGateESANet(nn.Module):
             c = self._cfg
             if c["encoder_depth"] != c["encoder"]:
                 raise NotImplementedError("the CUDA engine needs encoder_rgb == encoder_depth")
-            if c["encoder_decoder_fusion"] != "add":
-                raise NotImplementedError("the CUDA engine implements encoder_decoder_fusion='add'")
             cfg = EngineConfig(encoder=c["encoder"], encoder_block=c["encoder_block"], fuse=c["fuse"],
                                nr_decoder_blocks=c["nr_decoder_blocks"], num_classes=c["num_classes"],
                                upsampling=c["upsampling"], context_module=c["context_module"],
-                               activation=c["activation"], precision=getattr(self, "engine_precision", "bf16"))
+                               activation=c["activation"], precision=getattr(self, "engine_precision", "bf16"),
+                               encoder_decoder_fusion=c["encoder_decoder_fusion"])
             self._engine = FusionEngine(self.state_dict(), cfg, device)
             self._engine_key = key
             self._graphs = {}

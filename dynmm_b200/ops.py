@@ -887,7 +887,8 @@ def split_from_f32(x: Tensor) -> Tensor:
 
 def upsample2x_dw3x3(x: Tensor, weight: Tensor, bias: Optional[Tensor], skip: Optional[Tensor] = None,
                      to_nchw_f32: bool = False, out: Optional[Tensor] = None, labels: Optional[Tensor] = None,
-                     want_logits: bool = True, split: bool = False, replicate: bool = False):
+                     want_logits: bool = True, split: bool = False, replicate: bool = False,
+                     c_valid: Optional[int] = None):
     """x NHWC bf16; weight fp32 tap-major [9, c] (``conv.weight.reshape(c, 9).t().contiguous()``).
     Final upsampling (``to_nchw_f32``): returns the NCHW fp32 logits; with ``labels`` (uint8 [n,2h,2w]) the
     arg-max over channels is produced in the same pass, and ``want_logits=False`` skips the logits.
@@ -900,15 +901,16 @@ def upsample2x_dw3x3(x: Tensor, weight: Tensor, bias: Optional[Tensor], skip: Op
     flags = (1 if split else 0) | (2 if replicate else 0)       # DYNMM_UPSAMPLE_SPLIT | DYNMM_UPSAMPLE_REPLICATE
     fn = lib.dynmm_upsample2x_dw3x3_ex
     if to_nchw_f32 or labels is not None:
+        cv = c if c_valid is None else c_valid        # classes that exist (c may be padded to a multiple of 8)
         if want_logits:
-            out = torch.empty(n, c, 2 * h, 2 * w, dtype=torch.float32, device=x.device) if out is None else out
+            out = torch.empty(n, cv, 2 * h, 2 * w, dtype=torch.float32, device=x.device) if out is None else out
         else:
             out = None
-        check(fn(ptr(x), n, h, w, c, ptr(weight), ptr(bias), None, None, ptr(out), ptr(labels), flags, stream_ptr()),
+        check(fn(ptr(x), n, h, w, c, ptr(weight), ptr(bias), None, None, ptr(out), ptr(labels), flags, cv, stream_ptr()),
               "upsample2x_dw3x3")
     else:
         out = torch.empty(n, 2 * h, 2 * w, ld, dtype=torch.bfloat16, device=x.device) if out is None else out
-        check(fn(ptr(x), n, h, w, c, ptr(weight), ptr(bias), ptr(skip), ptr(out), None, None, flags, stream_ptr()),
+        check(fn(ptr(x), n, h, w, c, ptr(weight), ptr(bias), ptr(skip), ptr(out), None, None, flags, 0, stream_ptr()),
               "upsample2x_dw3x3")
     return out
 

@@ -517,9 +517,11 @@ int dynmm_upsample2x_dw3x3_split(const void* in, int n, int h, int w, int c, con
  * 'bilinear' of model.py:364-366). */
 #define DYNMM_UPSAMPLE_SPLIT 1
 #define DYNMM_UPSAMPLE_REPLICATE 2
+/* c_valid (0 = c): only the first c_valid channels exist in the NCHW output [n, c_valid, 2h, 2w] and take part in the
+ * arg-max -- a class count that is not a multiple of 8 (SUN RGB-D: 37) is carried as c = 40 NHWC channels. */
 int dynmm_upsample2x_dw3x3_ex(const void* in, int n, int h, int w, int c, const float* weight, const float* bias,
                               const void* skip, void* out_nhwc_bf16, float* out_nchw_f32, uint8_t* labels, int flags,
-                              void* stream);
+                              int c_valid, void* stream);
 /* PyramidPoolingModule with upsampling_mode='bilinear' (context_modules.py:79-81): F.interpolate(mode='bilinear',
  * align_corners=False) of src [n,hs,ws,c] into channels [c_off, c_off + c) of dst [n,h,w,ld]; split: [hi | lo] tensors. */
 int dynmm_bilinear_resize_into(const void* src, int n, int hs, int ws, int c, void* dst, int h, int w, int ld, int c_off,

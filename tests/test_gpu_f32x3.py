@@ -246,15 +246,59 @@ def test_other_upsampling_modes_on_the_engine(mode):
             assert err <= tol, f"{mode}/{precision}: relative L2 {err:.2e}"
 
 
-def test_37_classes_fall_back_to_the_module_graph():
-    """num_classes % 8 != 0 (SUN RGB-D: 37): the engine declines, the eval forward runs the PyTorch graph (one warning)."""
-    import warnings
+def test_37_classes_run_on_the_engine():
+    """num_classes % 8 != 0 (SUN RGB-D: 37): the engine carries 40 NHWC channels (zero weight rows, stencils and biases)
+    and the final kernel emits -- and arg-maxes over -- the 37 real classes only."""
     from dynmm_b200.fusion import SkipGateESANet
     from oracle.make_golden import sample_inputs
-    model = SkipGateESANet(height=64, width=64, num_classes=37).cuda().eval()
-    rgb, depth = (t.cuda() for t in sample_inputs(2, 2, 64, 64))
-    with warnings.catch_warnings(record=True) as rec, torch.no_grad():
-        warnings.simplefilter("always")
-        out = model(rgb, depth, True)
-    assert out.shape == (2, 37, 64, 64) and torch.isfinite(out).all()
-    assert any("CUDA engine does not implement" in str(r.message) for r in rec)
+    torch.manual_seed(11)
+    model = SkipGateESANet(height=64, width=96, num_classes=37).cuda().eval()
+    g = torch.Generator().manual_seed(12)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+                m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+        # push the logits down so that some pixels have only negative ones: a padded class (exactly 0) must not win there
+        model.decoder.upsample2.conv.bias.sub_(8.0)
+        model.gate_layer.fc.weight.mul_(40.0)
+    model.hard_gate = True
+    rgb, depth = (t.cuda() for t in sample_inputs(2, 3, 64, 96))
+    with torch.no_grad():
+        ref, w_ref = model._forward_torch(rgb, depth)
+        for precision, tol in (("f32x3", F32_TOL), ("bf16", 2e-2)):
+            model.engine_precision = precision
+            out, w = model(rgb, depth, True, True)
+            assert getattr(model, "_engine_unsupported", None) is None
+            assert out.shape == (3, 37, 64, 96) and torch.equal(w, w_ref)
+            err = _rel_l2(out, ref)
+            assert err <= tol, f"{precision}: relative L2 {err:.2e}"
+            labels = model.predict_labels(rgb, depth)
+            assert int(labels.max()) < 37
+            assert (labels.long() == out.argmax(1)).float().mean().item() == 1.0
+    assert (ref.max(1).values < 0).any(), "the scenario needs pixels whose real logits are all negative"
+
+
+def test_encoder_decoder_fusion_none_on_the_engine():
+    """encoder_decoder_fusion='None' (model.py:353-355: the decoder modules do not add the encoder skip tensors)."""
+    from dynmm_b200.fusion import SkipGateESANet
+    from oracle.make_golden import sample_inputs
+    torch.manual_seed(13)
+    model = SkipGateESANet(height=64, width=96, num_classes=40, encoder_decoder_fusion="None").cuda().eval()
+    g = torch.Generator().manual_seed(14)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+                m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+    model.hard_gate = True
+    rgb, depth = (t.cuda() for t in sample_inputs(3, 3, 64, 96))
+    with torch.no_grad():
+        ref, w_ref = model._forward_torch(rgb, depth)
+        for precision, tol in (("f32x3", F32_TOL), ("bf16", 2e-2)):
+            model.engine_precision = precision
+            out, w = model(rgb, depth, True, True)
+            assert getattr(model, "_engine_unsupported", None) is None and not model.engine().dec_fusion
+            assert torch.equal(w, w_ref)
+            err = _rel_l2(out, ref)
+            assert err <= tol, f"{precision}: relative L2 {err:.2e}"

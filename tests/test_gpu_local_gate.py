@@ -115,22 +115,24 @@ def test_hard_chain_is_monotone_on_device():
     model.end_weight()
 
 
-def _r34_model():
+def _r34_model(case="local_gate_r34_nbt1d_64x96"):
     from dynmm_b200.fusion import SkipESANet
     from oracle.make_golden_local import CASES, seeded_state
-    kw, seed, b = CASES["local_gate_r34_nbt1d_64x96"]
+    kw, seed, b = CASES[case]
     model = SkipESANet(pretrained_on_imagenet=False, **kw)
     model.load_state_dict(seeded_state(model.state_dict(), seed), strict=True)
     return model.cuda().eval(), kw, seed, b
 
 
+@pytest.mark.parametrize("case", ["local_gate_r34_nbt1d_64x96", "local_gate_r18_basic_64x64"])
 @pytest.mark.parametrize("tag", ["random", "static1111"])
-def test_engine_matches_reference_vectors(tag, golden_dir):
+def test_engine_matches_reference_vectors(tag, case, golden_dir):
     """Eval mode on CUDA runs FusionEngine.forward_local (bf16 kernels, per-stage skipping).  Modes whose decisions do
     not depend on the device generator have reference vectors: random policy (CPU randint) and the static rule."""
     from oracle.make_golden_local import MODES, apply_mode, sample_inputs
-    model, kw, seed, b = _r34_model()
-    gold = np.load(os.path.join(golden_dir, "local_gate_r34_nbt1d_64x96.npz"))
+    # the second case: ResNet-18 BasicBlock encoders, bilinear up-sampling, 37 classes (model_skip_mod.py defaults)
+    model, kw, seed, b = _r34_model(case)
+    gold = np.load(os.path.join(golden_dir, case + ".npz"))
     rgb, depth = (t.cuda() for t in sample_inputs(seed + 100, b, kw["height"], kw["width"]))
     _, rule, attrs, test, fseed = next(m for m in MODES if m[0] == tag)
     apply_mode(model, rule, attrs)
