@@ -10,8 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
-    config.addinivalue_line("markers", "first_run: GPU test written after the round's GPU budget was spent -- its first "
-                                       "run on a B200 is still pending, so it is ordered after the validated tests")
+    config.addinivalue_line("markers", "first_run: GPU test whose first run on a B200 is still pending -- ordered after the "
+                                       "validated tests (none at the end of round 2: every gpu test has run green)")
 
 
 def pytest_collection_modifyitems(config, items):

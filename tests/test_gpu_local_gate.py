@@ -14,7 +14,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-pytestmark = [pytest.mark.gpu, pytest.mark.first_run]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module", autouse=True)

@@ -56,7 +56,6 @@ def test_pair_count_and_maps():
         assert torch.equal(ref, got), f"active={active}"
 
 
-@pytest.mark.first_run
 def test_pair_rotated_store_order_is_bit_identical():
     """The conflict-avoiding chunk order in epilogue 1 is the default since round 2 (DYNMM_PAIR_ROT=0 selects the straight
     order): the switch is read once per process, so the bit-identity tests above are re-run in a child process with the

@@ -7,7 +7,7 @@ import random
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.first_run]
+pytestmark = pytest.mark.gpu
 
 MARGIN = 1e-3        # oracle top-2 logit margin (relative to the logit scale) below which a decision is not compared
 
