@@ -149,6 +149,7 @@ class _Packer:
 @dataclasses.dataclass
 class EngineConfig:
     encoder: str = "resnet34"
+    encoder_depth: Optional[str] = None     # None: the RGB encoder's architecture (model_skip_mod_globalgate.py:81-93)
     encoder_block: str = "NonBottleneck1D"
     fuse: str = "add"
     nr_decoder_blocks: Sequence[int] = (3, 3, 3)
@@ -219,15 +220,22 @@ class FusionEngine:
         self.stem_packed = None
         if cfg.fuse == "add" and os.environ.get("DYNMM_STEM", "s2d") == "s2d":
             self.stem_packed = ops.stem_s2d_pack_weights(self.stem["encoder_rgb"][0], self.stem["encoder_depth"][0])
-        block_kind = "bottleneck" if cfg.encoder == "resnet50" else \
-            {"NonBottleneck1D": "nbt1d", "BasicBlock": "basic"}[cfg.encoder_block]
-        make = getattr(p, block_kind)
+        # the two encoders may differ (e.g. ResNet-34 for RGB, ResNet-18 for depth); their stage outputs must have the
+        # same channel counts, because every fusion site adds them
+        enc_arch = {"encoder_rgb": cfg.encoder, "encoder_depth": cfg.encoder_depth or cfg.encoder}
         self.stages = {}
-        for enc in ("encoder_rgb", "encoder_depth"):
+        for enc, arch in enc_arch.items():
+            block_kind = "bottleneck" if arch == "resnet50" else \
+                {"NonBottleneck1D": "nbt1d", "BasicBlock": "basic"}[cfg.encoder_block]
+            make = getattr(p, block_kind)
             stages = []
-            for s, nblk in enumerate(_STAGE_BLOCKS[cfg.encoder]):
+            for s, nblk in enumerate(_STAGE_BLOCKS[arch]):
                 stages.append([make(f"{enc}.layer{s + 1}.{b}", 2 if (b == 0 and s > 0) else 1) for b in range(nblk)])
             self.stages[enc] = stages
+        self.same_encoders = enc_arch["encoder_rgb"] == enc_arch["encoder_depth"]
+        if [st[-1].convs[-1].c_out for st in self.stages["encoder_rgb"]] != \
+                [st[-1].convs[-1].c_out for st in self.stages["encoder_depth"]]:
+            raise NotImplementedError("the encoders' stage outputs must have equal channel counts (they are added)")
         self.stage_channels = [st[-1].convs[-1].c_out for st in self.stages["encoder_rgb"]]
         self.skips = [p.conv_bn_act(f"skip_layer{i}.0", 1) if f"skip_layer{i}.0.conv.weight" in sd else None
                       for i in (1, 2, 3)]
@@ -276,7 +284,7 @@ class FusionEngine:
         # one launch per convolution on two streams.  Same arithmetic, bit-identical results; measured slower at
         # batch 8 in round 1 (profiles/r1_program_*), so the per-launch path stays the default.
         self.use_programs = (cfg.fuse == "add" and os.environ.get("DYNMM_PROGRAM", "0") == "1" and not self.split and
-                             self.dec_fusion)
+                             self.dec_fusion and self.same_encoders)
         self.programs: list = []   # ConvPrograms of the last forward (a captured graph must keep them alive)
         # 64-channel NonBottleneck1D blocks: each 3x1 -> 1x3 pair as ONE fused kernel (dynmm_conv_pair_fwd, bit-identical
         # to the two launches); DYNMM_PAIR=0 keeps one launch per convolution
@@ -289,7 +297,8 @@ class FusionEngine:
         # launch (dynmm_conv_igemm_fwd2) on one stream; only the last convolution of a stage runs per encoder (the RGB
         # one adds g_s * depth_s, which the depth one has to finish first).  Stage 1 (64 channels: fused-pair kernels
         # with resident weights) keeps the two-stream form.
-        self.use_merge = cfg.fuse == "add" and os.environ.get("DYNMM_MERGE", "1") == "1" and not self.use_programs
+        self.use_merge = (cfg.fuse == "add" and os.environ.get("DYNMM_MERGE", "1") == "1" and not self.use_programs and
+                          self.same_encoders)
         # DYNMM_CHAIN (default on, merged stages only): blocks 2.. of an encoder stage (stride 1, 128 or 256 channels) run
         # as ONE chain kernel per stage for both encoders (dynmm_conv_chain_fwd: activations stay in shared memory from
         # layer to layer); the stage's first block (stride 2, down-sampling) and the RGB encoder's last convolution (gated

@@ -166,6 +166,8 @@ class SkipESANet(nn.Module):
         self._pending: List[List[Tensor]] = [[] for _ in range(4)]
         self.train_precision = "fp32"        # "bf16": stage convolutions on the tcgen05 kernels (modules.Conv2d)
         self.use_engine = True               # eval mode + CUDA tensors: FusionEngine.forward_local (bf16, real skipping)
+        self.use_cuda_graph = False          # opt-in: replay one captured graph per input shape / mode (static outputs)
+        self._graphs = {}
         self._engine = None
         self.last_counts = None              # device int32 [1] x 4: depth samples each stage processed (engine path)
 
@@ -230,20 +232,21 @@ class SkipESANet(nn.Module):
         key = (str(device), tuple(p._version for p in self._version_probe))
         if self._engine is None or self._engine_key != key:
             c = self._cfg
-            if c["encoder_depth"] != c["encoder"]:
-                raise NotImplementedError("the CUDA engine needs encoder_rgb == encoder_depth")
             # the reference's forward always blends by addition, whatever fuse_depth_in_rgb_encoder built (:241-311)
-            cfg = EngineConfig(encoder=c["encoder"], encoder_block=c["encoder_block"], fuse="add",
+            cfg = EngineConfig(encoder=c["encoder"], encoder_depth=c["encoder_depth"],
+                               encoder_block=c["encoder_block"], fuse="add",
                                nr_decoder_blocks=c["nr_decoder_blocks"], num_classes=c["num_classes"],
                                upsampling=c["upsampling"], context_module=c["context_module"],
                                activation=c["activation"], gate="local",
                                encoder_decoder_fusion=c["encoder_decoder_fusion"])
             self._engine = FusionEngine(self.state_dict(), cfg, device)
             self._engine_key = key
+            self._graphs = {}
         return self._engine
 
     def invalidate_engine(self):
         self._engine = None
+        self._graphs = {}
 
     def train(self, mode: bool = True):
         if mode:
@@ -256,9 +259,18 @@ class SkipESANet(nn.Module):
 
     def _forward_engine(self, rgb, depth, test):
         eng = self.engine(rgb.device)
-        out, weights, counts = eng.forward_local(rgb, depth, block_rule=self.block_rule, temp=float(self.gate_layer0.temp),
-                                                 hard=True if test else bool(self.hard_gate),
-                                                 random_policy=bool(self.random_policy), ini_stage=bool(self.ini_stage))
+        modes = dict(block_rule=tuple(self.block_rule), temp=float(self.gate_layer0.temp),
+                     hard=True if test else bool(self.hard_gate), random_policy=bool(self.random_policy),
+                     ini_stage=bool(self.ini_stage))
+        if self.use_cuda_graph and not self.random_policy:
+            from .graph import GraphedLocalForward
+            key = (tuple(rgb.shape), tuple(sorted(modes.items())))
+            g = self._graphs.get(key)
+            if g is None:
+                g = self._graphs[key] = GraphedLocalForward(eng, rgb, depth, modes)
+            out, weights, counts = g(rgb, depth)
+        else:
+            out, weights, counts = eng.forward_local(rgb, depth, **modes)
         self.last_counts = counts
         if self.save_weight_info:
             for i in range(4):

@@ -570,9 +570,8 @@ class SkipGateESANet(nn.Module):
         key = (str(device), self._state_version(), getattr(self, "engine_precision", "bf16"))
         if self._engine is None or self._engine_key != key:
             c = self._cfg
-            if c["encoder_depth"] != c["encoder"]:
-                raise NotImplementedError("the CUDA engine needs encoder_rgb == encoder_depth")
-            cfg = EngineConfig(encoder=c["encoder"], encoder_block=c["encoder_block"], fuse=c["fuse"],
+            cfg = EngineConfig(encoder=c["encoder"], encoder_depth=c["encoder_depth"],
+                               encoder_block=c["encoder_block"], fuse=c["fuse"],
                                nr_decoder_blocks=c["nr_decoder_blocks"], num_classes=c["num_classes"],
                                upsampling=c["upsampling"], context_module=c["context_module"],
                                activation=c["activation"], precision=getattr(self, "engine_precision", "bf16"),

@@ -302,3 +302,31 @@ def test_encoder_decoder_fusion_none_on_the_engine():
             assert torch.equal(w, w_ref)
             err = _rel_l2(out, ref)
             assert err <= tol, f"{precision}: relative L2 {err:.2e}"
+
+
+def test_different_encoders_on_the_engine():
+    """encoder_rgb != encoder_depth (ResNet-34 for RGB, ResNet-18 for depth: equal stage widths, different depths):
+    the encoders run as independent launch sequences on two streams (no merged launches, no chain)."""
+    from dynmm_b200.fusion import SkipGateESANet
+    from oracle.make_golden import sample_inputs
+    torch.manual_seed(15)
+    model = SkipGateESANet(height=64, width=96, num_classes=40, encoder_rgb="resnet34", encoder_depth="resnet18").cuda().eval()
+    g = torch.Generator().manual_seed(16)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+                m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+        model.gate_layer.fc.weight.mul_(40.0)
+    model.hard_gate = True
+    rgb, depth = (t.cuda() for t in sample_inputs(4, 4, 64, 96))
+    with torch.no_grad():
+        ref, w_ref = model._forward_torch(rgb, depth)
+        for precision, tol in (("f32x3", F32_TOL), ("bf16", 2e-2)):
+            model.engine_precision = precision
+            out, w = model(rgb, depth, True, True)
+            eng = model.engine()
+            assert getattr(model, "_engine_unsupported", None) is None and not eng.same_encoders and not eng.use_merge
+            assert torch.equal(w, w_ref)
+            err = _rel_l2(out, ref)
+            assert err <= tol, f"{precision}: relative L2 {err:.2e}"

@@ -206,3 +206,24 @@ def test_engine_matches_module_graph_on_device(rule, attrs, test):
             assert counts[s] <= 6
             if not later_add and not later_dyn:
                 assert counts[s] <= int((g != 0).sum())
+
+
+def test_local_gate_engine_graph_replay_matches_eager_launches():
+    """SkipESANet.use_cuda_graph: one captured graph (device-side slot planning, device generator) serves every decision;
+    with a forced static rule the result is deterministic and must equal the eager launches bit for bit, with dynamic
+    gates the replays stay finite and the chained counts monotone."""
+    from oracle.make_golden_local import apply_mode, sample_inputs
+    model, kw, seed, _ = _r34_model()
+    rgb, depth = (t.cuda() for t in sample_inputs(seed + 3, 4, kw["height"], kw["width"]))
+    apply_mode(model, [1, 0, 1, 1], dict())
+    with torch.no_grad():
+        eager = model(rgb, depth, True).clone()
+        model.use_cuda_graph = True
+        for _ in range(3):
+            out = model(rgb, depth, True)
+        assert torch.equal(out, eager)
+        apply_mode(model, [2, 2, 2, 2], dict(hard_gate=True))
+        for _ in range(4):
+            out = model(rgb, depth, True)
+            counts = [int(c.item()) for c in model.last_counts]
+            assert torch.isfinite(out).all() and all(counts[s] <= counts[s - 1] for s in range(1, 4))
