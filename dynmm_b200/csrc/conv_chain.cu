@@ -540,6 +540,12 @@ int plan_chain(int h, int w, int c, int total_slots, int sms, ChainGeom* g) {
     set_error("conv_chain: %dx%dx%d does not fit shared memory", h, w, c);
     return DYNMM_EUNSUPPORTED;
   }
+  // whole rows per strip: a row pitch that fills the 128-slot M tiles badly (e.g. w + 1 = 71: one row per tile) wastes
+  // more tensor work than the chain saves -- leave such maps to the per-layer kernel and its 2-D boxes
+  if (10 * g->rows * w1 < 7 * g->tiles * kBlockM && g->strips > 1) {
+    set_error("conv_chain: %d-slot rows fill %d-slot tiles to less than 70 %%", w1, g->tiles * kBlockM);
+    return DYNMM_EUNSUPPORTED;
+  }
   // strips of one sample wait for each other: all of a sample's CTAs must be resident together.  CTAs are dispatched
   // in order, so a launch larger than the GPU still completes, but it runs in dependent waves -- refuse beyond 2x.
   if ((long long)total_slots * g->strips > 2LL * sms) {
