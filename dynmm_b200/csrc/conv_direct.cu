@@ -43,7 +43,9 @@ __global__ void conv_direct_kernel(dynmm_conv_params p) {
       const int rn = p.res_map ? p.res_map[n] : n;
       v += __bfloat162float(res[((1LL * rn * p.h_out + h) * p.w_out + w) * p.res_ld + c]);
     }
-    if (p.relu) v = fmaxf(v, 0.f);
+    if (p.relu == 1) v = fmaxf(v, 0.f);
+    else if (p.relu == 2) v = v / (1.f + __expf(-v));
+    else if (p.relu == 3) v = v * fminf(fmaxf(v + 3.f, 0.f), 6.f) / 6.f;
     if (gated) {
       const float g = p.gate[n];
       if (g != 0.f) {

@@ -52,7 +52,8 @@ using namespace convk;
 // CTA typically runs one RGB and one depth tile back to back: the second tile's loads and UMMAs hide the first one's
 // epilogue, and the fixed cost of a launch (prologue, first-load latency, drain, launch gap) is paid once per LAYER
 // instead of once per layer and encoder.  args2.n == 0: single convolution.
-// kMode: 0 = one CTA per SM, 1 = two CTAs per SM (large C = 64 layers), 2 = split operands (DYNMM_CONV_SPLIT; one per SM)
+// kMode: 0 = one CTA per SM, 1 = two CTAs per SM (large C = 64 layers), 2 = split operands (DYNMM_CONV_SPLIT; one per SM),
+// 3 = mode 0 with the swish / h-swish activations compiled in (dynmm_conv_params.relu = 2 / 3)
 template <int kFlags, int kMode>
 __global__ void __launch_bounds__(kThreads, kMode == 1 ? 2 : 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
@@ -65,6 +66,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                   const __grid_constant__ CUtensorMap map2_out, const __grid_constant__ KernelArgs args2) {
   constexpr int kPerSm = kMode == 1 ? 2 : 1;
   constexpr bool kSplit = kMode == 2;
+  constexpr bool kAct = kMode == 3;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -416,7 +418,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
           const uint32_t out_smem = out_base + sbuf * stage_out_bytes;
           if (cols_live) {
-            epilogue_chunk<true, false, kSplit>(kFlags, ja, v, t.c0 + cb, args.tile_n - cb, valid, res_smem, out_smem, half * 4,
+            epilogue_chunk<true, false, kSplit, kAct>(kFlags, ja, v, t.c0 + cb, args.tile_n - cb, valid, res_smem, out_smem, half * 4,
                                          swz, pix, rpix, gpix, g, shift_j, kPreRes ? pre_hi : nullptr, pre_lo);
           }
           if (kPreRes && sub + 1 < n_sub) prefetch_res(t, sub + 1);
@@ -448,7 +450,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           pending = (publish && sub == n_sub - 1) ? ja.out_f.flags + flag_index(ja.out_f, t.n0, h0t, w0t) : nullptr;
           sbuf ^= 1;
         } else if (cols_live) {
-          epilogue_chunk<false, false, kSplit>(kFlags, ja, v, t.c0 + cb, args.tile_n - cb, valid, 0, 0, 0, 0, pix, rpix, gpix, g,
+          epilogue_chunk<false, false, kSplit, kAct>(kFlags, ja, v, t.c0 + cb, args.tile_n - cb, valid, 0, 0, 0, 0, pix, rpix, gpix, g,
                                         shift_j, kPreRes ? pre_hi : nullptr, pre_lo);
           if (kPreRes && sub + 1 < n_sub) prefetch_res(t, sub + 1);
         }
@@ -519,7 +521,7 @@ int launch_conv(const ConvPlan& p0, const ConvPlan* p1, int max_ctas, bool pdl, 
   typedef void (*KernelFn)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap,
                            KernelArgs, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap,
                            CUtensorMap, KernelArgs);
-  static const KernelFn table[48] = {
+  static const KernelFn table[64] = {
       conv_igemm_kernel<0, 0>,  conv_igemm_kernel<1, 0>,  conv_igemm_kernel<2, 0>,  conv_igemm_kernel<3, 0>,
       conv_igemm_kernel<4, 0>,  conv_igemm_kernel<5, 0>,  conv_igemm_kernel<6, 0>,  conv_igemm_kernel<7, 0>,
       conv_igemm_kernel<8, 0>,  conv_igemm_kernel<9, 0>,  conv_igemm_kernel<10, 0>, conv_igemm_kernel<11, 0>,
@@ -531,11 +533,15 @@ int launch_conv(const ConvPlan& p0, const ConvPlan* p1, int max_ctas, bool pdl, 
       conv_igemm_kernel<0, 2>,  conv_igemm_kernel<1, 2>,  conv_igemm_kernel<2, 2>,  conv_igemm_kernel<3, 2>,
       conv_igemm_kernel<4, 2>,  conv_igemm_kernel<5, 2>,  conv_igemm_kernel<6, 2>,  conv_igemm_kernel<7, 2>,
       conv_igemm_kernel<8, 2>,  conv_igemm_kernel<9, 2>,  conv_igemm_kernel<10, 2>, conv_igemm_kernel<11, 2>,
-      conv_igemm_kernel<12, 2>, conv_igemm_kernel<13, 2>, conv_igemm_kernel<14, 2>, conv_igemm_kernel<15, 2>};
+      conv_igemm_kernel<12, 2>, conv_igemm_kernel<13, 2>, conv_igemm_kernel<14, 2>, conv_igemm_kernel<15, 2>,
+      conv_igemm_kernel<0, 3>,  conv_igemm_kernel<1, 3>,  conv_igemm_kernel<2, 3>,  conv_igemm_kernel<3, 3>,
+      conv_igemm_kernel<4, 3>,  conv_igemm_kernel<5, 3>,  conv_igemm_kernel<6, 3>,  conv_igemm_kernel<7, 3>,
+      conv_igemm_kernel<8, 3>,  conv_igemm_kernel<9, 3>,  conv_igemm_kernel<10, 3>, conv_igemm_kernel<11, 3>,
+      conv_igemm_kernel<12, 3>, conv_igemm_kernel<13, 3>, conv_igemm_kernel<14, 3>, conv_igemm_kernel<15, 3>};
   static PerDeviceOnce attr_once;
   DYNMM_CUDA(attr_once.run([] {
     cudaError_t e = cudaSuccess;
-    for (int i = 0; i < 48 && e == cudaSuccess; ++i) {
+    for (int i = 0; i < 64 && e == cudaSuccess; ++i) {
       const bool two = i >= 16 && i < 32;
       e = cudaFuncSetAttribute(table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, two ? 113 * 1024 : kSmemBudget);
       if (e == cudaSuccess && two) e = cudaFuncSetAttribute(table[i], cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -560,7 +566,7 @@ int launch_conv(const ConvPlan& p0, const ConvPlan* p1, int max_ctas, bool pdl, 
   const ConvPlan& q = p1 ? *p1 : p0;
   KernelArgs a2 = q.a;
   if (!p1) a2.n = 0;
-  DYNMM_CUDA(cudaLaunchKernelEx(&cfg, table[a.flags + (a.split ? 32 : (a.two_per_sm ? 16 : 0))], p0.maps[0], p0.maps[1], p0.maps[2],
+  DYNMM_CUDA(cudaLaunchKernelEx(&cfg, table[a.flags + (a.split ? 32 : (a.act > 1 ? 48 : (a.two_per_sm ? 16 : 0)))], p0.maps[0], p0.maps[1], p0.maps[2],
                                 p0.maps[3], p0.map_b, p0.map_res, p0.map_out, a, q.maps[0], q.maps[1], q.maps[2], q.maps[3],
                                 q.map_b, q.map_res, q.map_out, a2));
   return DYNMM_OK;
@@ -573,7 +579,7 @@ bool same_tiling(const KernelArgs& x, const KernelArgs& y) {
       x.k_chunks != y.k_chunks || x.stages != y.stages || x.stage_bytes != y.stage_bytes || x.a_bytes != y.a_bytes ||
       x.a_rows != y.a_rows || x.acc_stride != y.acc_stride || x.tma_epi != y.tma_epi || x.aux_slots != y.aux_slots ||
       x.b_resident != y.b_resident || x.two_per_sm != y.two_per_sm || x.mt != y.mt || x.swap != y.swap ||
-      x.flags != y.flags || x.h_out != y.h_out || x.w_out != y.w_out || x.c_out != y.c_out || x.split != y.split ||
+      x.flags != y.flags || x.h_out != y.h_out || x.w_out != y.w_out || x.c_out != y.c_out || x.split != y.split || x.act != y.act ||
       x.kc_c != y.kc_c || x.in_lo_off != y.in_lo_off || x.out_lo_off != y.out_lo_off)
     return false;
   for (int g = 0; g < x.num_groups; ++g)

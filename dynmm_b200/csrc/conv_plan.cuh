@@ -71,6 +71,7 @@ struct KernelArgs {
   dynmm_tile_flags in_f, res_f, out_f;
   int kh, kw, stride_h, stride_w, pad_h, pad_w, h_in, w_in;   // input window of an output tile (flag waits)
   int split;                        // DYNMM_CONV_SPLIT: [hi | lo] activation halves, 3-product contraction
+  int act;                          // dynmm_conv_params.relu: 1 ReLU, 2 swish, 3 h-swish (kFlagRelu set for all three)
   int kc_c;                         // split: K chunks of one half (c_in / 64), 0 otherwise
   int in_lo_off;                    // split: first channel of the input's lo half (in_ld / 2)
   int out_lo_off;                   // split: first channel of the output's lo half (out_ld / 2)
@@ -185,7 +186,7 @@ __device__ __forceinline__ uint4 ld_feat(const __nv_bfloat16* p) {
 //   else: direct global loads / stores (narrow channel tiles, partially active sample boxes).
 //   kCg : residual / gated features were written earlier in the SAME kernel by other CTAs (program kernel):
 //         read them through L2 (ld.global.cg), never through the non-coherent path.
-template <bool kTma, bool kCg, bool kSplit = false>
+template <bool kTma, bool kCg, bool kSplit = false, bool kAct = false>
 __device__ __forceinline__ void epilogue_chunk(const int kFlags, const KernelArgs& args, const uint32_t (&v)[32], int c_first,
                                                int cols_left, bool valid, uint32_t res_smem, uint32_t out_smem,
                                                uint32_t chunk0, uint32_t swz, size_t pix, size_t rpix, size_t gpix,
@@ -238,8 +239,17 @@ __device__ __forceinline__ void epilogue_chunk(const int kFlags, const KernelArg
         }
       }
       if (kFlags & kFlagRelu) {
+        // kAct: the kernel variant that knows swish / h-swish.  A run-time test in the ReLU variants cost 6.5 % of the
+        // bf16 step (measured, gpurun_out/r2ao), so they do not contain it.
+        if (!kAct || args.act <= 1) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+          for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+        } else {
+          // swish x * sigmoid(x) (2) / h-swish x * relu6(x + 3) / 6 (3), model_utils.py:100-115
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            f[e] = args.act == 2 ? f[e] / (1.f + __expf(-f[e])) : f[e] * fminf(fmaxf(f[e] + 3.f, 0.f), 6.f) / 6.f;
+        }
       }
       if (kFlags & kFlagGated) {
         if (g != 0.f) {      // gated-off samples never touch the depth features
@@ -358,6 +368,9 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
   DYNMM_CHECK_ARG(!p->residual || p->res_ld % 8 == 0, "conv_igemm: res_ld %% 8");
   DYNMM_CHECK_ARG(!p->gated || (p->gated_ld % 8 == 0 && p->gate), "conv_igemm: gated needs gate[] and gated_ld %% 8");
   DYNMM_CHECK_ARG(p->n >= 1 && p->n_in >= 1, "conv_igemm: empty batch");
+  DYNMM_CHECK_ARG(p->relu >= 0 && p->relu <= 3, "conv_igemm: relu must be 0 (none), 1 (ReLU), 2 (swish) or 3 (h-swish)");
+  DYNMM_CHECK_ARG(!(split && p->relu > 1), "conv_igemm: DYNMM_CONV_SPLIT launches fuse ReLU only");
+  if (p->relu > 1) allow_two_per_sm = false;          // the swish / h-swish kernel variants run one CTA per SM
   DYNMM_CHECK_ARG(!split || (p->c_in % kBlockK == 0 && p->in_ld % 16 == 0 && p->in_ld >= 2 * p->c_in && p->out_ld % 16 == 0 &&
                              p->out_ld >= 2 * p->c_out && p->res_ld % 16 == 0 && p->gated_ld % 16 == 0 &&
                              !p->in_flags.flags && !p->out_flags.flags),
@@ -567,6 +580,7 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
   a.kh = p->kh; a.kw = p->kw; a.stride_h = p->stride_h; a.stride_w = p->stride_w; a.pad_h = p->pad_h; a.pad_w = p->pad_w;
   a.h_in = p->h_in; a.w_in = p->w_in;
   a.split = split ? 1 : 0;
+  a.act = p->relu;
   a.kc_c = split ? p->c_in / kBlockK : 0;
   a.in_lo_off = split ? p->in_ld / 2 : 0;
   a.out_lo_off = split ? p->out_ld / 2 : 0;

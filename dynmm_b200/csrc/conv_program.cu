@@ -595,7 +595,8 @@ extern "C" int dynmm_conv_program_build(const dynmm_conv_params* jobs, const int
                                         void* image_, long long image_bytes, int32_t* launch_cfg) {
   DYNMM_CHECK_ARG(jobs && phase_of_job && image_ && launch_cfg, "conv_program_build: null pointer");
   for (int j = 0; j < n_jobs; ++j)
-    DYNMM_CHECK_ARG(!(jobs[j].flags & DYNMM_CONV_SPLIT), "conv_program_build: DYNMM_CONV_SPLIT jobs are per-launch only");
+    DYNMM_CHECK_ARG(!(jobs[j].flags & DYNMM_CONV_SPLIT) && jobs[j].relu <= 1,
+                    "conv_program_build: DYNMM_CONV_SPLIT / swish / h-swish jobs are per-launch only");
   DYNMM_CHECK_ARG(n_jobs >= 1 && n_jobs <= kMaxJobs, "conv_program_build: 1..%d convolutions per program", kMaxJobs);
   DYNMM_CHECK_ARG(image_bytes >= dynmm_conv_program_bytes(n_jobs), "conv_program_build: image buffer too small");
   DYNMM_CHECK_ARG((reinterpret_cast<uintptr_t>(image_) & 127) == 0, "conv_program_build: image must be 128-byte aligned");

@@ -67,7 +67,7 @@ class ConvLayer:
     kw: int
     stride: tuple
     pad: tuple
-    relu: bool
+    relu: int                      # activation code of dynmm_conv_params.relu (0 none, 1 ReLU, 2 swish, 3 h-swish)
     split: bool = False            # fp32-grade mode: [hi | lo] activations, weight packed [W_hi | W_lo | W_hi]
 
     def __call__(self, x: Tensor, **kw) -> Tensor:
@@ -82,8 +82,8 @@ class Block:
 
 
 class _Packer:
-    def __init__(self, sd: Dict[str, Tensor], device, split: bool = False):
-        self.sd, self.dev, self.split = sd, device, split
+    def __init__(self, sd: Dict[str, Tensor], device, split: bool = False, act: int = 1):
+        self.sd, self.dev, self.split, self.act = sd, device, split, act
 
     def t(self, key):
         return self.sd[key].detach().float().to(self.dev)
@@ -108,7 +108,9 @@ class _Packer:
             if shift is not None:
                 shift = torch.cat([shift, torch.zeros(c_pad - c_out, device=shift.device)]).contiguous()
             c_out = c_pad
-        return ConvLayer(packed, None, shift, c_in, c_out, kh, kw, tuple(stride), tuple(pad), relu, self.split)
+        # `relu=True` means "the model's activation": its code for dynmm_conv_params.relu
+        return ConvLayer(packed, None, shift, c_in, c_out, kh, kw, tuple(stride), tuple(pad), self.act if relu else 0,
+                         self.split)
 
     def nbt1d(self, key, stride=1) -> Block:
         """resnet.py:124-147: 3x1 -> ReLU -> 1x3 -> BN(1e-3) -> ReLU -> 3x1 -> ReLU -> 1x3 -> BN -> +id -> ReLU."""
@@ -177,8 +179,15 @@ class FusionEngine:
 
     def _build(self, sd: Dict[str, Tensor], cfg: EngineConfig, device):
         _lib.require_device()
-        if cfg.activation.lower() != "relu":
-            raise NotImplementedError("the CUDA engine fuses ReLU epilogues only; got activation=" + cfg.activation)
+        if cfg.activation.lower() not in ("relu", "swish", "silu", "hswish"):
+            raise NotImplementedError("unknown activation " + cfg.activation)
+        # ReLU is the tuned path.  swish / h-swish (model_utils.py:100-115) run through the same convolution kernel
+        # (activation code in the epilogue); the fused 64-channel pair kernel, the chain kernel and the tensor-core
+        # stem hard-wire ReLU, so those models use per-layer launches and a library (cuDNN) stem.
+        self.act = ops.ACTIVATIONS[cfg.activation.lower()]
+        if self.act != 1 and (cfg.fuse != "add" or cfg.gate != "global"):
+            raise NotImplementedError("swish / h-swish are implemented for the global gate with fuse='add' (the SE "
+                                      "kernels and the local gates' squeeze-excite hard-wire ReLU)")
         if cfg.fuse not in ("add", "SE-add"):
             raise NotImplementedError("fuse_depth_in_rgb_encoder must be 'add' or 'SE-add', got " + str(cfg.fuse))
         if cfg.upsampling not in ("learned-3x3-zeropad", "learned-3x3", "bilinear", "nearest"):
@@ -188,13 +197,13 @@ class FusionEngine:
         if cfg.precision not in ("bf16", "f32x3"):
             raise ValueError("EngineConfig.precision must be 'bf16' or 'f32x3'")
         self.split = cfg.precision == "f32x3"
-        if self.split and (cfg.fuse != "add" or cfg.gate != "global"):
-            raise NotImplementedError("precision='f32x3' is implemented for the global gate with fuse='add'")
+        if self.split and (cfg.fuse != "add" or cfg.gate != "global" or cfg.activation.lower() != "relu"):
+            raise NotImplementedError("precision='f32x3' is implemented for the global gate with fuse='add' and ReLU")
         if cfg.encoder_decoder_fusion not in ("add", "None"):
             raise NotImplementedError("encoder_decoder_fusion must be 'add' or 'None'")
         self.dec_fusion = cfg.encoder_decoder_fusion == "add"
         self.cfg, self.dev = cfg, device
-        p = _Packer(sd, device, self.split)
+        p = _Packer(sd, device, self.split, self.act)
         if cfg.gate == "local":
             if cfg.fuse != "add":
                 raise NotImplementedError("the local-gate engine blends by addition (model_skip_mod.py:241-311)")
@@ -218,7 +227,7 @@ class FusionEngine:
             self.stem[enc] = (w, s, b)
         # plain `add` fusion: TMA-gathered stem (dynmm_stem_s2d_fwd); DYNMM_STEM=tc|fp32 selects the older kernels
         self.stem_packed = None
-        if cfg.fuse == "add" and os.environ.get("DYNMM_STEM", "s2d") == "s2d":
+        if cfg.fuse == "add" and os.environ.get("DYNMM_STEM", "s2d") == "s2d" and self.act == 1:
             self.stem_packed = ops.stem_s2d_pack_weights(self.stem["encoder_rgb"][0], self.stem["encoder_depth"][0])
         # the two encoders may differ (e.g. ResNet-34 for RGB, ResNet-18 for depth); their stage outputs must have the
         # same channel counts, because every fusion site adds them
@@ -284,11 +293,11 @@ class FusionEngine:
         # one launch per convolution on two streams.  Same arithmetic, bit-identical results; measured slower at
         # batch 8 in round 1 (profiles/r1_program_*), so the per-launch path stays the default.
         self.use_programs = (cfg.fuse == "add" and os.environ.get("DYNMM_PROGRAM", "0") == "1" and not self.split and
-                             self.dec_fusion and self.same_encoders)
+                             self.dec_fusion and self.same_encoders and self.act == 1)
         self.programs: list = []   # ConvPrograms of the last forward (a captured graph must keep them alive)
         # 64-channel NonBottleneck1D blocks: each 3x1 -> 1x3 pair as ONE fused kernel (dynmm_conv_pair_fwd, bit-identical
         # to the two launches); DYNMM_PAIR=0 keeps one launch per convolution
-        self.use_pairs = os.environ.get("DYNMM_PAIR", "1") != "0" and not self.split
+        self.use_pairs = os.environ.get("DYNMM_PAIR", "1") != "0" and not self.split and self.act == 1
         # DYNMM_TILE_FLAGS=1: convolutions publish per-tile completion flags and their consumers wait on those instead
         # of on the previous kernel as a whole (layer k+1 starts on the SMs layer k's early finishers free)
         self.flag_pool = ops.TileFlagPool(device) if (os.environ.get("DYNMM_TILE_FLAGS", "0") == "1" and
@@ -306,12 +315,30 @@ class FusionEngine:
         self.chain_imgs = {}
         self._num_sms = torch.cuda.get_device_properties(device).multi_processor_count
         self._may_skip = True
-        if self.use_merge and os.environ.get("DYNMM_CHAIN", "1") == "1" and not self.split:
+        if self.use_merge and os.environ.get("DYNMM_CHAIN", "1") == "1" and not self.split and self.act == 1:
             for s in {int(v) for v in os.environ.get("DYNMM_CHAIN_STAGES", "2").split(",") if v.strip()}:
                 if 1 <= s <= 3:
                     imgs = self._chain_images(s)
                     if imgs is not None:
                         self.chain_imgs[s] = imgs
+
+    def _library_stem(self, rgb: Tensor, depth: Tensor):
+        """resnet.py:352-358 + model_skip_mod_globalgate.py:256-261 for the activations the tensor-core stem does not
+        hard-wire (swish / h-swish): cuDNN convolution, folded BatchNorm, activation, add, max-pool, NHWC copies.
+        -> (rgb fp32 NHWC, depth fp32 NHWC, rgb bf16 NHWC, depth bf16 NHWC), pooled to 1/4 resolution."""
+        import torch.nn.functional as F
+
+        def act(x):
+            return x * torch.sigmoid(x) if self.act == 2 else x * F.relu6(x + 3.0) / 6.0
+
+        outs = []
+        for x, enc in ((rgb, "encoder_rgb"), (depth, "encoder_depth")):
+            w, s, b = self.stem[enc]                                   # [7][7][cin][64], folded BN scale / shift
+            y = F.conv2d(x, w.permute(3, 2, 0, 1).contiguous(), stride=2, padding=3)
+            outs.append(act(y * s.view(1, -1, 1, 1) + b.view(1, -1, 1, 1)))
+        r = F.max_pool2d(outs[0] + outs[1], 3, 2, 1).permute(0, 2, 3, 1).contiguous()
+        d = F.max_pool2d(outs[1], 3, 2, 1).permute(0, 2, 3, 1).contiguous()
+        return r, d, r.to(torch.bfloat16), d.to(torch.bfloat16)
 
     def _up_params(self, p: "_Packer", key: str, c: int):
         """(tap-major [9][c] stencil, bias or None) of one Upsample module for dynmm_upsample2x_dw3x3."""
@@ -620,7 +647,12 @@ class FusionEngine:
         wr, sr, br = self.stem["encoder_rgb"]
         wd, sdp, bd = self.stem["encoder_depth"]
         learned = weight is None and not baseline and not ini_stage
-        if self.split:
+        if self.act != 1:
+            r32, d32, r16, d16 = self._library_stem(rgb, depth)
+            if self.split:
+                r16, d16 = ops.split_from_f32(r32), ops.split_from_f32(d32)
+            self.launches += 10
+        elif self.split:
             # fp32-grade mode: the stem (three split products already) hands its fp32 maps on as [hi | lo] halves
             if self.stem_packed is not None:
                 r32, d32, _, _ = ops.stem_s2d(rgb, depth, self.stem_packed, sr, br, sdp, bd, want_f32=True)

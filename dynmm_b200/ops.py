@@ -128,6 +128,7 @@ class TileFlagPool:
 
 
 FLAG_POOL: Optional[TileFlagPool] = None
+ACTIVATIONS = {"none": 0, "relu": 1, "swish": 2, "silu": 2, "hswish": 3}
 
 
 def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 1), pad=(0, 0),
@@ -169,7 +170,9 @@ def conv(x: Tensor, weight: Tensor, *, c_out: int, kh: int, kw: int, stride=(1, 
     p.res_ld = residual.shape[3] if residual is not None else 0
     p.gated_ld = gated.shape[3] if gated is not None else 0
     p.kh, p.kw, p.stride_h, p.stride_w, p.pad_h, p.pad_w = kh, kw, stride[0], stride[1], pad[0], pad[1]
-    p.relu, p.tile_n, p.max_ctas = int(relu), tile_n, max_ctas
+    # activation code of dynmm_conv_params.relu: False / True (ReLU) or "relu" / "swish" / "hswish"
+    p.relu = ACTIVATIONS[relu] if isinstance(relu, str) else int(relu)
+    p.tile_n, p.max_ctas = tile_n, max_ctas
     p.flags = 1 if volatile_weights else 0       # DYNMM_CONV_VOLATILE_WEIGHTS: packed on this stream just before
     if dual is not None:                         # DYNMM_CONV_NO_DUAL / DYNMM_CONV_FORCE_DUAL (default: the planner decides)
         p.flags |= 4 if dual else 2

@@ -208,7 +208,8 @@ typedef struct dynmm_conv_params {
   int32_t h_out, w_out, c_out, out_ld;
   int32_t res_ld, gated_ld;
   int32_t kh, kw, stride_h, stride_w, pad_h, pad_w;
-  int32_t relu;
+  int32_t relu;           /* activation after the residual add: 0 none, 1 ReLU, 2 swish x*sigmoid(x), 3 h-swish x*relu6(x+3)/6
+                             (model_utils.py:100-115) */
   int32_t tile_n;         /* 0 = choose; else 16..256 output channels per CTA tile */
   int32_t max_ctas;       /* 0 = one per SM */
   int32_t flags;          /* DYNMM_CONV_* bits (fills the padding in front of `trace`: the layout is unchanged) */

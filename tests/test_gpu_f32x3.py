@@ -330,3 +330,33 @@ def test_different_encoders_on_the_engine():
             assert torch.equal(w, w_ref)
             err = _rel_l2(out, ref)
             assert err <= tol, f"{precision}: relative L2 {err:.2e}"
+
+
+@pytest.mark.parametrize("activation", ["swish", "hswish"])
+def test_swish_and_hswish_models_on_the_engine(activation):
+    """activation='swish' / 'hswish' (model_utils.py:100-115): activation code in the convolution epilogue, per-layer
+    launches, library stem; the bf16 engine against the module's own fp32 PyTorch graph (f32x3 fuses ReLU only: such a
+    model falls back to the PyTorch graph in that mode)."""
+    from dynmm_b200.fusion import SkipGateESANet
+    from oracle.make_golden import sample_inputs
+    torch.manual_seed(17)
+    model = SkipGateESANet(height=64, width=96, num_classes=40, activation=activation).cuda().eval()
+    g = torch.Generator().manual_seed(18)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+                m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+        model.gate_layer.fc.weight.mul_(40.0)
+    model.hard_gate = True
+    rgb, depth = (t.cuda() for t in sample_inputs(6, 3, 64, 96))
+    with torch.no_grad():
+        ref, w_ref = model._forward_torch(rgb, depth)
+        for precision, tol in (("bf16", 2e-2),):
+            model.engine_precision = precision
+            out, w = model(rgb, depth, True, True)
+            assert getattr(model, "_engine_unsupported", None) is None, model._engine_unsupported
+            assert model.engine().act == {"swish": 2, "hswish": 3}[activation]
+            assert torch.equal(w, w_ref)
+            err = _rel_l2(out, ref)
+            assert err <= tol, f"{activation}/{precision}: relative L2 {err:.2e}"
