@@ -81,7 +81,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_stage_out + (args.tma_epi ? 2 * stage_out_bytes : 0));
   // [jobs][c_out + 8]: per-channel shift (zeros if absent), 16-byte aligned for float4 broadcast loads
   float* smem_shift = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ctl + 1) + 15) & ~uintptr_t(15));
-  const int shift_stride = (args.c_out + 11) & ~3;
+  const int c_pad64 = (args.c_out + 63) & ~63;            // shift staged (zero padded) for whole 64-column sub-tiles
+  const int shift_stride = c_pad64 + 8;
   const bool two_jobs = kPerSm == 1 && args2.n > 0;      // two CTAs per SM: single-job launches only (registers)
 
   const int warp = threadIdx.x >> 5;
@@ -143,9 +144,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   if (warp >= 2) {
     // epilogue warps stage the shift vectors once (no global loads inside the tile loop); the global-load latency
     // overlaps the first TMA loads and UMMAs instead of delaying them: only the epilogue warps wait for it
-    for (int c = threadIdx.x - 64; c < args.c_out; c += 32 * kEpiWarps) {
-      smem_shift[c] = args.shift ? args.shift[c] : 0.f;
-      if (two_jobs) smem_shift[shift_stride + c] = args2.shift ? args2.shift[c] : 0.f;
+    for (int c = threadIdx.x - 64; c < c_pad64; c += 32 * kEpiWarps) {
+      smem_shift[c] = (args.shift && c < args.c_out) ? args.shift[c] : 0.f;
+      if (two_jobs) smem_shift[shift_stride + c] = (args2.shift && c < args.c_out) ? args2.shift[c] : 0.f;
     }
     named_barrier(3, 32 * kEpiWarps);
   }
@@ -418,7 +419,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
           const uint32_t out_smem = out_base + sbuf * stage_out_bytes;
           if (cols_live) {
-            epilogue_chunk<true, false, kSplit, kAct>(kFlags, ja, v, t.c0 + cb, args.tile_n - cb, valid, res_smem, out_smem, half * 4,
+            epilogue_chunk<true, false, kSplit, kAct, true>(kFlags, ja, v, t.c0 + cb, args.tile_n - cb, valid, res_smem, out_smem, half * 4,
                                          swz, pix, rpix, gpix, g, shift_j, kPreRes ? pre_hi : nullptr, pre_lo);
           }
           if (kPreRes && sub + 1 < n_sub) prefetch_res(t, sub + 1);

@@ -186,7 +186,9 @@ __device__ __forceinline__ uint4 ld_feat(const __nv_bfloat16* p) {
 //   else: direct global loads / stores (narrow channel tiles, partially active sample boxes).
 //   kCg : residual / gated features were written earlier in the SAME kernel by other CTAs (program kernel):
 //         read them through L2 (ld.global.cg), never through the non-coherent path.
-template <bool kTma, bool kCg, bool kSplit = false, bool kAct = false>
+// kFullCols (TMA epilogue of conv_igemm.cu): the sub-tile is a full 64-column one and the shift vector is staged (zero
+// padded) for every column of it, so the per-group bounds tests fall away; columns >= c_out are clipped by the TMA store
+template <bool kTma, bool kCg, bool kSplit = false, bool kAct = false, bool kFullCols = false>
 __device__ __forceinline__ void epilogue_chunk(const int kFlags, const KernelArgs& args, const uint32_t (&v)[32], int c_first,
                                                int cols_left, bool valid, uint32_t res_smem, uint32_t out_smem,
                                                uint32_t chunk0, uint32_t swz, size_t pix, size_t rpix, size_t gpix,
@@ -195,7 +197,7 @@ __device__ __forceinline__ void epilogue_chunk(const int kFlags, const KernelArg
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     const int c = c_first + j;
-    if (j < cols_left && c < args.c_out) {
+    if (kFullCols || (j < cols_left && c < args.c_out)) {
       float f[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
@@ -217,7 +219,8 @@ __device__ __forceinline__ void epilogue_chunk(const int kFlags, const KernelArg
         if (kTma && res_smem != 0) {
           r = lds128(res_smem + chunk);
         } else {
-          r = valid ? ld_feat<kCg>(args.residual + rpix * args.res_ld + c) : make_uint4(0, 0, 0, 0);
+          r = (valid && (!kFullCols || c < args.c_out)) ? ld_feat<kCg>(args.residual + rpix * args.res_ld + c)
+                                                        : make_uint4(0, 0, 0, 0);
         }
         if (kSplit) {
           // fp32-grade residual = hi + lo, reconstructed before it is added; both halves come from global memory --
@@ -227,7 +230,9 @@ __device__ __forceinline__ void epilogue_chunk(const int kFlags, const KernelArg
             r = pre_hi[j >> 3];
             q = pre_lo[j >> 3];
           } else {
-            q = valid ? ld_feat<kCg>(args.residual + rpix * args.res_ld + (args.res_ld >> 1) + c) : make_uint4(0, 0, 0, 0);
+            q = (valid && (!kFullCols || c < args.c_out))
+                    ? ld_feat<kCg>(args.residual + rpix * args.res_ld + (args.res_ld >> 1) + c)
+                    : make_uint4(0, 0, 0, 0);
           }
           f[0] += bf16_lo(r.x) + bf16_lo(q.x); f[1] += bf16_hi(r.x) + bf16_hi(q.x);
           f[2] += bf16_lo(r.y) + bf16_lo(q.y); f[3] += bf16_hi(r.y) + bf16_hi(q.y);
@@ -252,7 +257,7 @@ __device__ __forceinline__ void epilogue_chunk(const int kFlags, const KernelArg
         }
       }
       if (kFlags & kFlagGated) {
-        if (g != 0.f) {      // gated-off samples never touch the depth features
+        if (g != 0.f && (!kFullCols || c < args.c_out)) {      // gated-off samples never touch the depth features
           const uint4 r = ld_feat<kCg>(args.gated + gpix * args.gated_ld + c);
           if (kSplit) {
             const uint4 q = ld_feat<kCg>(args.gated + gpix * args.gated_ld + (args.gated_ld >> 1) + c);
@@ -492,7 +497,7 @@ inline int plan_conv(const dynmm_conv_params* p, ConvPlan* plan, int sms, int sm
     a.aux_slots = (a.tma_epi && p->residual && !small && !split) ? kAuxSlots : 0;
     a.b_resident = (a.c_tiles == 1 && b_total <= kResidentBudget && !merged) ? 1 : 0;
     if (a.b_resident && a.aux_slots) a.aux_slots = 2;
-    shift_bytes = ((p->c_out + 12) * 4) * (merged ? 2 : 1) + 16;
+    shift_bytes = (((p->c_out + 63) / 64 * 64 + 12) * 4) * (merged ? 2 : 1) + 16;     // staged per full 64-column sub-tile
     epi_bytes = (a.tma_epi ? (split ? 4 : 2) * kSubBytes : 0) + a.aux_slots * kSubBytes;
     a.stage_bytes = a.a_bytes + (a.b_resident ? 0 : a.tpg * b_tile_bytes);
     a.stages = (smem_budget - 2048 - epi_bytes - shift_bytes - (a.b_resident ? b_total : 0)) / a.stage_bytes;
