@@ -27,12 +27,16 @@
 // (TMEM -> BN + ReLU -> fuse -> horizontal 3-max by warp shuffles -> 7x7 row maxima in shared memory -> vertical 3-max ->
 // NHWC stores, 16 channels at a time), so the epilogues of tiles i and i+1 and the MMAs of tile i+2 overlap.  The split weights (128 KiB) stay in
 // shared memory for the kernel's lifetime.
+#include <cstring>
 #include "common.cuh"
 #include "tma_host.cuh"
 
 namespace dynmm {
 namespace stems2d {
 
+#ifndef DYNMM_STEM_TRACE
+#define DYNMM_STEM_TRACE 0   // experiments only: clock stamps of CTA 0 into the depth bf16 output (tools/stem_trace.py)
+#endif
 constexpr int kPW = 7, kPH = 3;             // pooled tile: 7 wide, 3 tall
 constexpr int kSW = 16;                     // stem columns fetched per tile (2*kPW + 1 = 15 used, +1 keeps views aligned)
 constexpr int kSH = 2 * kPH + 1;            // stem rows per tile (7)
@@ -50,12 +54,17 @@ constexpr int kGroupWarps = kEpiWarps / 2;  // two epilogue groups, one per accu
 constexpr int kOffW = 0;                                   // [4 qy][hi, lo][128 n][128 B]
 constexpr int kOffA = kOffW + 8 * kWSlab;                  // [kRing][hi, lo][160 rows][128 B]
 constexpr int kOffTile = kOffA + kRing * kStage;           // per group: row-maxima of the fused / depth maps,
-constexpr int kTileBytes = kSH * kPW * kPassCh * 4;        // [7 stem rows][7 pooled cols][16 ch] fp32 = 3136 B each
+constexpr int kTileBytes = (3 * 52 + 2 + kSH * kPW) * 16;     // channel-quad major, see h_off: 207 float4 = 3312 B each
 constexpr int kOffBn = kOffTile + 4 * kTileBytes;          // scale_rgb, shift_rgb, scale_d, shift_d (64 each)
 constexpr int kOffCtl = kOffBn + 256 * 4;
 constexpr int kSmemBytes = 1024 + kOffCtl + 256;
 static_assert(kSmemBytes <= 227 * 1024, "stem_s2d shared memory");
 static_assert(kPlane % 1024 == 0 && (kSW * 128) % 1024 == 0, "tap views must keep the 128B-swizzle phase");
+
+// BN scale / shift of both stems as a kernel parameter (constant bank): [scale_rgb | shift_rgb | scale_d | shift_d]
+struct StemBn {
+  float v[256];
+};
 
 struct __align__(8) Ctl {
   uint64_t full[kRing];
@@ -75,6 +84,9 @@ __device__ __forceinline__ void split1(float x, __nv_bfloat16& hi, __nv_bfloat16
 // ---- pre-pass: NCHW fp32 -> padded space-to-depth bf16 hi / lo planes [b][Hs2+3][Ws2+3][16]
 __global__ void s2d_pack_kernel(const float* __restrict__ rgb, const float* __restrict__ depth, int b, int H, int W,
                                 int Hp2, int Wp2, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+  // the stem kernel is launched with programmatic stream serialization: its prologue (TMEM allocation, 128 KiB of
+  // weights per CTA) runs under this kernel, its first load of the planes waits for this grid to complete
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   const long long total = 1LL * b * Hp2 * Wp2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int px = (int)(i % Wp2);
@@ -136,8 +148,15 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
                : "r"(taddr)
                : "memory");
 }
-// byte offset of (stem row ly, pooled column plx, channel ch) in a [7][7][16] fp32 tile of horizontal maxima
-__device__ __forceinline__ uint32_t h_off(int ly, int plx, int ch) { return ((ly * kPW + plx) * kPassCh + ch) * 4; }
+// byte offset of (stem row ly, pooled column plx, channel ch) in a tile of horizontal maxima.  Channel-quad major
+// [4 quads][7 x 7 positions] float4 with the quads at 16-byte units 0, 52, 106, 158 (= 0, 4, 2, 6 mod 8): the writers
+// of a warp (even lanes quad 2 h, odd lanes quad 2 h + 1, consecutive positions) and a quarter-warp of pooling
+// threads (2 positions x 4 quads) both touch every bank once -- the pixel-major [7][7][16] tile cost 7 wavefronts per
+// store
+__device__ __forceinline__ uint32_t h_off(int ly, int plx, int ch) {
+  const int q = ch >> 2;
+  return ((q * 52 + (q >> 1) * 2 + ly * kPW + plx) * 4 + (ch & 3)) * 4;
+}
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
@@ -146,9 +165,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                : "memory");
 }
 
+// kConstBn: the BN vectors come from the parameter `bn` (host copy, constant-bank loads) instead of shared memory --
+// eight LDS.128 per pass less in an epilogue that is bound by the shared-memory / shuffle instruction queue
+template <bool kConstBn>
 __global__ void __launch_bounds__(kThreads, 1)
 stem_s2d_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
-                const __grid_constant__ CUtensorMap map_w, int Hs, int Ws, const float* __restrict__ scale_rgb,
+                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ StemBn bn, int Hs, int Ws,
+                const float* __restrict__ scale_rgb,
                 const float* __restrict__ shift_rgb, const float* __restrict__ scale_d, const float* __restrict__ shift_d,
                 float* __restrict__ rgb_f32, float* __restrict__ depth_f32, __nv_bfloat16* __restrict__ rgb_bf16,
                 __nv_bfloat16* __restrict__ depth_bf16, int tiles_x, int tiles_y, int batch) {
@@ -186,7 +209,7 @@ stem_s2d_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
     tmem_alloc(&ctl->tmem_base, 512);      // the whole TMEM: base 0, MMA operands stay in uniform registers
     tmem_relinquish();
   }
-  if (tid >= 64 && tid < 128) {
+  if (!kConstBn && tid >= 64 && tid < 128) {
     const int c = tid - 64;
     s_bn[c] = scale_rgb[c];
     s_bn[64 + c] = shift_rgb[c];
@@ -201,6 +224,7 @@ stem_s2d_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer: two box loads per tile
     if (lane == 0) {
+      asm volatile("griddepcontrol.wait;\n" ::: "memory");     // the planes are written by the pre-pass
       int slot = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -229,10 +253,20 @@ stem_s2d_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
       int slot = 0;
       uint32_t phase = 0;
       int local = 0;
+#if DYNMM_STEM_TRACE
+      long long* trm = reinterpret_cast<long long*>(depth_bf16) + (static_cast<size_t>(blockIdx.x) * 20 + 16) * 1024;
+      int tm = 0;
+#define MSTAMP() do { if (blockIdx.x < 2 && lane == 0 && tm < 1024) trm[tm++] = clock64(); } while (0)
+#else
+#define MSTAMP() do { } while (0)
+#endif
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
         const uint32_t acc = local & 3;       // four 128-column accumulators: the MMAs run up to 3 tiles ahead
+        MSTAMP();
         mbar_wait(&ctl->acc_empty[acc], ((local >> 2) & 1) ^ 1);
+        MSTAMP();
         mbar_wait(&ctl->full[slot], phase);
+        MSTAMP();
         tc_fence_after();
         const uint32_t d_tmem = acc * 128;
         const uint32_t stage = a_base + slot * kStage;
@@ -272,13 +306,21 @@ stem_s2d_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
     const int half = (ewarp % kGroupWarps) >> 2;  // which 8 of the 16 channels of a pass
     const int row = quarter * 32 + lane;          // GEMM row = stem position ly * 16 + lx
     const int ly = row >> 4, lx = row & 15;
-    const bool writer = ly < kSH && (lx & 1) == 0 && lx <= 2 * (kPW - 1);
+    const bool odd = lane & 1;
+    const bool writer = ly < kSH && lx <= 2 * (kPW - 1) + 1;     // lane pair (2 p, 2 p + 1) owns pooled column p
     uint8_t* s_hf = smem + kOffTile + g * 2 * kTileBytes;     // horizontal maxima of rgb + depth
     uint8_t* s_hd = s_hf + kTileBytes;                        // ... of depth
     // pooling: the first 84 threads of the group own (pooled pixel pp = gt >> 2 < 21) x (channel quad c4 of the pass)
     const int pp = gt >> 2, c4 = (gt & 3) * 4;
     const int ply = pp / kPW, plx = pp - ply * kPW;
     const uint32_t t_lane = static_cast<uint32_t>(quarter * 32) << 16;
+#if DYNMM_STEM_TRACE
+    long long* trc = reinterpret_cast<long long*>(depth_bf16) + (static_cast<size_t>(blockIdx.x) * 20 + ewarp) * 1024;
+    int tn = 0;
+#define STAMP() do { if (blockIdx.x < 2 && lane == 0 && tn < 1024) trc[tn++] = clock64(); } while (0)
+#else
+#define STAMP() do { } while (0)
+#endif
     for (int local = g; blockIdx.x + static_cast<long long>(local) * gridDim.x < total_tiles; local += 2) {
       const int tile = blockIdx.x + local * gridDim.x;
       const int n = tile / (tiles_x * tiles_y);
@@ -290,8 +332,10 @@ stem_s2d_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
       const int gy = sy0 + ly, gx = sx0 + lx;
       const bool inside = ly < kSH && gy >= 0 && gy < Hs && gx >= 0 && gx < Ws;
       const uint32_t acc = local & 3;             // group g reads buffers g and g + 2
+      STAMP();
       mbar_wait(&ctl->acc_full[acc], (local >> 2) & 1);
       tc_fence_after();
+      STAMP();
       const uint32_t t_row = t_lane + acc * 128;
 #pragma unroll 1
       for (int pass = 0; pass < 64 / kPassCh; ++pass) {
@@ -300,6 +344,7 @@ stem_s2d_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         tmem_ld8(t_row + c, vr);
         tmem_ld8(t_row + 64 + c, vd);
         tmem_ld_wait();
+        STAMP();
         if (pass == 64 / kPassCh - 1) {
           // accumulator fully read: the MMAs of the tile after next may start
           tc_fence_before();
@@ -309,8 +354,17 @@ stem_s2d_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         float f[8], d[8];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          const float4 sr = *reinterpret_cast<const float4*>(s_bn + c + 4 * q), br = *reinterpret_cast<const float4*>(s_bn + 64 + c + 4 * q);
-          const float4 sd = *reinterpret_cast<const float4*>(s_bn + 128 + c + 4 * q), bd = *reinterpret_cast<const float4*>(s_bn + 192 + c + 4 * q);
+          float4 sr, br, sd, bd;
+          if (kConstBn) {
+            const int k = c + 4 * q;
+            sr = make_float4(bn.v[k], bn.v[k + 1], bn.v[k + 2], bn.v[k + 3]);
+            br = make_float4(bn.v[64 + k], bn.v[64 + k + 1], bn.v[64 + k + 2], bn.v[64 + k + 3]);
+            sd = make_float4(bn.v[128 + k], bn.v[128 + k + 1], bn.v[128 + k + 2], bn.v[128 + k + 3]);
+            bd = make_float4(bn.v[192 + k], bn.v[192 + k + 1], bn.v[192 + k + 2], bn.v[192 + k + 3]);
+          } else {
+            sr = *reinterpret_cast<const float4*>(s_bn + c + 4 * q), br = *reinterpret_cast<const float4*>(s_bn + 64 + c + 4 * q);
+            sd = *reinterpret_cast<const float4*>(s_bn + 128 + c + 4 * q), bd = *reinterpret_cast<const float4*>(s_bn + 192 + c + 4 * q);
+          }
           d[4 * q + 0] = fmaxf(fmaf(__uint_as_float(vd[4 * q + 0]), sd.x, bd.x), 0.f);
           d[4 * q + 1] = fmaxf(fmaf(__uint_as_float(vd[4 * q + 1]), sd.y, bd.y), 0.f);
           d[4 * q + 2] = fmaxf(fmaf(__uint_as_float(vd[4 * q + 2]), sd.z, bd.z), 0.f);
@@ -327,18 +381,33 @@ stem_s2d_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
             f[e] = -INFINITY;
             d[e] = -INFINITY;
           }
-          // horizontal 3-max over columns lx, lx+1, lx+2 (16-lane segments = one stem row)
-          f[e] = fmaxf(f[e], fmaxf(__shfl_down_sync(0xffffffffu, f[e], 1, 16), __shfl_down_sync(0xffffffffu, f[e], 2, 16)));
-          d[e] = fmaxf(d[e], fmaxf(__shfl_down_sync(0xffffffffu, d[e], 1, 16), __shfl_down_sync(0xffffffffu, d[e], 2, 16)));
         }
+        // horizontal 3-max over columns 2 p, 2 p + 1, 2 p + 2 for pooled column p, split over the lane pair (2 p, 2 p + 1):
+        // the even lane finishes channels 0..3, the odd lane channels 4..7.  Exchange A (partner lane): the even lane
+        // hands over its channels 4..7 and receives the odd lane's 0..3; exchange B (two lanes up, inside the 16-lane
+        // stem row): the even lane receives column 2 p + 2's channels 0..3 from their owner, the odd lane the channels
+        // 4..7 of that column from lane 2 p + 3, which got them in A.  8 shuffles per map instead of 16 -- the epilogue
+        // is bound by the shuffle / shared-memory instruction queue (tools/stem_trace.py: 1300 of a pass's 2700 cycles).
+        float hf[4], hd[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float own_f = odd ? f[e + 4] : f[e], own_d = odd ? d[e + 4] : d[e];
+          const float a_f = __shfl_xor_sync(0xffffffffu, odd ? f[e] : f[e + 4], 1);
+          const float a_d = __shfl_xor_sync(0xffffffffu, odd ? d[e] : d[e + 4], 1);
+          const float b_f = __shfl_down_sync(0xffffffffu, odd ? a_f : own_f, 2, 16);
+          const float b_d = __shfl_down_sync(0xffffffffu, odd ? a_d : own_d, 2, 16);
+          hf[e] = fmaxf(own_f, fmaxf(a_f, b_f));
+          hd[e] = fmaxf(own_d, fmaxf(a_d, b_d));
+        }
+        STAMP();
         if (writer) {
-          const uint32_t off = h_off(ly, lx >> 1, half * 8);
-          *reinterpret_cast<float4*>(s_hf + off) = make_float4(f[0], f[1], f[2], f[3]);
-          *reinterpret_cast<float4*>(s_hf + off + 16) = make_float4(f[4], f[5], f[6], f[7]);
-          *reinterpret_cast<float4*>(s_hd + off) = make_float4(d[0], d[1], d[2], d[3]);
-          *reinterpret_cast<float4*>(s_hd + off + 16) = make_float4(d[4], d[5], d[6], d[7]);
+          const uint32_t off = h_off(ly, lx >> 1, half * 8 + (odd ? 4 : 0));
+          *reinterpret_cast<float4*>(s_hf + off) = make_float4(hf[0], hf[1], hf[2], hf[3]);
+          *reinterpret_cast<float4*>(s_hd + off) = make_float4(hd[0], hd[1], hd[2], hd[3]);
         }
+        STAMP();
         named_barrier(1 + g, 32 * kGroupWarps);
+        STAMP();
         // vertical 3-max over stem rows 2*ply .. 2*ply+2: 21 pooled pixels x 4 channel quads
         if (item) {
           float4 mf = *reinterpret_cast<const float4*>(s_hf + h_off(2 * ply, plx, c4));
@@ -359,13 +428,14 @@ stem_s2d_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
             v.y = pack_bf16(mf.z, mf.w);
             *reinterpret_cast<uint2*>(rgb_bf16 + o) = v;
           }
-          if (depth_bf16) {
+          if (depth_bf16 && !DYNMM_STEM_TRACE) {
             uint2 v;
             v.x = pack_bf16(md.x, md.y);
             v.y = pack_bf16(md.z, md.w);
             *reinterpret_cast<uint2*>(depth_bf16 + o) = v;
           }
         }
+        STAMP();
         named_barrier(1 + g, 32 * kGroupWarps);   // the row maxima are consumed before the next pass overwrites them
       }
     }
@@ -409,7 +479,8 @@ extern "C" int dynmm_stem_s2d_pack_weights(const float* w_rgb, const float* w_d,
 extern "C" int dynmm_stem_s2d_fwd(const float* rgb, const float* depth, int b, int h, int w, const void* w_packed,
                                   const float* scale_rgb, const float* shift_rgb, const float* scale_d,
                                   const float* shift_d, void* workspace, long long workspace_bytes, float* rgb_f32,
-                                  float* depth_f32, void* rgb_bf16, void* depth_bf16, void* stream_) {
+                                  float* depth_f32, void* rgb_bf16, void* depth_bf16, const float* bn_host,
+                                  void* stream_) {
   using namespace stems2d;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DYNMM_CHECK_ARG(rgb && depth && w_packed && scale_rgb && shift_rgb && scale_d && shift_d && workspace,
@@ -448,16 +519,31 @@ extern "C" int dynmm_stem_s2d_fwd(const float* rgb, const float* depth, int b, i
   DYNMM_LAUNCH_CHECK();
 
   static PerDeviceOnce attr_once;
-  DYNMM_CUDA(attr_once.run(
-      [] { return cudaFuncSetAttribute(stem_s2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes); }));
+  DYNMM_CUDA(attr_once.run([] {
+    cudaError_t e = cudaFuncSetAttribute(stem_s2d_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    return e != cudaSuccess ? e
+                            : cudaFuncSetAttribute(stem_s2d_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  }));
   const int tiles_x = ceil_div(Wp, kPW), tiles_y = ceil_div(Hp, kPH);
   const long long total = 1LL * tiles_x * tiles_y * b;
   DYNMM_CHECK_ARG(total < (1LL << 30), "stem_s2d: too many tiles");
   const int grid = (int)(total < num_sms() ? total : num_sms());
-  stem_s2d_kernel<<<grid, kThreads, kSmemBytes, stream>>>(map_hi, map_lo, map_w, Hs, Ws, scale_rgb, shift_rgb, scale_d,
-                                                         shift_d, rgb_f32, depth_f32,
-                                                         static_cast<__nv_bfloat16*>(rgb_bf16),
-                                                         static_cast<__nv_bfloat16*>(depth_bf16), tiles_x, tiles_y, b);
+  StemBn bn{};
+  if (bn_host) memcpy(bn.v, bn_host, sizeof(bn.v));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DYNMM_CUDA(cudaLaunchKernelEx(&cfg, bn_host ? stem_s2d_kernel<true> : stem_s2d_kernel<false>, map_hi, map_lo, map_w, bn,
+                                Hs, Ws, scale_rgb, shift_rgb, scale_d, shift_d, rgb_f32, depth_f32,
+                                static_cast<__nv_bfloat16*>(rgb_bf16), static_cast<__nv_bfloat16*>(depth_bf16), tiles_x,
+                                tiles_y, b));
   DYNMM_LAUNCH_CHECK();
   return DYNMM_OK;
 }

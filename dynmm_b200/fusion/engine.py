@@ -229,6 +229,8 @@ class FusionEngine:
         self.stem_packed = None
         if cfg.fuse == "add" and os.environ.get("DYNMM_STEM", "s2d") == "s2d" and self.act == 1:
             self.stem_packed = ops.stem_s2d_pack_weights(self.stem["encoder_rgb"][0], self.stem["encoder_depth"][0])
+            # host copy of the BN vectors: they travel as a kernel parameter (constant bank) on every stem launch
+            self.stem_bn_host = ops.stem_s2d_bn_host(*self.stem["encoder_rgb"][1:], *self.stem["encoder_depth"][1:])
         # the two encoders may differ (e.g. ResNet-34 for RGB, ResNet-18 for depth); their stage outputs must have the
         # same channel counts, because every fusion site adds them
         enc_arch = {"encoder_rgb": cfg.encoder, "encoder_depth": cfg.encoder_depth or cfg.encoder}
@@ -655,13 +657,15 @@ class FusionEngine:
         elif self.split:
             # fp32-grade mode: the stem (three split products already) hands its fp32 maps on as [hi | lo] halves
             if self.stem_packed is not None:
-                r32, d32, _, _ = ops.stem_s2d(rgb, depth, self.stem_packed, sr, br, sdp, bd, want_f32=True)
+                r32, d32, _, _ = ops.stem_s2d(rgb, depth, self.stem_packed, sr, br, sdp, bd, want_f32=True,
+                                              want_bf16=False, bn_host=self.stem_bn_host)
             else:
                 r32, d32, _, _ = ops.stem(rgb, depth, wr, sr, br, wd, sdp, bd, want_f32=True)
             r16, d16 = ops.split_from_f32(r32), ops.split_from_f32(d32)
             self.launches += 4
         elif self.stem_packed is not None:
-            r32, d32, r16, d16 = ops.stem_s2d(rgb, depth, self.stem_packed, sr, br, sdp, bd, want_f32=learned)
+            r32, d32, r16, d16 = ops.stem_s2d(rgb, depth, self.stem_packed, sr, br, sdp, bd, want_f32=learned,
+                                              bn_host=self.stem_bn_host)
             self.launches += 2
         elif self.se is None:
             r32, d32, r16, d16 = ops.stem(rgb, depth, wr, sr, br, wd, sdp, bd, want_f32=learned)
@@ -871,7 +875,7 @@ class FusionEngine:
             z = torch.zeros(b, 64, device=dev)
             weights.append(self._local_gate_weight(0, z, z, None, None, **gate_kw))
         if self.stem_packed is not None:
-            _, _, r16, d16 = ops.stem_s2d(rgb, depth, self.stem_packed, sr, br, sdp, bd, want_f32=False)
+            _, _, r16, d16 = ops.stem_s2d(rgb, depth, self.stem_packed, sr, br, sdp, bd, want_f32=False, bn_host=self.stem_bn_host)
             self.launches += 2
         else:
             _, _, r16, d16 = ops.stem(rgb, depth, wr, sr, br, wd, sdp, bd, want_f32=False)

@@ -621,9 +621,17 @@ def stem_s2d_pack_weights(w_rgb: Tensor, w_d: Tensor) -> Tensor:
     return out
 
 
+def stem_s2d_bn_host(scale_rgb: Tensor, shift_rgb: Tensor, scale_d: Tensor, shift_d: Tensor) -> Tensor:
+    """Host copy [scale_rgb | shift_rgb | scale_d | shift_d] (256 fp32) of the stem's BN vectors for :func:`stem_s2d`'s
+    ``bn_host``: made once per engine (it synchronises), then passed as a kernel parameter on every launch."""
+    out = torch.cat([t.detach().float().reshape(64) for t in (scale_rgb, shift_rgb, scale_d, shift_d)]).cpu().contiguous()
+    return out
+
+
 def stem_s2d(rgb: Tensor, depth: Tensor, w_packed: Tensor, scale_rgb: Tensor, shift_rgb: Tensor, scale_d: Tensor,
-             shift_d: Tensor, want_f32: bool = True):
-    """:func:`stem` for plain `add` fusion with the im2col done by TMA (dynmm_stem_s2d_fwd); 2 launches."""
+             shift_d: Tensor, want_f32: bool = True, bn_host: Optional[Tensor] = None, want_bf16: bool = True):
+    """:func:`stem` for plain `add` fusion with the im2col done by TMA (dynmm_stem_s2d_fwd); 2 launches.
+    ``bn_host``: :func:`stem_s2d_bn_host` of the same four vectors (constant-bank path of the epilogue)."""
     lib = _lib.load()
     _cuda(rgb, depth, w_packed)
     b, _, h, w = rgb.shape
@@ -632,13 +640,18 @@ def stem_s2d(rgb: Tensor, depth: Tensor, w_packed: Tensor, scale_rgb: Tensor, sh
     dev = rgb.device
     r32 = torch.empty(b, hp, wp, 64, dtype=torch.float32, device=dev) if want_f32 else None
     d32 = torch.empty(b, hp, wp, 64, dtype=torch.float32, device=dev) if want_f32 else None
-    r16 = torch.empty(b, hp, wp, 64, dtype=torch.bfloat16, device=dev)
-    d16 = torch.empty(b, hp, wp, 64, dtype=torch.bfloat16, device=dev)
+    r16 = torch.empty(b, hp, wp, 64, dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    d16 = torch.empty(b, hp, wp, 64, dtype=torch.bfloat16, device=dev) if want_bf16 else None
     need = lib.dynmm_stem_s2d_workspace(b, h, w)
     ws_buf = torch.empty(need, dtype=torch.uint8, device=dev)
+    bn_ptr = None
+    if bn_host is not None:
+        if bn_host.is_cuda or bn_host.dtype != torch.float32 or bn_host.numel() != 256 or not bn_host.is_contiguous():
+            raise _lib.DynmmError("stem_s2d: bn_host must be a contiguous CPU float32 tensor of 256 values")
+        bn_ptr = bn_host.data_ptr()
     check(lib.dynmm_stem_s2d_fwd(ptr(rgb), ptr(depth), b, h, w, ptr(w_packed), ptr(scale_rgb), ptr(shift_rgb),
                                  ptr(scale_d), ptr(shift_d), ptr(ws_buf), need, ptr(r32), ptr(d32), ptr(r16), ptr(d16),
-                                 stream_ptr()), "stem_s2d")
+                                 bn_ptr, stream_ptr()), "stem_s2d")
     return r32, d32, r16, d16
 
 

@@ -205,6 +205,12 @@ def test_stem_and_gate_match_oracle(hw, kernel):
     if kernel == "s2d":      # TMA-gathered im2col (dynmm_stem_s2d_fwd)
         packed = ops.stem_s2d_pack_weights(wr, wd)
         r32, d32, r16, d16 = ops.stem_s2d(rgb.cuda(), depth.cuda(), packed, sr, br, sdp, bd)
+        # BN vectors as a kernel parameter (the engine's path): the same values through the constant bank, bit for bit
+        bn_host = ops.stem_s2d_bn_host(sr, br, sdp, bd)
+        r32c, d32c, r16c, d16c = ops.stem_s2d(rgb.cuda(), depth.cuda(), packed, sr, br, sdp, bd, bn_host=bn_host)
+        assert torch.equal(r32c, r32) and torch.equal(d32c, d32) and torch.equal(r16c, r16) and torch.equal(d16c, d16)
+        only32 = ops.stem_s2d(rgb.cuda(), depth.cuda(), packed, sr, br, sdp, bd, bn_host=bn_host, want_bf16=False)
+        assert only32[2] is None and torch.equal(only32[0], r32) and torch.equal(only32[1], d32)
     else:
         r32, d32, r16, d16 = ops.stem(rgb.cuda(), depth.cuda(), wr, sr, br, wd, sdp, bd)
     torch.cuda.synchronize()

@@ -26,6 +26,9 @@ def timeit(fn, name):
     return out
 
 a = timeit(lambda: ops.stem(rgb, depth, wr, sr, br, wd, sdp, bd), "stem_tc ")
-b = timeit(lambda: ops.stem_s2d(rgb, depth, packed, sr, br, sdp, bd), "stem_s2d")
+b = timeit(lambda: ops.stem_s2d(rgb, depth, packed, sr, br, sdp, bd), "stem_s2d (BN from shared memory)")
+bn_host = ops.stem_s2d_bn_host(sr, br, sdp, bd)
+timeit(lambda: ops.stem_s2d(rgb, depth, packed, sr, br, sdp, bd, bn_host=bn_host), "stem_s2d (BN as kernel parameter)")
+timeit(lambda: ops.stem_s2d(rgb, depth, packed, sr, br, sdp, bd, bn_host=bn_host, want_bf16=False), "stem_s2d (parameter BN, fp32 outputs only)")
 for x, y, n in zip(a, b, ("r32", "d32", "r16", "d16")):
     print(n, "max abs diff", (x.float() - y.float()).abs().max().item(), "max", x.float().abs().max().item())
