@@ -102,7 +102,7 @@ SIGNATURES = {
     "dynmm_stem_s2d_workspace": (c_longlong, [c_int, c_int, c_int]),
     "dynmm_stem_s2d_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "dynmm_stem_s2d_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p] + [c_void_p] * 4
-                           + [c_void_p, c_longlong] + [c_void_p] * 4 + [c_void_p, c_void_p]),
+                           + [c_void_p, c_longlong] + [c_void_p] * 4 + [c_int, c_void_p, c_void_p]),
     "dynmm_gap_workspace": (c_longlong, [c_int, c_int]),
     "dynmm_gap_partial": (c_int, [c_void_p, c_int, c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dynmm_se_mlp": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,

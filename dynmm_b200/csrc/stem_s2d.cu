@@ -174,7 +174,7 @@ stem_s2d_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                 const float* __restrict__ scale_rgb,
                 const float* __restrict__ shift_rgb, const float* __restrict__ scale_d, const float* __restrict__ shift_d,
                 float* __restrict__ rgb_f32, float* __restrict__ depth_f32, __nv_bfloat16* __restrict__ rgb_bf16,
-                __nv_bfloat16* __restrict__ depth_bf16, int tiles_x, int tiles_y, int batch) {
+                __nv_bfloat16* __restrict__ depth_bf16, int split, int tiles_x, int tiles_y, int batch) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_w = smem + kOffW;
@@ -422,17 +422,32 @@ stem_s2d_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
           const size_t o = ((static_cast<size_t>(n) * Hp + py) * Wp + px) * 64 + pass * kPassCh + c4;
           if (rgb_f32) *reinterpret_cast<float4*>(rgb_f32 + o) = mf;
           if (depth_f32) *reinterpret_cast<float4*>(depth_f32 + o) = md;
+          // bf16 maps; split: [hi | lo] halves of the fp32 value (128 channels per pixel), the activation format of the
+          // fp32-grade engine mode -- what dynmm_split_from_f32 would make of the fp32 maps
+          const size_t o16 = split ? o + (o & ~static_cast<size_t>(63)) : o;      // pixel * 128 + channel
           if (rgb_bf16) {
             uint2 v;
             v.x = pack_bf16(mf.x, mf.y);
             v.y = pack_bf16(mf.z, mf.w);
-            *reinterpret_cast<uint2*>(rgb_bf16 + o) = v;
+            *reinterpret_cast<uint2*>(rgb_bf16 + o16) = v;
+            if (split) {
+              uint2 l;
+              l.x = pack_bf16(mf.x - bf16_lo(v.x), mf.y - bf16_hi(v.x));
+              l.y = pack_bf16(mf.z - bf16_lo(v.y), mf.w - bf16_hi(v.y));
+              *reinterpret_cast<uint2*>(rgb_bf16 + o16 + 64) = l;
+            }
           }
           if (depth_bf16 && !DYNMM_STEM_TRACE) {
             uint2 v;
             v.x = pack_bf16(md.x, md.y);
             v.y = pack_bf16(md.z, md.w);
-            *reinterpret_cast<uint2*>(depth_bf16 + o) = v;
+            *reinterpret_cast<uint2*>(depth_bf16 + o16) = v;
+            if (split) {
+              uint2 l;
+              l.x = pack_bf16(md.x - bf16_lo(v.x), md.y - bf16_hi(v.x));
+              l.y = pack_bf16(md.z - bf16_lo(v.y), md.w - bf16_hi(v.y));
+              *reinterpret_cast<uint2*>(depth_bf16 + o16 + 64) = l;
+            }
           }
         }
         STAMP();
@@ -479,8 +494,8 @@ extern "C" int dynmm_stem_s2d_pack_weights(const float* w_rgb, const float* w_d,
 extern "C" int dynmm_stem_s2d_fwd(const float* rgb, const float* depth, int b, int h, int w, const void* w_packed,
                                   const float* scale_rgb, const float* shift_rgb, const float* scale_d,
                                   const float* shift_d, void* workspace, long long workspace_bytes, float* rgb_f32,
-                                  float* depth_f32, void* rgb_bf16, void* depth_bf16, const float* bn_host,
-                                  void* stream_) {
+                                  float* depth_f32, void* rgb_bf16, void* depth_bf16, int split,
+                                  const float* bn_host, void* stream_) {
   using namespace stems2d;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DYNMM_CHECK_ARG(rgb && depth && w_packed && scale_rgb && shift_rgb && scale_d && shift_d && workspace,
@@ -542,8 +557,8 @@ extern "C" int dynmm_stem_s2d_fwd(const float* rgb, const float* depth, int b, i
   cfg.numAttrs = 1;
   DYNMM_CUDA(cudaLaunchKernelEx(&cfg, bn_host ? stem_s2d_kernel<true> : stem_s2d_kernel<false>, map_hi, map_lo, map_w, bn,
                                 Hs, Ws, scale_rgb, shift_rgb, scale_d, shift_d, rgb_f32, depth_f32,
-                                static_cast<__nv_bfloat16*>(rgb_bf16), static_cast<__nv_bfloat16*>(depth_bf16), tiles_x,
-                                tiles_y, b));
+                                static_cast<__nv_bfloat16*>(rgb_bf16), static_cast<__nv_bfloat16*>(depth_bf16), split ? 1 : 0,
+                                tiles_x, tiles_y, b));
   DYNMM_LAUNCH_CHECK();
   return DYNMM_OK;
 }

@@ -656,13 +656,14 @@ class FusionEngine:
             self.launches += 10
         elif self.split:
             # fp32-grade mode: the stem (three split products already) hands its fp32 maps on as [hi | lo] halves
-            if self.stem_packed is not None:
-                r32, d32, _, _ = ops.stem_s2d(rgb, depth, self.stem_packed, sr, br, sdp, bd, want_f32=True,
-                                              want_bf16=False, bn_host=self.stem_bn_host)
+            if self.stem_packed is not None:       # the stem writes the halves itself
+                r32, d32, r16, d16 = ops.stem_s2d(rgb, depth, self.stem_packed, sr, br, sdp, bd, want_f32=learned,
+                                                  split=True, bn_host=self.stem_bn_host)
+                self.launches += 2
             else:
                 r32, d32, _, _ = ops.stem(rgb, depth, wr, sr, br, wd, sdp, bd, want_f32=True)
-            r16, d16 = ops.split_from_f32(r32), ops.split_from_f32(d32)
-            self.launches += 4
+                r16, d16 = ops.split_from_f32(r32), ops.split_from_f32(d32)
+                self.launches += 4
         elif self.stem_packed is not None:
             r32, d32, r16, d16 = ops.stem_s2d(rgb, depth, self.stem_packed, sr, br, sdp, bd, want_f32=learned,
                                               bn_host=self.stem_bn_host)

@@ -629,9 +629,11 @@ def stem_s2d_bn_host(scale_rgb: Tensor, shift_rgb: Tensor, scale_d: Tensor, shif
 
 
 def stem_s2d(rgb: Tensor, depth: Tensor, w_packed: Tensor, scale_rgb: Tensor, shift_rgb: Tensor, scale_d: Tensor,
-             shift_d: Tensor, want_f32: bool = True, bn_host: Optional[Tensor] = None, want_bf16: bool = True):
+             shift_d: Tensor, want_f32: bool = True, bn_host: Optional[Tensor] = None, want_bf16: bool = True,
+             split: bool = False):
     """:func:`stem` for plain `add` fusion with the im2col done by TMA (dynmm_stem_s2d_fwd); 2 launches.
-    ``bn_host``: :func:`stem_s2d_bn_host` of the same four vectors (constant-bank path of the epilogue)."""
+    ``bn_host``: :func:`stem_s2d_bn_host` of the same four vectors (constant-bank path of the epilogue).
+    ``split``: the bf16 outputs are [b, hp, wp, 128] = [hi | lo] halves (:func:`split_from_f32` of the fp32 maps)."""
     lib = _lib.load()
     _cuda(rgb, depth, w_packed)
     b, _, h, w = rgb.shape
@@ -640,8 +642,9 @@ def stem_s2d(rgb: Tensor, depth: Tensor, w_packed: Tensor, scale_rgb: Tensor, sh
     dev = rgb.device
     r32 = torch.empty(b, hp, wp, 64, dtype=torch.float32, device=dev) if want_f32 else None
     d32 = torch.empty(b, hp, wp, 64, dtype=torch.float32, device=dev) if want_f32 else None
-    r16 = torch.empty(b, hp, wp, 64, dtype=torch.bfloat16, device=dev) if want_bf16 else None
-    d16 = torch.empty(b, hp, wp, 64, dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    c16 = 128 if split else 64
+    r16 = torch.empty(b, hp, wp, c16, dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    d16 = torch.empty(b, hp, wp, c16, dtype=torch.bfloat16, device=dev) if want_bf16 else None
     need = lib.dynmm_stem_s2d_workspace(b, h, w)
     ws_buf = torch.empty(need, dtype=torch.uint8, device=dev)
     bn_ptr = None
@@ -651,7 +654,7 @@ def stem_s2d(rgb: Tensor, depth: Tensor, w_packed: Tensor, scale_rgb: Tensor, sh
         bn_ptr = bn_host.data_ptr()
     check(lib.dynmm_stem_s2d_fwd(ptr(rgb), ptr(depth), b, h, w, ptr(w_packed), ptr(scale_rgb), ptr(shift_rgb),
                                  ptr(scale_d), ptr(shift_d), ptr(ws_buf), need, ptr(r32), ptr(d32), ptr(r16), ptr(d16),
-                                 bn_ptr, stream_ptr()), "stem_s2d")
+                                 1 if split else 0, bn_ptr, stream_ptr()), "stem_s2d")
     return r32, d32, r16, d16
 
 

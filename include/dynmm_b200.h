@@ -124,6 +124,8 @@ long long dynmm_stem_gap_tiles(int b, int h, int w);
  * tensor-core path (three bf16 split products, fp32 accumulation).
  *   w_packed: bf16 [2 (hi, lo)][128][256] from dynmm_stem_s2d_pack_weights (inputs: the [7][7][cin][64] fp32
  *   weights dynmm_stem_fwd takes).  workspace: dynmm_stem_s2d_workspace(b, h, w) bytes of device scratch.
+ *   split != 0: rgb_bf16 / depth_bf16 are [b][hp][wp][128] = [hi | lo] halves of the fp32 values (what
+ *   dynmm_split_from_f32 makes of rgb_f32 / depth_f32), the input format of DYNMM_CONV_SPLIT convolutions.
  *   bn_host (optional, HOST memory, 256 floats [scale_rgb | shift_rgb | scale_d | shift_d]): a host copy of the four
  *   device vectors; when given it travels as a kernel parameter and the epilogue reads it from the constant bank
  *   instead of shared memory (same values, same arithmetic; the device vectors are then not read). */
@@ -132,7 +134,7 @@ int dynmm_stem_s2d_pack_weights(const float* w_rgb, const float* w_d, void* w_pa
 int dynmm_stem_s2d_fwd(const float* rgb, const float* depth, int b, int h, int w, const void* w_packed,
                        const float* scale_rgb, const float* shift_rgb, const float* scale_d, const float* shift_d,
                        void* workspace, long long workspace_bytes, float* rgb_f32, float* depth_f32,
-                       void* rgb_bf16, void* depth_bf16, const float* bn_host, void* stream);
+                       void* rgb_bf16, void* depth_bf16, int split, const float* bn_host, void* stream);
 
 /* ------------------------------------------------------ SE-add fusion */
 

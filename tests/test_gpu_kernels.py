@@ -211,6 +211,9 @@ def test_stem_and_gate_match_oracle(hw, kernel):
         assert torch.equal(r32c, r32) and torch.equal(d32c, d32) and torch.equal(r16c, r16) and torch.equal(d16c, d16)
         only32 = ops.stem_s2d(rgb.cuda(), depth.cuda(), packed, sr, br, sdp, bd, bn_host=bn_host, want_bf16=False)
         assert only32[2] is None and torch.equal(only32[0], r32) and torch.equal(only32[1], d32)
+        # [hi | lo] halves for the fp32-grade engine mode, written by the stem itself
+        _, _, rs, ds = ops.stem_s2d(rgb.cuda(), depth.cuda(), packed, sr, br, sdp, bd, bn_host=bn_host, split=True)
+        assert torch.equal(rs, ops.split_from_f32(r32)) and torch.equal(ds, ops.split_from_f32(d32))
     else:
         r32, d32, r16, d16 = ops.stem(rgb.cuda(), depth.cuda(), wr, sr, br, wd, sdp, bd)
     torch.cuda.synchronize()

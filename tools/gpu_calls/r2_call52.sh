@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call 52: stem with parameter BN + PDL after the pre-pass: suite, stem timing, quick bench lines
-O=gpurun_out/r2ar
+O=gpurun_out/r2at
 mkdir -p $O
 timeout 1500 python -m pytest tests -m gpu -q -x > $O/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $O/pytest_gpu.log
 grep -E "passed|failed|FAILED|Error" $O/pytest_gpu.log | tail -4 | cut -c1-250
