@@ -277,7 +277,10 @@ __global__ void upsample2x_dw_nhwc_kernel(const __nv_bfloat16* __restrict__ in, 
 // new row), produces the 2x2 output block with the 16 parity stencils precombined from the 3x3 weights once per
 // thread (16 FMAs per channel instead of 36) and stores 4 x 8 bytes; the per-pixel kernel above re-loads 9 inputs
 // and 18 weight vectors for every 16-byte store.
-constexpr int kUpStripRows = 8;      // longest strip; short maps use shorter strips so that the grid still fills the GPU
+// Strip length: the kernel holds 64 stencil + 36 window registers per thread, so two 256-thread CTAs fit an SM and a
+// launch runs in waves of 2 x SMs CTAs; every CTA loads rows + 2 input rows.  strip_rows() minimises
+// waves x (rows + 2) -- 8-row strips with "at least 4 CTAs per SM" gave 640 CTAs = 2.16 waves (three, the last one at
+// 16 %) for the 60x80 -> 120x160 module of the decoder.
 template <bool kSkip, bool kSplit = false>       // kSplit: in / skip / out are [hi | lo] halves with pitch 2c (f32x3 mode)
 __global__ void __launch_bounds__(256)
 upsample2x_dw_nhwc_strip_kernel(const __nv_bfloat16* __restrict__ in, int h, int w, int c,
@@ -852,6 +855,24 @@ extern "C" int dynmm_nhwc_bf16_to_nchw_f32(const void* in, int n, int c, int h, 
 }
 
 namespace {
+template <typename K>
+int strip_rows(K kernel, int ctas_x, int h, int n) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+  const long long slots = 1LL * per_sm * num_sms();
+  int best = 1;
+  long long best_cost = -1;
+  for (int rows = 1; rows <= h && rows <= 32; ++rows) {
+    const long long ctas = 1LL * ctas_x * ceil_div(h, rows) * n;
+    const long long cost = ceil_div_ll(ctas, slots) * (rows + 2);
+    if (best_cost < 0 || cost < best_cost) {      // ties: the shorter strip (more CTAs in the last wave)
+      best_cost = cost;
+      best = rows;
+    }
+  }
+  return best;
+}
+
 int upsample2x_impl(const void* in, int n, int h, int w, int c, const float* weight, const float* bias, const void* skip,
                     void* out_nhwc_bf16, float* out_nchw_f32, uint8_t* labels, bool split, int clamp, int c_valid,
                     void* stream_) {
@@ -863,9 +884,10 @@ int upsample2x_impl(const void* in, int n, int h, int w, int c, const float* wei
   if (c_valid <= 0) c_valid = c;
   DYNMM_CHECK_ARG(c_valid <= c && (c_valid == c || !out_nhwc_bf16), "upsample2x: c_valid applies to the NCHW / label outputs");
   if (out_nhwc_bf16 && split && n <= 65535 && getenv("DYNMM_UPSAMPLE") == nullptr) {
-    int rows = kUpStripRows;
-    while (rows > 1 && 1LL * ceil_div(w * (c / 4), 256) * ceil_div(h, rows) * n < 4LL * num_sms()) rows >>= 1;
-    dim3 grid(ceil_div(w * (c / 4), 256), ceil_div(h, rows), n);
+    const int ctas_x = ceil_div(w * (c / 4), 256);
+    const int rows = skip ? strip_rows(upsample2x_dw_nhwc_strip_kernel<true, true>, ctas_x, h, n)
+                          : strip_rows(upsample2x_dw_nhwc_strip_kernel<false, true>, ctas_x, h, n);
+    dim3 grid(ctas_x, ceil_div(h, rows), n);
     if (skip) {
       upsample2x_dw_nhwc_strip_kernel<true, true><<<grid, 256, 0, stream>>>(
           static_cast<const __nv_bfloat16*>(in), h, w, c, weight, bias, static_cast<const __nv_bfloat16*>(skip),
@@ -886,9 +908,10 @@ int upsample2x_impl(const void* in, int n, int h, int w, int c, const float* wei
       return !(e && e[0] == 'p');           // DYNMM_UPSAMPLE=pixel: the one-thread-per-output-pixel kernel
     }();
     if (use_strip && n <= 65535) {
-      int rows = kUpStripRows;       // a thread walks `rows` input rows: halve until there are >= 4 CTAs per SM
-      while (rows > 1 && 1LL * ceil_div(w * (c / 4), 256) * ceil_div(h, rows) * n < 4LL * num_sms()) rows >>= 1;
-      dim3 grid(ceil_div(w * (c / 4), 256), ceil_div(h, rows), n);
+      const int ctas_x = ceil_div(w * (c / 4), 256);
+      const int rows = skip ? strip_rows(upsample2x_dw_nhwc_strip_kernel<true, false>, ctas_x, h, n)
+                            : strip_rows(upsample2x_dw_nhwc_strip_kernel<false, false>, ctas_x, h, n);
+      dim3 grid(ctas_x, ceil_div(h, rows), n);
       if (skip) {
         upsample2x_dw_nhwc_strip_kernel<true><<<grid, 256, 0, stream>>>(
             static_cast<const __nv_bfloat16*>(in), h, w, c, weight, bias, static_cast<const __nv_bfloat16*>(skip),
