@@ -105,10 +105,13 @@ SIGNATURES = {
                            + [c_void_p, c_longlong] + [c_void_p] * 4 + [c_int, c_void_p, c_void_p]),
     "dynmm_gap_workspace": (c_longlong, [c_int, c_int]),
     "dynmm_gap_partial": (c_int, [c_void_p, c_int, c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "dynmm_gap_partial_split": (c_int, [c_void_p, c_int, c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dynmm_se_mlp": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_void_p]),
     "dynmm_se_gated_fuse": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong,
                                     c_int, c_int, c_void_p, c_void_p]),
+    "dynmm_se_gated_fuse_split": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_longlong,
+                                          c_int, c_int, c_void_p, c_void_p]),
     "dynmm_conv_igemm_fwd": (c_int, [POINTER(ConvParams), c_void_p]),
     "dynmm_conv_igemm_fwd2": (c_int, [POINTER(ConvParams), POINTER(ConvParams), c_void_p]),
     "dynmm_conv_tile_grid": (c_int, [POINTER(ConvParams), POINTER(TileFlags)]),

@@ -197,8 +197,8 @@ class FusionEngine:
         if cfg.precision not in ("bf16", "f32x3"):
             raise ValueError("EngineConfig.precision must be 'bf16' or 'f32x3'")
         self.split = cfg.precision == "f32x3"
-        if self.split and (cfg.fuse != "add" or cfg.gate != "global" or cfg.activation.lower() != "relu"):
-            raise NotImplementedError("precision='f32x3' is implemented for the global gate with fuse='add' and ReLU")
+        if self.split and (cfg.gate != "global" or cfg.activation.lower() != "relu"):
+            raise NotImplementedError("precision='f32x3' is implemented for the global gate with ReLU")
         if cfg.encoder_decoder_fusion not in ("add", "None"):
             raise NotImplementedError("encoder_decoder_fusion must be 'add' or 'None'")
         self.dec_fusion = cfg.encoder_decoder_fusion == "add"
@@ -511,11 +511,11 @@ class FusionEngine:
         layer = self.se[s + 1]
         n, hh, ww, c = rgb.shape
         inv_area = 1.0 / (hh * ww)
-        pr = ops.gap_partial(rgb)
-        pd = ops.gap_partial(depth, count=plan.count[s:s + 1])
+        pr = ops.gap_partial(rgb, split=self.split)
+        pd = ops.gap_partial(depth, count=plan.count[s:s + 1], split=self.split)
         sig_r = ops.se_mlp(pr, inv_area, *layer["se_rgb"])
         sig_d = ops.se_mlp(pd, inv_area, *layer["se_depth"], count=plan.count[s:s + 1])
-        fused = ops.se_gated_fuse(rgb, depth, sig_r, sig_d, plan.g[s], plan.slot, out=out)
+        fused = ops.se_gated_fuse(rgb, depth, sig_r, sig_d, plan.g[s], plan.slot, out=out, split=self.split)
         keep += [pr, pd, sig_r, sig_d, fused]
         self.launches += 5
         return fused
@@ -660,10 +660,18 @@ class FusionEngine:
                 r32, d32, r16, d16 = ops.stem_s2d(rgb, depth, self.stem_packed, sr, br, sdp, bd, want_f32=learned,
                                                   split=True, bn_host=self.stem_bn_host)
                 self.launches += 2
-            else:
+            elif self.se is None:
                 r32, d32, _, _ = ops.stem(rgb, depth, wr, sr, br, wd, sdp, bd, want_f32=True)
                 r16, d16 = ops.split_from_f32(r32), ops.split_from_f32(d32)
                 self.launches += 4
+            else:                                  # SE-add: squeeze pass, excite, SE-scaled stem (see below), then split
+                part, inv_area = ops.stem_squeeze(rgb, depth, wr, sr, br, wd, sdp, bd)
+                sig_r = ops.se_mlp(part, inv_area, *self.se[0]["se_rgb"], c_off=0, c=64)
+                sig_d = ops.se_mlp(part, inv_area, *self.se[0]["se_depth"], c_off=64, c=64)
+                r32, d32, _, _ = ops.stem(rgb, depth, wr, sr, br, wd, sdp, bd, want_f32=True, se_rgb=sig_r, se_depth=sig_d)
+                r16, d16 = ops.split_from_f32(r32), ops.split_from_f32(d32)
+                keep += [part, sig_r, sig_d]
+                self.launches += 7
         elif self.stem_packed is not None:
             r32, d32, r16, d16 = ops.stem_s2d(rgb, depth, self.stem_packed, sr, br, sdp, bd, want_f32=learned,
                                               bn_host=self.stem_bn_host)

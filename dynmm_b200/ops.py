@@ -673,14 +673,16 @@ def stem_squeeze(rgb: Tensor, depth: Tensor, w_rgb, scale_rgb, shift_rgb, w_d, s
     return partial, 1.0 / (hs * ws)
 
 
-def gap_partial(x: Tensor, c: Optional[int] = None, count: Optional[Tensor] = None) -> Tensor:
-    """x NHWC bf16 [n,h,w,ld] -> partial channel sums [n, 64, c] fp32 (deterministic)."""
+def gap_partial(x: Tensor, c: Optional[int] = None, count: Optional[Tensor] = None, split: bool = False) -> Tensor:
+    """x NHWC bf16 [n,h,w,ld] -> partial channel sums [n, 64, c] fp32 (deterministic).
+    ``split``: x is [hi | lo] (lo half at channel ld / 2); the sums are those of hi + lo."""
     lib = _lib.load()
     _cuda(x, count)
     n, h, w, ld = x.shape
-    c = ld if c is None else c
+    c = (ld // 2 if split else ld) if c is None else c
     out = torch.empty(n, 64, c, dtype=torch.float32, device=x.device)
-    check(lib.dynmm_gap_partial(ptr(x), n, h * w, c, ld, ptr(count), ptr(out), stream_ptr()), "gap_partial")
+    fn = lib.dynmm_gap_partial_split if split else lib.dynmm_gap_partial
+    check(fn(ptr(x), n, h * w, c, ld, ptr(count), ptr(out), stream_ptr()), "gap_partial")
     return out
 
 
@@ -700,11 +702,16 @@ def se_mlp(partial: Tensor, inv_area: float, w1: Tensor, b1: Tensor, w2: Tensor,
 
 
 def se_gated_fuse(rgb: Tensor, depth: Tensor, sig_r: Tensor, sig_d: Tensor, gate: Tensor,
-                  slot: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+                  slot: Optional[Tensor] = None, out: Optional[Tensor] = None, split: bool = False) -> Tensor:
+    """``split``: rgb / depth / out are [hi | lo] tensors (channels 2c; ``out`` may be wider, lo half at its middle)."""
     lib = _lib.load()
     _cuda(rgb, depth, sig_r, sig_d, gate, slot, out)
     n, h, w, c = rgb.shape
     out = torch.empty_like(rgb) if out is None else out
+    if split:
+        check(lib.dynmm_se_gated_fuse_split(ptr(rgb), ptr(depth), ptr(sig_r), ptr(sig_d), ptr(gate), ptr(slot), n, h * w,
+                                            c // 2, out.shape[3], ptr(out), stream_ptr()), "se_gated_fuse_split")
+        return out
     check(lib.dynmm_se_gated_fuse(ptr(rgb), ptr(depth), ptr(sig_r), ptr(sig_d), ptr(gate), ptr(slot), n, h * w, c,
                                   out.shape[3], ptr(out), stream_ptr()), "se_gated_fuse")
     return out

@@ -143,6 +143,9 @@ int dynmm_stem_s2d_fwd(const float* rgb, const float* depth, int b, int h, int w
 long long dynmm_gap_workspace(int n, int c);
 int dynmm_gap_partial(const void* x, int n, long long hw, int c, int ld, const int32_t* count, float* partial,
                       void* stream);
+/* ... of [hi | lo] tensors (DYNMM_CONV_SPLIT layout: pitch ld >= 2c, lo half at channel ld / 2): sums of hi + lo */
+int dynmm_gap_partial_split(const void* x, int n, long long hw, int c, int ld, const int32_t* count, float* partial,
+                            void* stream);
 /* Excite: sigma[row] = sigmoid(W2 relu(W1 mean + b1) + b2) with mean = inv_area * sum of `chunks` partial rows
  * (model_utils.py:40-45,49); partial rows have pitch ld and the c channels start at column c_off.
  * w1 [hidden][c], w2 [c][hidden] (the 1x1 conv weights). */
@@ -155,6 +158,11 @@ int dynmm_se_mlp(const float* partial, int rows, int chunks, int ld, int c_off, 
 int dynmm_se_gated_fuse(const void* rgb, const void* depth, const float* sig_r, const float* sig_d,
                         const float* gate, const int32_t* slot, int n, long long hw, int c, int out_ld, void* out,
                         void* stream);
+/* ... on [hi | lo] tensors: rgb / depth [*,hw,2c], out pitch out_ld >= 2c with its lo half at channel out_ld / 2;
+ * the blend runs in fp32 on hi + lo and is split again (the fp32-grade engine mode with 'SE-add' fusion). */
+int dynmm_se_gated_fuse_split(const void* rgb, const void* depth, const float* sig_r, const float* sig_d,
+                              const float* gate, const int32_t* slot, int n, long long hw, int c, int out_ld,
+                              void* out, void* stream);
 
 /* --------------------------------------------------------- encoder convs */
 

@@ -157,6 +157,65 @@ def test_f32x3_engine_matches_reference_golden_vectors(golden_dir):
     print("f32x3 vs reference fp32:", {k: f"{v:.1e}" for k, v in errs.items()})
 
 
+def test_split_se_kernels_match_fp32():
+    """Squeeze sums and the gated SE blend on [hi | lo] tensors (dynmm_gap_partial_split, dynmm_se_gated_fuse_split)."""
+    from dynmm_b200 import ops
+    torch.manual_seed(3)
+    dev = "cuda"
+    n, h, w, c = 4, 9, 11, 64
+    r32, d32 = torch.randn(n, h, w, c, device=dev), torch.randn(3, h, w, c, device=dev)
+    rs, ds = ops.split_from_f32(r32), ops.split_from_f32(d32)
+    part = ops.gap_partial(rs, split=True)
+    assert part.shape == (n, 64, c)
+    ref_sum = _join(rs).double().sum((1, 2))
+    assert ((part.double().sum(1) - ref_sum).abs().max() / ref_sum.abs().max()).item() < 1e-6
+    count = torch.tensor([2], dtype=torch.int32, device=dev)
+    part_d = ops.gap_partial(ds, count=count, split=True)
+    assert torch.allclose(part_d[:2].double().sum(1), _join(ds)[:2].double().sum((1, 2)), rtol=1e-5, atol=1e-4)
+    sig_r, sig_d = torch.rand(n, c, device=dev), torch.rand(3, c, device=dev)
+    gate = torch.tensor([0.0, 1.0, 0.25, 1.0], device=dev)
+    slot = torch.tensor([2, 0, 1, 2], dtype=torch.int32, device=dev)
+    wide = torch.zeros(n, h, w, 2 * (c + 32), dtype=torch.bfloat16, device=dev)      # e.g. the pyramid-pooling concat buffer
+    for out in (None, wide):
+        got = ops.se_gated_fuse(rs, ds, sig_r, sig_d, gate, slot, out=out, split=True)
+        half = got.shape[-1] // 2
+        val = got[..., :c].float() + got[..., half:half + c].float()
+        g = gate.view(n, 1, 1, 1)
+        dd = _join(ds)[slot.long()]
+        ref = _join(rs) * (1 - g + g * sig_r.view(n, 1, 1, c)) + g * sig_d[slot.long()].view(n, 1, 1, c) * dd
+        assert _rel_l2(val, ref) < 1e-5
+        assert torch.equal(val[0], _join(rs)[0])          # a gated-off sample keeps its RGB features bit for bit
+
+
+@pytest.mark.parametrize("name", ["fusion_r34_nbt1d_seadd_64x64", "fusion_r50_seadd_decr_64x64"])
+def test_f32x3_engine_se_add_matches_reference_golden_vectors(name, golden_dir):
+    """'SE-add' fusion (the reference's CLI default, args.py:159) in the fp32-grade mode: the reference's own fp32
+    outputs to 1e-3 relative, hard decisions bit-exact."""
+    from tests.test_oracle_golden import CASES
+    from oracle.make_golden import sample_inputs
+    cfg, seed, b = CASES[name]
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    model, sd = _build(cfg, seed, float(gold["gate_scale"]))
+    rgb, depth = sample_inputs(seed + 1, b, cfg.height, cfg.width)
+    rgb, depth = rgb.cuda(), depth.cuda()
+    errs = {}
+    with torch.no_grad():
+        for tag, temp, hard in (("hard_t1", 1.0, True), ("soft_t1", 1.0, False)):
+            model.temp, model.hard_gate = temp, hard
+            out, w = model(rgb, depth, True, True)
+            assert model.engine().split and model.engine().se is not None
+            if hard:
+                np.testing.assert_array_equal(w.cpu().numpy(), gold[tag + "_weight"])
+            errs[tag] = _rel_l2(out[:, :, ::4, ::4].cpu(), torch.from_numpy(gold[tag + "_out_sample"]))
+        eng = model.engine()
+        for k in (0, 2, 4):
+            wk = torch.eye(5)[torch.full((b,), k)].cuda()
+            out, _ = eng.forward(rgb, depth, weight=wk)
+            errs[f"branch{k}"] = _rel_l2(out[:, :, ::4, ::4].cpu(), torch.from_numpy(gold[f"branch{k}_out_sample"]))
+    assert max(errs.values()) <= F32_TOL, errs
+    print(name, "f32x3 vs reference fp32:", {k: f"{v:.1e}" for k, v in errs.items()})
+
+
 def test_full_size_batch_8_both_precisions_match_oracle():
     """480x640, the whole batch of 8 (the bench workload's shape) against the fp32 CPU oracle: f32x3 logits 1e-3
     relative and (almost) every arg-max label; the bf16 engine on the same images within its stated 2e-2."""
