@@ -197,8 +197,8 @@ class FusionEngine:
         if cfg.precision not in ("bf16", "f32x3"):
             raise ValueError("EngineConfig.precision must be 'bf16' or 'f32x3'")
         self.split = cfg.precision == "f32x3"
-        if self.split and (cfg.gate != "global" or cfg.activation.lower() != "relu"):
-            raise NotImplementedError("precision='f32x3' is implemented for the global gate with ReLU")
+        if self.split and cfg.activation.lower() != "relu":
+            raise NotImplementedError("precision='f32x3' is implemented for ReLU models")
         if cfg.encoder_decoder_fusion not in ("add", "None"):
             raise NotImplementedError("encoder_decoder_fusion must be 'add' or 'None'")
         self.dec_fusion = cfg.encoder_decoder_fusion == "add"
@@ -884,8 +884,13 @@ class FusionEngine:
             z = torch.zeros(b, 64, device=dev)
             weights.append(self._local_gate_weight(0, z, z, None, None, **gate_kw))
         if self.stem_packed is not None:
-            _, _, r16, d16 = ops.stem_s2d(rgb, depth, self.stem_packed, sr, br, sdp, bd, want_f32=False, bn_host=self.stem_bn_host)
+            _, _, r16, d16 = ops.stem_s2d(rgb, depth, self.stem_packed, sr, br, sdp, bd, want_f32=False,
+                                          split=self.split, bn_host=self.stem_bn_host)
             self.launches += 2
+        elif self.split:
+            r32, d32, _, _ = ops.stem(rgb, depth, wr, sr, br, wd, sdp, bd, want_f32=True)
+            r16, d16 = ops.split_from_f32(r32), ops.split_from_f32(d32)
+            self.launches += 3
         else:
             _, _, r16, d16 = ops.stem(rgb, depth, wr, sr, br, wd, sdp, bd, want_f32=False)
             self.launches += 1
@@ -949,7 +954,8 @@ class FusionEngine:
                 last_kw = {}
                 if s == 3:
                     c4 = self.stage_channels[3]
-                    cat = torch.empty(b, h // 32, w // 32, c4 + self.ppm_c, dtype=torch.bfloat16, device=dev)
+                    cat = torch.empty(b, h // 32, w // 32, (c4 + self.ppm_c) * (2 if self.split else 1),
+                                      dtype=torch.bfloat16, device=dev)
                     last_kw.update(out=cat, out_c_off=0)
                 if rule != 0:
                     last_kw.update(gated=d, gate=g, gated_slot=gated_slot)
@@ -970,11 +976,11 @@ class FusionEngine:
                 skip_done.append(None)
                 # gate s + 1 looks at the stage outputs BEFORE the blend (:260, :278, :296):
                 # gap(rgb) = gap(fuse) - g * gap(depth) (the blend is linear)
+                c = r.shape[3] // (2 if self.split else 1)
                 if dynamic[s + 1] and not random_policy:
-                    c = r.shape[3]
                     inv_area = 1.0 / (r.shape[1] * r.shape[2])
-                    pf = ops.gap_partial(r, c=c)
-                    pd = ops.gap_partial(d, c=c, count=count)
+                    pf = ops.gap_partial(r, c=c, split=self.split)
+                    pd = ops.gap_partial(d, c=c, count=count, split=self.split)
                     gap_f = pf.sum(dim=1) * inv_area
                     gap_d_slots = pd.sum(dim=1) * inv_area
                     has = slot >= 0
@@ -984,7 +990,7 @@ class FusionEngine:
                     self.launches += 2
                     nxt = self._local_gate_weight(s + 1, gap_r, gap_d, has, None, **gate_kw)
                 else:
-                    z = torch.zeros(b, r.shape[3], device=dev)
+                    z = torch.zeros(b, c, device=dev)
                     nxt = self._local_gate_weight(s + 1, z, z, None, None, **gate_kw)
                 if rule == 2 and not ini_stage:
                     prev_w = weights[s][:, 1]

@@ -165,7 +165,8 @@ class SkipESANet(nn.Module):
         self.weight_list = [torch.Tensor() for _ in range(4)]
         self._pending: List[List[Tensor]] = [[] for _ in range(4)]
         self.train_precision = "fp32"        # "bf16": stage convolutions on the tcgen05 kernels (modules.Conv2d)
-        self.use_engine = True               # eval mode + CUDA tensors: FusionEngine.forward_local (bf16, real skipping)
+        self.use_engine = True               # eval mode + CUDA tensors: FusionEngine.forward_local (real skipping)
+        self.engine_precision = "bf16"       # "f32x3": fp32-grade engine arithmetic (logits within 1e-3 of fp32)
         self.use_cuda_graph = False          # opt-in: replay one captured graph per input shape / mode (static outputs)
         self._graphs = {}
         self._engine = None
@@ -229,7 +230,7 @@ class SkipESANet(nn.Module):
         device = device or next(self.parameters()).device
         if self._engine is None:
             self._version_probe = list(self.parameters()) + list(self.buffers())
-        key = (str(device), tuple(p._version for p in self._version_probe))
+        key = (str(device), tuple(p._version for p in self._version_probe), getattr(self, "engine_precision", "bf16"))
         if self._engine is None or self._engine_key != key:
             c = self._cfg
             # the reference's forward always blends by addition, whatever fuse_depth_in_rgb_encoder built (:241-311)
@@ -238,7 +239,8 @@ class SkipESANet(nn.Module):
                                nr_decoder_blocks=c["nr_decoder_blocks"], num_classes=c["num_classes"],
                                upsampling=c["upsampling"], context_module=c["context_module"],
                                activation=c["activation"], gate="local",
-                               encoder_decoder_fusion=c["encoder_decoder_fusion"])
+                               encoder_decoder_fusion=c["encoder_decoder_fusion"],
+                               precision=getattr(self, "engine_precision", "bf16"))
             self._engine = FusionEngine(self.state_dict(), cfg, device)
             self._engine_key = key
             self._graphs = {}
