@@ -294,8 +294,13 @@ class SkipESANet(nn.Module):
                               self._engine_unsupported + "); eval forwards run the PyTorch graph instead")
         low = rgb.is_cuda and self.train_precision == "bf16"
         gate_args = dict(hard=self.hard_gate, random=self.random_policy, test=test)
-        rgb = self.encoder_rgb.forward_first_conv(rgb)
-        depth = self.encoder_depth.forward_first_conv(depth)
+        if low:
+            from .modules import stem_channels_last
+            rgb = stem_channels_last(self.encoder_rgb, rgb)
+            depth = stem_channels_last(self.encoder_depth, depth)
+        else:
+            rgb = self.encoder_rgb.forward_first_conv(rgb)
+            depth = self.encoder_depth.forward_first_conv(depth)
         fuse = rgb + depth
         weights: List[Tensor] = [self.gate_layer0(rgb, depth, **gate_args)]
         rgb = F.max_pool2d(fuse, kernel_size=3, stride=2, padding=1)
