@@ -41,6 +41,26 @@ using namespace convk;
     if (args.trace) args.trace[blockIdx.x * 16 + (slot)] = (unsigned long long)clock64(); \
   } while (0)
 
+// Experiments only (-DDYNMM_TRACE_TILES=1, tools/conv_trace.py with TILES=1): per-tile stamps of the first 16 tiles of a
+// CTA in a trace buffer of 64 slots per CTA -- [16 + l] MMAs of tile l issued, [32 + l] accumulator l seen full by the
+// epilogue, [48 + l] epilogue of tile l done.
+#ifndef DYNMM_TRACE_TILES
+#define DYNMM_TRACE_TILES 0
+#endif
+#if DYNMM_TRACE_TILES
+#define DYNMM_TRACE_T(base, l)                                                                          \
+  do {                                                                                                  \
+    if (args.trace && (l) < 16) args.trace[blockIdx.x * 64 + (base) + (l)] = (unsigned long long)clock64(); \
+  } while (0)
+#undef DYNMM_TRACE
+#define DYNMM_TRACE(slot)                                                              \
+  do {                                                                                 \
+    if (args.trace) args.trace[blockIdx.x * 64 + (slot)] = (unsigned long long)clock64(); \
+  } while (0)
+#else
+#define DYNMM_TRACE_T(base, l) do { } while (0)
+#endif
+
 // (The per-job code below is written as lambdas that take the job's KernelArgs / tensor maps BY REFERENCE and are
 // called once per job with the kernel parameters themselves: after inlining every field access is a direct
 // constant-bank operand, as in a single-job kernel.  Selecting the job through a run-time pointer instead costs a
@@ -317,6 +337,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
         }
         if (lane == 0 && local == 0) DYNMM_TRACE(4);
+        if (lane == 0) DYNMM_TRACE_T(16, local);
       }
     }
   } else {
@@ -380,6 +401,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       mbar_wait(&ctl->acc_full[acc], acc_phase);
       tc_fence_after();
       if (leader && local == 0) DYNMM_TRACE(5);
+      if (leader) DYNMM_TRACE_T(32, local);
      for (int wt = 0; wt < nact; ++wt) {             // the unit's pixel tiles, one after the other
       const TileCoord t = decode_tile(args, (q * mt + wt) * args.c_tiles + ct);
       const int n = t.n0 + nl;
@@ -468,6 +490,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->acc_empty[acc]);
       if (leader && local == 0) DYNMM_TRACE(6);
+      if (leader) DYNMM_TRACE_T(48, local);
     };
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       if (kPerSm == 2 || tile < units0) {
@@ -483,7 +506,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     }
     if (leader) {
       DYNMM_TRACE(8);
-      if (args.trace) args.trace[blockIdx.x * 16 + 10] = local;
+      if (args.trace) args.trace[blockIdx.x * (DYNMM_TRACE_TILES ? 64 : 16) + 10] = local;
     }
   }
 

@@ -29,7 +29,9 @@ def main():
             r = ops.split_from_f32(torch.randn(n, ho, wo, cout, device=dev))
         sh = torch.randn(cout, device=dev)
         out = torch.empty(n, ho, wo, cout * (2 if split else 1), dtype=torch.bfloat16, device=dev)
-        trace = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+        tiles_mode = os.environ.get("TILES") == "1"      # library built with -DDYNMM_TRACE_TILES=1: 64 slots per CTA
+        per = 64 if tiles_mode else 16
+        trace = torch.zeros(148 * per, dtype=torch.int64, device=dev)
         dual = {"0": False, "1": True}.get(os.environ.get("DUAL", ""), None)
         kw_ = dict(c_out=cout, kh=kh, kw=kw, stride=stride, pad=(kh // 2, kw // 2), shift=sh, residual=r, relu=True,
                    out=out, dual=dual, split=split, c_in=cin)
@@ -37,7 +39,7 @@ def main():
             ops.conv(x, wt, **kw_)
         ops.conv(x, wt, trace=trace, **kw_)
         torch.cuda.synchronize()
-        t = trace.view(148, 16).cpu()
+        t = trace.view(148, per).cpu()
         used = t[:, 0] > 0
         t = t[used]
         rel = (t[:, :16] - t[:, :1]).float()
@@ -47,6 +49,16 @@ def main():
         for i in order:
             nm = NAMES[i]
             print(f"   {nm:22s} mean {rel[:, i].mean():9.0f}  max {rel[:, i].max():9.0f} cycles")
+        if tiles_mode:
+            for cta in (0, 1, 77):
+                if cta >= t.shape[0]:
+                    continue
+                row = t[cta]
+                nt = int(row[10])
+                t0 = int(row[0])
+                print(f"   CTA {cta}: per tile (cycles since entry): MMAs issued | accumulator seen full | epilogue done")
+                for l in range(min(nt, 16)):
+                    print(f"      tile {l:2d}: {int(row[16 + l]) - t0:8d} {int(row[32 + l]) - t0:8d} {int(row[48 + l]) - t0:8d}")
 
 if __name__ == "__main__":
     main()
