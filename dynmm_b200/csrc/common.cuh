@@ -211,6 +211,31 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+// 16 columns into r[kOff .. kOff + 15] of a 32-register fragment, and the wait that makes exactly those registers
+// valid (they are operands of the wait, so no use of them can be scheduled above it).  Pattern: load half 0, wait,
+// load half 1, convert half 0 while half 1 is in flight, wait, convert half 1 -- tcgen05.wait::ld waits for EVERY
+// outstanding load of the thread, so the second load must be issued after the first wait.
+template <int kOff>
+__device__ __forceinline__ void tmem_ld16_half(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[kOff + 0]), "=r"(r[kOff + 1]), "=r"(r[kOff + 2]), "=r"(r[kOff + 3]), "=r"(r[kOff + 4]), "=r"(r[kOff + 5]),
+        "=r"(r[kOff + 6]), "=r"(r[kOff + 7]), "=r"(r[kOff + 8]), "=r"(r[kOff + 9]), "=r"(r[kOff + 10]),
+        "=r"(r[kOff + 11]), "=r"(r[kOff + 12]), "=r"(r[kOff + 13]), "=r"(r[kOff + 14]), "=r"(r[kOff + 15])
+      : "r"(taddr)
+      : "memory");
+}
+template <int kOff>
+__device__ __forceinline__ void tmem_ld_wait_half(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+               : "+r"(r[kOff + 0]), "+r"(r[kOff + 1]), "+r"(r[kOff + 2]), "+r"(r[kOff + 3]), "+r"(r[kOff + 4]),
+                 "+r"(r[kOff + 5]), "+r"(r[kOff + 6]), "+r"(r[kOff + 7]), "+r"(r[kOff + 8]), "+r"(r[kOff + 9]),
+                 "+r"(r[kOff + 10]), "+r"(r[kOff + 11]), "+r"(r[kOff + 12]), "+r"(r[kOff + 13]), "+r"(r[kOff + 14]),
+                 "+r"(r[kOff + 15])
+               :
+               : "memory");
+}
 
 // K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {

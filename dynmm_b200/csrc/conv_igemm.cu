@@ -429,8 +429,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         const bool cols_live = cb < args.acc_stride;
         uint32_t v[32];
         if (cols_live) {                            // warp-uniform
-          tmem_ld32(t_row + cb, v);
-          tmem_ld_wait();
+          if (tile_tma) {                           // second half in flight while the first is converted
+            tmem_ld16_half<0>(t_row + cb, v);
+            tmem_ld_wait_half<0>(v);
+            tmem_ld16_half<16>(t_row + cb + 16, v);
+          } else {
+            tmem_ld32(t_row + cb, v);
+            tmem_ld_wait();
+          }
         }
         if (leader && local == 0 && sub == 0) DYNMM_TRACE(13);
         if (tile_tma) {
@@ -441,8 +447,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
           const uint32_t out_smem = out_base + sbuf * stage_out_bytes;
           if (cols_live) {
-            epilogue_chunk<true, false, kSplit, kAct, true>(kFlags, ja, v, t.c0 + cb, args.tile_n - cb, valid, res_smem, out_smem, half * 4,
-                                         swz, pix, rpix, gpix, g, shift_j, kPreRes ? pre_hi : nullptr, pre_lo);
+            epilogue_chunk<true, false, kSplit, kAct, true, 0, 16>(kFlags, ja, v, t.c0 + cb, args.tile_n - cb, valid, res_smem,
+                                                                   out_smem, half * 4, swz, pix, rpix, gpix, g, shift_j,
+                                                                   kPreRes ? pre_hi : nullptr, pre_lo);
+            tmem_ld_wait_half<16>(v);
+            epilogue_chunk<true, false, kSplit, kAct, true, 16, 32>(kFlags, ja, v, t.c0 + cb, args.tile_n - cb, valid, res_smem,
+                                                                    out_smem, half * 4, swz, pix, rpix, gpix, g, shift_j,
+                                                                    kPreRes ? pre_hi : nullptr, pre_lo);
           }
           if (kPreRes && sub + 1 < n_sub) prefetch_res(t, sub + 1);
           if (aux_on) {

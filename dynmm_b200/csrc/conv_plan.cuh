@@ -188,14 +188,16 @@ __device__ __forceinline__ uint4 ld_feat(const __nv_bfloat16* p) {
 //         read them through L2 (ld.global.cg), never through the non-coherent path.
 // kFullCols (TMA epilogue of conv_igemm.cu): the sub-tile is a full 64-column one and the shift vector is staged (zero
 // padded) for every column of it, so the per-group bounds tests fall away; columns >= c_out are clipped by the TMA store
-template <bool kTma, bool kCg, bool kSplit = false, bool kAct = false, bool kFullCols = false>
+// [kJ0, kJ1): which of the thread's 32 columns this call converts (the TMA epilogue converts the first 16 while the
+// TMEM load of the other 16 is in flight)
+template <bool kTma, bool kCg, bool kSplit = false, bool kAct = false, bool kFullCols = false, int kJ0 = 0, int kJ1 = 32>
 __device__ __forceinline__ void epilogue_chunk(const int kFlags, const KernelArgs& args, const uint32_t (&v)[32], int c_first,
                                                int cols_left, bool valid, uint32_t res_smem, uint32_t out_smem,
                                                uint32_t chunk0, uint32_t swz, size_t pix, size_t rpix, size_t gpix,
                                                float g, const float* shift_smem, const uint4* pre_hi = nullptr,
                                                const uint4* pre_lo = nullptr) {
 #pragma unroll
-  for (int j = 0; j < 32; j += 8) {
+  for (int j = kJ0; j < kJ1; j += 8) {
     const int c = c_first + j;
     if (kFullCols || (j < cols_left && c < args.c_out)) {
       float f[8];

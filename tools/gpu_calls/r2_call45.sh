@@ -1,6 +1,6 @@
 #!/bin/bash
-# round 2, call 45: A/B of the TMA epilogue without per-group bounds tests (new .so in tree, previous one in tools/bin)
-O=gpurun_out/r2ak
+# round 2, call 45 / 66: A/B of a conv epilogue change (new .so in tree, previous one in tools/bin)
+O=gpurun_out/r2bb
 mkdir -p $O
 timeout 1500 python -m pytest tests -m gpu -q -x > $O/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $O/pytest_gpu.log
 grep -E "passed|failed|FAILED" $O/pytest_gpu.log | tail -4 | cut -c1-250
