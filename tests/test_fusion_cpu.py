@@ -157,3 +157,28 @@ def test_chain_layer_lists_follow_the_block_structure():
     assert [l[5] for l in cut[:-1]] == [0, 0, 0, 1, 0, 0, 0, 1, 0, 0]
     one = ops.nbt1d_chain_layers(blocks[:1], drop_last=True)               # a two-block stage: nothing stored to `out`
     assert [l[5] for l in one] == [0, 0, 2]
+
+
+def test_stem_bn_host_vector_layout():
+    """The host copy of the stem's BN vectors that travels as a kernel parameter (dynmm_stem_s2d_fwd's ``bn_host``):
+    [scale_rgb | shift_rgb | scale_d | shift_d], 256 contiguous fp32 values on the host."""
+    from dynmm_b200 import ops
+    parts = [torch.arange(64, dtype=torch.float32) + 100 * i for i in range(4)]
+    v = ops.stem_s2d_bn_host(parts[0], parts[1].double(), parts[2], parts[3].reshape(64, 1))
+    assert v.dtype == torch.float32 and not v.is_cuda and v.is_contiguous() and v.shape == (256,)
+    assert torch.equal(v, torch.cat([p.reshape(64).float() for p in parts]))
+
+
+def test_training_stem_switches_to_channels_last_only_for_the_bf16_graph(monkeypatch):
+    """`stem_channels_last` (bf16 training graph on CUDA) is a layout change only: same values as forward_first_conv."""
+    from dynmm_b200.fusion.modules import stem_channels_last
+    m = _model(fo.FusionConfig(height=64, width=64))
+    m.train()
+    x = torch.randn(2, 3, 64, 64)
+    torch.manual_seed(0)
+    ref = m.encoder_rgb.forward_first_conv(x)
+    got = stem_channels_last(m.encoder_rgb, x)
+    assert got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.allclose(got, ref, rtol=1e-5, atol=1e-5)
+    monkeypatch.setenv("DYNMM_TRAIN_STEM", "nchw")
+    assert stem_channels_last(m.encoder_rgb, x).is_contiguous()
